@@ -1,0 +1,111 @@
+/* zq_b200.h -- C ABI of libzqb200.so: the B200 (sm_100a) implementation of zpaqfranz's two
+ * data-parallel hot paths: libzpaq block compression and the dedup fragmenter with
+ * its fragment/file hashes.  Plain pointers and sizes only; no C++/torch types cross this line.
+ *
+ * Every entry point cites the reference interface it replaces ("Z:" = zpaqfranz.cpp line).
+ * All functions return 0 on success and a negative code on failure; zq_last_error() gives the text
+ * the reference would have passed to libzpaq::error() (Z:12560 / Z:27148).  There is NO CPU
+ * fallback: without a usable CUDA device zq_create() fails and every compute entry point returns
+ * ZQ_E_NODEVICE.
+ */
+#ifndef ZQ_B200_H
+#define ZQ_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zq_ctx zq_ctx;
+
+enum {
+  ZQ_OK = 0,
+  ZQ_E_NODEVICE = -1,   /* no CUDA device / driver error                      */
+  ZQ_E_ARG = -2,        /* bad argument                                       */
+  ZQ_E_METHOD = -3,     /* libzpaq::error() text in zq_last_error()           */
+  ZQ_E_NOMEM = -4,      /* device or host allocation failed ("Out of memory") */
+  ZQ_E_OUTPUT = -5,     /* caller's output buffer too small                   */
+  ZQ_E_UNSUPPORTED = -6 /* valid ZPAQ input this build has no device path for */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* One context per host thread / CUDA device (mirrors "one Compressor per thread", ZSFX/libzpaq.h:56). */
+zq_ctx* zq_create(int device);
+void zq_destroy(zq_ctx* ctx);
+const char* zq_last_error(zq_ctx* ctx);      /* ctx may be NULL: error of the last failed zq_create */
+const char* zq_version(void);
+
+/* ---- host-side planning (no GPU needed) ------------------------------------------------------ */
+/* What libzpaq::compressBlock derives before touching data (Z:20262-20394): the expanded method,
+ * makeConfig's args and the assembled block header / PCOMP bytes (Compiler, Z:15904).
+ * Buffers may be NULL to query sizes.  data/n are only read for digit levels >= 5. */
+int zq_plan_block(const char* method, const uint8_t* data, uint32_t n,
+                  char* expanded, size_t expanded_cap, int args9[9],
+                  uint8_t* header, uint32_t* header_len,   /* in: capacity, out: length */
+                  uint8_t* pcomp, uint32_t* pcomp_len,
+                  char* errbuf, size_t errcap);
+
+/* ---- block compression ------------------------------------------------------------------------
+ * Element-wise == libzpaq::compressBlock(StringBuffer* in, Writer* out, method, filename, comment,
+ * dosha1) (Z:20255): unit u reads in_base[in_off[u] .. +in_len[u]) and produces one complete ZPAQ
+ * block (tag .. 0xFF) at out_base[out_off[u] .. +out_len[u]).  Blocks are laid out back to back in
+ * unit order, so the concatenation is a valid archive stream.
+ *   method/filename/comment: arrays of n C strings, or NULL; if `uniform` != 0 only element [0] of
+ *   each non-NULL array is read and applied to every unit.
+ * Host variant: in_base/out_base are host pointers (pinned or pageable); H2D/D2H are part of the call. */
+int zq_compress_blocks(zq_ctx* ctx, int n,
+                       const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                       const char* const* method, const char* const* filename,
+                       const char* const* comment, int uniform, int dosha1,
+                       uint8_t* out_base, uint64_t out_cap,
+                       uint64_t* out_off, uint32_t* out_len);
+
+/* Device variant: in_base/out_base are device pointers on ctx's device; offsets/lengths stay on the
+ * host.  Used for HBM-resident measurement and by callers that already staged data. */
+int zq_compress_blocks_device(zq_ctx* ctx, int n,
+                              const uint8_t* d_in_base, const uint64_t* in_off, const uint32_t* in_len,
+                              const char* const* method, const char* const* filename,
+                              const char* const* comment, int uniform, int dosha1,
+                              uint8_t* d_out_base, uint64_t out_cap,
+                              uint64_t* out_off, uint32_t* out_len);
+
+/* Upper bound of one block's compressed size for an n-byte input (any method, names <= 255 bytes). */
+uint64_t zq_compress_bound(uint32_t n);
+
+/* ---- hashes: n independent buffers -> n digests ----------------------------------------------
+ * == libzpaq::SHA1::write+result (Z:12637), libzpaq::SHA256 (Z:12828), XXH3_128bits (Z:24710,
+ * printed high64||low64, Z:67189), blake3_hasher_* (Z:22143-22221).  Host pointers. */
+int zq_sha1(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests20);
+int zq_sha256(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests32);
+int zq_xxh3_128(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests16);
+int zq_blake3(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests32);
+/* device-pointer variants (digests also written to device memory) */
+int zq_sha1_device(zq_ctx* ctx, int n, const uint8_t* d_base, const uint64_t* off, const uint64_t* len, uint8_t* d_digests20);
+
+/* ---- dedup fragmenter --------------------------------------------------------------------------
+ * == the content-defined chunker inlined in Jidac::add (Z:122180-122574; canonical loop
+ * Z:95604-95633; constants Z:121626-121631): for each of nfiles independent byte streams emit the
+ * fragment lengths, per-fragment `hits` and per-fragment SHA-1 (the dedup key, Z:122569).
+ * Output arrays are filled file after file; frag_first[f] .. frag_first[f+1] index file f's fragments
+ * (frag_first has nfiles+1 entries).  `fragment` is -fragment N (default 6); blocksize as in
+ * Z:121622-121625.  Host pointers. */
+int zq_fragment(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* off, const uint64_t* len,
+                int fragment, uint32_t blocksize,
+                uint32_t* frag_len, uint32_t* frag_hits, uint8_t* frag_sha1 /* may be NULL */,
+                uint64_t frag_cap, uint64_t* frag_first);
+
+/* ---- introspection for tests / bench ---------------------------------------------------------- */
+/* number of kernel launches issued by this context since creation */
+uint64_t zq_launch_count(zq_ctx* ctx);
+/* elapsed device time (ms, CUDA events on the context's stream) of the stages of the most recent
+ * zq_compress_blocks* call: [0] total, [1] sha1, [2] suffix sort + lcp, [3] lz parse, [4] framing/
+ * gather, [5] modeling/coding, [6] h2d, [7] d2h.  Unused stages are 0. */
+int zq_last_timings(zq_ctx* ctx, float ms[8]);
+/* debugging aid for the parity tests: suffix array (u32[n]) of one buffer, computed on the device */
+int zq_suffix_array(zq_ctx* ctx, const uint8_t* data, uint32_t n, uint32_t* sa_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZQ_B200_H */

@@ -1,0 +1,89 @@
+"""Parity of the CUDA block compressor (through the C ABI) with the oracle and the reference."""
+import numpy as np
+import pytest
+
+from zpaqfranz_b200 import corpus
+
+pytestmark = pytest.mark.gpu
+
+
+def _arena(units):
+    lens = np.array([len(u) for u in units], dtype=np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens.astype(np.uint64))[:-1]]).astype(np.uint64)
+    arena = np.frombuffer(b"".join(units) + b"\0", dtype=np.uint8)
+    return arena, offs, lens
+
+
+EDGE_UNITS = [
+    b"", b"a", b"ab", b"abc", b"abcd", b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", bytes(5), bytes(4097), bytes(65536),
+    bytes([255]) * 70000, b"abcabcabcabcabc" * 10, bytes([0, 0, 1, 0, 0, 0, 1, 0]) * 500,
+    corpus.text_unit(1, 65536), corpus.text_unit(2, 65535), corpus.text_unit(3, 65537), corpus.random_unit(4, 20000),
+    corpus.repeats_unit(5, 65536), corpus.text_unit(6, 1000), corpus.text_unit(7, 200000), corpus.repeats_unit(8, 300000),
+    (corpus.text_unit(9, 30000) * 3), corpus.random_unit(10, 70000) + corpus.random_unit(10, 70000),
+]
+
+
+def test_sha1_many(ctx, oracle):
+    arena, offs, lens = _arena(EDGE_UNITS + [corpus.random_unit(s, 1 + 61 * s) for s in range(40)])
+    # unaligned starts on purpose: shift the arena by 1..3 bytes
+    for shift in (0, 1, 3):
+        a2 = np.concatenate([np.zeros(shift, np.uint8), arena])
+        dg = ctx.sha1(a2, offs + np.uint64(shift), lens)
+        for i in range(len(offs)):
+            o, l = int(offs[i]), int(lens[i])
+            assert dg[i].tobytes() == oracle.sha1(arena[o:o + l].tobytes()), (shift, i)
+
+
+def test_suffix_array_matches_oracle(ctx, oracle):
+    for u in EDGE_UNITS:
+        if not u:
+            continue
+        sa = ctx.suffix_array(u)
+        assert (sa == oracle.suffix_array(u)).all(), len(u)
+
+
+@pytest.mark.parametrize("method", ["2", "0", "26,200,1", "x0,0", "x0,1,4,0,7,21,1", "x0,1,4,0,7,21,0", "x0,1,6,0,5,21,2",
+                                     "x0,1,4,0,4,21,1"])
+def test_unmodeled_blocks_bit_exact(ctx, zq, oracle, ref, method):
+    arena, offs, lens = _arena(EDGE_UNITS)
+    out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method=method, filename="nm", comment="jDC\x01")
+    for i, u in enumerate(EDGE_UNITS):
+        got = out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes()
+        p = zq.plan_block(method, u)
+        s = oracle.lz_stream(u, p["args"]) if (p["args"][1] & 3) else u
+        want = oracle.block_unmodeled(p["header"], p["pcomp"], b"nm", ("%d jDC\x01" % len(u)).encode(), s, oracle.sha1(u))
+        assert got == want, (method, i, len(u))
+        assert got == ref.compress_block(u, method, "nm", "jDC\x01"), (method, i, len(u))
+    # the concatenation is a valid archive stream: the reference decoder restores every unit
+    total = int(ooff[-1]) + int(olen[-1])
+    assert ref.decompress(out[:total].tobytes(), int(lens.sum())) == b"".join(EDGE_UNITS)
+
+
+def test_per_unit_methods_and_names(ctx, ref):
+    units = [corpus.text_unit(s, 20000 + 1000 * s) for s in range(6)]
+    methods = ["2", "0", "x0,0", "2", "26,200,1", "x0,1,4,0,7,21,1"]
+    names = ["f%d" % i for i in range(6)]
+    arena, offs, lens = _arena(units)
+    out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method=methods, filename=names, comment=["c"] * 6, dosha1=False)
+    for i, u in enumerate(units):
+        got = out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes()
+        assert got == ref.compress_block(u, methods[i], names[i], "c", dosha1=False), i
+
+
+def test_batch_of_text_units_m2(ctx, ref):
+    n = 296
+    arena = corpus.text_corpus(n)
+    offs = np.arange(n, dtype=np.uint64) * 65536
+    lens = np.full(n, 65536, dtype=np.uint32)
+    out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method="2", filename="", comment="")
+    for i in list(range(0, n, 37)) + [n - 1]:
+        u = arena[i * 65536:(i + 1) * 65536].tobytes()
+        assert out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes() == ref.compress_block(u, "2", "", ""), i
+    total = int(ooff[-1]) + int(olen[-1])
+    assert ref.decompress(out[:total].tobytes(), n * 65536) == arena.tobytes()
+
+
+def test_unsupported_is_loud(ctx, zq):
+    arena, offs, lens = _arena([corpus.text_unit(1, 5000)])
+    with pytest.raises(zq.ZqError):
+        ctx.compress_blocks(arena, offs, lens, method="x0,1,2,0,3,20")   # LZ77 min match too small / hash path

@@ -1,0 +1,49 @@
+"""Pins the plain-C oracle (oracle/zq_oracle.c) against (a) the reference's own known-answer vectors
+and (b) the reference compiled here (oracle/_ref/libzpaqref.so)."""
+import pytest
+
+from zpaqfranz_b200 import corpus
+
+CASES = [
+    corpus.text_unit(1, 65536), corpus.random_unit(2, 20000), corpus.repeats_unit(3, 65536), bytes(70000), b"", b"a",
+    b"abcabcabcabcabc" * 10, corpus.text_unit(5, 200000), bytes([0, 0, 1, 0, 0, 0, 1, 0]) * 500,
+]
+
+
+def test_sha1_known_answers(oracle):
+    # reference autotest KAT: SHA-1("ABCDE") (Z:77129-77160); FIPS 180 "abc"; empty input (Z:20670-20724)
+    assert oracle.sha1(b"ABCDE").hex().upper() == "7BE07AAF460D593A323D0DB33DA05B64BFDCB3A5"
+    assert oracle.sha1(b"abc").hex() == "a9993e364706816aba3e25717850c26c9cd0d89d"
+    assert oracle.sha1(b"").hex() == "da39a3ee5e6b4b0d3255bfef95601890afd80709"
+
+
+def test_sha1_and_suffix_array_vs_reference(oracle, ref):
+    for d in CASES:
+        assert oracle.sha1(d) == ref.sha1(d)
+        if d:
+            assert (oracle.suffix_array(d) == ref.divsufsort(d)).all()
+
+
+@pytest.mark.parametrize("method", ["2", "1", "3", "1,10,0", "1,20,0", "2,10,0", "4,8,0", "0", "26,100,0"])
+def test_lz_stream_and_block_vs_reference(zq, oracle, ref, method):
+    for d in CASES:
+        p = zq.plan_block(method, d)
+        a = p["args"]
+        if (a[1] & 3) == 3 or a[1] >= 4:
+            continue
+        s = d
+        if a[1] & 3:
+            s = oracle.lz_stream(d, a)
+            assert s == ref.lz_stream(d, a)
+        if p["header"][6] == 0:
+            blk = oracle.block_unmodeled(p["header"], p["pcomp"], b"nm", ("%d cm" % len(d)).encode(), s, oracle.sha1(d))
+            assert blk == ref.compress_block(d, method, "nm", "cm")
+            assert ref.decompress(blk, len(d)) == d
+
+
+def test_fragmenter_restatement_agrees(oracle, ref):
+    d = corpus.text_unit(9, 400000) + corpus.random_unit(9, 300000) + bytes(600000)
+    for frag in (6, 4, 0):
+        a, b = oracle.fragment(d, frag), ref.fragment(d, frag)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+        assert int(a[0].sum()) == len(d)

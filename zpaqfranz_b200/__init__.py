@@ -1,0 +1,219 @@
+"""zpaqfranz_b200 -- B200-native (sm_100a) implementation of zpaqfranz's block compressor and dedup
+fragmenter hot paths, behind the reference's libzpaq API.
+
+This package is a thin ctypes view of the C-ABI shared library (include/zq_b200.h).  The compute is
+hand-written CUDA inside libzqb200.so; there is no CPU fallback: without the built library the import
+fails, and without a CUDA device `Context()` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libzqb200.so")
+
+ZQ_OK, ZQ_E_NODEVICE, ZQ_E_ARG, ZQ_E_METHOD, ZQ_E_NOMEM, ZQ_E_OUTPUT, ZQ_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+
+
+class ZqError(RuntimeError):
+    """Raised where the reference would call libzpaq::error() (Z:12560)."""
+
+    def __init__(self, code, msg):
+        super().__init__("zq error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            "libzqb200.so is not built: run `python -m zpaqfranz_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback.")
+    lib = C.CDLL(_LIB_PATH)
+    u8p, u32p, u64p, cpp = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_char_p)
+    lib.zq_create.restype = C.c_void_p
+    lib.zq_create.argtypes = [C.c_int]
+    lib.zq_destroy.argtypes = [C.c_void_p]
+    lib.zq_last_error.restype = C.c_char_p
+    lib.zq_last_error.argtypes = [C.c_void_p]
+    lib.zq_version.restype = C.c_char_p
+    lib.zq_compress_bound.restype = C.c_uint64
+    lib.zq_compress_bound.argtypes = [C.c_uint32]
+    lib.zq_plan_block.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_int),
+                                  C.c_void_p, u32p, C.c_void_p, u32p, C.c_char_p, C.c_size_t]
+    for name in ("zq_compress_blocks", "zq_compress_blocks_device"):
+        f = getattr(lib, name)
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, cpp, cpp, cpp, C.c_int, C.c_int,
+                      C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    for name in ("zq_sha1", "zq_sha256", "zq_xxh3_128", "zq_blake3", "zq_sha1_device"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.zq_fragment.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.zq_launch_count.restype = C.c_uint64
+    lib.zq_launch_count.argtypes = [C.c_void_p]
+    lib.zq_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.zq_suffix_array.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    return lib
+
+
+lib = _load()
+
+TIMING_KEYS = ("total", "sha1", "sufsort", "lzparse", "frame", "model", "h2d", "d2h")
+
+
+def plan_block(method, data=b""):
+    """Host-side planning (== the part of libzpaq::compressBlock before the data is touched).
+    Returns dict(method=expanded, args=[9], header=bytes, pcomp=bytes)."""
+    data = bytes(data)
+    exp = C.create_string_buffer(1024)
+    args = (C.c_int * 9)()
+    hdr = C.create_string_buffer(70000)
+    pc = C.create_string_buffer(70000)
+    hl, pl = C.c_uint32(70000), C.c_uint32(70000)
+    err = C.create_string_buffer(512)
+    rc = lib.zq_plan_block(method.encode(), data, len(data), exp, 1024, args, hdr, C.byref(hl), pc, C.byref(pl), err, 512)
+    if rc:
+        raise ZqError(rc, err.value.decode(errors="replace"))
+    return dict(method=exp.value.decode(), args=list(args), header=hdr.raw[:hl.value], pcomp=pc.raw[:pl.value])
+
+
+def _cstr_array(v, n, uniform):
+    if v is None:
+        return None
+    if isinstance(v, (str, bytes)):
+        v = [v]
+    arr = (C.c_char_p * len(v))(*[(s.encode() if isinstance(s, str) else s) for s in v])
+    return arr
+
+
+class Context:
+    """One CUDA device context (== one libzpaq Compressor-owning thread)."""
+
+    def __init__(self, device=0):
+        self._h = lib.zq_create(int(device))
+        if not self._h:
+            raise ZqError(ZQ_E_NODEVICE, lib.zq_last_error(None).decode(errors="replace"))
+
+    def close(self):
+        if self._h:
+            lib.zq_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise ZqError(rc, lib.zq_last_error(self._h).decode(errors="replace"))
+
+    # -- block compression ------------------------------------------------------------------------
+    def compress_blocks(self, arena, offsets, lengths, method="2", filename=None, comment=None, dosha1=True, out=None):
+        """Element-wise libzpaq::compressBlock over units arena[offsets[i]:offsets[i]+lengths[i]].
+        `arena` is a contiguous uint8 numpy array (pinned or pageable host memory).
+        method/filename/comment: one string for all units, or a list per unit.
+        Returns (out_array, out_off, out_len)."""
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+        n = len(off)
+        uniform = all(isinstance(x, (str, bytes)) or x is None for x in (method, filename, comment))
+        if not uniform:
+            def expand(x):
+                return [x] * n if isinstance(x, (str, bytes)) else x
+            method, filename, comment = expand(method), expand(filename), expand(comment)
+        m, f, cm = _cstr_array(method, n, uniform), _cstr_array(filename, n, uniform), _cstr_array(comment, n, uniform)
+        if out is None:
+            cap = int(sum(int(lib.zq_compress_bound(int(x))) for x in np.unique(ln)) if n < 64 else
+                      int(lib.zq_compress_bound(int(ln.max()))) * n)
+            out = np.empty(cap, dtype=np.uint8)
+        ooff = np.zeros(n, dtype=np.uint64)
+        olen = np.zeros(n, dtype=np.uint32)
+        rc = lib.zq_compress_blocks(self._h, n, arena.ctypes.data, off.ctypes.data, ln.ctypes.data, m, f, cm,
+                                    1 if uniform else 0, 1 if dosha1 else 0, out.ctypes.data, out.size,
+                                    ooff.ctypes.data, olen.ctypes.data)
+        self._check(rc)
+        return out, ooff, olen
+
+    def compress_blocks_device(self, d_in_ptr, offsets, lengths, d_out_ptr, out_cap, method="2", filename=None,
+                               comment=None, dosha1=True):
+        """Same, with device pointers (ints) for the input arena and the output buffer."""
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+        n = len(off)
+        m, f, cm = _cstr_array(method, n, True), _cstr_array(filename, n, True), _cstr_array(comment, n, True)
+        ooff = np.zeros(n, dtype=np.uint64)
+        olen = np.zeros(n, dtype=np.uint32)
+        rc = lib.zq_compress_blocks_device(self._h, n, d_in_ptr, off.ctypes.data, ln.ctypes.data, m, f, cm, 1,
+                                           1 if dosha1 else 0, d_out_ptr, out_cap, ooff.ctypes.data, olen.ctypes.data)
+        self._check(rc)
+        return ooff, olen
+
+    def compress_block(self, data, method="1", filename=None, comment=None, dosha1=True):
+        """Single-block convenience: bytes in, one ZPAQ block out (== compressBlock)."""
+        a = np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(0, dtype=np.uint8)
+        out, ooff, olen = self.compress_blocks(a if len(a) else np.zeros(1, np.uint8), [0], [len(data)], method, filename, comment, dosha1)
+        return out[: int(olen[0])].tobytes()
+
+    # -- hashes -------------------------------------------------------------------------------------
+    def _hash(self, fn, dlen, arena, offsets, lengths):
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        out = np.zeros((len(off), dlen), dtype=np.uint8)
+        self._check(fn(self._h, len(off), arena.ctypes.data, off.ctypes.data, ln.ctypes.data, out.ctypes.data))
+        return out
+
+    def sha1(self, arena, offsets, lengths):
+        return self._hash(lib.zq_sha1, 20, arena, offsets, lengths)
+
+    def sha256(self, arena, offsets, lengths):
+        return self._hash(lib.zq_sha256, 32, arena, offsets, lengths)
+
+    def xxh3_128(self, arena, offsets, lengths):
+        return self._hash(lib.zq_xxh3_128, 16, arena, offsets, lengths)
+
+    def blake3(self, arena, offsets, lengths):
+        return self._hash(lib.zq_blake3, 32, arena, offsets, lengths)
+
+    # -- fragmenter ---------------------------------------------------------------------------------
+    def fragment(self, arena, offsets, lengths, fragment=6, blocksize=(1 << 26) - 4096, want_sha1=True):
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        nf = len(off)
+        minf = min(64 << fragment, blocksize - 12)
+        cap = int(sum(int(x) // minf + 2 for x in ln))
+        fl = np.zeros(cap, dtype=np.uint32)
+        fh = np.zeros(cap, dtype=np.uint32)
+        fs = np.zeros((cap, 20), dtype=np.uint8) if want_sha1 else None
+        first = np.zeros(nf + 1, dtype=np.uint64)
+        self._check(lib.zq_fragment(self._h, nf, arena.ctypes.data, off.ctypes.data, ln.ctypes.data, fragment, blocksize,
+                                    fl.ctypes.data, fh.ctypes.data, fs.ctypes.data if want_sha1 else None, cap,
+                                    first.ctypes.data))
+        k = int(first[nf])
+        return fl[:k], fh[:k], (fs[:k] if want_sha1 else None), first
+
+    # -- introspection ------------------------------------------------------------------------------
+    def launch_count(self):
+        return int(lib.zq_launch_count(self._h))
+
+    def last_timings(self):
+        ms = (C.c_float * 8)()
+        lib.zq_last_timings(self._h, ms)
+        return dict(zip(TIMING_KEYS, [float(x) for x in ms]))
+
+    def suffix_array(self, data):
+        a = np.frombuffer(bytes(data), dtype=np.uint8)
+        sa = np.zeros(len(a), dtype=np.uint32)
+        if len(a):
+            self._check(lib.zq_suffix_array(self._h, a.ctypes.data, len(a), sa.ctypes.data))
+        return sa

@@ -1,0 +1,468 @@
+// zq_api.cu -- context, wave orchestration and the extern "C" boundary (include/zq_b200.h).
+// Host C++ above the C ABI stays tiny: method planning (zq_config.cpp), descriptor upload, kernel
+// launches on one stream, one small D2H (stream lengths) to lay the finished blocks back to back.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zq_b200.h"
+#include "zq_common.cuh"
+#include "zq_config.h"
+#include "zq_frame.cuh"
+#include "zq_lz77.cuh"
+#include "zq_sha1.cuh"
+#include "zq_sufsort.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  bool used = false;
+};
+
+}  // namespace
+
+struct zq_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_sa, d_isa, d_lcp, d_lz, d_lzlen, d_sha,
+      d_kbuf, d_vbuf, d_err, d_misc;
+  Timer tm[8];
+  float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  size_t wave_elems = (size_t)1 << 30;  // suffix-array elements per wave (10 B each)
+};
+
+namespace {
+
+int fail(zq_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+#define ZQ_CUDA(c, call)                                                                          \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(c, e_ == cudaErrorMemoryAllocation ? ZQ_E_NOMEM : ZQ_E_NODEVICE,                 \
+                  std::string(e_ == cudaErrorMemoryAllocation ? "Out of memory: " : "CUDA error: ") + \
+                      cudaGetErrorString(e_) + " at " #call);                                      \
+  } while (0)
+
+void tstart(zq_ctx* c, int k) { cudaEventRecord(c->tm[k].a, c->stream); c->tm[k].used = true; }
+void tstop(zq_ctx* c, int k) { cudaEventRecord(c->tm[k].b, c->stream); }
+
+struct HostPlan {
+  zq::BlockPlan bp;
+  std::vector<uint8_t> payload;  // selector + pcomp
+};
+
+static const unsigned char kTag[13] = {0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83, 0xd3, 0x8c, 0xb2, 0x28, 0xb0, 0xd3};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// The core: inputs and outputs already on the device.
+int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len,
+                  const char* const* method, const char* const* filename, const char* const* comment,
+                  int uniform, int dosha1, uint8_t* d_out, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
+                  const uint8_t* h_in /* host copy of the arena or null */) {
+  using namespace zqdev;
+  if (n < 0 || (n > 0 && (!in_off || !in_len || !out_off || !out_len))) return fail(c, ZQ_E_ARG, "bad argument");
+  if (n == 0) return ZQ_OK;
+  // ---- plans -----------------------------------------------------------------------------------
+  std::vector<HostPlan> plans;
+  std::map<std::string, int> plan_idx;
+  std::vector<ZqUnit> units(n);
+  std::vector<uint8_t> blob;
+  std::vector<uint32_t> prefix_len(n);
+  try {
+    for (int u = 0; u < n; ++u) {
+      const char* m = method ? method[uniform ? 0 : u] : "1";
+      if (!m || !*m) return fail(c, ZQ_E_ARG, "empty method");
+      const uint32_t len = in_len[u];
+      int arg0 = zq::bitlen(len + 4095) - 20; if (arg0 < 0) arg0 = 0;
+      const bool data_dependent = isdigit((unsigned char)m[0]) && m[0] >= '5';
+      std::string key = std::string(m) + "|" + std::to_string(arg0);
+      int pi;
+      auto it = data_dependent ? plan_idx.end() : plan_idx.find(key);
+      if (it != plan_idx.end()) pi = it->second;
+      else {
+        if (data_dependent && !h_in) return fail(c, ZQ_E_UNSUPPORTED, "method level >= 5 needs host-visible input for its period analysis");
+        HostPlan hp;
+        hp.bp = zq::plan_block(m, data_dependent ? h_in + in_off[u] : nullptr, len);
+        const auto& pc = hp.bp.code.pcomp;
+        if (!pc.empty()) { hp.payload.push_back(1); hp.payload.push_back(pc.size() & 255); hp.payload.push_back(pc.size() >> 8); hp.payload.insert(hp.payload.end(), pc.begin(), pc.end()); }
+        else hp.payload.push_back(0);
+        pi = (int)plans.size();
+        plans.push_back(std::move(hp));
+        if (!data_dependent) plan_idx[key] = pi;
+      }
+      const HostPlan& hp = plans[pi];
+      ZqUnit& zu = units[u];
+      memset(&zu, 0, sizeof zu);
+      zu.in_off = in_off[u]; zu.n = len; zu.plan = (u32)pi;
+      // prefix: tag, "zPQ", level, 1, header, 1, filename, 0, "<n>[ comment]", 0, 0
+      zu.prefix_off = (u32)blob.size();
+      blob.insert(blob.end(), kTag, kTag + 13);
+      blob.push_back('z'); blob.push_back('P'); blob.push_back('Q');
+      blob.push_back(1 + (hp.bp.code.ncomp == 0)); blob.push_back(1);
+      blob.insert(blob.end(), hp.bp.code.header.begin(), hp.bp.code.header.end());
+      blob.push_back(1);
+      const char* fn = filename ? filename[uniform ? 0 : u] : nullptr;
+      if (fn) blob.insert(blob.end(), fn, fn + strlen(fn));
+      blob.push_back(0);
+      std::string cs = std::to_string(len);
+      const char* cm = comment ? comment[uniform ? 0 : u] : nullptr;
+      if (cm) { cs += " "; cs += cm; }
+      blob.insert(blob.end(), cs.begin(), cs.end());
+      blob.push_back(0); blob.push_back(0);
+      zu.prefix_len = (u32)blob.size() - zu.prefix_off;
+      prefix_len[u] = zu.prefix_len;
+    }
+  } catch (const zq::Error& e) {
+    return fail(c, ZQ_E_METHOD, e.msg);
+  }
+  std::vector<ZqPlan> dplans(plans.size());
+  for (size_t i = 0; i < plans.size(); ++i) {
+    ZqPlan& p = dplans[i];
+    memcpy(p.args, plans[i].bp.args, sizeof p.args);
+    p.payload_off = (u32)blob.size(); p.payload_len = (u32)plans[i].payload.size();
+    blob.insert(blob.end(), plans[i].payload.begin(), plans[i].payload.end());
+    p.lz_level = plans[i].bp.lz_level; p.use_sa = plans[i].bp.use_sa; p.e8e9 = plans[i].bp.e8e9;
+    p.modeled = plans[i].bp.code.ncomp > 0;
+    if (p.modeled) return fail(c, ZQ_E_UNSUPPORTED, "context-mixing methods are not on the device yet: " + plans[i].bp.method);
+    if (p.e8e9) return fail(c, ZQ_E_UNSUPPORTED, "E8E9 pre-filter is not on the device yet: " + plans[i].bp.method);
+    if (p.lz_level && !p.use_sa) return fail(c, ZQ_E_UNSUPPORTED, "hash-table LZ77 is not on the device yet: " + plans[i].bp.method);
+  }
+  // ---- device tables -----------------------------------------------------------------------------
+  for (int k = 0; k < 8; ++k) c->tm[k].used = false;
+  tstart(c, 0);
+  ZQ_CUDA(c, c->d_plans.ensure(dplans.size() * sizeof(ZqPlan)));
+  ZQ_CUDA(c, c->d_blob.ensure(blob.size()));
+  ZQ_CUDA(c, c->d_units.ensure((size_t)n * sizeof(ZqUnit)));
+  ZQ_CUDA(c, c->d_outoff.ensure((size_t)n * 8));
+  ZQ_CUDA(c, c->d_lzlen.ensure((size_t)n * 4));
+  ZQ_CUDA(c, c->d_todo.ensure((size_t)n * 4));
+  ZQ_CUDA(c, c->d_err.ensure(64));
+  if (dosha1) ZQ_CUDA(c, c->d_sha.ensure((size_t)n * 20));
+  ZQ_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 64, c->stream));
+  // waves: contiguous unit ranges whose suffix-array footprint fits wave_elems
+  std::vector<uint32_t> lz_len_h(n, 0);
+  uint64_t out_pos = 0;
+  int w0 = 0;
+  while (w0 < n) {
+    size_t elems = 0, lzbytes = 0, maxn = 0;
+    int w1 = w0;
+    std::vector<int> todo_sa;
+    while (w1 < n) {
+      ZqUnit& zu = units[w1];
+      const ZqPlan& p = dplans[zu.plan];
+      size_t e = p.use_sa ? align_up((size_t)zu.n + 1, 64) : 0;
+      if (w1 > w0 && elems + e > c->wave_elems) break;
+      zu.work_off = elems; elems += e;
+      if (p.lz_level) {
+        zu.lz_off = lzbytes; zu.lz_cap = zu.n + zu.n / 32 + 64; lzbytes += align_up(zu.lz_cap, 16);
+        if (p.use_sa) { todo_sa.push_back(w1 - w0); maxn = std::max(maxn, (size_t)zu.n); }
+      }
+      ++w1;
+    }
+    const int wn = w1 - w0;
+    ZQ_CUDA(c, cudaMemcpyAsync(c->d_units.p, units.data() + w0, (size_t)wn * sizeof(ZqUnit), cudaMemcpyHostToDevice, c->stream));
+    ZQ_CUDA(c, cudaMemcpyAsync(c->d_plans.p, dplans.data(), dplans.size() * sizeof(ZqPlan), cudaMemcpyHostToDevice, c->stream));
+    ZQ_CUDA(c, cudaMemcpyAsync(c->d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+    const ZqUnit* du = c->d_units.as<ZqUnit>();
+    const ZqPlan* dp = c->d_plans.as<ZqPlan>();
+    if (dosha1) {
+      tstart(c, 1);
+      k_sha1_units<<<(wn + 127) / 128, 128, 0, c->stream>>>(d_in, du, wn, c->d_sha.as<u8>());
+      ++c->launches;
+      tstop(c, 1);
+    }
+    if (!todo_sa.empty()) {
+      const int nt = (int)todo_sa.size();
+      ZQ_CUDA(c, c->d_sa.ensure(elems * 4));
+      ZQ_CUDA(c, c->d_isa.ensure(elems * 4));
+      ZQ_CUDA(c, c->d_lcp.ensure(elems * 2));
+      ZQ_CUDA(c, c->d_lz.ensure(lzbytes));
+      const size_t scr = align_up(maxn + 1, 64);
+      const int sort_grid = std::min(nt, c->num_sms);
+      ZQ_CUDA(c, c->d_kbuf.ensure((size_t)sort_grid * 2 * scr * 8));
+      ZQ_CUDA(c, c->d_vbuf.ensure((size_t)sort_grid * 4 * scr * 4));
+      ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo.p, todo_sa.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
+      tstart(c, 2);
+      k_suffix_sort<<<sort_grid, SORT_THREADS, sizeof(SortSmem), c->stream>>>(
+          d_in, du, c->d_todo.as<int>(), nt, c->d_sa.as<u32>(), c->d_isa.as<u32>(), c->d_lcp.as<u16>(),
+          c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr);
+      ++c->launches;
+      tstop(c, 2);
+      tstart(c, 3);
+      const int pgrid = std::min((nt + 3) / 4, c->num_sms * 16);
+      k_lz77_sa<<<pgrid, 128, 0, c->stream>>>(d_in, du, dp, c->d_todo.as<int>(), nt, c->d_sa.as<u32>(), c->d_isa.as<u32>(),
+                                               c->d_lcp.as<u16>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_err.as<u32>());
+      ++c->launches;
+      tstop(c, 3);
+      ZQ_CUDA(c, cudaMemcpyAsync(lz_len_h.data() + w0, c->d_lzlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
+      ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    // final layout of this wave's blocks
+    std::vector<uint64_t> ooff(wn);
+    std::vector<int> todo_all(wn);
+    for (int k = 0; k < wn; ++k) {
+      const ZqUnit& zu = units[w0 + k];
+      const ZqPlan& p = dplans[zu.plan];
+      const uint64_t slen = p.lz_level ? lz_len_h[w0 + k] : zu.n;
+      const uint64_t sz = unmodeled_block_size(zu.prefix_len, (uint64_t)p.payload_len + slen, dosha1 != 0);
+      if (sz > 0xffffffffull) return fail(c, ZQ_E_OUTPUT, "block too large");
+      ooff[k] = out_pos; out_off[w0 + k] = out_pos; out_len[w0 + k] = (uint32_t)sz;
+      out_pos += sz;
+      todo_all[k] = k;
+    }
+    if (out_pos > out_cap) return fail(c, ZQ_E_OUTPUT, "output buffer too small");
+    ZQ_CUDA(c, cudaMemcpyAsync(c->d_outoff.p, ooff.data(), (size_t)wn * 8, cudaMemcpyHostToDevice, c->stream));
+    ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo.p, todo_all.data(), (size_t)wn * 4, cudaMemcpyHostToDevice, c->stream));
+    tstart(c, 4);
+    k_frame_unmodeled<<<std::min(wn, c->num_sms * 8), 256, 0, c->stream>>>(
+        du, dp, c->d_todo.as<int>(), wn, c->d_blob.as<u8>(), d_in, c->d_lz.as<u8>(), c->d_lzlen.as<u32>(),
+        dosha1 ? c->d_sha.as<u8>() : nullptr, c->d_outoff.as<u64>(), d_out);
+    ++c->launches;
+    tstop(c, 4);
+    ZQ_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors of this wave go out of scope
+    w0 = w1;
+  }
+  tstop(c, 0);
+  uint32_t errflag = 0;
+  ZQ_CUDA(c, cudaMemcpyAsync(&errflag, c->d_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  ZQ_CUDA(c, cudaGetLastError());
+  if (errflag) return fail(c, ZQ_E_OUTPUT, "internal: pre-pass stream exceeded its bound");
+  for (int k = 0; k < 8; ++k) {
+    c->last_ms[k] = 0;
+    if (c->tm[k].used) cudaEventElapsedTime(&c->last_ms[k], c->tm[k].a, c->tm[k].b);
+  }
+  return ZQ_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* zq_version(void) { return "zpaqfranz_b200 0.1 (sm_100a)"; }
+
+zq_ctx* zq_create(int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "bad device index"; return nullptr; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return nullptr; }
+  zq_ctx* c = new zq_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  c->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream creation failed"; delete c; return nullptr; }
+  for (int k = 0; k < 8; ++k) { cudaEventCreate(&c->tm[k].a); cudaEventCreate(&c->tm[k].b); }
+  if (const char* s = getenv("ZQ_WAVE_ELEMS")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->wave_elems = v; }
+  return c;
+}
+
+void zq_destroy(zq_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_sa, &c->d_isa,
+                    &c->d_lcp, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
+  for (DevBuf* b : bufs) b->release();
+  for (int k = 0; k < 8; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* zq_last_error(zq_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+uint64_t zq_compress_bound(uint32_t n) {
+  // stored/LZ worst case: n + n/32 + 64 stream bytes, 4 per 64 KiB chunk, prefix <= 13+5+64 KiB header,
+  // names <= 2*256, trailer 26. Generous and cheap.
+  return (uint64_t)n + n / 16 + 70000;
+}
+
+int zq_plan_block(const char* method, const uint8_t* data, uint32_t n, char* expanded, size_t expanded_cap, int args9[9],
+                  uint8_t* header, uint32_t* header_len, uint8_t* pcomp, uint32_t* pcomp_len, char* errbuf, size_t errcap) {
+  try {
+    if (!method || !*method) throw zq::Error("empty method");
+    zq::BlockPlan p = zq::plan_block(method, data, n);
+    if (expanded && expanded_cap) { strncpy(expanded, p.method.c_str(), expanded_cap - 1); expanded[expanded_cap - 1] = 0; }
+    if (args9) memcpy(args9, p.args, 9 * sizeof(int));
+    if (header_len) {
+      if (header && *header_len >= p.code.header.size()) memcpy(header, p.code.header.data(), p.code.header.size());
+      *header_len = (uint32_t)p.code.header.size();
+    }
+    if (pcomp_len) {
+      if (pcomp && *pcomp_len >= p.code.pcomp.size() && !p.code.pcomp.empty()) memcpy(pcomp, p.code.pcomp.data(), p.code.pcomp.size());
+      *pcomp_len = (uint32_t)p.code.pcomp.size();
+    }
+    return ZQ_OK;
+  } catch (const zq::Error& e) {
+    if (errbuf && errcap) { strncpy(errbuf, e.msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
+    return ZQ_E_METHOD;
+  }
+}
+
+int zq_compress_blocks_device(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len,
+                              const char* const* method, const char* const* filename, const char* const* comment,
+                              int uniform, int dosha1, uint8_t* d_out, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len) {
+  if (!c) return ZQ_E_NODEVICE;
+  cudaSetDevice(c->device);
+  return compress_core(c, n, d_in, in_off, in_len, method, filename, comment, uniform, dosha1, d_out, out_cap, out_off, out_len, nullptr);
+}
+
+int zq_compress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                       const char* const* method, const char* const* filename, const char* const* comment,
+                       int uniform, int dosha1, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len) {
+  if (!c) return ZQ_E_NODEVICE;
+  if (n < 0 || (n > 0 && (!in_base || !in_off || !in_len || !out_base))) return fail(c, ZQ_E_ARG, "bad argument");
+  if (n == 0) return ZQ_OK;
+  cudaSetDevice(c->device);
+  // stage the touched range of the arena
+  uint64_t lo = ~0ull, hi = 0, bound = 0;
+  for (int u = 0; u < n; ++u) {
+    lo = std::min(lo, in_off[u]); hi = std::max(hi, in_off[u] + in_len[u]);
+    bound += zq_compress_bound(in_len[u]);
+  }
+  if (hi < lo) hi = lo;
+  const uint64_t span = hi - lo;
+  ZQ_CUDA(c, c->d_in.ensure(span + 64));
+  ZQ_CUDA(c, c->d_out.ensure(std::min<uint64_t>(bound, std::max<uint64_t>(out_cap, 1)) + 64));
+  cudaEvent_t e0, e1, e2, e3;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+  cudaEventRecord(e0, c->stream);
+  if (span) ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, in_base + lo, span, cudaMemcpyHostToDevice, c->stream));
+  cudaEventRecord(e1, c->stream);
+  std::vector<uint64_t> roff(n);
+  for (int u = 0; u < n; ++u) roff[u] = in_off[u] - lo;
+  int rc = compress_core(c, n, c->d_in.as<uint8_t>(), roff.data(), in_len, method, filename, comment, uniform, dosha1,
+                         c->d_out.as<uint8_t>(), std::min<uint64_t>(c->d_out.cap, out_cap), out_off, out_len, in_base + lo);
+  if (rc == ZQ_OK) {
+    const uint64_t total = out_off[n - 1] + out_len[n - 1];
+    cudaEventRecord(e2, c->stream);
+    cudaError_t e = cudaMemcpyAsync(out_base, c->d_out.p, total, cudaMemcpyDeviceToHost, c->stream);
+    cudaEventRecord(e3, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = fail(c, ZQ_E_NODEVICE, std::string("CUDA error: ") + cudaGetErrorString(e));
+    else { cudaEventElapsedTime(&c->last_ms[6], e0, e1); cudaEventElapsedTime(&c->last_ms[7], e2, e3); }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+  return rc;
+}
+
+// ---- hashes --------------------------------------------------------------------------------------
+int zq_sha1_device(zq_ctx* c, int n, const uint8_t* d_base, const uint64_t* off, const uint64_t* len, uint8_t* d_digests) {
+  if (!c) return ZQ_E_NODEVICE;
+  if (n <= 0) return n == 0 ? ZQ_OK : fail(c, ZQ_E_ARG, "bad argument");
+  cudaSetDevice(c->device);
+  ZQ_CUDA(c, c->d_misc.ensure((size_t)n * 16));
+  u64* d_off = c->d_misc.as<u64>(); u64* d_len = d_off + n;
+  ZQ_CUDA(c, cudaMemcpyAsync(d_off, off, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, cudaMemcpyAsync(d_len, len, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  zqdev::k_sha1_many<<<(n + 127) / 128, 128, 0, c->stream>>>(d_base, d_off, nullptr, d_len, n, d_digests);
+  ++c->launches;
+  ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  ZQ_CUDA(c, cudaGetLastError());
+  return ZQ_OK;
+}
+
+static int stage_buffers(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, std::vector<uint64_t>& roff) {
+  uint64_t lo = ~0ull, hi = 0;
+  for (int i = 0; i < n; ++i) { lo = std::min(lo, off[i]); hi = std::max(hi, off[i] + len[i]); }
+  if (hi < lo) hi = lo;
+  ZQ_CUDA(c, c->d_in.ensure(hi - lo + 64));
+  if (hi > lo) ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, base + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+  roff.resize(n);
+  for (int i = 0; i < n; ++i) roff[i] = off[i] - lo;
+  return ZQ_OK;
+}
+
+int zq_sha1(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
+  if (!c) return ZQ_E_NODEVICE;
+  if (n <= 0) return n == 0 ? ZQ_OK : fail(c, ZQ_E_ARG, "bad argument");
+  cudaSetDevice(c->device);
+  std::vector<uint64_t> roff;
+  int rc = stage_buffers(c, n, base, off, len, roff);
+  if (rc) return rc;
+  ZQ_CUDA(c, c->d_sha.ensure((size_t)n * 20));
+  rc = zq_sha1_device(c, n, c->d_in.as<uint8_t>(), roff.data(), len, c->d_sha.as<uint8_t>());
+  if (rc) return rc;
+  ZQ_CUDA(c, cudaMemcpy(digests, c->d_sha.p, (size_t)n * 20, cudaMemcpyDeviceToHost));
+  return ZQ_OK;
+}
+
+int zq_sha256(zq_ctx* c, int, const uint8_t*, const uint64_t*, const uint64_t*, uint8_t*) { return c ? fail(c, ZQ_E_UNSUPPORTED, "sha256: not built yet") : ZQ_E_NODEVICE; }
+int zq_xxh3_128(zq_ctx* c, int, const uint8_t*, const uint64_t*, const uint64_t*, uint8_t*) { return c ? fail(c, ZQ_E_UNSUPPORTED, "xxh3: not built yet") : ZQ_E_NODEVICE; }
+int zq_blake3(zq_ctx* c, int, const uint8_t*, const uint64_t*, const uint64_t*, uint8_t*) { return c ? fail(c, ZQ_E_UNSUPPORTED, "blake3: not built yet") : ZQ_E_NODEVICE; }
+int zq_fragment(zq_ctx* c, int, const uint8_t*, const uint64_t*, const uint64_t*, int, uint32_t, uint32_t*, uint32_t*, uint8_t*, uint64_t, uint64_t*) {
+  return c ? fail(c, ZQ_E_UNSUPPORTED, "fragmenter: not built yet") : ZQ_E_NODEVICE;
+}
+
+// ---- introspection -------------------------------------------------------------------------------
+uint64_t zq_launch_count(zq_ctx* c) { return c ? c->launches : 0; }
+int zq_last_timings(zq_ctx* c, float ms[8]) {
+  if (!c) return ZQ_E_NODEVICE;
+  memcpy(ms, c->last_ms, sizeof c->last_ms);
+  return ZQ_OK;
+}
+
+int zq_suffix_array(zq_ctx* c, const uint8_t* data, uint32_t n, uint32_t* sa_out) {
+  using namespace zqdev;
+  if (!c) return ZQ_E_NODEVICE;
+  if (n == 0) return ZQ_OK;
+  cudaSetDevice(c->device);
+  const size_t scr = align_up((size_t)n + 1, 64);
+  ZQ_CUDA(c, c->d_in.ensure(n + 64));
+  ZQ_CUDA(c, c->d_sa.ensure(scr * 4)); ZQ_CUDA(c, c->d_isa.ensure(scr * 4)); ZQ_CUDA(c, c->d_lcp.ensure(scr * 2));
+  ZQ_CUDA(c, c->d_kbuf.ensure(2 * scr * 8)); ZQ_CUDA(c, c->d_vbuf.ensure(4 * scr * 4));
+  ZQ_CUDA(c, c->d_units.ensure(sizeof(ZqUnit))); ZQ_CUDA(c, c->d_todo.ensure(4));
+  ZqUnit u; memset(&u, 0, sizeof u); u.n = n;
+  int zero = 0;
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, data, n, cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_units.p, &u, sizeof u, cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo.p, &zero, 4, cudaMemcpyHostToDevice, c->stream));
+  k_suffix_sort<<<1, SORT_THREADS, sizeof(SortSmem), c->stream>>>(c->d_in.as<u8>(), c->d_units.as<ZqUnit>(), c->d_todo.as<int>(), 1,
+                                                                 c->d_sa.as<u32>(), c->d_isa.as<u32>(), c->d_lcp.as<u16>(),
+                                                                 c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr);
+  ++c->launches;
+  ZQ_CUDA(c, cudaMemcpyAsync(sa_out, c->d_sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  ZQ_CUDA(c, cudaGetLastError());
+  return ZQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// zq_common.cuh -- shared device helpers and descriptors for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define ZQ_FULL 0xffffffffu
+
+// One compression unit (== one libzpaq::compressBlock call, Z:20255) as the kernels see it.
+struct ZqUnit {
+  u64 in_off;    // byte offset of the input in the device input arena
+  u64 work_off;  // element offset into the per-wave sa / isa / lcp arrays
+  u64 lz_off;    // byte offset into the pre-pass stream buffer
+  u64 out_off;   // byte offset of the finished block in the output arena
+  u32 n;         // input length
+  u32 plan;      // index into the plan table
+  u32 lz_cap;    // capacity reserved at lz_off
+  u32 prefix_off, prefix_len;  // block prefix (tag .. segment header) in the blob
+  u32 pad;
+};
+
+// Per (method, block size class) constants (== makeConfig's args, Z:19620-19628).
+struct ZqPlan {
+  int args[9];
+  u32 payload_off, payload_len;  // selector + PCOMP bytes that precede the stream, in the blob
+  u32 lz_level;                  // 0 none, 1 var-length codes, 2 byte codes, 3 BWT
+  u32 use_sa;
+  u32 e8e9;
+  u32 modeled;                   // ncomp > 0
+};
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lanemask_lt() {
+  u32 m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+// floor(log2(x))+1, 0 for 0 (== reference lg(), Z:19269)
+__device__ __forceinline__ int zq_bitlen(u32 x) { return 32 - __clz(x); }

@@ -1,0 +1,62 @@
+// zq_frame.cuh -- assembles the finished ZPAQ block of an UNMODELED method (n components == 0:
+// store, -m1, -m2): what Compressor::{writeTag,startBlock,startSegment,postProcess,compress,
+// endSegment,endBlock} (Z:15970-16187) and the unmodeled branch of Encoder::compress
+// (Z:15590-15600) write.  One CTA per block; pure byte movement (HBM bound, ~2 B moved per
+// output byte).
+//
+//   prefix  = tag[13] 'z' 'P' 'Q' lvl 1 header 01 filename 00 comment 00 00      (built on the host)
+//   payload = selector/PCOMP bytes (host) followed by the pre-pass stream (device)
+//   body    = payload cut in <= 65536-byte chunks, each preceded by its big-endian u32 length
+//   trailer = 00 00 00 00 (FD sha1[20] | FE) FF
+#pragma once
+#include "zq_common.cuh"
+
+namespace zqdev {
+
+__host__ __device__ inline u64 unmodeled_block_size(u32 prefix_len, u64 payload_total, bool sha) {
+  const u64 nchunks = (payload_total + 65535) >> 16;
+  return prefix_len + payload_total + 4 * nchunks + 4 + (sha ? 21 : 1) + 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_frame_unmodeled(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, const int* __restrict__ todo, int ntodo,
+                  const u8* __restrict__ blob, const u8* __restrict__ in_base, const u8* __restrict__ lz_base,
+                  const u32* __restrict__ lz_len, const u8* __restrict__ sha1 /* 20 B per unit or null */,
+                  const u64* __restrict__ out_off, u8* __restrict__ out_base) {
+  for (int t = blockIdx.x; t < ntodo; t += gridDim.x) {
+    const int ui = todo[t];
+    const ZqUnit u = units[ui];
+    const ZqPlan pl = plans[u.plan];
+    u8* __restrict__ out = out_base + out_off[ui];
+    const u8* __restrict__ stream; u32 slen;
+    if (pl.lz_level) { stream = lz_base + u.lz_off; slen = lz_len[ui]; }
+    else { stream = in_base + u.in_off; slen = u.n; }
+    for (u32 k = threadIdx.x; k < u.prefix_len; k += blockDim.x) out[k] = blob[u.prefix_off + k];
+    const u32 plen = pl.payload_len;
+    const u64 total = (u64)plen + slen;
+    const u64 nchunks = (total + 65535) >> 16;
+    u8* __restrict__ body = out + u.prefix_len;
+    for (u64 c = threadIdx.x; c < nchunks; c += blockDim.x) {
+      const u64 rem = total - (c << 16);
+      const u32 cl = rem < 65536 ? (u32)rem : 65536u;
+      u8* h = body + c * 65540;
+      h[0] = cl >> 24; h[1] = cl >> 16; h[2] = cl >> 8; h[3] = cl;
+    }
+    for (u64 s = threadIdx.x; s < total; s += blockDim.x) {
+      const u8 b = s < plen ? blob[pl.payload_off + s] : stream[s - plen];
+      body[s + 4 * ((s >> 16) + 1)] = b;
+    }
+    u8* tr = body + total + 4 * nchunks;
+    if (threadIdx.x < 4) tr[threadIdx.x] = 0;
+    if (sha1) {
+      if (threadIdx.x == 4) tr[4] = 253;
+      if (threadIdx.x >= 32 && threadIdx.x < 52) tr[5 + threadIdx.x - 32] = sha1[(size_t)ui * 20 + threadIdx.x - 32];
+      if (threadIdx.x == 5) tr[25] = 255;
+    } else {
+      if (threadIdx.x == 4) tr[4] = 254;
+      if (threadIdx.x == 5) tr[5] = 255;
+    }
+  }
+}
+
+}  // namespace zqdev
