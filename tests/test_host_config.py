@@ -43,9 +43,8 @@ def test_digit_method_headers_match_reference(zq, ref, level):
 
 def test_level5_period_analysis_matches_reference(zq, ref):
     # periodic data makes compressBlock add "c0,0,999+P,255i1[c0,Pi1]" models (Z:20367-20387)
-    rec = bytes(range(37))
     for period, reps in ((37, 300), (300, 60)):
-        data = (rec * (period // 37 + 1))[:period] * reps
+        data = corpus.random_unit(period, period) * reps
         blk = ref.compress_block(data, "5", "", "")
         hs = blk[18] + 256 * blk[19]
         p = zq.plan_block("5", data)
