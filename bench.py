@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: MB/s compressed, -m2, 64 KiB units (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W              our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...    the reference's own CPU compressBlock
+
+A "step" = one pass of the hot path over one batch of synthetic input: U units x 64 KiB of synthetic
+text, one libzpaq::compressBlock-equivalent per unit, method "2".  Per rank the batch is fixed (weak
+scaling); `value` = units of all ranks x 64 KiB / max-over-ranks device time.
+  value : inputs and outputs resident in HBM (zq_compress_blocks_device)
+  e2e   : the reference-facing call with HOST buffers (zq_compress_blocks): H2D of the batch and D2H
+          of the compressed blocks inside the timed region.
+Timing: CUDA events on the stream the kernels are launched on (the context is switched onto torch's
+current stream), barrier + synchronize on both sides, max over ranks.  Inputs (655 MB/step) exceed L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UNIT = 65536
+METHOD = "2"
+MB = 1e6
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([x.strip() for x in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference_throughput(sample_units, threads, arena_bytes):
+    """Times the reference's own compressBlock (oracle/_ref, built from /root/reference) on host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ctypes as C
+    import oracle_bindings as ob
+    ref = ob.load_ref()
+    if ref is None:
+        return None
+    t0 = time.perf_counter()
+    tot = ref.lib.zref_compress_units_mt(arena_bytes.ctypes.data_as(C.c_void_p), C.c_uint(UNIT), C.c_int(sample_units),
+                                         METHOD.encode(), C.c_int(threads))
+    dt = time.perf_counter() - t0
+    if tot < 0:
+        return None
+    return sample_units * UNIT / MB / dt, dt, int(tot)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from zpaqfranz_b200 import corpus
+    threads = os.cpu_count() or 1
+    # bounded sample per step: ~6 units per thread (each unit costs ~7 ms of one core)
+    sample = max(threads * 6, 64)
+    arena = corpus.text_corpus(sample)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_throughput(min(sample, threads), threads, arena)
+    times = []
+    for _ in range(args.steps):
+        r = cpu_reference_throughput(sample, threads, arena)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libzpaqref.so missing"}))
+            return 0
+        times.append(r[1])
+    tot = sum(times)
+    v = args.steps * sample * UNIT / MB / tot
+    line = {
+        "impl": "reference", "metric": "MB/s compressed (-m2, 64 KiB frags)", "value": round(v, 2), "unit": "MB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000 * tot / args.steps, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%d x 64KiB synthetic text fragments per step (bounded sample of the 10000-unit workload), "
+                               "-m2, reference libzpaq::compressBlock on %d host threads" % (sample, threads),
+                   "method": METHOD, "unit_bytes": UNIT},
+        "cpu_baseline": {"value": round(v, 2), "unit": "MB/s", "cores": threads, "kind": "reference",
+                         "sample": "%d units x 64 KiB per step" % sample},
+        "e2e": {"value": round(v, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--units", type=int, default=10000, help="units per GPU per step (configs[1]: 10000)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import zpaqfranz_b200 as zq
+    from zpaqfranz_b200 import corpus
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; this benchmark has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    U = args.units
+    nbytes = U * UNIT
+    # host batch in pinned memory (the e2e leg copies from here); device-resident copy for `value`
+    h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    corpus.text_corpus(U, UNIT, seed0=rank, out=h_in.numpy())
+    d_in = h_in.cuda()
+    cap = int(zq.lib.zq_compress_bound(UNIT)) * U
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    offs = (np.arange(U, dtype=np.uint64) * UNIT)
+    lens = np.full(U, UNIT, dtype=np.uint32)
+
+    ctx = zq.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        return ctx.compress_blocks_device(d_in.data_ptr(), offs, lens, d_out.data_ptr(), cap, method=METHOD, filename="", comment="")
+
+    def step_host():
+        return ctx.compress_blocks(h_in.numpy(), offs, lens, method=METHOD, filename="", comment="", out=h_out.numpy())
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage = np.zeros(8)
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+            t = ctx.last_timings()
+            stage += np.array([t[k] for k in zq.TIMING_KEYS])
+        e1.record(stream)
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, stage / steps, ctx.launch_count() - l0
+
+    for _ in range(args.warmup):
+        ooff, olen = step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, stage_dev, launches = timed(step_device, args.steps)
+    for _ in range(max(1, args.warmup - 1)):
+        step_host()
+    ms_e2e, stage_e2e, _ = timed(step_host, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    out_bytes = int(ooff[-1]) + int(olen[-1])
+
+    # parity spot check, outside the timed region (the checker is oracle/_ref, never the product path)
+    parity = "unchecked"
+    if rank == 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_bindings as ob
+            ref = ob.load_ref()
+            if ref is not None:
+                ho = h_out.numpy()
+                o2, l2 = step_host()[1:]
+                for i in (0, 1, U // 2, U - 1):
+                    want = ref.compress_block(h_in.numpy()[i * UNIT:(i + 1) * UNIT].tobytes(), METHOD, "", "")
+                    assert ho[int(o2[i]): int(o2[i]) + int(l2[i])].tobytes() == want, "unit %d differs from the reference" % i
+                parity = "bit-exact vs reference on sampled units"
+        except AssertionError as e:
+            parity = "MISMATCH: %s" % e
+
+    total_units = U * world
+    value = total_units * UNIT / MB / (ms_dev / 1000 / args.steps)
+    e2e_v = total_units * UNIT / MB / (ms_e2e / 1000 / args.steps)
+    peak, peak_src = load_peaks()
+    # dominant kernel of the device-resident step
+    names = {1: "k_sha1_units", 2: "k_suffix_sort", 3: "k_lz77_sa", 4: "k_frame_unmodeled"}
+    dom = max(names, key=lambda k: stage_dev[k])
+    lz_bytes = out_bytes  # stream ~= block size (framing adds ~60 B per unit)
+    algo = {1: nbytes + 20 * U,                 # read input, write digests
+            2: nbytes + 10 * nbytes,            # read text, write SA + ISA (u32) + LCP (u16)
+            3: nbytes + 10 * nbytes + lz_bytes,  # read text + SA/ISA/LCP, write stream
+            4: 2 * out_bytes}[dom]
+    achieved = algo / 1e9 / (stage_dev[dom] / 1000)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(names[dom])
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "MB/s compressed (-m2, 64 KiB frags)", "value": round(value, 2), "unit": "MB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%d x 64KiB synthetic text fragments per GPU, -m2 (x0,1,4,0,7,21,1), one compressBlock per unit" % U,
+                   "method": METHOD, "units_per_gpu": U, "unit_bytes": UNIT, "parallelism": "units sharded, no collective",
+                   "l2": "inputs %.0f MB per step > 126 MB L2 (no flush needed)" % (nbytes / MB), "parity": parity,
+                   "compressed_ratio": round(out_bytes / nbytes, 4)},
+        "e2e": {"value": round(e2e_v, 2), "unit": "MB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": out_bytes,
+                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "stage_ms": {k: round(float(v), 3) for k, v in zip(zq.TIMING_KEYS, stage_dev)},
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 5), "traffic": traffic, "algorithmic_bytes_per_launch": int(algo),
+                     "kernel_ms": round(float(stage_dev[dom]), 3), "peak_source": peak_src},
+        "clocks": sampler.summary(),
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = min(U, max(threads * 6, 64))
+        r = cpu_reference_throughput(sample, threads, h_in.numpy())
+        if r is not None:
+            line["cpu_baseline"] = {"value": round(r[0], 2), "unit": "MB/s", "cores": threads, "kind": "reference",
+                                    "sample": "%d of the %d units (64 KiB each), all host threads, %.1f s" % (sample, U, r[1])}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

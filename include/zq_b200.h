@@ -35,6 +35,9 @@ zq_ctx* zq_create(int device);
 void zq_destroy(zq_ctx* ctx);
 const char* zq_last_error(zq_ctx* ctx);      /* ctx may be NULL: error of the last failed zq_create */
 const char* zq_version(void);
+/* Run all of this context's work on the caller's CUDA stream (a cudaStream_t, e.g. torch's current
+ * stream) instead of the context's own; pass NULL to go back. The stream is not owned. */
+int zq_set_stream(zq_ctx* ctx, void* cuda_stream);
 
 /* ---- host-side planning (no GPU needed) ------------------------------------------------------ */
 /* What libzpaq::compressBlock derives before touching data (Z:20262-20394): the expanded method,

@@ -27,7 +27,7 @@ class ZqError(RuntimeError):
 def _load():
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
-            "libzqb200.so is not built: run `python -m zpaqfranz_b200.build` "
+            "libzqb200.so is not built: run `python zpaqfranz_b200/build.py` "
             "(or __graft_entry__.build()). There is no CPU fallback.")
     lib = C.CDLL(_LIB_PATH)
     u8p, u32p, u64p, cpp = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_char_p)
@@ -37,6 +37,7 @@ def _load():
     lib.zq_last_error.restype = C.c_char_p
     lib.zq_last_error.argtypes = [C.c_void_p]
     lib.zq_version.restype = C.c_char_p
+    lib.zq_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.zq_compress_bound.restype = C.c_uint64
     lib.zq_compress_bound.argtypes = [C.c_uint32]
     lib.zq_plan_block.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_int),
@@ -114,6 +115,10 @@ class Context:
     def _check(self, rc):
         if rc:
             raise ZqError(rc, lib.zq_last_error(self._h).decode(errors="replace"))
+
+    def set_stream(self, cuda_stream_ptr):
+        """Issue this context's work on the given cudaStream_t (int), e.g. torch.cuda.current_stream().cuda_stream."""
+        self._check(lib.zq_set_stream(self._h, cuda_stream_ptr))
 
     # -- block compression ------------------------------------------------------------------------
     def compress_blocks(self, arena, offsets, lengths, method="2", filename=None, comment=None, dosha1=True, out=None):

@@ -1,6 +1,6 @@
 """Builds libzqb200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-Usage: python -m zpaqfranz_b200.build [--force]
+Usage: python zpaqfranz_b200/build.py [--force] [-v]   (run by path: the package itself needs the library)
 The built .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
 import os

@@ -82,8 +82,19 @@ def text_corpus(nunits, unit=65536, seed0=0, out=None):
     if out is None:
         out = np.empty(nunits * unit, dtype=np.uint8)
     group = max(1, (8 << 20) // unit)
-    for g in range(0, nunits, group):
+
+    def fill(g):
         k = min(group, nunits - g)
         # one long stream per group, then cut: units stay deterministic per (seed0, g)
         out[g * unit:(g + k) * unit] = text_bytes(1000003 * seed0 + g, k * unit)
+
+    starts = list(range(0, nunits, group))
+    if len(starts) > 2:
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            list(ex.map(fill, starts))
+    else:
+        for g in starts:
+            fill(g)
     return out

@@ -51,6 +51,7 @@ struct zq_ctx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   std::string err;
   uint64_t launches = 0;
   DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_sa, d_isa, d_lcp, d_lz, d_lzlen, d_sha,
@@ -289,7 +290,8 @@ zq_ctx* zq_create(int device) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   c->num_sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream creation failed"; delete c; return nullptr; }
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream creation failed"; delete c; return nullptr; }
+  c->stream = c->own_stream;
   for (int k = 0; k < 8; ++k) { cudaEventCreate(&c->tm[k].a); cudaEventCreate(&c->tm[k].b); }
   if (const char* s = getenv("ZQ_WAVE_ELEMS")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->wave_elems = v; }
   return c;
@@ -303,8 +305,15 @@ void zq_destroy(zq_ctx* c) {
                     &c->d_lcp, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
   for (DevBuf* b : bufs) b->release();
   for (int k = 0; k < 8; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
-  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->own_stream);
   delete c;
+}
+
+int zq_set_stream(zq_ctx* c, void* s) {
+  if (!c) return ZQ_E_NODEVICE;
+  cudaStreamSynchronize(c->stream);
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return ZQ_OK;
 }
 
 const char* zq_last_error(zq_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
