@@ -54,11 +54,13 @@ struct zq_ctx {
   cudaStream_t own_stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_sa, d_isa, d_lcp, d_lz, d_lzlen, d_sha,
+  DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_todo2, d_lz, d_lzlen, d_sha,
       d_kbuf, d_vbuf, d_err, d_misc;
   Timer tm[8];
   float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  size_t wave_elems = (size_t)1 << 30;  // suffix-array elements per wave (10 B each)
+  size_t wave_bytes = (size_t)12 << 30;  // sa|isa|lcp bytes per wave
+  int sort_nt = 512, sort_minb = 2;       // suffix-sort CTA size and CTAs per SM
+  int lz_occ = 6;                         // CTAs (4 warps) per SM the LZ parse kernel is compiled for
 };
 
 namespace {
@@ -184,8 +186,9 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
     while (w1 < n) {
       ZqUnit& zu = units[w1];
       const ZqPlan& p = dplans[zu.plan];
-      size_t e = p.use_sa ? align_up((size_t)zu.n + 1, 64) : 0;
-      if (w1 > w0 && elems + e > c->wave_elems) break;
+      zu.idx16 = zu.n <= 65536 ? 1 : 0;
+      size_t e = p.use_sa ? (size_t)zq_work_bytes(zu.n, zu.idx16 ? 2 : 4) : 0;
+      if (w1 > w0 && elems + e > c->wave_bytes) break;
       zu.work_off = elems; elems += e;
       if (p.lz_level) {
         zu.lz_off = lzbytes; zu.lz_cap = zu.n + zu.n / 32 + 64; lzbytes += align_up(zu.lz_cap, 16);
@@ -207,26 +210,66 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
     }
     if (!todo_sa.empty()) {
       const int nt = (int)todo_sa.size();
-      ZQ_CUDA(c, c->d_sa.ensure(elems * 4));
-      ZQ_CUDA(c, c->d_isa.ensure(elems * 4));
-      ZQ_CUDA(c, c->d_lcp.ensure(elems * 2));
+      ZQ_CUDA(c, c->d_work.ensure(elems));
       ZQ_CUDA(c, c->d_lz.ensure(lzbytes));
       const size_t scr = align_up(maxn + 1, 64);
-      const int sort_grid = std::min(nt, c->num_sms);
+      int sort_nt = c->sort_nt, sort_minb = c->sort_minb;
+      const int sort_grid = std::min(nt, c->num_sms * sort_minb);
       ZQ_CUDA(c, c->d_kbuf.ensure((size_t)sort_grid * 2 * scr * 8));
-      ZQ_CUDA(c, c->d_vbuf.ensure((size_t)sort_grid * 4 * scr * 4));
+      ZQ_CUDA(c, c->d_vbuf.ensure((size_t)sort_grid * 6 * scr * 4));
       ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo.p, todo_sa.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
       tstart(c, 2);
-      k_suffix_sort<<<sort_grid, SORT_THREADS, sizeof(SortSmem), c->stream>>>(
-          d_in, du, c->d_todo.as<int>(), nt, c->d_sa.as<u32>(), c->d_isa.as<u32>(), c->d_lcp.as<u16>(),
-          c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr);
+#define ZQ_SORT_LAUNCH(NT, MB) k_suffix_sort<NT, MB><<<sort_grid, NT, sizeof(SortSmem<NT>), c->stream>>>( \
+          d_in, du, c->d_todo.as<int>(), nt, c->d_work.as<u8>(), c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr)
+      if (sort_nt == 1024) ZQ_SORT_LAUNCH(1024, 1);
+      else if (sort_nt == 512 && sort_minb == 2) ZQ_SORT_LAUNCH(512, 2);
+      else if (sort_nt == 512) ZQ_SORT_LAUNCH(512, 4);
+      else if (sort_nt == 256 && sort_minb == 4) ZQ_SORT_LAUNCH(256, 4);
+      else if (sort_nt == 256) ZQ_SORT_LAUNCH(256, 8);
+      else if (sort_nt == 128 && sort_minb == 8) ZQ_SORT_LAUNCH(128, 8);
+      else ZQ_SORT_LAUNCH(128, 16);
+#undef ZQ_SORT_LAUNCH
       ++c->launches;
       tstop(c, 2);
       tstart(c, 3);
-      const int pgrid = std::min((nt + 3) / 4, c->num_sms * 16);
-      k_lz77_sa<<<pgrid, 128, 0, c->stream>>>(d_in, du, dp, c->d_todo.as<int>(), nt, c->d_sa.as<u32>(), c->d_isa.as<u32>(),
-                                               c->d_lcp.as<u16>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_err.as<u32>());
-      ++c->launches;
+      {
+        // one launch per (index width, parse flavour) present in the wave
+        std::vector<int> lists[4];
+        for (int t : todo_sa) {
+          const ZqUnit& zu = units[w0 + t];
+          const bool pipe = dplans[zu.plan].args[6] <= 1;
+          lists[(zu.idx16 ? 0 : 2) + (pipe ? 0 : 1)].push_back(t);
+        }
+        size_t lo = 0;
+        std::vector<int> flat;
+        for (auto& l : lists) flat.insert(flat.end(), l.begin(), l.end());
+        ZQ_CUDA(c, c->d_todo2.ensure(flat.size() * 4));
+        ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo2.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        for (int v = 0; v < 4; ++v) {
+          const int cnt = (int)lists[v].size();
+          if (!cnt) continue;
+          const int* tl = c->d_todo2.as<int>() + lo;
+          lo += cnt;
+          const int pgrid = std::min((cnt + 3) / 4, c->num_sms * std::max(c->lz_occ, 6));
+          u32* ctr = c->d_err.as<u32>() + 4 + v;
+          ZQ_CUDA(c, cudaMemsetAsync(ctr, 0, 4, c->stream));
+#define ZQ_LZ_LAUNCH(IDX, PIPE)                                                                              \
+  do {                                                                                                       \
+    auto kern = k_lz77_sa<IDX, PIPE, 6>;                                                                     \
+    if (c->lz_occ >= 12) kern = k_lz77_sa<IDX, PIPE, 12>;                                                    \
+    else if (c->lz_occ >= 10) kern = k_lz77_sa<IDX, PIPE, 10>;                                               \
+    else if (c->lz_occ >= 8) kern = k_lz77_sa<IDX, PIPE, 8>;                                                 \
+    kern<<<pgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), c->d_lz.as<u8>(),           \
+                                       c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);                       \
+  } while (0)
+          if (v == 0) ZQ_LZ_LAUNCH(u16, true);
+          else if (v == 1) ZQ_LZ_LAUNCH(u16, false);
+          else if (v == 2) ZQ_LZ_LAUNCH(u32, true);
+          else ZQ_LZ_LAUNCH(u32, false);
+#undef ZQ_LZ_LAUNCH
+          ++c->launches;
+        }
+      }
       tstop(c, 3);
       ZQ_CUDA(c, cudaMemcpyAsync(lz_len_h.data() + w0, c->d_lzlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
       ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -293,7 +336,15 @@ zq_ctx* zq_create(int device) {
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream creation failed"; delete c; return nullptr; }
   c->stream = c->own_stream;
   for (int k = 0; k < 8; ++k) { cudaEventCreate(&c->tm[k].a); cudaEventCreate(&c->tm[k].b); }
-  if (const char* s = getenv("ZQ_WAVE_ELEMS")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->wave_elems = v; }
+  if (const char* s = getenv("ZQ_LZ_OCC")) c->lz_occ = atoi(s);
+  if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
+  if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);
+  if (c->sort_nt != 1024 && c->sort_nt != 512 && c->sort_nt != 256 && c->sort_nt != 128) c->sort_nt = 256;
+  if (c->sort_nt == 1024) c->sort_minb = 1;
+  else if (c->sort_nt == 512) c->sort_minb = c->sort_minb >= 4 ? 4 : 2;
+  else if (c->sort_nt == 256) c->sort_minb = c->sort_minb >= 8 ? 8 : 4;
+  else c->sort_minb = c->sort_minb >= 16 ? 16 : 8;
+  if (const char* s = getenv("ZQ_WAVE_BYTES")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->wave_bytes = v; }
   return c;
 }
 
@@ -301,8 +352,7 @@ void zq_destroy(zq_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_sa, &c->d_isa,
-                    &c->d_lcp, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
+  DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_work, &c->d_todo2, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
   for (DevBuf* b : bufs) b->release();
   for (int k = 0; k < 8; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
   cudaStreamDestroy(c->own_stream);
@@ -456,19 +506,18 @@ int zq_suffix_array(zq_ctx* c, const uint8_t* data, uint32_t n, uint32_t* sa_out
   cudaSetDevice(c->device);
   const size_t scr = align_up((size_t)n + 1, 64);
   ZQ_CUDA(c, c->d_in.ensure(n + 64));
-  ZQ_CUDA(c, c->d_sa.ensure(scr * 4)); ZQ_CUDA(c, c->d_isa.ensure(scr * 4)); ZQ_CUDA(c, c->d_lcp.ensure(scr * 2));
-  ZQ_CUDA(c, c->d_kbuf.ensure(2 * scr * 8)); ZQ_CUDA(c, c->d_vbuf.ensure(4 * scr * 4));
+  ZQ_CUDA(c, c->d_work.ensure(zq_work_bytes(n, 4)));
+  ZQ_CUDA(c, c->d_kbuf.ensure(2 * scr * 8)); ZQ_CUDA(c, c->d_vbuf.ensure(6 * scr * 4));
   ZQ_CUDA(c, c->d_units.ensure(sizeof(ZqUnit))); ZQ_CUDA(c, c->d_todo.ensure(4));
   ZqUnit u; memset(&u, 0, sizeof u); u.n = n;
   int zero = 0;
   ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, data, n, cudaMemcpyHostToDevice, c->stream));
   ZQ_CUDA(c, cudaMemcpyAsync(c->d_units.p, &u, sizeof u, cudaMemcpyHostToDevice, c->stream));
   ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo.p, &zero, 4, cudaMemcpyHostToDevice, c->stream));
-  k_suffix_sort<<<1, SORT_THREADS, sizeof(SortSmem), c->stream>>>(c->d_in.as<u8>(), c->d_units.as<ZqUnit>(), c->d_todo.as<int>(), 1,
-                                                                 c->d_sa.as<u32>(), c->d_isa.as<u32>(), c->d_lcp.as<u16>(),
-                                                                 c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr);
+  k_suffix_sort<256, 4><<<1, 256, sizeof(SortSmem<256>), c->stream>>>(c->d_in.as<u8>(), c->d_units.as<ZqUnit>(), c->d_todo.as<int>(), 1,
+                                                                 c->d_work.as<u8>(), c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr);
   ++c->launches;
-  ZQ_CUDA(c, cudaMemcpyAsync(sa_out, c->d_sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  ZQ_CUDA(c, cudaMemcpyAsync(sa_out, c->d_work.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
   ZQ_CUDA(c, cudaGetLastError());
   return ZQ_OK;

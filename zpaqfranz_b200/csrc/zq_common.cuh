@@ -13,14 +13,14 @@ typedef uint64_t u64;
 // One compression unit (== one libzpaq::compressBlock call, Z:20255) as the kernels see it.
 struct ZqUnit {
   u64 in_off;    // byte offset of the input in the device input arena
-  u64 work_off;  // element offset into the per-wave sa / isa / lcp arrays
+  u64 work_off;  // byte offset of this unit's sa | isa | lcp region in the per-wave work arena
   u64 lz_off;    // byte offset into the pre-pass stream buffer
   u64 out_off;   // byte offset of the finished block in the output arena
   u32 n;         // input length
   u32 plan;      // index into the plan table
   u32 lz_cap;    // capacity reserved at lz_off
   u32 prefix_off, prefix_len;  // block prefix (tag .. segment header) in the blob
-  u32 pad;
+  u32 idx16;     // 1: sa/isa stored as u16 (n <= 65536), 0: u32
 };
 
 // Per (method, block size class) constants (== makeConfig's args, Z:19620-19628).
@@ -32,6 +32,10 @@ struct ZqPlan {
   u32 e8e9;
   u32 modeled;                   // ncomp > 0
 };
+
+// per-unit work region: sa | isa (index width w = 2 or 4) | lcp (u16) | bwt (u8), each padded to 128 B
+__host__ __device__ inline u64 zq_work_stride(u32 n, u32 w) { return (((u64)n + 1) * w + 127) & ~(u64)127; }
+__host__ __device__ inline u64 zq_work_bytes(u32 n, u32 w) { return 2 * zq_work_stride(n, w) + zq_work_stride(n, 2) + zq_work_stride(n, 1); }
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ u32 lanemask_lt() {

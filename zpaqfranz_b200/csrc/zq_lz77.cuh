@@ -17,33 +17,42 @@
 
 namespace zqdev {
 
-// Sequential byte/bit sink owned by one warp. State is warp-uniform; lane 0 performs scalar stores.
+// Sequential byte/bit sink owned by one warp. State is warp-uniform; stores are spread over lanes.
 struct WarpSink {
   u8* out;      // next byte to write
   u8* end;      // capacity guard (overflow -> flag, bytes dropped)
-  u32 bits;     // pending bits (level-1 codes are LSB first)
+  u64 bits;     // pending bits, LSB first (level-1 codes); always < 8 of them between calls
   u32 nbits;
   u32 overflow;
-  __device__ __forceinline__ void init(u8* o, u32 cap) { out = o; end = o + cap; bits = nbits = overflow = 0; }
+  __device__ __forceinline__ void init(u8* o, u32 cap) { out = o; end = o + cap; bits = 0; nbits = overflow = 0; }
   __device__ __forceinline__ void byte(u32 c) {
     if (out < end) { if (lane_id() == 0) *out = (u8)c; } else overflow = 1;
     ++out;
   }
-  __device__ __forceinline__ void putb(u32 x, int k) {  // k <= 24
-    x &= (1u << k) - 1;
-    bits |= x << nbits; nbits += k;
-    while (nbits > 7) { byte(bits & 255); bits >>= 8; nbits -= 8; }
+  // append the k (<= 56) low bits of x; whole bytes are stored by lanes 0..7 in one instruction
+  __device__ __forceinline__ void putb(u64 x, u32 k) {
+    bits |= (x & ((1ull << k) - 1)) << nbits;
+    nbits += k;
+    const u32 nb = nbits >> 3;
+    if (nb) {
+      const u32 lane = lane_id();
+      if (lane < nb) { if (out + lane < end) out[lane] = (u8)(bits >> (8 * lane)); else overflow = 1; }
+      if (out + nb > end) overflow = 1;
+      out += nb;
+      bits = nb < 8 ? bits >> (8 * nb) : 0;
+      nbits &= 7;
+    }
   }
-  __device__ __forceinline__ void flush() { if (nbits > 0) byte(bits & 255); bits = nbits = 0; }
+  __device__ __forceinline__ void flush() { if (nbits > 0) byte((u32)bits & 255); bits = 0; nbits = 0; }
   // append cnt bytes src[0..cnt) at the current bit phase (== cnt x putb(byte, 8)); all lanes help
   __device__ __forceinline__ void bytes(const u8* __restrict__ src, u32 cnt) {
     const u32 lane = lane_id();
     const u32 s = nbits;  // 0..7 pending bits
-    u32 carry = bits;
+    u32 carry = (u32)bits;
     for (u32 b = 0; b < cnt; b += 32) {
       const u32 idx = b + lane;
       const u32 c = idx < cnt ? (u32)src[idx] : 0u;
-      u32 prev = __shfl_up_sync(ZQ_FULL, c, 1);
+      const u32 prev = __shfl_up_sync(ZQ_FULL, c, 1);
       const u32 low = lane == 0 ? carry : (prev >> (8 - s));
       const u32 o = (low | (c << s)) & 255u;
       if (idx < cnt) { if (out + idx < end) out[idx] = (u8)o; else overflow = 1; }
@@ -61,14 +70,27 @@ struct LzParams {
   u32 minMatch, lookahead, bucket, rb, checkbits;
 };
 
+// Interleaved Elias-gamma body of v >= 1 as the reference emits it LSB first: for every bit of v
+// below the leading one, MSB first: a 1 then the bit; then a terminating 0 (Z:19535-19543,
+// Z:19572-19576).  Returns the bits; *nb = 2*(bitlen(v)-1)+1.
+__device__ __forceinline__ u32 gamma_code(u32 v, u32* nb) {
+  const u32 L = (u32)zq_bitlen(v);
+  *nb = 2 * (L - 1) + 1;
+  if (L <= 1) return 0;
+  u32 r = __brev(v) >> (33 - L);       // bit j = bit (L-2-j) of v
+  r = (r | (r << 8)) & 0x00FF00FFu;
+  r = (r | (r << 4)) & 0x0F0F0F0Fu;
+  r = (r | (r << 2)) & 0x33333333u;
+  r = (r | (r << 1)) & 0x55555555u;    // bit j -> position 2j
+  return ((r << 1) | 0x55555555u) & ((1u << (2 * (L - 1))) - 1);
+}
+
 __device__ __forceinline__ void lz_write_literal(WarpSink& sk, const LzParams& P, const u8* __restrict__ in, u32 i, u32& lit) {
   if (P.level == 1) {
     if (lit < 1) return;
-    int ll = zq_bitlen(lit);
-    sk.putb(0, 2);
-    --ll;
-    while (--ll >= 0) { sk.putb(1, 1); sk.putb((lit >> ll) & 1, 1); }
-    sk.putb(0, 1);
+    u32 nb;
+    const u32 g = gamma_code(lit, &nb);
+    sk.putb((u64)g << 2, nb + 2);      // "00" then the length
     sk.bytes(in + (i - lit), lit);
     lit = 0;
   } else {
@@ -83,16 +105,15 @@ __device__ __forceinline__ void lz_write_literal(WarpSink& sk, const LzParams& P
 
 __device__ __forceinline__ void lz_write_match(WarpSink& sk, const LzParams& P, u32 len, u32 off) {
   if (P.level == 1) {
-    int ll = zq_bitlen(len) - 1;
     off += (1u << P.rb) - 1;
-    const int lo = zq_bitlen(off) - 1 - (int)P.rb;
-    sk.putb((lo + 8) >> 3, 2);
-    sk.putb(lo & 7, 3);
-    while (--ll >= 2) { sk.putb(1, 1); sk.putb((len >> ll) & 1, 1); }
-    sk.putb(0, 1);
-    sk.putb(len & 3, 2);
-    sk.putb(off, P.rb);
-    sk.putb(off >> P.rb, lo);
+    const u32 lo = (u32)zq_bitlen(off) - 1 - P.rb;
+    u32 nb;
+    const u32 g = gamma_code(len >> 2, &nb);
+    // mm, mmm, gamma(len/4), ll
+    const u64 head = (u64)((lo + 8) >> 3) | ((u64)(lo & 7) << 2) | ((u64)g << 5) | ((u64)(len & 3) << (5 + nb));
+    sk.putb(head, 7 + nb);
+    // r (rb low offset bits), q (lo bits below the leading one)
+    sk.putb(((u64)off & ((1u << P.rb) - 1)) | ((u64)((off >> P.rb) & ((1u << lo) - 1)) << P.rb), P.rb + lo);
   } else {
     const u32 mm = P.minMatch;
     --off;
@@ -118,69 +139,248 @@ __device__ __forceinline__ u32 warp_match_len(const u8* __restrict__ a, const u8
   return limit;
 }
 
-// Parse block in[0..n) with its suffix array; returns stream length in *out_len (lane-uniform).
-__device__ void lz77_sa_parse(const u8* __restrict__ in, u32 n, const u32* __restrict__ sa, const u32* __restrict__ isa,
-                              const u16* __restrict__ lcp, const LzParams P, WarpSink& sk) {
+struct LzBest { u32 blen, bp, blit; int bscore; };
+
+// One candidate per lane, in scan order = ascending lane inside the segment `segmask`.
+struct LzCand {
+  bool valid, capped;
+  u32 p, l, l1;
+  int score;
+};
+
+// The 16 suffix-array neighbours below (lanes 0-15) and above (lanes 16-31) row q: suffix start,
+// LCP with the adjacent row towards q (raw, not yet a running minimum), preceding text byte.
+struct LzChunk { u32 s, e, bw; bool inr; };
+
+template <typename IdxT>
+__device__ __forceinline__ LzChunk lz_chunk_issue(const IdxT* __restrict__ sa, const u16* __restrict__ lcp,
+                                                  const u8* __restrict__ bwt, u32 n, u32 q, u32 bucket, bool enable) {
+  const u32 lane = lane_id(), half = lane >> 4, kk = (lane & 15) + 1;
+  LzChunk c;
+  c.inr = enable && kk <= bucket && (half == 0 ? q >= kk : (u64)q + kk < n);
+  const u32 x = half == 0 ? q - kk : q + kk;
+  c.s = 0; c.e = 0; c.bw = 0;
+  if (c.inr) { c.s = sa[x]; c.e = lcp[half == 0 ? x + 1 : x]; c.bw = bwt[x]; }
+  return c;
+}
+
+__device__ __forceinline__ int lz_score(u32 l, u32 l1, u32 dist, u32 lit, u32 h) {
+  int sc = (int)(l - l1) * 8 - zq_bitlen(dist) - ((lit == 0 && l1 > 0) ? 4 : 0) - 11;
+  for (u32 a = 0; a < h; ++a) sc = sc * 5 / 8;
+  return sc;
+}
+
+// Per-lane evaluation of the neighbour s (= sa[x]) whose LCP with the suffix at i+h is pm.
+// bw = in[s-1] (the row's BWT byte), ci = in[i+h-1]: first step of the backward extension.
+__device__ __forceinline__ LzCand lz_eval(const u8* __restrict__ in, u32 i, u32 h, u32 lit, bool inr, u32 s, u32 pm, u32 bw, u32 ci) {
+  LzCand c;
+  c.p = s - h;                       // wraps for s < h; rejected by p < i exactly like the reference
+  c.valid = inr && c.p < i;
+  c.capped = pm >= ZQ_LCP_CAP;
+  c.l = h + pm;
+  u32 l1 = h;
+  if (h > 0 && c.valid && bw == ci) { --l1; while (l1 > 0 && in[c.p + l1 - 1] == in[i + l1 - 1]) --l1; }
+  c.l1 = l1;
+  c.score = lz_score(c.l, l1, i - c.p, lit, h);
+  return c;
+}
+
+// Replays the reference's sequential candidate loop (Z:19414-19426) over the lanes of one segment:
+// take a candidate iff its score beats every earlier one (strict), stop after the first candidate
+// whose length is below the current best / below minMatch / above 255.  `exmax` is the exclusive
+// running maximum of the valid scores inside the segment.  Returns true if the scan ended.
+__device__ __forceinline__ bool lz_resolve(u32 segmask, const LzCand& c, int exmax, LzBest& b, u32 minMatch,
+                                           const u8* __restrict__ in, u32 i, u32 h, u32 lit, u32 lmax) {
   const u32 lane = lane_id();
-  const u32 maxMatch = 3u << 14, maxLiteral = 1u << 12;
-  const u32 minMatch = P.minMatch;
+  const u32 vm = __ballot_sync(ZQ_FULL, c.valid) & segmask;
+  if (!vm) return false;
+  const int f = __ffs(vm) - 1;
+  if (__shfl_sync(ZQ_FULL, (int)c.capped, f)) {
+    // LCP >= 256: the only candidate the reference evaluates from here on; measure it exactly
+    const u32 cp = __shfl_sync(ZQ_FULL, c.p, f);
+    u32 l = warp_match_len(in + cp, in + i, h + ZQ_LCP_CAP, lmax);
+    l = min(l, lmax);
+    const u32 l1 = __shfl_sync(ZQ_FULL, c.l1, f);
+    const int sc = lz_score(l, l1, i - cp, lit, h);
+    if (sc > b.bscore) { b.blen = l; b.bp = cp; b.blit = l1; b.bscore = sc; }
+    return true;   // l > 255 always ends the scan
+  }
+  const int M = max(b.bscore, exmax);
+  const bool acc = c.valid && c.score > M;
+  const u32 am = __ballot_sync(ZQ_FULL, acc) & segmask;
+  const u32 la = am & (lanemask_lt() | (1u << lane));
+  const u32 lsrc = __shfl_sync(ZQ_FULL, c.l, la ? 31 - __clz(la) : lane);
+  const u32 bl = la ? lsrc : b.blen;
+  const bool brk = c.valid && (c.l < bl || c.l < minMatch || c.l > 255);
+  const u32 bm = __ballot_sync(ZQ_FULL, brk) & segmask;
+  const u32 upto = bm ? (0xffffffffu >> (31 - (__ffs(bm) - 1))) : 0xffffffffu;
+  const u32 fa = am & upto;
+  if (fa) {
+    const int w = 31 - __clz(fa);
+    b.blen = __shfl_sync(ZQ_FULL, c.l, w);
+    b.bp = __shfl_sync(ZQ_FULL, c.p, w);
+    b.blit = __shfl_sync(ZQ_FULL, c.l1, w);
+    b.bscore = __shfl_sync(ZQ_FULL, c.score, w);
+  }
+  return bm != 0;
+}
+
+// All candidates of look-ahead h at position i (row q = isa[i+h], first 16 neighbours per
+// direction already in `ch`): both directions, in the reference's order, updating b.
+// Fast path: in most scans the first usable neighbour already ends the scan (its match is shorter
+// than minMatch or than the best so far), so it alone is evaluated, with warp-uniform scalars; its
+// LCP with row q is one REDUX min over the lanes between it and q.  Only otherwise are all lanes
+// scored and the sequential semantics resolved with scans (lz_resolve).
+template <typename IdxT>
+__device__ __forceinline__ void lz_scan_pos(const u8* __restrict__ in, u32 n, const IdxT* __restrict__ sa,
+                                            const u16* __restrict__ lcp, const u8* __restrict__ bwt, const LzParams& P,
+                                            u32 i, u32 h, u32 lit, u32 lmax, u32 q, const LzChunk& ch, LzBest& b) {
+  const u32 lane = lane_id();
+  const u32 ci = h > 0 ? (u32)in[i + h - 1] : 0u;
+  const u32 p = ch.s - h;
+  const u32 vm_all = __ballot_sync(ZQ_FULL, ch.inr && p < i);
+  const u32 outm = __ballot_sync(ZQ_FULL, !ch.inr);
+  bool have = false;
+  LzCand c; int exmax = INT_MIN; u32 pm = 0;
+  for (u32 dir = 0; dir < 2; ++dir) {
+    const u32 segmask = dir ? 0xffff0000u : 0x0000ffffu;
+    const u32 vm = vm_all & segmask;
+    bool stop = false;
+    if (vm) {
+      const int f = __ffs(vm) - 1;
+      const u32 upto = segmask & (0xffffffffu >> (31 - f));
+      const u32 pmf = __reduce_min_sync(ZQ_FULL, ((upto >> lane) & 1u) ? ch.e : 0xffffffffu);
+      if (pmf < ZQ_LCP_CAP) {
+        const u32 cp = __shfl_sync(ZQ_FULL, p, f);
+        const u32 lf = h + pmf;
+        u32 l1 = h;
+        if (h > 0 && __shfl_sync(ZQ_FULL, ch.bw, f) == ci) { --l1; while (l1 > 0 && in[cp + l1 - 1] == in[i + l1 - 1]) --l1; }
+        const int sc = lz_score(lf, l1, i - cp, lit, h);
+        const bool acc = sc > b.bscore;
+        const u32 bl = acc ? lf : b.blen;
+        if (lf < bl || lf < P.minMatch || lf > 255) {
+          if (acc) { b.blen = lf; b.bp = cp; b.blit = l1; b.bscore = sc; }
+          stop = true;
+        }
+      }
+      if (!stop) {
+        if (!have) {
+          pm = ch.e;
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) { const u32 t = __shfl_up_sync(ZQ_FULL, pm, o, 16); if ((lane & 15) >= (u32)o) pm = min(pm, t); }
+          c = lz_eval(in, i, h, lit, ch.inr, ch.s, pm, ch.bw, ci);
+          int im = c.valid ? c.score : INT_MIN;
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(ZQ_FULL, im, o, 16); if ((lane & 15) >= (u32)o) im = max(im, t); }
+          exmax = __shfl_up_sync(ZQ_FULL, im, 1, 16);
+          if ((lane & 15) == 0) exmax = INT_MIN;
+          have = true;
+        }
+        stop = lz_resolve(segmask, c, exmax, b, P.minMatch, in, i, h, lit, lmax);
+      }
+    }
+    if (stop || (outm & segmask)) continue;
+    // ---- rare: more than 16 neighbours needed in this direction; 32 per round from k = 17
+    u32 run_min = __reduce_min_sync(ZQ_FULL, ((segmask >> lane) & 1u) ? ch.e : 0xffffffffu);
+    for (u32 k0 = 16; k0 < P.bucket && !stop; k0 += 32) {
+      const u32 k = k0 + lane + 1;
+      const bool inr2 = k <= P.bucket && (dir == 0 ? q >= k : (u64)q + k < n);
+      const u32 x2 = dir == 0 ? q - k : q + k;
+      u32 s2 = 0, pm2 = 0, bw2 = 0;
+      if (inr2) { s2 = sa[x2]; pm2 = lcp[dir == 0 ? x2 + 1 : x2]; bw2 = bwt[x2]; }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(ZQ_FULL, pm2, o); if (lane >= (u32)o) pm2 = min(pm2, t); }
+      pm2 = min(pm2, run_min);
+      run_min = __shfl_sync(ZQ_FULL, pm2, 31);
+      const LzCand c2 = lz_eval(in, i, h, lit, inr2, s2, pm2, bw2, ci);
+      int im2 = c2.valid ? c2.score : INT_MIN;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(ZQ_FULL, im2, o); if (lane >= (u32)o) im2 = max(im2, t); }
+      int ex2 = __shfl_up_sync(ZQ_FULL, im2, 1);
+      if (lane == 0) ex2 = INT_MIN;
+      stop = lz_resolve(0xffffffffu, c2, ex2, b, P.minMatch, in, i, h, lit, lmax);
+      if (__ballot_sync(ZQ_FULL, !inr2)) break;   // ran off the suffix array: nothing further
+    }
+  }
+}
+
+// token decision + output (Z:19472-19519); returns how far i advances
+__device__ __forceinline__ u32 lz_emit_step(WarpSink& sk, const LzParams& P, const u8* __restrict__ in, u32 i,
+                                            const LzBest& b, u32& lit) {
+  const u32 off = i - b.bp;
+  u32 adv;
+  if (off > 0 && b.bscore > 0 &&
+      b.blen - b.blit >= P.minMatch + (P.level == 2 ? (u32)(off >= (1u << 16)) + (u32)(off >= (1u << 24)) : 0u)) {
+    lit += b.blit;
+    lz_write_literal(sk, P, in, i + b.blit, lit);
+    lz_write_match(sk, P, b.blen - b.blit, off);
+    adv = b.blen;
+  } else {
+    adv = 1; ++lit;
+  }
+  if (lit >= (1u << 12)) lz_write_literal(sk, P, in, i + adv, lit);
+  return adv;
+}
+
+// Parse block in[0..n) with its suffix array / inverse / capped LCP / BWT bytes (index type u16 for
+// n <= 65536).  Generic form: any look-ahead.
+template <typename IdxT>
+__device__ void lz77_sa_parse(const u8* __restrict__ in, u32 n, const IdxT* __restrict__ sa, const IdxT* __restrict__ isa,
+                              const u16* __restrict__ lcp, const u8* __restrict__ bwt, const LzParams P, WarpSink& sk) {
+  const u32 maxMatch = 3u << 14;
   u32 i = 0, lit = 0;
   while (i < n) {
-    u32 blen = minMatch - 1, bp = 0, blit = 0; int bscore = 0;
+    LzBest b; b.blen = P.minMatch - 1; b.bp = 0; b.blit = 0; b.bscore = 0;
+    const u32 lmax = min(maxMatch, n - i);
     for (u32 h = 0; h <= P.lookahead; ++h) {
       const u32 pos = i + h;
       // the reference's windowed ISA only resolves positions in i's 2^checkbits window (Z:19405-19412)
       if (pos >= n || (pos >> P.checkbits) != (i >> P.checkbits)) continue;
       const u32 q = isa[pos];
-      for (int dir = 0; dir < 2; ++dir) {           // 0: towards smaller suffixes, 1: larger
-        u32 run_min = 0xffffffffu;
-        bool stop = false;
-        for (u32 k0 = 0; k0 < P.bucket && !stop; k0 += 32) {
-          const u32 k = k0 + lane + 1;
-          const bool inr = k <= P.bucket && (dir == 0 ? q >= k : (u64)q + k < n);
-          const u32 x = dir == 0 ? q - k : q + k;
-          u32 s = 0, e = 0;
-          if (inr) { s = sa[x]; e = lcp[dir == 0 ? x + 1 : x]; }
-          // running minimum of adjacent LCPs = LCP(sa[x], sa[q])
-          u32 pm = e;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(ZQ_FULL, pm, o); if (lane >= (u32)o) pm = min(pm, t); }
-          pm = min(pm, run_min);
-          run_min = __shfl_sync(ZQ_FULL, pm, 31);
-          const u32 p = s - h;                       // wraps for s < h, rejected by p < i as in the reference
-          u32 vmask = __ballot_sync(ZQ_FULL, inr && p < i);
-          while (vmask) {
-            const int src = __ffs(vmask) - 1;
-            vmask &= vmask - 1;
-            const u32 cp = __shfl_sync(ZQ_FULL, p, src);
-            const u32 cm = __shfl_sync(ZQ_FULL, pm, src);
-            u32 l = h + cm;
-            const u32 lmax = min(maxMatch, n - i);
-            if (cm >= ZQ_LCP_CAP) l = warp_match_len(in + cp, in + i, l, lmax);
-            l = min(l, lmax);
-            u32 l1 = h;
-            while (l1 > 0 && in[cp + l1 - 1] == in[i + l1 - 1]) --l1;
-            int score = (int)(l - l1) * 8 - zq_bitlen(i - cp) - 4 * (lit == 0 && l1 > 0) - 11;
-            for (u32 a = 0; a < h; ++a) score = score * 5 / 8;
-            if (score > bscore) { blen = l; bp = cp; blit = l1; bscore = score; }
-            if (l < blen || l < minMatch || l > 255) { stop = true; break; }
-          }
-          if (!stop && __ballot_sync(ZQ_FULL, !inr)) break;  // ran off the suffix array: nothing further
-        }
-      }
-      if (bscore <= 0 || blen < minMatch) break;
+      const LzChunk ch = lz_chunk_issue(sa, lcp, bwt, n, q, P.bucket, true);
+      lz_scan_pos(in, n, sa, lcp, bwt, P, i, h, lit, lmax, q, ch, b);
+      if (b.bscore <= 0 || b.blen < P.minMatch) break;
     }
-    const u32 off = i - bp;
-    if (off > 0 && bscore > 0 &&
-        blen - blit >= minMatch + (P.level == 2 ? (u32)(off >= (1u << 16)) + (u32)(off >= (1u << 24)) : 0u)) {
-      lit += blit;
-      lz_write_literal(sk, P, in, i + blit, lit);
-      lz_write_match(sk, P, blen - blit, off);
-    } else {
-      blen = 1; ++lit;
+    i += lz_emit_step(sk, P, in, i, b, lit);
+  }
+  lz_write_literal(sk, P, in, n, lit);
+  sk.flush();
+}
+
+// Same parse for look-ahead <= 1 (every built-in method), software pipelined: the neighbourhood of
+// position i+1 is requested before position i is evaluated; it serves the h=1 look-ahead of this
+// step and, when the step ends as a literal, IS the h=0 neighbourhood of the next step.  That takes
+// the isa -> sa/lcp dependent-load chain off the critical path of literal steps.
+template <typename IdxT>
+__device__ void lz77_sa_parse_pipe(const u8* __restrict__ in, u32 n, const IdxT* __restrict__ sa, const IdxT* __restrict__ isa,
+                                   const u16* __restrict__ lcp, const u8* __restrict__ bwt, const LzParams P, WarpSink& sk) {
+  const u32 maxMatch = 3u << 14;
+  const u32 lane = lane_id();
+  u32 i = 0, lit = 0;
+  if (n == 0) { sk.flush(); return; }
+  // rows of i, i+1 (lane0/lane1 fetch adjacent isa entries in one request)
+  u32 qv = (lane < 2 && i + lane < n) ? (u32)isa[i + lane] : 0u;
+  u32 qA = __shfl_sync(ZQ_FULL, qv, 0), qB = __shfl_sync(ZQ_FULL, qv, 1);
+  LzChunk A = lz_chunk_issue(sa, lcp, bwt, n, qA, P.bucket, true);
+  while (i < n) {
+    const bool haveB = i + 1 < n;
+    LzChunk B = lz_chunk_issue(sa, lcp, bwt, n, qB, P.bucket, haveB);
+    const u32 qC = i + 2 < n ? (u32)isa[i + 2] : 0u;
+    LzBest b; b.blen = P.minMatch - 1; b.bp = 0; b.blit = 0; b.bscore = 0;
+    const u32 lmax = min(maxMatch, n - i);
+    lz_scan_pos(in, n, sa, lcp, bwt, P, i, 0, lit, lmax, qA, A, b);
+    if (P.lookahead >= 1 && !(b.bscore <= 0 || b.blen < P.minMatch) && haveB &&
+        ((i + 1) >> P.checkbits) == (i >> P.checkbits)) {
+      lz_scan_pos(in, n, sa, lcp, bwt, P, i, 1, lit, lmax, qB, B, b);
     }
-    i += blen;
-    if (lit >= maxLiteral) lz_write_literal(sk, P, in, i, lit);
+    const u32 adv = lz_emit_step(sk, P, in, i, b, lit);
+    i += adv;
+    if (adv == 1) { A = B; qA = qB; qB = qC; }
+    else if (i < n) {
+      qv = (lane < 2 && i + lane < n) ? (u32)isa[i + lane] : 0u;
+      qA = __shfl_sync(ZQ_FULL, qv, 0); qB = __shfl_sync(ZQ_FULL, qv, 1);
+      A = lz_chunk_issue(sa, lcp, bwt, n, qA, P.bucket, true);
+    }
   }
   lz_write_literal(sk, P, in, n, lit);
   sk.flush();
@@ -203,16 +403,21 @@ __device__ void bwt_emit(const u8* __restrict__ in, u32 n, const u32* __restrict
   if (threadIdx.x < 4) out[n + 1 + threadIdx.x] = (u8)(*idx_slot >> (8 * threadIdx.x));
 }
 
-// One warp per unit (grid-stride over the wave's units that use the SA parse).
-__global__ void __launch_bounds__(128)
+// One warp per unit (grid-stride over the listed units). Instantiated per index width and per
+// parse flavour so each variant gets its own register allocation; the host sorts units into lists.
+// work layout per unit (bytes from work_base + work_off): sa | isa | lcp | bwt, index width 2 B when
+// n <= 65536 (ZqUnit::idx16) else 4 B, each array padded to 128 B.
+template <typename IdxT, bool PIPE, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_lz77_sa(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
-          const int* __restrict__ todo, int ntodo,
-          const u32* __restrict__ sa_all, const u32* __restrict__ isa_all, const u16* __restrict__ lcp_all,
-          u8* __restrict__ lz_base, u32* __restrict__ lz_len, u32* __restrict__ err_flag) {
-  const int warps_per_cta = blockDim.x >> 5;
-  const int gw = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
-  const int nw = gridDim.x * warps_per_cta;
-  for (int t = gw; t < ntodo; t += nw) {
+          const int* __restrict__ todo, int ntodo, const u8* __restrict__ work_base,
+          u8* __restrict__ lz_base, u32* __restrict__ lz_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit) {
+  // persistent warps pull units from a shared counter: unit costs vary a lot, a static split leaves a tail
+  for (;;) {
+    int t = 0;
+    if (lane_id() == 0) t = (int)atomicAdd(next_unit, 1u);
+    t = __shfl_sync(ZQ_FULL, t, 0);
+    if (t >= ntodo) break;
     const int ui = todo[t];
     const ZqUnit u = units[ui];
     const ZqPlan pl = plans[u.plan];
@@ -220,7 +425,13 @@ k_lz77_sa(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, cons
     P.level = pl.lz_level; P.minMatch = pl.args[2]; P.lookahead = pl.args[6];
     P.bucket = (1u << pl.args[4]) - 1; P.rb = pl.args[0] > 4 ? pl.args[0] - 4 : 0; P.checkbits = 17 + pl.args[0];
     WarpSink sk; sk.init(lz_base + u.lz_off, u.lz_cap);
-    lz77_sa_parse(in_base + u.in_off, u.n, sa_all + u.work_off, isa_all + u.work_off, lcp_all + u.work_off, P, sk);
+    const u8* w = work_base + u.work_off;
+    const u64 stride = zq_work_stride(u.n, sizeof(IdxT));
+    const u16* lcp = (const u16*)(w + 2 * stride);
+    const u8* bwt = w + 2 * stride + zq_work_stride(u.n, 2);
+    const u8* in = in_base + u.in_off;
+    if (PIPE) lz77_sa_parse_pipe<IdxT>(in, u.n, (const IdxT*)w, (const IdxT*)(w + stride), lcp, bwt, P, sk);
+    else lz77_sa_parse<IdxT>(in, u.n, (const IdxT*)w, (const IdxT*)(w + stride), lcp, bwt, P, sk);
     if (lane_id() == 0) {
       lz_len[ui] = (u32)(sk.out - (lz_base + u.lz_off));
       if (sk.overflow) atomicOr(err_flag, 1u);
