@@ -14,6 +14,7 @@ class Oracle:
         lib.zqo_lz_stream.restype = C.c_longlong
         lib.zqo_block_unmodeled.restype = C.c_longlong
         lib.zqo_fragment.restype = C.c_longlong
+        lib.zqo_block_modeled.restype = C.c_longlong
 
     def sha1(self, data):
         out = C.create_string_buffer(20)
@@ -56,6 +57,21 @@ class Oracle:
         if r < 0:
             raise RuntimeError("zqo_block_unmodeled failed %d" % r)
         return out.raw[:r]
+
+    def block_modeled(self, header, pcomp, filename, comment_full, stream, sha1):
+        cap = len(stream) + len(stream) // 8 + len(header) + len(pcomp) + 4096
+        out = C.create_string_buffer(cap)
+        r = self.lib.zqo_block_modeled(bytes(header), C.c_uint32(len(header)), bytes(pcomp), C.c_uint32(len(pcomp)),
+                                       filename, comment_full, bytes(stream), C.c_uint64(len(stream)), sha1, out,
+                                       C.c_uint64(cap))
+        if r < 0:
+            raise RuntimeError("zqo_block_modeled failed %d" % r)
+        return out.raw[:r]
+
+    def table_sums(self):
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        self.lib.zqo_table_sums(C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def fragment(self, data, fragment=6, blocksize=(1 << 26) - 4096):
         data = bytes(data)
