@@ -83,6 +83,42 @@ def test_batch_of_text_units_m2(ctx, ref):
     assert ref.decompress(out[:total].tobytes(), n * 65536) == arena.tobytes()
 
 
+CM_UNITS = [
+    b"", b"a", b"abcabcabcabcabc" * 10, bytes(3000), corpus.text_unit(1, 20000), corpus.random_unit(2, 3000),
+    corpus.repeats_unit(3, 30000), corpus.text_unit(4, 65536), corpus.mixed_unit(6, 9000),
+]
+
+
+@pytest.mark.parametrize("method", ["3", "36,200,1", "4", "46,200,1", "5", "56,180,1", "3,100,0", "4,30,0",
+                                     "x0,0c0,0,255i2,13m8,24s", "x0,0c0,7i1c1004,0,1256i1s8,32,255",
+                                     "x0,0c2,1100,255,0,128a24,1,1t16,20", "s0,0c0,0,255,255i3", "x0,3ci1",
+                                     "x0,0c8,0,255c0,0,255,255a16,2,2t8", "x0,2,12,0,7,21,1c0,0,511i2"])
+def test_modeled_blocks_bit_exact(ctx, zq, oracle, ref, method):
+    units = CM_UNITS if method not in ("5", "56,180,1") else CM_UNITS[:7]
+    arena, offs, lens = _arena(units)
+    out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method=method, filename="nm", comment="jDC\x01")
+    for i, u in enumerate(units):
+        got = out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes()
+        want = ref.compress_block(u, method, "nm", "jDC\x01")
+        if got != want:
+            k = next((j for j in range(min(len(got), len(want))) if got[j] != want[j]), -1)
+            raise AssertionError("method %s unit %d (n=%d): %d vs %d bytes, first difference at %d" %
+                                 (method, i, len(u), len(got), len(want), k))
+    total = int(ooff[-1]) + int(olen[-1])
+    assert ref.decompress(out[:total].tobytes(), int(lens.sum())) == b"".join(units)
+
+
+def test_modeled_matches_c_oracle(ctx, zq, oracle):
+    u = corpus.text_unit(11, 12000)
+    arena, offs, lens = _arena([u])
+    for method in ("3", "4", "36,200,1"):
+        out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method=method, filename="", comment="")
+        p = zq.plan_block(method, u)
+        s = oracle.lz_stream(u, p["args"]) if (p["args"][1] & 3) else u
+        want = oracle.block_modeled(p["header"], p["pcomp"], b"", b"%d " % len(u), s, oracle.sha1(u))
+        assert out[: int(olen[0])].tobytes() == want, method
+
+
 def test_unsupported_is_loud(ctx, zq):
     arena, offs, lens = _arena([corpus.text_unit(1, 5000)])
     with pytest.raises(zq.ZqError):

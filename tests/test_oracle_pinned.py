@@ -47,3 +47,26 @@ def test_fragmenter_restatement_agrees(oracle, ref):
         a, b = oracle.fragment(d, frag), ref.fragment(d, frag)
         assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
         assert int(a[0].sum()) == len(d)
+
+
+def test_cm_tables_match_reference_checksums(oracle):
+    # the reference's own KAT for the stretch/squash tables (Z:14949-14950)
+    assert oracle.table_sums() == (3887533746, 2278286169)
+
+
+@pytest.mark.parametrize("method", ["3", "36,200,1", "4", "46,200,1", "5", "3,100,0", "x0,0c0,0,255i2,13m8,24s",
+                                     "x0,0c0,7i1c1004,0,1256i1s8,32,255", "x0,0c2,1100,255,0,128a24,1,1t16,20",
+                                     "s0,0c0,0,255,255i3", "x0,0c8,0,255c0,0,255,255a16,2,2t8"])
+def test_cm_restatement_vs_reference(zq, oracle, ref, method):
+    cases = [corpus.text_unit(1, 12000), corpus.random_unit(2, 2000), corpus.repeats_unit(3, 9000), bytes(3000), b"", b"a",
+             b"abcabcabcabcabc" * 10]
+    if method == "5":
+        cases = cases[3:] + [corpus.text_unit(1, 2500)]
+    for d in cases:
+        p = zq.plan_block(method, d)
+        a = p["args"]
+        if a[1] >= 4:
+            continue
+        s = oracle.lz_stream(d, a) if (a[1] & 3) else d
+        blk = oracle.block_modeled(p["header"], p["pcomp"], b"nm", ("%d cm" % len(d)).encode(), s, oracle.sha1(d))
+        assert blk == ref.compress_block(d, method, "nm", "cm"), (method, len(d))

@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "../../include/zq_b200.h"
+#include "zq_cm.cuh"
+#include "zq_cm_host.h"
 #include "zq_common.cuh"
 #include "zq_config.h"
 #include "zq_frame.cuh"
@@ -54,11 +56,12 @@ struct zq_ctx {
   cudaStream_t own_stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_todo2, d_lz, d_lzlen, d_sha,
+  DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_todo2, d_todo3, d_lz, d_lzlen, d_sha, d_tables, d_cmplans, d_fills, d_model, d_coded, d_codedlen,
       d_kbuf, d_vbuf, d_err, d_misc;
   Timer tm[8];
   float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   size_t wave_bytes = (size_t)12 << 30;  // sa|isa|lcp bytes per wave
+  size_t model_budget = (size_t)120 << 30; // component-table bytes per wave (capped by free memory)
   int sort_nt = 512, sort_minb = 2;       // suffix-sort CTA size and CTAs per SM
   int lz_occ = 6;                         // CTAs (4 warps) per SM the LZ parse kernel is compiled for
 };
@@ -100,10 +103,10 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
   if (n == 0) return ZQ_OK;
   // ---- plans -----------------------------------------------------------------------------------
   std::vector<HostPlan> plans;
-  std::map<std::string, int> plan_idx;
+  std::map<std::string, int> plan_idx;   // expanded method | size class -> plan
+  std::map<std::string, std::string> expand_cache;
   std::vector<ZqUnit> units(n);
   std::vector<uint8_t> blob;
-  std::vector<uint32_t> prefix_len(n);
   try {
     for (int u = 0; u < n; ++u) {
       const char* m = method ? method[uniform ? 0 : u] : "1";
@@ -111,20 +114,29 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       const uint32_t len = in_len[u];
       int arg0 = zq::bitlen(len + 4095) - 20; if (arg0 < 0) arg0 = 0;
       const bool data_dependent = isdigit((unsigned char)m[0]) && m[0] >= '5';
-      std::string key = std::string(m) + "|" + std::to_string(arg0);
+      std::string expanded;
+      if (data_dependent) {
+        if (!h_in) return fail(c, ZQ_E_UNSUPPORTED, "method level >= 5 needs host-visible input for its period analysis");
+        expanded = zq::expand_method(m, h_in + in_off[u], len);
+      } else {
+        const std::string ck = std::string(m) + "|" + std::to_string(arg0);
+        auto it = expand_cache.find(ck);
+        if (it == expand_cache.end()) it = expand_cache.emplace(ck, zq::expand_method(m, nullptr, len)).first;
+        expanded = it->second;
+      }
+      const std::string key = expanded + "|" + std::to_string(arg0);
       int pi;
-      auto it = data_dependent ? plan_idx.end() : plan_idx.find(key);
+      auto it = plan_idx.find(key);
       if (it != plan_idx.end()) pi = it->second;
       else {
-        if (data_dependent && !h_in) return fail(c, ZQ_E_UNSUPPORTED, "method level >= 5 needs host-visible input for its period analysis");
         HostPlan hp;
-        hp.bp = zq::plan_block(m, data_dependent ? h_in + in_off[u] : nullptr, len);
+        hp.bp = zq::plan_block(expanded, nullptr, len);
         const auto& pc = hp.bp.code.pcomp;
         if (!pc.empty()) { hp.payload.push_back(1); hp.payload.push_back(pc.size() & 255); hp.payload.push_back(pc.size() >> 8); hp.payload.insert(hp.payload.end(), pc.begin(), pc.end()); }
         else hp.payload.push_back(0);
         pi = (int)plans.size();
         plans.push_back(std::move(hp));
-        if (!data_dependent) plan_idx[key] = pi;
+        plan_idx[key] = pi;
       }
       const HostPlan& hp = plans[pi];
       ZqUnit& zu = units[u];
@@ -146,60 +158,109 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       blob.insert(blob.end(), cs.begin(), cs.end());
       blob.push_back(0); blob.push_back(0);
       zu.prefix_len = (u32)blob.size() - zu.prefix_off;
-      prefix_len[u] = zu.prefix_len;
     }
   } catch (const zq::Error& e) {
     return fail(c, ZQ_E_METHOD, e.msg);
   }
   std::vector<ZqPlan> dplans(plans.size());
+  std::vector<ZqCmPlan> cmplans;
+  std::vector<ZqCmFill> fills;
+  bool any_modeled = false;
   for (size_t i = 0; i < plans.size(); ++i) {
     ZqPlan& p = dplans[i];
     memcpy(p.args, plans[i].bp.args, sizeof p.args);
     p.payload_off = (u32)blob.size(); p.payload_len = (u32)plans[i].payload.size();
     blob.insert(blob.end(), plans[i].payload.begin(), plans[i].payload.end());
     p.lz_level = plans[i].bp.lz_level; p.use_sa = plans[i].bp.use_sa; p.e8e9 = plans[i].bp.e8e9;
-    p.modeled = plans[i].bp.code.ncomp > 0;
-    if (p.modeled) return fail(c, ZQ_E_UNSUPPORTED, "context-mixing methods are not on the device yet: " + plans[i].bp.method);
+    p.modeled = plans[i].bp.code.ncomp > 0; p.cm_plan = 0;
     if (p.e8e9) return fail(c, ZQ_E_UNSUPPORTED, "E8E9 pre-filter is not on the device yet: " + plans[i].bp.method);
     if (p.lz_level && !p.use_sa) return fail(c, ZQ_E_UNSUPPORTED, "hash-table LZ77 is not on the device yet: " + plans[i].bp.method);
+    if ((p.lz_level == 1 || p.lz_level == 2) && (p.args[2] < (p.lz_level == 1 ? 4 : 1) || p.args[2] > 64 + 191 * (p.lz_level == 1)))
+      return fail(c, ZQ_E_METHOD, "match length $3 too small");
+    if (p.modeled) {
+      any_modeled = true;
+      try {
+        ZqCmPlan cp = zq::make_cm_plan(plans[i].bp.code, fills);
+        cp.hcomp_off = (u32)blob.size(); cp.hcomp_len = (u32)plans[i].bp.code.hcomp.size();
+        blob.insert(blob.end(), plans[i].bp.code.hcomp.begin(), plans[i].bp.code.hcomp.end());
+        p.cm_plan = (u32)cmplans.size();
+        cmplans.push_back(cp);
+      } catch (const zq::Error& e) {
+        return fail(c, ZQ_E_UNSUPPORTED, e.msg + ": " + plans[i].bp.method);
+      }
+    }
+  }
+  if (any_modeled && !c->d_tables.p) {
+    try {
+      const zq::CmTables& t = zq::cm_tables();
+      ZQ_CUDA(c, c->d_tables.ensure(sizeof(zq::CmTables)));
+      ZQ_CUDA(c, cudaMemcpyAsync(c->d_tables.p, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
+    } catch (const zq::Error& e) { return fail(c, ZQ_E_METHOD, e.msg); }
   }
   // ---- device tables -----------------------------------------------------------------------------
   for (int k = 0; k < 8; ++k) c->tm[k].used = false;
   tstart(c, 0);
   ZQ_CUDA(c, c->d_plans.ensure(dplans.size() * sizeof(ZqPlan)));
-  ZQ_CUDA(c, c->d_blob.ensure(blob.size()));
+  ZQ_CUDA(c, c->d_blob.ensure(blob.size() + 16));
   ZQ_CUDA(c, c->d_units.ensure((size_t)n * sizeof(ZqUnit)));
   ZQ_CUDA(c, c->d_outoff.ensure((size_t)n * 8));
   ZQ_CUDA(c, c->d_lzlen.ensure((size_t)n * 4));
+  ZQ_CUDA(c, c->d_codedlen.ensure((size_t)n * 4));
   ZQ_CUDA(c, c->d_todo.ensure((size_t)n * 4));
   ZQ_CUDA(c, c->d_err.ensure(64));
   if (dosha1) ZQ_CUDA(c, c->d_sha.ensure((size_t)n * 20));
   ZQ_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 64, c->stream));
-  // waves: contiguous unit ranges whose suffix-array footprint fits wave_elems
-  std::vector<uint32_t> lz_len_h(n, 0);
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_plans.p, dplans.data(), dplans.size() * sizeof(ZqPlan), cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+  if (!cmplans.empty()) {
+    ZQ_CUDA(c, c->d_cmplans.ensure(cmplans.size() * sizeof(ZqCmPlan)));
+    ZQ_CUDA(c, c->d_fills.ensure(fills.size() * sizeof(ZqCmFill)));
+    ZQ_CUDA(c, cudaMemcpyAsync(c->d_cmplans.p, cmplans.data(), cmplans.size() * sizeof(ZqCmPlan), cudaMemcpyHostToDevice, c->stream));
+    ZQ_CUDA(c, cudaMemcpyAsync(c->d_fills.p, fills.data(), fills.size() * sizeof(ZqCmFill), cudaMemcpyHostToDevice, c->stream));
+  }
+  size_t model_budget = c->model_budget;
+  if (any_modeled) {
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    fr += c->d_model.cap;                       // our own cached arena can be reused
+    model_budget = std::min<size_t>(model_budget, fr > ((size_t)6 << 30) ? fr - ((size_t)6 << 30) : fr / 2);
+  }
+  // waves: contiguous unit ranges whose suffix-array and model footprints fit the budgets
+  std::vector<uint32_t> lz_len_h(n, 0), coded_len_h(n, 0);
   uint64_t out_pos = 0;
   int w0 = 0;
   while (w0 < n) {
-    size_t elems = 0, lzbytes = 0, maxn = 0;
-    int w1 = w0;
-    std::vector<int> todo_sa;
+    size_t work = 0, lzbytes = 0, maxn = 0, model = 0, coded = 0;
+    int w1 = w0, maxjobs = 0;
+    std::vector<int> todo_sa, todo_bwt, todo_cm;
     while (w1 < n) {
       ZqUnit& zu = units[w1];
       const ZqPlan& p = dplans[zu.plan];
       zu.idx16 = zu.n <= 65536 ? 1 : 0;
-      size_t e = p.use_sa ? (size_t)zq_work_bytes(zu.n, zu.idx16 ? 2 : 4) : 0;
-      if (w1 > w0 && elems + e > c->wave_bytes) break;
-      zu.work_off = elems; elems += e;
+      const size_t e = p.use_sa ? (size_t)zq_work_bytes(zu.n, zu.idx16 ? 2 : 4) : 0;
+      const size_t mb = p.modeled ? (size_t)cmplans[p.cm_plan].model_bytes : 0;
+      if (w1 > w0 && (work + e > c->wave_bytes || model + mb > model_budget)) break;
+      zu.work_off = work; work += e;
+      uint32_t slen_max = zu.n;
       if (p.lz_level) {
         zu.lz_off = lzbytes; zu.lz_cap = zu.n + zu.n / 32 + 64; lzbytes += align_up(zu.lz_cap, 16);
+        slen_max = zu.lz_cap;
+        if (p.lz_level == 3) todo_bwt.push_back(w1 - w0);
         if (p.use_sa) { todo_sa.push_back(w1 - w0); maxn = std::max(maxn, (size_t)zu.n); }
+      }
+      if (p.modeled) {
+        zu.model_off = model; model += mb;
+        zu.coded_off = coded; zu.coded_cap = slen_max + slen_max / 8 + p.payload_len * 2 + 1024; coded += align_up(zu.coded_cap, 16);
+        todo_cm.push_back(w1 - w0);
+        maxjobs = std::max(maxjobs, (int)cmplans[p.cm_plan].fill_count);
       }
       ++w1;
     }
     const int wn = w1 - w0;
+    if (model > model_budget && wn == 1 && model > c->d_model.cap) {
+      // a single block whose model does not fit: let cudaMalloc decide
+    }
     ZQ_CUDA(c, cudaMemcpyAsync(c->d_units.p, units.data() + w0, (size_t)wn * sizeof(ZqUnit), cudaMemcpyHostToDevice, c->stream));
-    ZQ_CUDA(c, cudaMemcpyAsync(c->d_plans.p, dplans.data(), dplans.size() * sizeof(ZqPlan), cudaMemcpyHostToDevice, c->stream));
-    ZQ_CUDA(c, cudaMemcpyAsync(c->d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
     const ZqUnit* du = c->d_units.as<ZqUnit>();
     const ZqPlan* dp = c->d_plans.as<ZqPlan>();
     if (dosha1) {
@@ -208,10 +269,10 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       ++c->launches;
       tstop(c, 1);
     }
+    if (lzbytes) ZQ_CUDA(c, c->d_lz.ensure(lzbytes));
     if (!todo_sa.empty()) {
       const int nt = (int)todo_sa.size();
-      ZQ_CUDA(c, c->d_work.ensure(elems));
-      ZQ_CUDA(c, c->d_lz.ensure(lzbytes));
+      ZQ_CUDA(c, c->d_work.ensure(work));
       const size_t scr = align_up(maxn + 1, 64);
       int sort_nt = c->sort_nt, sort_minb = c->sort_minb;
       const int sort_grid = std::min(nt, c->num_sms * sort_minb);
@@ -233,17 +294,19 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       tstop(c, 2);
       tstart(c, 3);
       {
-        // one launch per (index width, parse flavour) present in the wave
+        // LZ77 parse: one launch per (index width, parse flavour) present; BWT units go to their own kernel
         std::vector<int> lists[4];
         for (int t : todo_sa) {
           const ZqUnit& zu = units[w0 + t];
+          if (dplans[zu.plan].lz_level == 3) continue;
           const bool pipe = dplans[zu.plan].args[6] <= 1;
           lists[(zu.idx16 ? 0 : 2) + (pipe ? 0 : 1)].push_back(t);
         }
         size_t lo = 0;
         std::vector<int> flat;
         for (auto& l : lists) flat.insert(flat.end(), l.begin(), l.end());
-        ZQ_CUDA(c, c->d_todo2.ensure(flat.size() * 4));
+        flat.insert(flat.end(), todo_bwt.begin(), todo_bwt.end());
+        ZQ_CUDA(c, c->d_todo2.ensure(flat.size() * 4 + 4));
         ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo2.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, c->stream));
         for (int v = 0; v < 4; ++v) {
           const int cnt = (int)lists[v].size();
@@ -269,19 +332,50 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
 #undef ZQ_LZ_LAUNCH
           ++c->launches;
         }
+        if (!todo_bwt.empty()) {
+          k_bwt_stream<<<std::min((int)todo_bwt.size(), c->num_sms * 8), 256, 0, c->stream>>>(
+              d_in, du, c->d_todo2.as<int>() + lo, (int)todo_bwt.size(), c->d_work.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>());
+          ++c->launches;
+        }
       }
       tstop(c, 3);
-      ZQ_CUDA(c, cudaMemcpyAsync(lz_len_h.data() + w0, c->d_lzlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
-      ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
     }
+    if (!todo_cm.empty()) {
+      const int nt = (int)todo_cm.size();
+      ZQ_CUDA(c, c->d_model.ensure(model));
+      ZQ_CUDA(c, c->d_coded.ensure(coded));
+      ZQ_CUDA(c, c->d_todo3.ensure((size_t)nt * 4));
+      ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo3.p, todo_cm.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
+      u32* ctr = c->d_err.as<u32>() + 8;
+      ZQ_CUDA(c, cudaMemsetAsync(ctr, 0, 4, c->stream));
+      tstart(c, 5);
+      k_cm_init<<<nt * maxjobs, 256, 0, c->stream>>>(du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_fills.as<ZqCmFill>(), c->d_todo3.as<int>(), nt,
+                                                     maxjobs, c->d_tables.as<CmTablesDev>(), c->d_model.as<u8>());
+      ++c->launches;
+      static bool attr_set = false;
+      if (!attr_set) { cudaFuncSetAttribute(k_cm_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem)); attr_set = true; }
+      const int cgrid = std::min((nt + 15) / 16, c->num_sms * 2);
+      k_cm_encode<<<cgrid, 512, sizeof(CmSmem), c->stream>>>(d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt,
+                                                             c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(),
+                                                             c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr);
+      ++c->launches;
+      tstop(c, 5);
+      ZQ_CUDA(c, cudaMemcpyAsync(coded_len_h.data() + w0, c->d_codedlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (!todo_sa.empty()) ZQ_CUDA(c, cudaMemcpyAsync(lz_len_h.data() + w0, c->d_lzlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (!todo_sa.empty() || !todo_cm.empty()) ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
     // final layout of this wave's blocks
     std::vector<uint64_t> ooff(wn);
     std::vector<int> todo_all(wn);
     for (int k = 0; k < wn; ++k) {
       const ZqUnit& zu = units[w0 + k];
       const ZqPlan& p = dplans[zu.plan];
-      const uint64_t slen = p.lz_level ? lz_len_h[w0 + k] : zu.n;
-      const uint64_t sz = unmodeled_block_size(zu.prefix_len, (uint64_t)p.payload_len + slen, dosha1 != 0);
+      uint64_t sz;
+      if (p.modeled) sz = (uint64_t)zu.prefix_len + coded_len_h[w0 + k] + 4 + (dosha1 ? 21 : 1) + 1;
+      else {
+        const uint64_t slen = p.lz_level ? lz_len_h[w0 + k] : zu.n;
+        sz = unmodeled_block_size(zu.prefix_len, (uint64_t)p.payload_len + slen, dosha1 != 0);
+      }
       if (sz > 0xffffffffull) return fail(c, ZQ_E_OUTPUT, "block too large");
       ooff[k] = out_pos; out_off[w0 + k] = out_pos; out_len[w0 + k] = (uint32_t)sz;
       out_pos += sz;
@@ -291,9 +385,9 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
     ZQ_CUDA(c, cudaMemcpyAsync(c->d_outoff.p, ooff.data(), (size_t)wn * 8, cudaMemcpyHostToDevice, c->stream));
     ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo.p, todo_all.data(), (size_t)wn * 4, cudaMemcpyHostToDevice, c->stream));
     tstart(c, 4);
-    k_frame_unmodeled<<<std::min(wn, c->num_sms * 8), 256, 0, c->stream>>>(
+    k_frame<<<std::min(wn, c->num_sms * 8), 256, 0, c->stream>>>(
         du, dp, c->d_todo.as<int>(), wn, c->d_blob.as<u8>(), d_in, c->d_lz.as<u8>(), c->d_lzlen.as<u32>(),
-        dosha1 ? c->d_sha.as<u8>() : nullptr, c->d_outoff.as<u64>(), d_out);
+        c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), dosha1 ? c->d_sha.as<u8>() : nullptr, c->d_outoff.as<u64>(), d_out);
     ++c->launches;
     tstop(c, 4);
     ZQ_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors of this wave go out of scope
@@ -304,7 +398,8 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
   ZQ_CUDA(c, cudaMemcpyAsync(&errflag, c->d_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
   ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
   ZQ_CUDA(c, cudaGetLastError());
-  if (errflag) return fail(c, ZQ_E_OUTPUT, "internal: pre-pass stream exceeded its bound");
+  if (errflag & 2) return fail(c, ZQ_E_METHOD, "ZPAQL execution error");
+  if (errflag) return fail(c, ZQ_E_OUTPUT, "internal: intermediate stream exceeded its bound");
   for (int k = 0; k < 8; ++k) {
     c->last_ms[k] = 0;
     if (c->tm[k].used) cudaEventElapsedTime(&c->last_ms[k], c->tm[k].a, c->tm[k].b);
@@ -336,6 +431,7 @@ zq_ctx* zq_create(int device) {
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream creation failed"; delete c; return nullptr; }
   c->stream = c->own_stream;
   for (int k = 0; k < 8; ++k) { cudaEventCreate(&c->tm[k].a); cudaEventCreate(&c->tm[k].b); }
+  if (const char* s = getenv("ZQ_MODEL_BUDGET")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->model_budget = v; }
   if (const char* s = getenv("ZQ_LZ_OCC")) c->lz_occ = atoi(s);
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
   if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);
@@ -352,7 +448,7 @@ void zq_destroy(zq_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_work, &c->d_todo2, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
+  DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_work, &c->d_todo2, &c->d_todo3, &c->d_tables, &c->d_cmplans, &c->d_fills, &c->d_model, &c->d_coded, &c->d_codedlen, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
   for (DevBuf* b : bufs) b->release();
   for (int k = 0; k < 8; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
   cudaStreamDestroy(c->own_stream);

@@ -15,12 +15,15 @@ struct ZqUnit {
   u64 in_off;    // byte offset of the input in the device input arena
   u64 work_off;  // byte offset of this unit's sa | isa | lcp region in the per-wave work arena
   u64 lz_off;    // byte offset into the pre-pass stream buffer
-  u64 out_off;   // byte offset of the finished block in the output arena
+  u64 model_off; // byte offset of this unit's component tables + VM memory in the model arena
+  u64 coded_off; // byte offset of the arithmetic coder's output
   u32 n;         // input length
   u32 plan;      // index into the plan table
   u32 lz_cap;    // capacity reserved at lz_off
   u32 prefix_off, prefix_len;  // block prefix (tag .. segment header) in the blob
   u32 idx16;     // 1: sa/isa stored as u16 (n <= 65536), 0: u32
+  u32 coded_cap; // capacity reserved at coded_off
+  u32 pad;
 };
 
 // Per (method, block size class) constants (== makeConfig's args, Z:19620-19628).
@@ -31,6 +34,8 @@ struct ZqPlan {
   u32 use_sa;
   u32 e8e9;
   u32 modeled;                   // ncomp > 0
+  u32 cm_plan;                   // index into the ZqCmPlan table when modeled
+  u32 pad;
 };
 
 // per-unit work region: sa | isa (index width w = 2 or 4) | lcp (u16) | bwt (u8), each padded to 128 B

@@ -18,16 +18,38 @@ __host__ __device__ inline u64 unmodeled_block_size(u32 prefix_len, u64 payload_
   return prefix_len + payload_total + 4 * nchunks + 4 + (sha ? 21 : 1) + 1;
 }
 
+__device__ __forceinline__ void frame_trailer(u8* tr, const u8* sha1, int ui) {
+  if (threadIdx.x < 4) tr[threadIdx.x] = 0;
+  if (sha1) {
+    if (threadIdx.x == 4) tr[4] = 253;
+    if (threadIdx.x >= 32 && threadIdx.x < 52) tr[5 + threadIdx.x - 32] = sha1[(size_t)ui * 20 + threadIdx.x - 32];
+    if (threadIdx.x == 5) tr[25] = 255;
+  } else {
+    if (threadIdx.x == 4) tr[4] = 254;
+    if (threadIdx.x == 5) tr[5] = 255;
+  }
+}
+
+// Modeled blocks (n components > 0): prefix | arithmetic-coded bytes | trailer.
 __global__ void __launch_bounds__(256)
-k_frame_unmodeled(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, const int* __restrict__ todo, int ntodo,
-                  const u8* __restrict__ blob, const u8* __restrict__ in_base, const u8* __restrict__ lz_base,
-                  const u32* __restrict__ lz_len, const u8* __restrict__ sha1 /* 20 B per unit or null */,
-                  const u64* __restrict__ out_off, u8* __restrict__ out_base) {
+k_frame(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, const int* __restrict__ todo, int ntodo,
+        const u8* __restrict__ blob, const u8* __restrict__ in_base, const u8* __restrict__ lz_base,
+        const u32* __restrict__ lz_len, const u8* __restrict__ coded_base, const u32* __restrict__ coded_len,
+        const u8* __restrict__ sha1 /* 20 B per unit or null */, const u64* __restrict__ out_off, u8* __restrict__ out_base) {
   for (int t = blockIdx.x; t < ntodo; t += gridDim.x) {
     const int ui = todo[t];
     const ZqUnit u = units[ui];
     const ZqPlan pl = plans[u.plan];
     u8* __restrict__ out = out_base + out_off[ui];
+    if (pl.modeled) {
+      for (u32 k = threadIdx.x; k < u.prefix_len; k += blockDim.x) out[k] = blob[u.prefix_off + k];
+      const u32 cl = coded_len[ui];
+      const u8* __restrict__ src = coded_base + u.coded_off;
+      u8* __restrict__ body = out + u.prefix_len;
+      for (u32 k = threadIdx.x; k < cl; k += blockDim.x) body[k] = src[k];
+      frame_trailer(body + cl, sha1, ui);
+      continue;
+    }
     const u8* __restrict__ stream; u32 slen;
     if (pl.lz_level) { stream = lz_base + u.lz_off; slen = lz_len[ui]; }
     else { stream = in_base + u.in_off; slen = u.n; }
@@ -46,16 +68,7 @@ k_frame_unmodeled(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ p
       const u8 b = s < plen ? blob[pl.payload_off + s] : stream[s - plen];
       body[s + 4 * ((s >> 16) + 1)] = b;
     }
-    u8* tr = body + total + 4 * nchunks;
-    if (threadIdx.x < 4) tr[threadIdx.x] = 0;
-    if (sha1) {
-      if (threadIdx.x == 4) tr[4] = 253;
-      if (threadIdx.x >= 32 && threadIdx.x < 52) tr[5 + threadIdx.x - 32] = sha1[(size_t)ui * 20 + threadIdx.x - 32];
-      if (threadIdx.x == 5) tr[25] = 255;
-    } else {
-      if (threadIdx.x == 4) tr[4] = 254;
-      if (threadIdx.x == 5) tr[5] = 255;
-    }
+    frame_trailer(body + total + 4 * nchunks, sha1, ui);
   }
 }
 

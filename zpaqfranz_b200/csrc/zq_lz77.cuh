@@ -387,20 +387,36 @@ __device__ void lz77_sa_parse_pipe(const u8* __restrict__ in, u32 n, const IdxT*
 }
 
 // BWT pre-pass (LZBuffer::fill level 3, Z:19383-19393): last column with the end-of-string row
-// coded as 255, then that row's index, 4 bytes LSB first. Whole CTA.
-__device__ void bwt_emit(const u8* __restrict__ in, u32 n, const u32* __restrict__ sa, u8* __restrict__ out, u32* idx_slot) {
-  // out[0] = in[n-1] (255 if empty); out[i] for i=1..n: sa[i-1]==0 ? 255 (idx=i) : in[sa[i-1]-1]
+// coded as 255, then that row's index, 4 bytes LSB first (n+5 bytes). One CTA per block.
+template <typename IdxT>
+__device__ void bwt_emit(const u8* __restrict__ in, u32 n, const IdxT* __restrict__ sa, u8* __restrict__ out) {
+  __shared__ u32 idx_s;
+  if (threadIdx.x == 0) idx_s = 0;
+  __syncthreads();
   for (u32 i = threadIdx.x; i <= n; i += blockDim.x) {
     if (i == 0) out[0] = n > 0 ? in[n - 1] : 255;
     else {
       const u32 s = sa[i - 1];
-      if (s == 0) { out[i] = 255; *idx_slot = i; }
+      if (s == 0) { out[i] = 255; idx_s = i; }
       else out[i] = in[s - 1];
     }
   }
-  if (n == 0 && threadIdx.x == 0) *idx_slot = 0;
   __syncthreads();
-  if (threadIdx.x < 4) out[n + 1 + threadIdx.x] = (u8)(*idx_slot >> (8 * threadIdx.x));
+  if (threadIdx.x < 4) out[n + 1 + threadIdx.x] = (u8)(idx_s >> (8 * threadIdx.x));
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_bwt_stream(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const int* __restrict__ todo, int ntodo,
+             const u8* __restrict__ work_base, u8* __restrict__ lz_base, u32* __restrict__ lz_len) {
+  for (int t = blockIdx.x; t < ntodo; t += gridDim.x) {
+    const int ui = todo[t];
+    const ZqUnit u = units[ui];
+    const u8* w = work_base + u.work_off;
+    if (u.idx16) bwt_emit<u16>(in_base + u.in_off, u.n, (const u16*)w, lz_base + u.lz_off);
+    else bwt_emit<u32>(in_base + u.in_off, u.n, (const u32*)w, lz_base + u.lz_off);
+    if (threadIdx.x == 0) lz_len[ui] = u.n + 5;
+  }
 }
 
 // One warp per unit (grid-stride over the listed units). Instantiated per index width and per
