@@ -119,7 +119,57 @@ def test_modeled_matches_c_oracle(ctx, zq, oracle):
         assert out[: int(olen[0])].tobytes() == want, method
 
 
+def _exe_like(seed, n):
+    """bytes with many E8/E9 xx xx xx 00/FF patterns so that the E8E9 filter has work to do"""
+    rng = np.random.Generator(np.random.PCG64([seed, 5]))
+    a = rng.integers(0, 256, n, dtype=np.uint8)
+    for pos in rng.integers(0, max(n - 8, 1), n // 24):
+        a[pos] = 0xE8 + int(rng.integers(0, 2))
+        a[pos + 4] = 0x00 if rng.integers(0, 2) else 0xFF
+    return a.tobytes()
+
+
+HASH_METHODS = ["1", "1,10,0", "1,20,0", "1,40,0", "1,250,0", "2,10,0", "3,10,0", "4,5,0", "14,128,0", "x0,1,4,0,3,20",
+                "x0,1,5,0,3,20", "x0,2,6,0,2,18", "x0,2,12,0,5,16", "x0,1,4,0,6,20", "x0,1,4,4,3,20,1", "x0,2,5,7,2,19"]
+
+
+@pytest.mark.parametrize("method", HASH_METHODS)
+def test_hash_lz77_blocks_bit_exact(ctx, ref, method):
+    units = EDGE_UNITS[:12] + [corpus.text_unit(1, 65536), corpus.random_unit(4, 20000), corpus.repeats_unit(5, 65536),
+                               corpus.text_unit(7, 200000), bytes(1 << 20)]
+    arena, offs, lens = _arena(units)
+    out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method=method, filename="nm", comment="c")
+    for i, u in enumerate(units):
+        got = out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes()
+        assert got == ref.compress_block(u, method, "nm", "c"), (method, i, len(u))
+
+
+@pytest.mark.parametrize("method", ["1,128,2", "2,128,2", "3,100,2", "3,200,3", "4,128,2", "0", "x0,4", "x0,5,4,0,3,20",
+                                     "x0,6,12,0,7,21,1c0,0,511i2", "x0,7ci1", "x0,4c0,0,255i1"])
+def test_e8e9_blocks_bit_exact(ctx, ref, method):
+    units = [_exe_like(1, 30000), _exe_like(2, 65536), _exe_like(3, 7), _exe_like(4, 5), b"\xe8\x01\x02\x03\x00" * 30,
+             corpus.text_unit(1, 5000), b""]
+    arena, offs, lens = _arena(units)
+    out, ooff, olen = ctx.compress_blocks(arena.copy(), offs, lens, method=method, filename="x", comment="")
+    for i, u in enumerate(units):
+        got = out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes()
+        assert got == ref.compress_block(u, method, "x", ""), (method, i, len(u))
+    total = int(ooff[-1]) + int(olen[-1])
+    assert ref.decompress(out[:total].tobytes(), int(lens.sum())) == b"".join(units)
+
+
+def test_config1_one_mib_of_zeros_m1(ctx, ref):
+    # BASELINE.json configs[0]: single 1 MiB zero-filled buffer, -m1, byte-compare with the reference
+    u = bytes(1 << 20)
+    arena, offs, lens = _arena([u])
+    for m in ("1", "14,0,0"):
+        out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method=m, filename="", comment="")
+        assert out[: int(olen[0])].tobytes() == ref.compress_block(u, m, "", "")
+
+
 def test_unsupported_is_loud(ctx, zq):
     arena, offs, lens = _arena([corpus.text_unit(1, 5000)])
     with pytest.raises(zq.ZqError):
-        ctx.compress_blocks(arena, offs, lens, method="x0,1,2,0,3,20")   # LZ77 min match too small / hash path
+        ctx.compress_blocks(arena, offs, lens, method="x0,1,2,0,3,20")   # LZ77 min match too small
+    with pytest.raises(zq.ZqError):
+        ctx.compress_blocks(arena, offs, lens, method="q1")

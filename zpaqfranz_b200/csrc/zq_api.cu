@@ -56,7 +56,7 @@ struct zq_ctx {
   cudaStream_t own_stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_todo2, d_todo3, d_lz, d_lzlen, d_sha, d_tables, d_cmplans, d_fills, d_model, d_coded, d_codedlen,
+  DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_ht, d_todo2, d_todo3, d_todo4, d_todo5, d_lz, d_lzlen, d_sha, d_tables, d_cmplans, d_fills, d_model, d_coded, d_codedlen,
       d_kbuf, d_vbuf, d_err, d_misc;
   Timer tm[8];
   float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -173,8 +173,8 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
     blob.insert(blob.end(), plans[i].payload.begin(), plans[i].payload.end());
     p.lz_level = plans[i].bp.lz_level; p.use_sa = plans[i].bp.use_sa; p.e8e9 = plans[i].bp.e8e9;
     p.modeled = plans[i].bp.code.ncomp > 0; p.cm_plan = 0;
-    if (p.e8e9) return fail(c, ZQ_E_UNSUPPORTED, "E8E9 pre-filter is not on the device yet: " + plans[i].bp.method);
-    if (p.lz_level && !p.use_sa) return fail(c, ZQ_E_UNSUPPORTED, "hash-table LZ77 is not on the device yet: " + plans[i].bp.method);
+    if (p.lz_level && !p.use_sa && (p.args[5] < 4 || p.args[5] > 30 || p.args[4] > 16 || p.args[0] > 11))
+      return fail(c, ZQ_E_UNSUPPORTED, "LZ77 hash table parameters outside the device path: " + plans[i].bp.method);
     if ((p.lz_level == 1 || p.lz_level == 2) && (p.args[2] < (p.lz_level == 1 ? 4 : 1) || p.args[2] > 64 + 191 * (p.lz_level == 1)))
       return fail(c, ZQ_E_METHOD, "match length $3 too small");
     if (p.modeled) {
@@ -230,17 +230,21 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
   uint64_t out_pos = 0;
   int w0 = 0;
   while (w0 < n) {
-    size_t work = 0, lzbytes = 0, maxn = 0, model = 0, coded = 0;
+    size_t work = 0, lzbytes = 0, maxn = 0, model = 0, coded = 0, htbytes = 0;
     int w1 = w0, maxjobs = 0;
-    std::vector<int> todo_sa, todo_bwt, todo_cm;
+    std::vector<int> todo_sa, todo_bwt, todo_cm, todo_hash, todo_e8;
     while (w1 < n) {
       ZqUnit& zu = units[w1];
       const ZqPlan& p = dplans[zu.plan];
       zu.idx16 = zu.n <= 65536 ? 1 : 0;
+      const bool hashlz = p.lz_level && !p.use_sa;
+      if (p.e8e9) todo_e8.push_back(w1 - w0);
       const size_t e = p.use_sa ? (size_t)zq_work_bytes(zu.n, zu.idx16 ? 2 : 4) : 0;
+      const size_t hb = hashlz ? ((size_t)4 << p.args[5]) : 0;
       const size_t mb = p.modeled ? (size_t)cmplans[p.cm_plan].model_bytes : 0;
-      if (w1 > w0 && (work + e > c->wave_bytes || model + mb > model_budget)) break;
-      zu.work_off = work; work += e;
+      if (w1 > w0 && (work + e + htbytes + hb > c->wave_bytes || model + mb > model_budget)) break;
+      if (hashlz) { zu.work_off = htbytes; htbytes += hb; todo_hash.push_back(w1 - w0); }
+      else { zu.work_off = work; work += e; }
       uint32_t slen_max = zu.n;
       if (p.lz_level) {
         zu.lz_off = lzbytes; zu.lz_cap = zu.n + zu.n / 32 + 64; lzbytes += align_up(zu.lz_cap, 16);
@@ -270,6 +274,13 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       tstop(c, 1);
     }
     if (lzbytes) ZQ_CUDA(c, c->d_lz.ensure(lzbytes));
+    if (!todo_e8.empty()) {   // after the SHA-1 of the original bytes, like compressBlock (Z:20285 then Z:19363/20414)
+      const int nt = (int)todo_e8.size();
+      ZQ_CUDA(c, c->d_todo5.ensure((size_t)nt * 4));
+      ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo5.p, todo_e8.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
+      k_e8e9<<<(nt + 63) / 64, 64, 0, c->stream>>>(const_cast<u8*>(d_in), du, c->d_todo5.as<int>(), nt);
+      ++c->launches;
+    }
     if (!todo_sa.empty()) {
       const int nt = (int)todo_sa.size();
       ZQ_CUDA(c, c->d_work.ensure(work));
@@ -340,6 +351,20 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       }
       tstop(c, 3);
     }
+    if (!todo_hash.empty()) {
+      const int nt = (int)todo_hash.size();
+      ZQ_CUDA(c, c->d_ht.ensure(htbytes));
+      ZQ_CUDA(c, cudaMemsetAsync(c->d_ht.p, 0, htbytes, c->stream));
+      ZQ_CUDA(c, c->d_todo4.ensure((size_t)nt * 4));
+      ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo4.p, todo_hash.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
+      u32* ctr = c->d_err.as<u32>() + 9;
+      ZQ_CUDA(c, cudaMemsetAsync(ctr, 0, 4, c->stream));
+      if (todo_sa.empty()) tstart(c, 3);
+      k_lz77_hash<8><<<std::min((nt + 3) / 4, c->num_sms * 8), 128, 0, c->stream>>>(
+          d_in, du, dp, c->d_todo4.as<int>(), nt, c->d_ht.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);
+      ++c->launches;
+      tstop(c, 3);
+    }
     if (!todo_cm.empty()) {
       const int nt = (int)todo_cm.size();
       ZQ_CUDA(c, c->d_model.ensure(model));
@@ -362,8 +387,8 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       tstop(c, 5);
       ZQ_CUDA(c, cudaMemcpyAsync(coded_len_h.data() + w0, c->d_codedlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
     }
-    if (!todo_sa.empty()) ZQ_CUDA(c, cudaMemcpyAsync(lz_len_h.data() + w0, c->d_lzlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (!todo_sa.empty() || !todo_cm.empty()) ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (lzbytes) ZQ_CUDA(c, cudaMemcpyAsync(lz_len_h.data() + w0, c->d_lzlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (lzbytes || !todo_cm.empty()) ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
     // final layout of this wave's blocks
     std::vector<uint64_t> ooff(wn);
     std::vector<int> todo_all(wn);
@@ -448,7 +473,7 @@ void zq_destroy(zq_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_work, &c->d_todo2, &c->d_todo3, &c->d_tables, &c->d_cmplans, &c->d_fills, &c->d_model, &c->d_coded, &c->d_codedlen, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
+  DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_work, &c->d_ht, &c->d_todo2, &c->d_todo3, &c->d_todo4, &c->d_todo5, &c->d_tables, &c->d_cmplans, &c->d_fills, &c->d_model, &c->d_coded, &c->d_codedlen, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
   for (DevBuf* b : bufs) b->release();
   for (int k = 0; k < 8; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
   cudaStreamDestroy(c->own_stream);

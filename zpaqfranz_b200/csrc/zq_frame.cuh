@@ -72,4 +72,21 @@ k_frame(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, cons
   }
 }
 
+// E8E9 pre-filter (e8e9(), Z:19162): x86 CALL/JMP rel32 operands become absolute, scanning
+// backwards; a transform changes bytes a later (lower) position tests, so it is sequential per
+// block: one thread per block (rare: only "exe" typed blocks ask for it).
+__global__ void __launch_bounds__(64)
+k_e8e9(u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const int* __restrict__ todo, int ntodo) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntodo) return;
+  const ZqUnit u = units[todo[t]];
+  u8* buf = in_base + u.in_off;
+  for (int i = (int)u.n - 5; i >= 0; --i) {
+    if ((buf[i] & 254) == 0xe8 && ((buf[i + 4] + 1) & 254) == 0) {
+      const u32 a = ((u32)buf[i + 1] | (u32)buf[i + 2] << 8 | (u32)buf[i + 3] << 16) + (u32)i;
+      buf[i + 1] = (u8)a; buf[i + 2] = (u8)(a >> 8); buf[i + 3] = (u8)(a >> 16);
+    }
+  }
+}
+
 }  // namespace zqdev

@@ -386,6 +386,154 @@ __device__ void lz77_sa_parse_pipe(const u8* __restrict__ in, u32 n, const IdxT*
   sk.flush();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Hash-table search variant of the same parse (LZBuffer::fill, Z:19434-19471, index update
+// Z:19490-19515): methods with args[5]-args[0] < 21, i.e. -m1 and the low-redundancy forms of -m2..-m4.
+// One warp per block.  The reference's rolling context hashes
+//     h1 <- ((h1*5 << shift1) + (in[i+minMatch]+1)*123456791) mod 2^bits
+// forget a byte after ceil(bits/shift1) steps (the multiplier is 5*2^shift1), so the hash in force at
+// position j is a closed form of the next few input bytes: every lane derives it for its own position
+// and 32 positions are indexed per round, the highest position winning a slot like the sequential loop.
+// The bucket probes ht[h1^k] are fetched by the lanes at once and resolved in k order.
+struct LzHashParams {
+  u32 minMatch2, htbits, shift1, shift2, checkbits, frozen_from;  // updates stop at i + minMatchBoth >= n
+};
+
+__device__ __forceinline__ u32 lz_roll_hash(const u8* __restrict__ in, u32 j, u32 upto, u32 bits, u32 shift, u32 mult, u32 cmul, u32 ahead) {
+  // hash state before position j (after updates of positions 0..j-1), j <= upto
+  (void)upto;
+  const u32 T = (bits + shift - 1) / shift;       // updates that still influence the low `bits` bits
+  u32 h = 0;
+  const u32 first = j > T ? j - T : 0;
+  for (u32 t = first; t < j; ++t) h = (h * mult << shift) + ((u32)in[t + ahead] + 1u) * cmul;
+  return h & ((1u << bits) - 1u);
+}
+
+__device__ void lz77_hash_parse(const u8* __restrict__ in, u32 n, u32* __restrict__ ht, const LzParams P, const LzHashParams Q,
+                                WarpSink& sk) {
+  const u32 lane = lane_id();
+  const u32 maxMatch = 3u << 14;
+  const u32 mask = (1u << Q.checkbits) - 1;
+  const u32 htmask = (1u << Q.htbits) - 1;
+  const u32 stop = Q.frozen_from;   // positions >= stop no longer update the index (i + minMatchBoth >= n)
+  u32 i = 0, lit = 0;
+  while (i < n) {
+    LzBest b; b.blen = P.minMatch - 1; b.bp = 0; b.blit = 0; b.bscore = 0;
+    const u32 lmax = min(maxMatch, n - i);
+    const u32 hpos = min(i, stop);
+    if (P.level == 1 || P.minMatch <= 64) {
+      for (int pass = (Q.minMatch2 > 0 ? 0 : 1); pass < 2; ++pass) {
+        if (pass == 1 && Q.minMatch2 && b.blen >= Q.minMatch2) break;
+        const bool hi = pass == 0;   // high-order context first
+        const u32 hh = hi ? lz_roll_hash(in, hpos, stop, Q.htbits, Q.shift2, 9u, 23456789u, Q.minMatch2 + P.lookahead)
+                          : lz_roll_hash(in, hpos, stop, Q.htbits, Q.shift1, 5u, 123456791u, P.minMatch);
+        const u32 start = hi ? P.lookahead : 0u;
+        const u32 ci3 = i + 3 < n ? (u32)in[i + 3] : 0u;
+        bool done = false;
+        for (u32 k0 = 0; k0 <= P.bucket && !done; k0 += 32) {
+          const u32 k = k0 + lane;
+          u32 p = 0; bool ok = false; u32 l = 0;
+          if (k <= P.bucket) {
+            p = ht[(hh ^ k) & htmask];
+            ok = p != 0 && (hi || i + 3 < n) && (p & mask) == (ci3 & mask);
+            p >>= Q.checkbits;
+            ok = ok && p < i;
+            if (ok) { l = start; const u32 cap = min(lmax, start + 64u); while (l < cap && in[p + l] == in[i + l]) ++l; }
+          }
+          u32 vm = __ballot_sync(ZQ_FULL, k <= P.bucket);
+          const u32 okm = __ballot_sync(ZQ_FULL, ok);
+          while (vm) {   // k order; state-dependent pre-check replayed literally
+            const int src = __ffs(vm) - 1;
+            vm &= vm - 1;
+            if ((okm >> src) & 1u) {
+              const u32 cp = __shfl_sync(ZQ_FULL, p, src);
+              u32 cl = __shfl_sync(ZQ_FULL, l, src);
+              if (i + b.blen <= n && in[cp + b.blen - 1] == in[i + b.blen - 1]) {
+                if (cl >= start + 64u) cl = warp_match_len(in + cp, in + i, cl, lmax);
+                if (hi) {
+                  if (cl >= Q.minMatch2 + P.lookahead) {
+                    u32 l1 = P.lookahead;
+                    while (l1 > 0 && in[cp + l1 - 1] == in[i + l1 - 1]) --l1;
+                    const int sc = (int)(cl - l1) * 8 - zq_bitlen(i - cp) - ((lit == 0 && l1 > 0) ? 8 : 0) - 11;
+                    if (sc > b.bscore) { b.blen = cl; b.bp = cp; b.blit = l1; b.bscore = sc; }
+                  }
+                } else {
+                  const int sc = (int)cl * 8 - zq_bitlen(i - cp) - (lit > 0 ? 2 : 0) - 11;
+                  if (sc > b.bscore) { b.blen = cl; b.bp = cp; b.blit = 0; b.bscore = sc; }
+                }
+              }
+            }
+            if (b.blen >= 128) { done = true; break; }
+          }
+        }
+      }
+    }
+    const u32 adv = lz_emit_step(sk, P, in, i, b, lit);
+    // index the adv consumed positions
+    const u32 jend = min(i + adv, stop);
+    if (Q.minMatch2 == 0) {
+      for (u32 j0 = i; j0 < jend; j0 += 32) {
+        const u32 j = j0 + lane;
+        const bool act = j < jend;
+        u32 slot = 0xffffffffu, val = 0;
+        if (act) {
+          const u32 h1 = lz_roll_hash(in, j, stop, Q.htbits, Q.shift1, 5u, 123456791u, P.minMatch);
+          const u32 ih = ((j * 1234547u) >> 19) & P.bucket;
+          slot = (h1 ^ ih) & htmask;
+          val = (j << Q.checkbits) | ((u32)in[j + 3] & mask);
+        }
+        const u32 peers = __match_any_sync(ZQ_FULL, slot);
+        if (act && lane == (u32)(31 - __clz(peers))) ht[slot] = val;   // the later position wins a shared slot
+      }
+    } else if (lane == 0) {
+      // second context order present (never produced by the digit methods): literal sequential update
+      for (u32 j = i; j < jend; ++j) {
+        const u32 ih = ((j * 1234547u) >> 19) & P.bucket;
+        const u32 val = (j << Q.checkbits) | ((u32)in[j + 3] & mask);
+        const u32 h2 = lz_roll_hash(in, j, stop, Q.htbits, Q.shift2, 9u, 23456789u, Q.minMatch2 + P.lookahead);
+        const u32 h1 = lz_roll_hash(in, j, stop, Q.htbits, Q.shift1, 5u, 123456791u, P.minMatch);
+        ht[(h2 ^ ih) & htmask] = val;
+        ht[(h1 ^ ih) & htmask] = val;
+      }
+    }
+    __syncwarp();
+    i += adv;
+  }
+  lz_write_literal(sk, P, in, n, lit);
+  sk.flush();
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_lz77_hash(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
+            const int* __restrict__ todo, int ntodo, u8* __restrict__ work_base,
+            u8* __restrict__ lz_base, u32* __restrict__ lz_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit) {
+  for (;;) {
+    int t = 0;
+    if (lane_id() == 0) t = (int)atomicAdd(next_unit, 1u);
+    t = __shfl_sync(ZQ_FULL, t, 0);
+    if (t >= ntodo) break;
+    const int ui = todo[t];
+    const ZqUnit u = units[ui];
+    const ZqPlan pl = plans[u.plan];
+    LzParams P;
+    P.level = pl.lz_level; P.minMatch = pl.args[2]; P.lookahead = pl.args[6];
+    P.bucket = (1u << pl.args[4]) - 1; P.rb = pl.args[0] > 4 ? pl.args[0] - 4 : 0; P.checkbits = 12 - pl.args[0];
+    LzHashParams Q;
+    Q.minMatch2 = pl.args[3]; Q.htbits = pl.args[5]; Q.checkbits = 12 - pl.args[0];
+    Q.shift1 = P.minMatch > 0 ? (pl.args[5] - 1) / P.minMatch + 1 : 1;
+    Q.shift2 = Q.minMatch2 > 0 ? (pl.args[5] - 1) / Q.minMatch2 + 1 : 0;
+    const u32 mmb = max(P.minMatch, Q.minMatch2 + P.lookahead) + 4;
+    Q.frozen_from = u.n > mmb ? u.n - mmb : 0;
+    WarpSink sk; sk.init(lz_base + u.lz_off, u.lz_cap);
+    lz77_hash_parse(in_base + u.in_off, u.n, (u32*)(work_base + u.work_off), P, Q, sk);
+    if (lane_id() == 0) {
+      lz_len[ui] = (u32)(sk.out - (lz_base + u.lz_off));
+      if (sk.overflow) atomicOr(err_flag, 1u);
+    }
+  }
+}
+
 // BWT pre-pass (LZBuffer::fill level 3, Z:19383-19393): last column with the end-of-string row
 // coded as 255, then that row's index, 4 bytes LSB first (n+5 bytes). One CTA per block.
 template <typename IdxT>
