@@ -16,7 +16,9 @@
 #include "zq_cm_host.h"
 #include "zq_common.cuh"
 #include "zq_config.h"
+#include "zq_fragment.cuh"
 #include "zq_frame.cuh"
+#include "zq_hashes.cuh"
 #include "zq_lz77.cuh"
 #include "zq_sha1.cuh"
 #include "zq_sufsort.cuh"
@@ -63,6 +65,7 @@ struct zq_ctx {
   size_t wave_bytes = (size_t)12 << 30;  // sa|isa|lcp bytes per wave
   size_t model_budget = (size_t)120 << 30; // component-table bytes per wave (capped by free memory)
   int sort_nt = 512, sort_minb = 2;       // suffix-sort CTA size and CTAs per SM
+  uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_occ = 6;                         // CTAs (4 warps) per SM the LZ parse kernel is compiled for
 };
 
@@ -432,6 +435,41 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
   return ZQ_OK;
 }
 
+static int stage_buffers(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, std::vector<uint64_t>& roff) {
+  uint64_t lo = ~0ull, hi = 0;
+  for (int i = 0; i < n; ++i) { lo = std::min(lo, off[i]); hi = std::max(hi, off[i] + len[i]); }
+  if (hi < lo) hi = lo;
+  ZQ_CUDA(c, c->d_in.ensure(hi - lo + 64));
+  if (hi > lo) ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, base + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+  roff.resize(n);
+  for (int i = 0; i < n; ++i) roff[i] = off[i] - lo;
+  return ZQ_OK;
+}
+
+
+// shared front end of the host-pointer hash entry points: stage data, upload (off,len), run, fetch digests
+template <class Launch>
+static int hash_many(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests, int dlen, Launch launch) {
+  if (!c) return ZQ_E_NODEVICE;
+  if (n <= 0) return n == 0 ? ZQ_OK : fail(c, ZQ_E_ARG, "bad argument");
+  if (!base || !off || !len || !digests) return fail(c, ZQ_E_ARG, "bad argument");
+  cudaSetDevice(c->device);
+  std::vector<uint64_t> roff;
+  int rc = stage_buffers(c, n, base, off, len, roff);
+  if (rc) return rc;
+  ZQ_CUDA(c, c->d_misc.ensure((size_t)n * 16));
+  ZQ_CUDA(c, c->d_sha.ensure((size_t)n * dlen));
+  u64* d_off = c->d_misc.as<u64>(); u64* d_len = d_off + n;
+  ZQ_CUDA(c, cudaMemcpyAsync(d_off, roff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, cudaMemcpyAsync(d_len, len, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  rc = launch(d_off, d_len, roff);
+  if (rc) return rc;
+  ZQ_CUDA(c, cudaMemcpyAsync(digests, c->d_sha.p, (size_t)n * dlen, cudaMemcpyDeviceToHost, c->stream));
+  ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  ZQ_CUDA(c, cudaGetLastError());
+  return ZQ_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -457,6 +495,7 @@ zq_ctx* zq_create(int device) {
   c->stream = c->own_stream;
   for (int k = 0; k < 8; ++k) { cudaEventCreate(&c->tm[k].a); cudaEventCreate(&c->tm[k].b); }
   if (const char* s = getenv("ZQ_MODEL_BUDGET")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->model_budget = v; }
+  if (const char* s = getenv("ZQ_FRAG_SEG")) { uint64_t v = strtoull(s, nullptr, 10); if (v >= 64) c->frag_seg = v; }
   if (const char* s = getenv("ZQ_LZ_OCC")) c->lz_occ = atoi(s);
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
   if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);
@@ -580,17 +619,6 @@ int zq_sha1_device(zq_ctx* c, int n, const uint8_t* d_base, const uint64_t* off,
   return ZQ_OK;
 }
 
-static int stage_buffers(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, std::vector<uint64_t>& roff) {
-  uint64_t lo = ~0ull, hi = 0;
-  for (int i = 0; i < n; ++i) { lo = std::min(lo, off[i]); hi = std::max(hi, off[i] + len[i]); }
-  if (hi < lo) hi = lo;
-  ZQ_CUDA(c, c->d_in.ensure(hi - lo + 64));
-  if (hi > lo) ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, base + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
-  roff.resize(n);
-  for (int i = 0; i < n; ++i) roff[i] = off[i] - lo;
-  return ZQ_OK;
-}
-
 int zq_sha1(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
   if (!c) return ZQ_E_NODEVICE;
   if (n <= 0) return n == 0 ? ZQ_OK : fail(c, ZQ_E_ARG, "bad argument");
@@ -605,11 +633,147 @@ int zq_sha1(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const ui
   return ZQ_OK;
 }
 
-int zq_sha256(zq_ctx* c, int, const uint8_t*, const uint64_t*, const uint64_t*, uint8_t*) { return c ? fail(c, ZQ_E_UNSUPPORTED, "sha256: not built yet") : ZQ_E_NODEVICE; }
-int zq_xxh3_128(zq_ctx* c, int, const uint8_t*, const uint64_t*, const uint64_t*, uint8_t*) { return c ? fail(c, ZQ_E_UNSUPPORTED, "xxh3: not built yet") : ZQ_E_NODEVICE; }
-int zq_blake3(zq_ctx* c, int, const uint8_t*, const uint64_t*, const uint64_t*, uint8_t*) { return c ? fail(c, ZQ_E_UNSUPPORTED, "blake3: not built yet") : ZQ_E_NODEVICE; }
-int zq_fragment(zq_ctx* c, int, const uint8_t*, const uint64_t*, const uint64_t*, int, uint32_t, uint32_t*, uint32_t*, uint8_t*, uint64_t, uint64_t*) {
-  return c ? fail(c, ZQ_E_UNSUPPORTED, "fragmenter: not built yet") : ZQ_E_NODEVICE;
+int zq_sha256(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
+  return hash_many(c, n, base, off, len, digests, 32, [&](u64* d_off, u64* d_len, std::vector<uint64_t>&) {
+    zqdev::k_sha256_many<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_in.as<u8>(), d_off, d_len, n, c->d_sha.as<u8>());
+    ++c->launches;
+    return ZQ_OK;
+  });
+}
+
+int zq_xxh3_128(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
+  return hash_many(c, n, base, off, len, digests, 16, [&](u64* d_off, u64* d_len, std::vector<uint64_t>&) {
+    zqdev::k_xxh3_128_many<<<(n + 3) / 4, 128, 0, c->stream>>>(c->d_in.as<u8>(), d_off, d_len, n, c->d_sha.as<u8>());
+    ++c->launches;
+    return ZQ_OK;
+  });
+}
+
+int zq_blake3(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
+  return hash_many(c, n, base, off, len, digests, 32, [&](u64* d_off, u64* d_len, std::vector<uint64_t>&) -> int {
+    std::vector<uint64_t> first(n + 1);
+    std::vector<int> multi;
+    uint64_t tot = 0;
+    for (int i = 0; i < n; ++i) {
+      first[i] = tot;
+      const uint64_t k = len[i] ? (len[i] + 1023) / 1024 : 1;
+      if (k > 1) multi.push_back(i);
+      tot += k;
+    }
+    first[n] = tot;
+    ZQ_CUDA(c, c->d_work.ensure(tot * 64 + (size_t)(n + 1) * 8 + multi.size() * 4 + 1024));
+    u8* W = c->d_work.as<u8>();
+    u32* cvA = (u32*)W; u32* cvB = (u32*)(W + tot * 32);
+    u64* d_first = (u64*)(W + tot * 64); int* d_multi = (int*)(W + tot * 64 + (size_t)(n + 1) * 8);
+    ZQ_CUDA(c, cudaMemcpyAsync(d_first, first.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (!multi.empty()) ZQ_CUDA(c, cudaMemcpyAsync(d_multi, multi.data(), multi.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    zqdev::k_blake3_chunks<<<(unsigned)((tot + 127) / 128), 128, 0, c->stream>>>(c->d_in.as<u8>(), d_off, d_len, d_first, n, tot, cvA, c->d_sha.as<u8>());
+    ++c->launches;
+    if (!multi.empty()) {
+      zqdev::k_blake3_tree<<<(int)std::min<size_t>(multi.size(), (size_t)c->num_sms * 8), 256, 0, c->stream>>>(d_first, d_multi, (int)multi.size(), cvA, cvB, c->d_sha.as<u8>());
+      ++c->launches;
+    }
+    ZQ_CUDA(c, cudaStreamSynchronize(c->stream));   // host vectors go out of scope
+    return ZQ_OK;
+  });
+}
+
+int zq_fragment(zq_ctx* c, int nfiles, const uint8_t* base, const uint64_t* off, const uint64_t* len, int fragment,
+                uint32_t blocksize, uint32_t* frag_len, uint32_t* frag_hits, uint8_t* frag_sha1, uint64_t frag_cap,
+                uint64_t* frag_first) {
+  using namespace zqdev;
+  if (!c) return ZQ_E_NODEVICE;
+  if (nfiles < 0 || (nfiles > 0 && (!base || !off || !len)) || !frag_first || fragment < 0 || blocksize < 64)
+    return fail(c, ZQ_E_ARG, "bad argument");
+  cudaSetDevice(c->device);
+  // constants exactly as Jidac::add derives them (Z:121626-121631)
+  uint64_t maxf64 = fragment <= 19 ? ((uint64_t)8128 << fragment) : (uint64_t)blocksize - 12;
+  if (maxf64 > (uint64_t)blocksize - 12) maxf64 = blocksize - 12;
+  uint64_t minf64 = fragment <= 25 ? ((uint64_t)64 << fragment) : maxf64;
+  if (minf64 > maxf64) minf64 = maxf64;
+  const uint32_t maxf = (uint32_t)maxf64, minf = (uint32_t)minf64;
+  const uint32_t thresh = fragment <= 22 ? (1u << (22 - fragment)) : 0u;
+  frag_first[0] = 0;
+  if (nfiles == 0) return ZQ_OK;
+  std::vector<uint64_t> roff;
+  int rc = stage_buffers(c, nfiles, base, off, len, roff);
+  if (rc) return rc;
+  // segments
+  uint64_t seg = c->frag_seg;
+  if (seg < minf) seg = minf;
+  std::vector<ZqSeg> segs;
+  std::vector<uint32_t> seg_first_of_file(nfiles + 1, 0);
+  for (int f = 0; f < nfiles; ++f) {
+    seg_first_of_file[f] = (uint32_t)segs.size();
+    for (uint64_t p = 0; p < len[f]; p += seg) {
+      ZqSeg sg; sg.begin = roff[f] + p; sg.end = roff[f] + std::min<uint64_t>(len[f], p + seg); sg.file_end = roff[f] + len[f];
+      sg.first = p == 0; sg.pad = 0;
+      segs.push_back(sg);
+    }
+  }
+  seg_first_of_file[nfiles] = (uint32_t)segs.size();
+  const int nseg = (int)segs.size();
+  if (nseg == 0) { for (int f = 0; f <= nfiles; ++f) frag_first[f] = 0; return ZQ_OK; }
+  const uint32_t cap = (uint32_t)((seg + maxf) / std::max<uint32_t>(minf, 1) + 3);
+  const size_t per = (size_t)nseg * cap;
+  // layout in d_work: segs | exitA exitB entry | bndA bndB | hitsA hitsB | cntA cntB | flags
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  const size_t o_segs = take(sizeof(ZqSeg) * nseg), o_exA = take(8 * (size_t)nseg), o_exB = take(8 * (size_t)nseg), o_ent = take(8 * (size_t)nseg);
+  const size_t o_bA = take(8 * per), o_bB = take(8 * per), o_hA = take(4 * per), o_hB = take(4 * per);
+  const size_t o_cA = take(4 * (size_t)nseg), o_cB = take(4 * (size_t)nseg), o_fl = take(64), o_first = take(8 * (size_t)nseg);
+  ZQ_CUDA(c, c->d_work.ensure(o));
+  u8* W = c->d_work.as<u8>();
+  ZQ_CUDA(c, cudaMemcpyAsync(W + o_segs, segs.data(), sizeof(ZqSeg) * nseg, cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, cudaMemsetAsync(W + o_fl, 0, 64, c->stream));
+  int cur = 0;
+  for (int round = 0; round <= nseg; ++round) {
+    ZQ_CUDA(c, cudaMemsetAsync(W + o_fl, 0, 4, c->stream));
+    const size_t exP = cur ? o_exB : o_exA, exN = cur ? o_exA : o_exB, bP = cur ? o_bB : o_bA, bN = cur ? o_bA : o_bB;
+    const size_t hP = cur ? o_hB : o_hA, hN = cur ? o_hA : o_hB, cP = cur ? o_cB : o_cA, cN = cur ? o_cA : o_cB;
+    k_fragment_round<<<(nseg + FRAG_THREADS - 1) / FRAG_THREADS, FRAG_THREADS, 0, c->stream>>>(
+        c->d_in.as<u8>(), (const ZqSeg*)(W + o_segs), nseg, round, minf, maxf, thresh, cap, (const u64*)(W + exP), (u64*)(W + exN),
+        (u64*)(W + o_ent), (const u64*)(W + bP), (const u32*)(W + hP), (const u32*)(W + cP), (u64*)(W + bN), (u32*)(W + hN),
+        (u32*)(W + cN), (u32*)(W + o_fl), (u32*)(W + o_fl + 4));
+    ++c->launches;
+    cur ^= 1;
+    uint32_t flags[2] = {0, 0};
+    ZQ_CUDA(c, cudaMemcpyAsync(flags, W + o_fl, 8, cudaMemcpyDeviceToHost, c->stream));
+    ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (flags[1]) return fail(c, ZQ_E_OUTPUT, "internal: fragment table overflow");
+    if (!flags[0]) break;
+  }
+  // current chains are in the buffers last written ("next" of the final round) == index cur^1 ... after the flip: prev set
+  const size_t bF = cur ? o_bB : o_bA, hF = cur ? o_hB : o_hA, cF = cur ? o_cB : o_cA;
+  std::vector<uint32_t> cnt(nseg);
+  ZQ_CUDA(c, cudaMemcpyAsync(cnt.data(), W + cF, 4 * (size_t)nseg, cudaMemcpyDeviceToHost, c->stream));
+  ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<uint64_t> first(nseg);
+  uint64_t total = 0;
+  for (int f = 0; f < nfiles; ++f) {
+    frag_first[f] = total;
+    for (uint32_t k = seg_first_of_file[f]; k < seg_first_of_file[f + 1]; ++k) { first[k] = total; total += cnt[k]; }
+  }
+  frag_first[nfiles] = total;
+  if (total > frag_cap) return fail(c, ZQ_E_OUTPUT, "fragment arrays too small");
+  if (total == 0) return ZQ_OK;
+  ZQ_CUDA(c, cudaMemcpyAsync(W + o_first, first.data(), 8 * (size_t)nseg, cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, c->d_misc.ensure(total * 16));
+  u32* d_fl = c->d_misc.as<u32>(); u32* d_fh = d_fl + total; u64* d_fo = (u64*)(d_fh + total);
+  k_fragment_gather<<<(nseg + 127) / 128, 128, 0, c->stream>>>((const ZqSeg*)(W + o_segs), nseg, cap, (const u64*)(W + bF), (const u32*)(W + hF),
+                                                               (const u32*)(W + cF), (const u64*)(W + o_first), (const u64*)(W + o_ent), d_fl, d_fh, d_fo);
+  ++c->launches;
+  if (frag_len) ZQ_CUDA(c, cudaMemcpyAsync(frag_len, d_fl, total * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (frag_hits) ZQ_CUDA(c, cudaMemcpyAsync(frag_hits, d_fh, total * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (frag_sha1) {
+    ZQ_CUDA(c, c->d_sha.ensure(total * 20));
+    k_sha1_many<<<(int)((total + 127) / 128), 128, 0, c->stream>>>(c->d_in.as<u8>(), d_fo, d_fl, nullptr, (int)total, c->d_sha.as<u8>());
+    ++c->launches;
+    ZQ_CUDA(c, cudaMemcpyAsync(frag_sha1, c->d_sha.p, total * 20, cudaMemcpyDeviceToHost, c->stream));
+  }
+  ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  ZQ_CUDA(c, cudaGetLastError());
+  return ZQ_OK;
 }
 
 // ---- introspection -------------------------------------------------------------------------------
