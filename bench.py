@@ -249,8 +249,8 @@ def main():
     dom = max(names, key=lambda k: stage_dev[k])
     lz_bytes = out_bytes  # stream ~= block size (framing adds ~60 B per unit)
     algo = {1: nbytes + 20 * U,                 # read input, write digests
-            2: nbytes + 10 * nbytes,            # read text, write SA + ISA (u32) + LCP (u16)
-            3: nbytes + 10 * nbytes + lz_bytes,  # read text + SA/ISA/LCP, write stream
+            2: nbytes + 7 * nbytes,             # read text, write SA + ISA + LCP (u16 each) + BWT byte
+            3: nbytes + 7 * nbytes + lz_bytes,  # read text + SA/ISA/LCP/BWT, write stream
             4: 2 * out_bytes}[dom]
     achieved = algo / 1e9 / (stage_dev[dom] / 1000)
     traffic = None
