@@ -9,8 +9,8 @@
 //   libzpaq::compressBlock(...)       Z:13476 / Z:20255   one input buffer -> one ZPAQ block
 //
 // plus the batch form the GPU wants (compressBlocks), which is what a modified
-// CompressJob::appendz (Z:71364) would call.  Decompresser/decompress stay the reference's own CPU
-// code until the device decoder lands.
+// CompressJob::appendz (Z:71364) would call, and decompress() for whole streams of such blocks
+// (the streaming Decompresser class with its per-segment callbacks stays the reference's own).
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -66,5 +66,9 @@ void compressBlock(StringBuffer* in, Writer* out, const char* method, const char
 // Batch form: n inputs -> n blocks appended to outs[i] (same per-element semantics).
 void compressBlocks(int n, StringBuffer* const* ins, Writer* const* outs, const char* const* methods,
                     const char* const* filenames, const char* const* comments, bool dosha1 = true);
+
+// == libzpaq::decompress(Reader*, Writer*) (Z:15536) for a stream of blocks as compressBlock writes
+// them (one segment per block): every block found in `in` is restored on the device and appended to out.
+void decompress(Reader* in, Writer* out);
 
 }  // namespace libzpaq_b200

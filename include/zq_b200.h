@@ -73,6 +73,19 @@ int zq_compress_blocks_device(zq_ctx* ctx, int n,
                               uint8_t* d_out_base, uint64_t out_cap,
                               uint64_t* out_off, uint32_t* out_len);
 
+/* ---- block decompression -------------------------------------------------------------------------
+ * Element-wise == Decompresser::findBlock/findFilename/readComment/decompress/readSegmentEnd for one
+ * block holding one segment (what compressBlock writes; Z:15418-15534) and libzpaq::decompress (Z:15536):
+ * unit u is a complete block at in_base[in_off[u] .. +in_len[u]) (the 13-byte locator tag is optional);
+ * the restored bytes go to out_base[out_off[u] .. +out_len[u]), laid out back to back.  The expected size
+ * of each block is taken from expect_len[u] or, when expect_len is NULL, from the decimal number that
+ * starts the segment comment (the archiver writes "<n> jDC\x01", Z:20404).  A stored SHA-1 is verified
+ * on the device.  Host pointers. */
+int zq_decompress_blocks(zq_ctx* ctx, int n,
+                         const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                         const uint32_t* expect_len /* may be NULL */,
+                         uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len);
+
 /* Upper bound of one block's compressed size for an n-byte input (any method, names <= 255 bytes). */
 uint64_t zq_compress_bound(uint32_t n);
 

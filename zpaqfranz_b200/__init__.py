@@ -46,6 +46,8 @@ def _load():
         f = getattr(lib, name)
         f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, cpp, cpp, cpp, C.c_int, C.c_int,
                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zq_decompress_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_uint64, C.c_void_p, C.c_void_p]
     for name in ("zq_sha1", "zq_sha256", "zq_xxh3_128", "zq_blake3", "zq_sha1_device"):
         getattr(lib, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.zq_fragment.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
@@ -167,6 +169,24 @@ class Context:
         a = np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(0, dtype=np.uint8)
         out, ooff, olen = self.compress_blocks(a if len(a) else np.zeros(1, np.uint8), [0], [len(data)], method, filename, comment, dosha1)
         return out[: int(olen[0])].tobytes()
+
+    def decompress_blocks(self, arena, offsets, lengths, expect_len=None, out_cap=None):
+        """Element-wise libzpaq::decompress of complete blocks arena[offsets[i]:+lengths[i]].
+        Returns (out_array, out_off, out_len)."""
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+        n = len(off)
+        ex = None if expect_len is None else np.ascontiguousarray(expect_len, dtype=np.uint32)
+        if out_cap is None:
+            out_cap = int(ex.sum()) if ex is not None else int(ln.sum()) * 64 + (1 << 20)
+        out = np.empty(max(out_cap, 1), dtype=np.uint8)
+        ooff = np.zeros(n, dtype=np.uint64)
+        olen = np.zeros(n, dtype=np.uint32)
+        self._check(lib.zq_decompress_blocks(self._h, n, arena.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                             ex.ctypes.data if ex is not None else None, out.ctypes.data, out.size,
+                                             ooff.ctypes.data, olen.ctypes.data))
+        return out, ooff, olen
 
     # -- hashes -------------------------------------------------------------------------------------
     def _hash(self, fn, dlen, arena, offsets, lengths):

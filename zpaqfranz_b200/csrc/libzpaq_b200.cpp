@@ -76,4 +76,36 @@ void compressBlock(StringBuffer* in, Writer* out, const char* method, const char
   compressBlocks(1, &in, &out, &method, filename ? &filename : nullptr, comment ? &comment : nullptr, dosha1);
 }
 
+void decompress(Reader* in, Writer* out) {
+  // slurp the stream, split it at block starts (13-byte locator tag, Z:15973 / findBlock Z:15418)
+  std::vector<uint8_t> buf;
+  { char tmp[1 << 16]; int r; while ((r = in->read(tmp, sizeof tmp)) > 0) buf.insert(buf.end(), tmp, tmp + r); }
+  static const unsigned char tag[13] = {0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83, 0xd3, 0x8c, 0xb2, 0x28, 0xb0, 0xd3};
+  std::vector<uint64_t> off;
+  for (size_t i = 0; i + 16 <= buf.size(); ++i)
+    if (memcmp(&buf[i], tag, 13) == 0 && buf[i + 13] == 'z' && buf[i + 14] == 'P' && buf[i + 15] == 'Q') off.push_back(i);
+  if (off.empty()) return;
+  const int n = (int)off.size();
+  std::vector<uint32_t> len(n), olen(n);
+  std::vector<uint64_t> ooff(n);
+  uint64_t cap = 0;
+  for (int i = 0; i < n; ++i) {
+    len[i] = (uint32_t)((i + 1 < n ? off[i + 1] : buf.size()) - off[i]);
+    // expected size = decimal number opening the segment comment (after the filename)
+    size_t p = off[i] + 18;
+    p += 2 + buf[p] + 256u * buf[p + 1];      // header
+    ++p;                                      // segment marker
+    while (p < buf.size() && buf[p]) ++p;     // filename
+    ++p;
+    uint64_t e = 0;
+    while (p < buf.size() && buf[p] >= '0' && buf[p] <= '9') e = e * 10 + (buf[p++] - '0');
+    cap += e;
+  }
+  std::vector<uint8_t> outbuf(cap + 16);
+  zq_ctx* c = t_ctx.get();
+  int rc = zq_decompress_blocks(c, n, buf.data(), off.data(), len.data(), nullptr, outbuf.data(), outbuf.size(), ooff.data(), olen.data());
+  if (rc != ZQ_OK) error(zq_last_error(c));
+  for (int i = 0; i < n; ++i) out->write((const char*)outbuf.data() + ooff[i], (int)olen[i]);
+}
+
 }  // namespace libzpaq_b200

@@ -16,6 +16,7 @@
 #include "zq_cm_host.h"
 #include "zq_common.cuh"
 #include "zq_config.h"
+#include "zq_decode.cuh"
 #include "zq_fragment.cuh"
 #include "zq_frame.cuh"
 #include "zq_hashes.cuh"
@@ -601,6 +602,168 @@ int zq_compress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t*
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   return rc;
+}
+
+// ---- block decompression ---------------------------------------------------------------------------
+int zq_decompress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                         const uint32_t* expect_len, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len) {
+  using namespace zqdev;
+  if (!c) return ZQ_E_NODEVICE;
+  if (n < 0 || (n > 0 && (!in_base || !in_off || !in_len || !out_base || !out_off || !out_len))) return fail(c, ZQ_E_ARG, "bad argument");
+  if (n == 0) return ZQ_OK;
+  cudaSetDevice(c->device);
+  static const unsigned char tag[13] = {0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83, 0xd3, 0x8c, 0xb2, 0x28, 0xb0, 0xd3};
+  std::vector<ZqDecUnit> units(n);
+  std::vector<ZqCmPlan> cmplans;
+  std::vector<ZqCmFill> fills;
+  std::vector<uint8_t> blob;
+  std::map<std::string, int> plan_idx;
+  uint64_t lo = ~0ull, hi = 0;
+  for (int u = 0; u < n; ++u) { lo = std::min(lo, in_off[u]); hi = std::max(hi, in_off[u] + in_len[u]); }
+  if (hi < lo) hi = lo;
+  uint64_t out_pos = 0;
+  try {
+    for (int u = 0; u < n; ++u) {
+      const uint8_t* b = in_base + in_off[u];
+      size_t len = in_len[u], p = 0;
+      if (len >= 13 && memcmp(b, tag, 13) == 0) p = 13;
+      if (len < p + 5 || b[p] != 'z' || b[p + 1] != 'P' || b[p + 2] != 'Q') return fail(c, ZQ_E_METHOD, "block does not start with a ZPAQ block header");
+      const int level = b[p + 3];
+      if (level != 1 && level != 2) return fail(c, ZQ_E_METHOD, "unsupported ZPAQ level");
+      if (b[p + 4] != 1) return fail(c, ZQ_E_METHOD, "unsupported ZPAQL type");
+      p += 5;
+      size_t used = 0;
+      zq::Assembled code = zq::parse_block_header(b + p, len - p, &used);
+      if (level == 1 && code.ncomp == 0) return fail(c, ZQ_E_METHOD, "ZPAQ level 1 requires at least 1 component");
+      const std::string key((const char*)b + p, used);
+      p += used;
+      int pi;
+      auto it = plan_idx.find(key);
+      if (it != plan_idx.end()) pi = it->second;
+      else {
+        ZqCmPlan cp = zq::make_cm_plan(code, fills);
+        zq::add_pcomp_region(cp, code.ph, code.pm, fills);
+        cp.hcomp_off = (u32)blob.size(); cp.hcomp_len = (u32)code.hcomp.size();
+        blob.insert(blob.end(), code.hcomp.begin(), code.hcomp.end());
+        pi = (int)cmplans.size();
+        cmplans.push_back(cp);
+        plan_idx[key] = pi;
+      }
+      if (p >= len || b[p] != 1) return fail(c, ZQ_E_METHOD, "missing segment or end of block");
+      ++p;
+      while (p < len && b[p]) ++p;   // filename
+      if (p >= len) return fail(c, ZQ_E_METHOD, "unexpected EOF");
+      ++p;
+      const size_t cstart = p;
+      while (p < len && b[p]) ++p;   // comment
+      if (p + 1 >= len) return fail(c, ZQ_E_METHOD, "unexpected EOF");
+      uint64_t expect = 0; bool have = false;
+      if (expect_len) { expect = expect_len[u]; have = true; }
+      else { size_t q = cstart; while (q < p && isdigit(b[q])) { expect = expect * 10 + (b[q] - '0'); ++q; have = true; } }
+      if (!have || expect > 0xfffffff0ull) return fail(c, ZQ_E_ARG, "block size unknown: pass expect_len (segment comment carries no size)");
+      ++p;
+      if (b[p] != 0) return fail(c, ZQ_E_METHOD, "missing reserved byte");
+      ++p;
+      ZqDecUnit& du = units[u];
+      du.data_off = in_off[u] - lo + p; du.data_len = len - p; du.out_off = out_pos; du.out_cap = (u32)expect; du.plan = (u32)pi; du.model_off = 0;
+      out_off[u] = out_pos; out_pos += expect;
+    }
+  } catch (const zq::Error& e) { return fail(c, ZQ_E_METHOD, e.msg); }
+  if (out_pos > out_cap) return fail(c, ZQ_E_OUTPUT, "output buffer too small");
+  if (!c->d_tables.p) {
+    try {
+      const zq::CmTables& t = zq::cm_tables();
+      ZQ_CUDA(c, c->d_tables.ensure(sizeof(zq::CmTables)));
+      ZQ_CUDA(c, cudaMemcpyAsync(c->d_tables.p, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
+    } catch (const zq::Error& e) { return fail(c, ZQ_E_METHOD, e.msg); }
+  }
+  ZQ_CUDA(c, c->d_in.ensure(hi - lo + 64));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, in_base + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, c->d_out.ensure(out_pos + 64));
+  ZQ_CUDA(c, c->d_blob.ensure(blob.size() + 16));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, c->d_cmplans.ensure(cmplans.size() * sizeof(ZqCmPlan)));
+  ZQ_CUDA(c, c->d_fills.ensure(fills.size() * sizeof(ZqCmFill)));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_cmplans.p, cmplans.data(), cmplans.size() * sizeof(ZqCmPlan), cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_fills.p, fills.data(), fills.size() * sizeof(ZqCmFill), cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, c->d_err.ensure(64));
+  size_t budget = c->model_budget;
+  { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); fr += c->d_model.cap; budget = std::min<size_t>(budget, fr > ((size_t)6 << 30) ? fr - ((size_t)6 << 30) : fr / 2); }
+  std::vector<ZqDecResult> res(n);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_cm_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem)); attr_set = true; }
+  int w0 = 0;
+  while (w0 < n) {
+    size_t model = 0; int w1 = w0, maxjobs = 1;
+    std::vector<uint64_t> moff; std::vector<uint32_t> pof;
+    while (w1 < n) {
+      const ZqCmPlan& cp = cmplans[units[w1].plan];
+      if (w1 > w0 && model + cp.model_bytes > budget) break;
+      units[w1].model_off = model; model += cp.model_bytes;
+      moff.push_back(units[w1].model_off); pof.push_back(units[w1].plan);
+      maxjobs = std::max(maxjobs, (int)cp.fill_count);
+      ++w1;
+    }
+    const int wn = w1 - w0;
+    ZQ_CUDA(c, c->d_model.ensure(model));
+    ZQ_CUDA(c, c->d_units.ensure((size_t)wn * sizeof(ZqDecUnit)));
+    ZQ_CUDA(c, c->d_misc.ensure((size_t)wn * 12 + (size_t)wn * sizeof(ZqDecResult) + 256));
+    u64* d_moff = c->d_misc.as<u64>(); u32* d_pof = (u32*)(d_moff + wn); ZqDecResult* d_res = (ZqDecResult*)(c->d_misc.as<u8>() + align_up((size_t)wn * 12, 16));
+    ZQ_CUDA(c, cudaMemcpyAsync(c->d_units.p, units.data() + w0, (size_t)wn * sizeof(ZqDecUnit), cudaMemcpyHostToDevice, c->stream));
+    ZQ_CUDA(c, cudaMemcpyAsync(d_moff, moff.data(), (size_t)wn * 8, cudaMemcpyHostToDevice, c->stream));
+    ZQ_CUDA(c, cudaMemcpyAsync(d_pof, pof.data(), (size_t)wn * 4, cudaMemcpyHostToDevice, c->stream));
+    u32* ctr = c->d_err.as<u32>() + 10;
+    ZQ_CUDA(c, cudaMemsetAsync(ctr, 0, 4, c->stream));
+    k_cm_init_pairs<<<wn * maxjobs, 256, 0, c->stream>>>(d_moff, d_pof, c->d_cmplans.as<ZqCmPlan>(), c->d_fills.as<ZqCmFill>(), wn, maxjobs,
+                                                        c->d_tables.as<CmTablesDev>(), c->d_model.as<u8>());
+    ++c->launches;
+    k_cm_decode<<<std::min((wn + 15) / 16, c->num_sms), 512, sizeof(CmSmem), c->stream>>>(
+        c->d_in.as<u8>(), c->d_units.as<ZqDecUnit>(), c->d_cmplans.as<ZqCmPlan>(), wn, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
+        c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr);
+    ++c->launches;
+    ZQ_CUDA(c, cudaMemcpyAsync(res.data() + w0, d_res, (size_t)wn * sizeof(ZqDecResult), cudaMemcpyDeviceToHost, c->stream));
+    ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    ZQ_CUDA(c, cudaGetLastError());
+    w0 = w1;
+  }
+  // results, trailers, checksums
+  std::vector<uint64_t> soff; std::vector<uint64_t> slen; std::vector<int> sidx;
+  for (int u = 0; u < n; ++u) {
+    const ZqDecResult& r = res[u];
+    static const char* msg[] = {"", "archive corrupted", "unexpected end of file", "decoded size exceeds the expected size", "ZPAQL execution error", "unknown post processing type"};
+    if (r.error) return fail(c, r.error == 3 ? ZQ_E_OUTPUT : ZQ_E_METHOD, msg[r.error < 6 ? r.error : 1]);
+    out_len[u] = r.out_len;
+    const uint8_t* b = in_base + in_off[u];
+    const size_t p = (size_t)(units[u].data_off + lo - in_off[u]) + r.consumed;
+    if (p >= in_len[u]) return fail(c, ZQ_E_METHOD, "missing end of segment marker");
+    if (b[p] == 253) {
+      if (p + 21 > in_len[u]) return fail(c, ZQ_E_METHOD, "unexpected EOF");
+      soff.push_back(units[u].out_off); slen.push_back(r.out_len); sidx.push_back(u);
+    } else if (b[p] != 254) return fail(c, ZQ_E_METHOD, "missing end of segment marker");
+    const size_t e = p + (b[p] == 253 ? 21 : 1);
+    if (e < in_len[u] && b[e] == 1) return fail(c, ZQ_E_UNSUPPORTED, "blocks with more than one segment have no device path yet");
+  }
+  if (!sidx.empty()) {
+    const int k = (int)sidx.size();
+    ZQ_CUDA(c, c->d_misc.ensure((size_t)k * 16));
+    ZQ_CUDA(c, c->d_sha.ensure((size_t)k * 20));
+    u64* d_off = c->d_misc.as<u64>(); u64* d_len = d_off + k;
+    ZQ_CUDA(c, cudaMemcpyAsync(d_off, soff.data(), (size_t)k * 8, cudaMemcpyHostToDevice, c->stream));
+    ZQ_CUDA(c, cudaMemcpyAsync(d_len, slen.data(), (size_t)k * 8, cudaMemcpyHostToDevice, c->stream));
+    k_sha1_many<<<(k + 127) / 128, 128, 0, c->stream>>>(c->d_out.as<u8>(), d_off, nullptr, d_len, k, c->d_sha.as<u8>());
+    ++c->launches;
+    std::vector<uint8_t> dg((size_t)k * 20);
+    ZQ_CUDA(c, cudaMemcpyAsync(dg.data(), c->d_sha.p, dg.size(), cudaMemcpyDeviceToHost, c->stream));
+    ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < k; ++i) {
+      const int u = sidx[i];
+      const uint8_t* b = in_base + in_off[u];
+      const size_t p = (size_t)(units[u].data_off + lo - in_off[u]) + res[u].consumed;
+      if (memcmp(b + p + 1, dg.data() + (size_t)i * 20, 20) != 0) return fail(c, ZQ_E_METHOD, "SHA-1 checksum mismatch after decompression");
+    }
+  }
+  if (out_pos) ZQ_CUDA(c, cudaMemcpy(out_base, c->d_out.p, out_pos, cudaMemcpyDeviceToHost));
+  return ZQ_OK;
 }
 
 // ---- hashes --------------------------------------------------------------------------------------

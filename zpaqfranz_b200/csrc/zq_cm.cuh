@@ -38,19 +38,10 @@ struct CmSmem {           // what the coder needs per bit
 };
 
 // ---- model initialisation ------------------------------------------------------------------------
-// grid.x = units in the wave * fill jobs of the largest plan; every CTA writes one job of one unit.
-__global__ void __launch_bounds__(256)
-k_cm_init(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, const ZqCmPlan* __restrict__ cmplans,
-          const ZqCmFill* __restrict__ fills, const int* __restrict__ todo, int ntodo, int maxjobs,
-          const CmTablesDev* __restrict__ tab, u8* __restrict__ model_base) {
-  const int t = blockIdx.x / maxjobs, j = blockIdx.x % maxjobs;
-  if (t >= ntodo) return;
-  const ZqUnit u = units[todo[t]];
-  const ZqCmPlan& cp = cmplans[plans[u.plan].cm_plan];
-  if (j >= (int)cp.fill_count) return;
-  const ZqCmFill f = fills[cp.fill_first + j];
-  u8* __restrict__ dst = model_base + u.model_off + f.off;
-  const u64 nq = f.bytes >> 4;  // all regions are 256 B aligned and sized in multiples of 16
+// One CTA writes one fill job (a table's initial values, Z:14968-15032) of one unit's model region.
+__device__ __forceinline__ void cm_fill_job(const ZqCmFill f, const CmTablesDev* __restrict__ tab, u8* __restrict__ region) {
+  u8* __restrict__ dst = region + f.off;
+  const u64 nq = f.bytes >> 4;  // regions are 256 B aligned; tails shorter than 16 B are written bytewise
   uint4* __restrict__ d4 = (uint4*)dst;
   if (f.kind == ZQ_FILL_ZERO || f.kind == ZQ_FILL_U32 || f.kind == ZQ_FILL_U16 || f.kind == ZQ_FILL_MATCHBUF) {
     u32 v = f.kind == ZQ_FILL_U32 ? f.value : f.kind == ZQ_FILL_U16 ? (f.value | f.value << 16) : 0u;
@@ -74,6 +65,29 @@ k_cm_init(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
     u32* d = (u32*)dst;
     for (u32 k = threadIdx.x; k < f.bytes / 4; k += blockDim.x) d[k] = src[k];
   }
+}
+
+// grid.x = units in the wave * fill jobs of the largest plan
+__global__ void __launch_bounds__(256)
+k_cm_init(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, const ZqCmPlan* __restrict__ cmplans,
+          const ZqCmFill* __restrict__ fills, const int* __restrict__ todo, int ntodo, int maxjobs,
+          const CmTablesDev* __restrict__ tab, u8* __restrict__ model_base) {
+  const int t = blockIdx.x / maxjobs, j = blockIdx.x % maxjobs;
+  if (t >= ntodo) return;
+  const ZqUnit u = units[todo[t]];
+  const ZqCmPlan& cp = cmplans[plans[u.plan].cm_plan];
+  if (j >= (int)cp.fill_count) return;
+  cm_fill_job(fills[cp.fill_first + j], tab, model_base + u.model_off);
+}
+// same, for explicit (model offset, plan) pairs (decoder)
+__global__ void __launch_bounds__(256)
+k_cm_init_pairs(const u64* __restrict__ model_off, const u32* __restrict__ plan_of, const ZqCmPlan* __restrict__ cmplans,
+                const ZqCmFill* __restrict__ fills, int n, int maxjobs, const CmTablesDev* __restrict__ tab, u8* __restrict__ model_base) {
+  const int t = blockIdx.x / maxjobs, j = blockIdx.x % maxjobs;
+  if (t >= n) return;
+  const ZqCmPlan& cp = cmplans[plan_of[t]];
+  if (j >= (int)cp.fill_count) return;
+  cm_fill_job(fills[cp.fill_first + j], tab, model_base + model_off[t]);
 }
 
 // ---- per-warp coder state ------------------------------------------------------------------------

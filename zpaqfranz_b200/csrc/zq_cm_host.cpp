@@ -205,4 +205,45 @@ ZqCmPlan make_cm_plan(const Assembled& code, std::vector<ZqCmFill>& fills) {
   return p;
 }
 
+void add_pcomp_region(ZqCmPlan& p, int ph, int pm, std::vector<ZqCmFill>& fills) {
+  if (ph > 26 || pm > 30) throw Error("PCOMP memory too large for the device path");
+  p.ph = ph; p.pm = pm;
+  uint64_t off = p.model_bytes;
+  const uint64_t begin = off;
+  p.pm_off = off; off = align256(off + ((uint64_t)1 << pm));
+  p.ph_off = off; off = align256(off + ((uint64_t)4 << ph));
+  p.pr_off = off; off = align256(off + 1024);
+  p.pcode_off = off; off = align256(off + 65536 + 512);
+  ZqCmFill f; f.off = begin; f.bytes = off - begin; f.kind = ZQ_FILL_ZERO; f.value = 0;
+  fills.push_back(f);
+  p.model_bytes = off;
+  p.fill_count = (uint32_t)fills.size() - p.fill_first;
+}
+
+Assembled parse_block_header(const uint8_t* hdr, size_t avail, size_t* consumed) {
+  Assembled a;
+  if (avail < 8) throw Error("unexpected end of file");
+  const size_t hsize = hdr[0] + 256u * hdr[1];
+  if (avail < hsize + 2) throw Error("unexpected end of file");
+  a.hh = hdr[2]; a.hm = hdr[3]; a.ph = hdr[4]; a.pm = hdr[5]; a.ncomp = hdr[6];
+  size_t p = 7;
+  for (int i = 0; i < a.ncomp; ++i) {
+    if (p >= hsize + 2) throw Error("COMP overflows header");
+    const int type = hdr[p];
+    if (type < 1 || type > 9) throw Error("Invalid component type");
+    const int sz = kCompBytes[type];
+    if (p + sz > hsize + 2) throw Error("COMP overflows header");
+    a.comp.insert(a.comp.end(), hdr + p, hdr + p + sz);
+    p += sz;
+  }
+  if (p >= hsize + 2 || hdr[p] != 0) throw Error("missing COMP END");
+  ++p;
+  if (hsize + 2 <= p) throw Error("missing HCOMP");
+  a.hcomp.assign(hdr + p, hdr + hsize + 2);
+  if (a.hcomp.empty() || a.hcomp.back() != 0) throw Error("missing HCOMP END");
+  a.header.assign(hdr, hdr + hsize + 2);
+  *consumed = hsize + 2;
+  return a;
+}
+
 }  // namespace zq

@@ -26,5 +26,9 @@ const CmTables& cm_tables();
 
 // Device layout of one modeled method. Throws zq::Error for configurations without a device path.
 ZqCmPlan make_cm_plan(const Assembled& code, std::vector<ZqCmFill>& fills);
+// Decoder: append the post-processor's memory (M 2^pm, H 2^ph, R, 64 KiB code) to the model region.
+void add_pcomp_region(ZqCmPlan& p, int ph, int pm, std::vector<ZqCmFill>& fills);
+// Parse the COMP/HCOMP header of a block as stored in the archive (ZPAQL::read, Z:14104) into `code`.
+Assembled parse_block_header(const uint8_t* hdr, size_t avail, size_t* consumed);
 
 }  // namespace zq
