@@ -167,6 +167,18 @@ def test_config1_one_mib_of_zeros_m1(ctx, ref):
         assert out[: int(olen[0])].tobytes() == ref.compress_block(u, m, "", "")
 
 
+def test_parallel_parse_variant_is_bit_exact(zq, ref, monkeypatch):
+    # the candidates/chain/emit form of the SA parse (zq_lz77_par.cuh), selected with ZQ_LZ_PAR=1
+    monkeypatch.setenv("ZQ_LZ_PAR", "1")
+    units = EDGE_UNITS[3:] + [corpus.text_unit(21, 65536), corpus.repeats_unit(22, 65536)]
+    arena, offs, lens = _arena(units)
+    with zq.Context(0) as c2:
+        for method in ("2", "x0,2,12,0,7,21,1", "x0,1,4,0,5,21,2"):
+            out, ooff, olen = c2.compress_blocks(arena, offs, lens, method=method, filename="", comment="")
+            for i, u in enumerate(units):
+                assert out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes() == ref.compress_block(u, method, "", ""), (method, i)
+
+
 def test_unsupported_is_loud(ctx, zq):
     arena, offs, lens = _arena([corpus.text_unit(1, 5000)])
     with pytest.raises(zq.ZqError):

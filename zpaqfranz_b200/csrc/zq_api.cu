@@ -21,6 +21,7 @@
 #include "zq_frame.cuh"
 #include "zq_hashes.cuh"
 #include "zq_lz77.cuh"
+#include "zq_lz77_par.cuh"
 #include "zq_sha1.cuh"
 #include "zq_sufsort.cuh"
 
@@ -59,7 +60,7 @@ struct zq_ctx {
   cudaStream_t own_stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_ht, d_todo2, d_todo3, d_todo4, d_todo5, d_lz, d_lzlen, d_sha, d_tables, d_cmplans, d_fills, d_model, d_coded, d_codedlen,
+  DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_ht, d_todo2, d_todo3, d_todo4, d_todo5, d_dec, d_tok, d_bitpos, d_lz, d_lzlen, d_sha, d_tables, d_cmplans, d_fills, d_model, d_coded, d_codedlen,
       d_kbuf, d_vbuf, d_err, d_misc;
   Timer tm[8];
   float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -67,6 +68,7 @@ struct zq_ctx {
   size_t model_budget = (size_t)120 << 30; // component-table bytes per wave (capped by free memory)
   int sort_nt = 512, sort_minb = 2;       // suffix-sort CTA size and CTAs per SM
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
+  int lz_old = 1;                         // 1: warp-per-block LZ77 parser (default, faster today); 0: candidates/chain/emit form (ZQ_LZ_PAR=1)
   int lz_occ = 6;                         // CTAs (4 warps) per SM the LZ parse kernel is compiled for
 };
 
@@ -295,8 +297,12 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       ZQ_CUDA(c, c->d_vbuf.ensure((size_t)sort_grid * 6 * scr * 4));
       ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo.p, todo_sa.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
       tstart(c, 2);
-#define ZQ_SORT_LAUNCH(NT, MB) k_suffix_sort<NT, MB><<<sort_grid, NT, sizeof(SortSmem<NT>), c->stream>>>( \
-          d_in, du, c->d_todo.as<int>(), nt, c->d_work.as<u8>(), c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr)
+#define ZQ_SORT_LAUNCH(NT, MB)                                                                                            \
+  do {                                                                                                                   \
+    cudaFuncSetAttribute(k_suffix_sort<NT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<NT>)); \
+    k_suffix_sort<NT, MB><<<sort_grid, NT, sizeof(SortSmem<NT>), c->stream>>>(                                           \
+        d_in, du, c->d_todo.as<int>(), nt, c->d_work.as<u8>(), c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr);          \
+  } while (0)
       if (sort_nt == 1024) ZQ_SORT_LAUNCH(1024, 1);
       else if (sort_nt == 512 && sort_minb == 2) ZQ_SORT_LAUNCH(512, 2);
       else if (sort_nt == 512) ZQ_SORT_LAUNCH(512, 4);
@@ -320,9 +326,43 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
         size_t lo = 0;
         std::vector<int> flat;
         for (auto& l : lists) flat.insert(flat.end(), l.begin(), l.end());
+        const size_t nlz = flat.size();
         flat.insert(flat.end(), todo_bwt.begin(), todo_bwt.end());
         ZQ_CUDA(c, c->d_todo2.ensure(flat.size() * 4 + 4));
         ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo2.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        if (!c->lz_old && nlz) {
+          // parallel form: candidates per position -> sequential chain per block -> parallel bit emission
+          std::vector<uint64_t> dec_off(nlz), tok_off(nlz);
+          uint64_t npos = 0, ntokcap = 0; uint32_t maxlen = 0;
+          for (size_t k = 0; k < nlz; ++k) {
+            const ZqUnit& zu = units[w0 + flat[k]];
+            const ZqPlan& p = dplans[zu.plan];
+            dec_off[k] = npos; npos += zu.n;
+            tok_off[k] = ntokcap; ntokcap += zu.n / std::max(p.args[2], 1) + zu.n / 4096 + 4;
+            maxlen = std::max(maxlen, zu.n);
+          }
+          ZQ_CUDA(c, c->d_dec.ensure(npos * 16 + 64));
+          ZQ_CUDA(c, c->d_tok.ensure(ntokcap * 16 + 64));
+          ZQ_CUDA(c, c->d_bitpos.ensure(ntokcap * 8 + 64));
+          ZQ_CUDA(c, c->d_misc.ensure(nlz * 20 + 64));
+          u64* d_decoff = c->d_misc.as<u64>(); u64* d_tokoff = d_decoff + nlz; u32* d_ntok = (u32*)(d_tokoff + nlz);
+          ZQ_CUDA(c, cudaMemcpyAsync(d_decoff, dec_off.data(), nlz * 8, cudaMemcpyHostToDevice, c->stream));
+          ZQ_CUDA(c, cudaMemcpyAsync(d_tokoff, tok_off.data(), nlz * 8, cudaMemcpyHostToDevice, c->stream));
+          ZQ_CUDA(c, cudaMemsetAsync(c->d_lz.p, 0, lzbytes, c->stream));
+          if (maxlen) {
+            dim3 g((maxlen + LZC_CHUNK - 1) / LZC_CHUNK, (unsigned)nlz);
+            k_lz_candidates<<<g, 256, 0, c->stream>>>(d_in, du, dp, c->d_todo2.as<int>(), c->d_work.as<u8>(), d_decoff, c->d_dec.as<u64>());
+            ++c->launches;
+          }
+          k_lz_chain<<<(unsigned)((nlz + 63) / 64), 64, 0, c->stream>>>(d_in, du, dp, c->d_todo2.as<int>(), (int)nlz, c->d_work.as<u8>(), d_decoff,
+                                                                        c->d_dec.as<u64>(), d_tokoff, c->d_tok.as<LzToken>(), d_ntok);
+          ++c->launches;
+          k_lz_emit<<<(unsigned)std::min<size_t>(nlz, (size_t)c->num_sms * 8), 256, 0, c->stream>>>(
+              d_in, du, dp, c->d_todo2.as<int>(), (int)nlz, d_tokoff, c->d_tok.as<LzToken>(), d_ntok, c->d_bitpos.as<u64>(), c->d_lz.as<u8>(),
+              c->d_lzlen.as<u32>(), c->d_err.as<u32>());
+          ++c->launches;
+          lo = nlz;
+        } else
         for (int v = 0; v < 4; ++v) {
           const int cnt = (int)lists[v].size();
           if (!cnt) continue;
@@ -498,6 +538,7 @@ zq_ctx* zq_create(int device) {
   if (const char* s = getenv("ZQ_MODEL_BUDGET")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->model_budget = v; }
   if (const char* s = getenv("ZQ_FRAG_SEG")) { uint64_t v = strtoull(s, nullptr, 10); if (v >= 64) c->frag_seg = v; }
   if (const char* s = getenv("ZQ_LZ_OCC")) c->lz_occ = atoi(s);
+  if (const char* s = getenv("ZQ_LZ_PAR")) c->lz_old = atoi(s) ? 0 : 1;
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
   if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);
   if (c->sort_nt != 1024 && c->sort_nt != 512 && c->sort_nt != 256 && c->sort_nt != 128) c->sort_nt = 256;
@@ -513,7 +554,7 @@ void zq_destroy(zq_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_work, &c->d_ht, &c->d_todo2, &c->d_todo3, &c->d_todo4, &c->d_todo5, &c->d_tables, &c->d_cmplans, &c->d_fills, &c->d_model, &c->d_coded, &c->d_codedlen, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
+  DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_work, &c->d_ht, &c->d_todo2, &c->d_todo3, &c->d_todo4, &c->d_todo5, &c->d_dec, &c->d_tok, &c->d_bitpos, &c->d_tables, &c->d_cmplans, &c->d_fills, &c->d_model, &c->d_coded, &c->d_codedlen, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
   for (DevBuf* b : bufs) b->release();
   for (int k = 0; k < 8; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
   cudaStreamDestroy(c->own_stream);

@@ -482,8 +482,11 @@ __device__ void lz77_hash_parse(const u8* __restrict__ in, u32 n, u32* __restric
           slot = (h1 ^ ih) & htmask;
           val = (j << Q.checkbits) | ((u32)in[j + 3] & mask);
         }
-        const u32 peers = __match_any_sync(ZQ_FULL, slot);
-        if (act && lane == (u32)(31 - __clz(peers))) ht[slot] = val;   // the later position wins a shared slot
+        // the later position wins a shared slot: a lane stores unless a higher lane targets the same slot
+        bool loses = false;
+#pragma unroll
+        for (int o = 1; o < 32; ++o) { const u32 other = __shfl_down_sync(ZQ_FULL, slot, o); if (lane + o < 32 && other == slot) loses = true; }
+        if (act && !loses) ht[slot] = val;
       }
     } else if (lane == 0) {
       // second context order present (never produced by the digit methods): literal sequential update

@@ -33,6 +33,10 @@ struct SortSmem {
   u32 base[SORT_MAXD];
   u32 wsum[32];
   u32 misc[4];
+  u32 tot[SORT_MAXD];      // digit totals of the current tile
+  u32 tstart[SORT_MAXD];   // exclusive scan of tot: where a digit's run starts inside the staged tile
+  u64 stage_k[NT * SORT_ITEMS];   // the tile in digit order, so that the global write-out is coalesced runs
+  u32 stage_v[NT * SORT_ITEMS];
 };
 
 // Per-CTA scratch (global memory), sized for the largest block of the wave.
@@ -83,6 +87,19 @@ __device__ __forceinline__ u32 block_scan_incl_max(u32 v, SortSmem<NT>& sm, u32&
   return max(v, pre);
 }
 
+// lanes of the warp holding the same 8-bit digit (among active lanes): 8 ballots.  (match.any is
+// emulated by a loop over the distinct values on this architecture -- up to 32 rounds per call.)
+__device__ __forceinline__ u32 warp_peers8(u32 d, bool act) {
+  u32 peers = __ballot_sync(ZQ_FULL, act);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const u32 bal = __ballot_sync(ZQ_FULL, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+
 // One stable LSD pass on digit (key >> shift) & 255 over m (key,value) pairs. Returns false (and
 // moves nothing) when every key has the same digit.
 template <int NT>
@@ -95,8 +112,8 @@ __device__ bool radix_pass(const u64* __restrict__ kin, const u32* __restrict__ 
   for (u32 b = 0; b < m; b += NT) {
     const u32 idx = b + tid;
     const bool act = idx < m;
-    const u32 d = act ? (u32)(kin[idx] >> shift) & 255u : 0xffffffffu;
-    const u32 peers = __match_any_sync(ZQ_FULL, d);
+    const u32 d = act ? (u32)(kin[idx] >> shift) & 255u : 0u;
+    const u32 peers = warp_peers8(d, act);
     if (act && lane == (u32)(__ffs(peers) - 1)) atomicAdd(&sm.hist[d], __popc(peers));
   }
   __syncthreads();
@@ -123,9 +140,9 @@ __device__ bool radix_pass(const u64* __restrict__ kin, const u32* __restrict__ 
     for (int it = 0; it < SORT_ITEMS; ++it) {
       const u32 idx = tile + warp * (SORT_ITEMS * 32) + it * 32 + lane;
       const bool act = idx < m;
-      u32 d = 0xffffffffu;
+      u32 d = 0u;
       if (act) { k[it] = kin[idx]; v[it] = vin[idx]; d = (u32)(k[it] >> shift) & 255u; }
-      const u32 peers = __match_any_sync(ZQ_FULL, d);
+      const u32 peers = warp_peers8(d, act);
       u32 cnt = 0;
       if (act) { cnt = sm.wcount[warp * SORT_MAXD + d]; r[it] = (d << 16) | (cnt + __popc(peers & lanemask_lt())); }
       else r[it] = 0xffffffffu;
@@ -134,20 +151,43 @@ __device__ bool radix_pass(const u64* __restrict__ kin, const u32* __restrict__ 
       __syncwarp();
     }
     __syncthreads();
-    for (u32 d = tid; d < SORT_MAXD; d += NT) {
-      u32 run = sm.base[d];
+    for (u32 d = tid; d < SORT_MAXD; d += NT) {   // per digit: offsets of each warp's share inside the tile
+      u32 run = 0;
 #pragma unroll 8
       for (int w = 0; w < NT / 32; ++w) { const u32 c = sm.wcount[w * SORT_MAXD + d]; sm.wcount[w * SORT_MAXD + d] = run; run += c; }
-      sm.base[d] = run;
+      sm.tot[d] = run;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      u32 loc[8], sum = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { loc[q] = sm.tot[lane * 8 + q]; sum += loc[q]; }
+      u32 inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(ZQ_FULL, inc, o); if (lane >= (u32)o) inc += t; }
+      u32 run = inc - sum;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { sm.tstart[lane * 8 + q] = run; run += loc[q]; }
     }
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < SORT_ITEMS; ++it) {
       if (r[it] != 0xffffffffu) {
-        const u32 pos = sm.wcount[warp * SORT_MAXD + (r[it] >> 16)] + (r[it] & 0xffffu);
-        kout[pos] = k[it]; vout[pos] = v[it];
+        const u32 d = r[it] >> 16;
+        const u32 lp = sm.tstart[d] + sm.wcount[warp * SORT_MAXD + d] + (r[it] & 0xffffu);
+        sm.stage_k[lp] = k[it]; sm.stage_v[lp] = v[it];
       }
     }
+    __syncthreads();
+    const u32 tcount = min((u32)(NT * SORT_ITEMS), m - tile);
+    for (u32 sidx = tid; sidx < tcount; sidx += NT) {
+      const u64 kk = sm.stage_k[sidx];
+      const u32 d = (u32)(kk >> shift) & 255u;
+      const u32 gp = sm.base[d] + (sidx - sm.tstart[d]);
+      kout[gp] = kk; vout[gp] = sm.stage_v[sidx];
+    }
+    __syncthreads();
+    for (u32 d = tid; d < SORT_MAXD; d += NT) sm.base[d] += sm.tot[d];
     __syncthreads();
   }
   return true;
