@@ -69,6 +69,7 @@ struct zq_ctx {
   int sort_nt = 512, sort_minb = 2;       // suffix-sort CTA size and CTAs per SM
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 1;                         // 1: warp-per-block LZ77 parser (default, faster today); 0: candidates/chain/emit form (ZQ_LZ_PAR=1)
+  int cm_occ = 2;                         // CTAs (16 warps) per SM of the CM coder
   int lz_occ = 6;                         // CTAs (4 warps) per SM the LZ parse kernel is compiled for
 };
 
@@ -422,9 +423,14 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
                                                      maxjobs, c->d_tables.as<CmTablesDev>(), c->d_model.as<u8>());
       ++c->launches;
       static bool attr_set = false;
-      if (!attr_set) { cudaFuncSetAttribute(k_cm_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem)); attr_set = true; }
-      const int cgrid = std::min((nt + 15) / 16, c->num_sms * 2);
-      k_cm_encode<<<cgrid, 512, sizeof(CmSmem), c->stream>>>(d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt,
+      if (!attr_set) {
+        cudaFuncSetAttribute(k_cm_encode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem));
+        cudaFuncSetAttribute(k_cm_encode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem));
+        attr_set = true;
+      }
+      const int cgrid = std::min((nt + 15) / 16, c->num_sms * (c->cm_occ >= 2 ? 2 : 1));
+      auto cmk = c->cm_occ >= 2 ? k_cm_encode<2> : k_cm_encode<1>;
+      cmk<<<cgrid, 512, sizeof(CmSmem), c->stream>>>(d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt,
                                                              c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(),
                                                              c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr);
       ++c->launches;
@@ -538,6 +544,7 @@ zq_ctx* zq_create(int device) {
   if (const char* s = getenv("ZQ_MODEL_BUDGET")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->model_budget = v; }
   if (const char* s = getenv("ZQ_FRAG_SEG")) { uint64_t v = strtoull(s, nullptr, 10); if (v >= 64) c->frag_seg = v; }
   if (const char* s = getenv("ZQ_LZ_OCC")) c->lz_occ = atoi(s);
+  if (const char* s = getenv("ZQ_CM_OCC")) c->cm_occ = atoi(s);
   if (const char* s = getenv("ZQ_LZ_PAR")) c->lz_old = atoi(s) ? 0 : 1;
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
   if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);

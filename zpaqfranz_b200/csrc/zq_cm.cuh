@@ -403,7 +403,8 @@ __device__ __forceinline__ void cm_code_byte(CmCoder& E, CmLane& L, CmCtx& X, co
 }
 
 // grid of persistent 16-warp CTAs; warps pull modeled units from a counter
-__global__ void __launch_bounds__(512, 1)
+template <int MINB>
+__global__ void __launch_bounds__(512, MINB)
 k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
             const ZqCmPlan* __restrict__ cmplans, const int* __restrict__ todo, int ntodo,
             const CmTablesDev* __restrict__ tab, const u8* __restrict__ blob, const u8* __restrict__ lz_base,
