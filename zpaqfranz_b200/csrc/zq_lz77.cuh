@@ -368,7 +368,12 @@ __device__ void lz77_sa_parse_pipe(const u8* __restrict__ in, u32 n, const IdxT*
     const u32 qC = i + 2 < n ? (u32)isa[i + 2] : 0u;
     LzBest b; b.blen = P.minMatch - 1; b.bp = 0; b.blit = 0; b.bscore = 0;
     const u32 lmax = min(maxMatch, n - i);
-    lz_scan_pos(in, n, sa, lcp, bwt, P, i, 0, lit, lmax, qA, A, b);
+    // If neither SA neighbour of row qA shares minMatch bytes with suffix i, no candidate can reach
+    // minMatch: whatever the scan accepts (a shorter, positive-score match) ends as a literal with no
+    // other effect on the parse state (Z:19428, Z:19476-19486), so the scan is skipped.
+    const u32 adj = max(__shfl_sync(ZQ_FULL, A.inr ? A.e : 0u, 0), __shfl_sync(ZQ_FULL, A.inr ? A.e : 0u, 16));
+    if (adj >= P.minMatch)
+      lz_scan_pos(in, n, sa, lcp, bwt, P, i, 0, lit, lmax, qA, A, b);
     if (P.lookahead >= 1 && !(b.bscore <= 0 || b.blen < P.minMatch) && haveB &&
         ((i + 1) >> P.checkbits) == (i >> P.checkbits)) {
       lz_scan_pos(in, n, sa, lcp, bwt, P, i, 1, lit, lmax, qB, B, b);

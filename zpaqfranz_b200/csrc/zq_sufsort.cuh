@@ -33,6 +33,7 @@ struct SortSmem {
   u32 base[SORT_MAXD];
   u32 wsum[32];
   u32 misc[4];
+  u32 hist_next[SORT_MAXD]; // digit histogram of the NEXT pass, gathered while this pass writes out
   u32 tot[SORT_MAXD];      // digit totals of the current tile
   u32 tstart[SORT_MAXD];   // exclusive scan of tot: where a digit's run starts inside the staged tile
   u64 stage_k[NT * SORT_ITEMS];   // the tile in digit order, so that the global write-out is coalesced runs
@@ -103,19 +104,25 @@ __device__ __forceinline__ u32 warp_peers8(u32 d, bool act) {
 // One stable LSD pass on digit (key >> shift) & 255 over m (key,value) pairs. Returns false (and
 // moves nothing) when every key has the same digit.
 template <int NT>
+// have_hist: sm.hist_next already holds this pass's histogram (counted by the previous pass);
+// next_shift >= 0: count the next pass's digits while writing out.
 __device__ bool radix_pass(const u64* __restrict__ kin, const u32* __restrict__ vin,
-                           u64* __restrict__ kout, u32* __restrict__ vout, u32 m, int shift, SortSmem<NT>& sm) {
+                           u64* __restrict__ kout, u32* __restrict__ vout, u32 m, int shift, SortSmem<NT>& sm,
+                           bool have_hist = false, int next_shift = -1) {
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (u32 d = tid; d < SORT_MAXD; d += NT) sm.hist[d] = 0;
+  for (u32 d = tid; d < SORT_MAXD; d += NT) sm.hist[d] = have_hist ? sm.hist_next[d] : 0u;
   if (tid == 0) sm.misc[0] = 0;
   __syncthreads();
-  for (u32 b = 0; b < m; b += NT) {
-    const u32 idx = b + tid;
-    const bool act = idx < m;
-    const u32 d = act ? (u32)(kin[idx] >> shift) & 255u : 0u;
-    const u32 peers = warp_peers8(d, act);
-    if (act && lane == (u32)(__ffs(peers) - 1)) atomicAdd(&sm.hist[d], __popc(peers));
+  if (!have_hist) {
+    for (u32 b = 0; b < m; b += NT) {
+      const u32 idx = b + tid;
+      const bool act = idx < m;
+      const u32 d = act ? (u32)(kin[idx] >> shift) & 255u : 0u;
+      const u32 peers = warp_peers8(d, act);
+      if (act && lane == (u32)(__ffs(peers) - 1)) atomicAdd(&sm.hist[d], __popc(peers));
+    }
   }
+  for (u32 d = tid; d < SORT_MAXD; d += NT) sm.hist_next[d] = 0;
   __syncthreads();
   for (u32 d = tid; d < SORT_MAXD; d += NT) if (sm.hist[d] == m) sm.misc[0] = 1;
   __syncthreads();
@@ -185,6 +192,7 @@ __device__ bool radix_pass(const u64* __restrict__ kin, const u32* __restrict__ 
       const u32 d = (u32)(kk >> shift) & 255u;
       const u32 gp = sm.base[d] + (sidx - sm.tstart[d]);
       kout[gp] = kk; vout[gp] = sm.stage_v[sidx];
+      if (next_shift >= 0) atomicAdd(&sm.hist_next[(u32)(kk >> next_shift) & 255u], 1u);
     }
     __syncthreads();
     for (u32 d = tid; d < SORT_MAXD; d += NT) sm.base[d] += sm.tot[d];
@@ -196,8 +204,12 @@ __device__ bool radix_pass(const u64* __restrict__ kin, const u32* __restrict__ 
 // LSD sort on key bits [lo, hi); ping-pongs between (kA,vA) and (kB,vB); returns which holds the result
 template <int NT>
 __device__ int radix_sort_bits(u64*& kA, u32*& vA, u64*& kB, u32*& vB, u32 m, int lo, int hi, SortSmem<NT>& sm) {
+  bool have = false;
   for (int s = lo; s < hi; s += 8) {
-    if (radix_pass<NT>(kA, vA, kB, vB, m, s, sm)) { u64* tk = kA; kA = kB; kB = tk; u32* tv = vA; vA = vB; vB = tv; }
+    const int nxt = s + 8 < hi ? s + 8 : -1;
+    const bool moved = radix_pass<NT>(kA, vA, kB, vB, m, s, sm, have, nxt);
+    if (moved) { u64* tk = kA; kA = kB; kB = tk; u32* tv = vA; vA = vB; vB = tv; }
+    have = moved && nxt >= 0;     // a skipped pass (all digits equal) counted nothing for its successor
     __syncthreads();
   }
   return 0;
