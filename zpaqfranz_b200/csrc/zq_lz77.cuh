@@ -246,24 +246,28 @@ __device__ __forceinline__ void lz_scan_pos(const u8* __restrict__ in, u32 n, co
     const u32 segmask = dir ? 0xffff0000u : 0x0000ffffu;
     const u32 vm = vm_all & segmask;
     bool stop = false;
+    bool general = false;
     if (vm) {
-      const int f = __ffs(vm) - 1;
-      const u32 upto = segmask & (0xffffffffu >> (31 - f));
-      const u32 pmf = __reduce_min_sync(ZQ_FULL, ((upto >> lane) & 1u) ? ch.e : 0xffffffffu);
-      if (pmf < ZQ_LCP_CAP) {
+      // serial fast path: up to three usable neighbours, each with warp-uniform scalars
+      u32 rest = vm;
+      for (int tries = 0; rest; ++tries) {
+        if (tries == 3) { general = true; break; }
+        const int f = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const u32 upto = segmask & (0xffffffffu >> (31 - f));
+        const u32 pmf = __reduce_min_sync(ZQ_FULL, ((upto >> lane) & 1u) ? ch.e : 0xffffffffu);
+        if (pmf >= ZQ_LCP_CAP) { general = true; break; }   // only ever the first one (LCPs shrink away from q)
         const u32 cp = __shfl_sync(ZQ_FULL, p, f);
         const u32 lf = h + pmf;
         u32 l1 = h;
         if (h > 0 && __shfl_sync(ZQ_FULL, ch.bw, f) == ci) { --l1; while (l1 > 0 && in[cp + l1 - 1] == in[i + l1 - 1]) --l1; }
         const int sc = lz_score(lf, l1, i - cp, lit, h);
-        const bool acc = sc > b.bscore;
-        const u32 bl = acc ? lf : b.blen;
-        if (lf < bl || lf < P.minMatch || lf > 255) {
-          if (acc) { b.blen = lf; b.bp = cp; b.blit = l1; b.bscore = sc; }
-          stop = true;
-        }
+        if (sc > b.bscore) { b.blen = lf; b.bp = cp; b.blit = l1; b.bscore = sc; }
+        if (lf < b.blen || lf < P.minMatch || lf > 255) { stop = true; break; }
       }
-      if (!stop) {
+      // (re-running the neighbours already taken above through the full resolve is idempotent: their
+      //  scores no longer beat the best and their lengths are not below it)
+      if (general) {
         if (!have) {
           pm = ch.e;
 #pragma unroll
