@@ -236,7 +236,8 @@ __device__ __forceinline__ void cm_row_switch(CmLane& L, u32 cxt) {
 
 struct CmCtx {             // warp-uniform per-block state
   int n, nlevels, c8, hmap4;
-  u32 mix_mask;
+  u32 mix_mask;            // lanes that are MIX components
+  u32 mix_levels;          // bit L: some MIX sits at dependency level L
 };
 
 // p for the next bit: Predictor::predict0 (Z:15041)
@@ -298,7 +299,7 @@ __device__ int cm_predict(CmLane& L, const CmCtx& X, const CmSmem& T) {
       }
     }
     // mixers of this level: lanes j0..j0+m-1 each multiply their own p by their weight, one REDUX sums
-    u32 mm = __ballot_sync(ZQ_FULL, L.type == ZQ_MIX && (int)L.level == lev);
+    u32 mm = ((X.mix_levels >> lev) & 1u) ? __ballot_sync(ZQ_FULL, L.type == ZQ_MIX && (int)L.level == lev) : 0u;
     while (mm) {
       const int xl = __ffs(mm) - 1;
       mm &= mm - 1;
@@ -435,6 +436,7 @@ k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, co
       const ZqCmComp c = cp.comp[lane < (u32)cp.n ? lane : 0];
       const bool act = lane < (u32)cp.n;
       L.type = act ? c.type : 0; L.a1 = c.a1; L.a2 = c.a2; L.a3 = c.a3; L.a4 = c.a4; L.a5 = c.a5; L.level = act ? c.level : 255;
+      X.mix_levels = __reduce_or_sync(ZQ_FULL, (act && c.type == ZQ_MIX) ? (1u << c.level) : 0u);
       L.cm = (u32*)(model + c.cm_off); L.ht = model + c.ht_off; L.cm_mask = c.cm_mask; L.ht_mask = c.ht_mask;
       L.in1 = 0; L.in2 = 0;
       if (L.type == ZQ_AVG) { L.in1 = c.a1; L.in2 = c.a2; }

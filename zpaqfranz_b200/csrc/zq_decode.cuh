@@ -169,6 +169,7 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
       const ZqCmComp c = cp.comp[lane < (u32)cp.n ? lane : 0];
       const bool act = lane < (u32)cp.n;
       L.type = act ? c.type : 0; L.a1 = c.a1; L.a2 = c.a2; L.a3 = c.a3; L.a4 = c.a4; L.a5 = c.a5; L.level = act ? c.level : 255;
+      X.mix_levels = __reduce_or_sync(ZQ_FULL, (act && c.type == ZQ_MIX) ? (1u << c.level) : 0u);
       L.cm = (u32*)(model + c.cm_off); L.ht = model + c.ht_off; L.cm_mask = c.cm_mask; L.ht_mask = c.ht_mask;
       L.in1 = 0; L.in2 = 0;
       if (L.type == ZQ_AVG) { L.in1 = c.a1; L.in2 = c.a2; }
