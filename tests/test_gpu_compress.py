@@ -179,6 +179,22 @@ def test_parallel_parse_variant_is_bit_exact(zq, ref, monkeypatch):
                 assert out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes() == ref.compress_block(u, method, "", ""), (method, i)
 
 
+def test_level5_period_models_on_device(ctx, zq, ref):
+    # byte-gap analysis (Z:20355-20388) runs on the device: periodic data adds "c0,0,999+P,255i1[c0,Pi1]" models
+    units = [corpus.random_unit(37, 37) * 300, corpus.random_unit(300, 300) * 60, corpus.text_unit(3, 9000), bytes(5000)]
+    arena, offs, lens = _arena(units)
+    out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method="5", filename="p", comment="")
+    for i, u in enumerate(units):
+        assert "c0,0,%d" % (999 + 37) in zq.plan_block("5", units[0])["method"]
+        assert out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes() == ref.compress_block(u, "5", "p", ""), i
+    # text + two periodic models = 33 components: no device path, reported loudly (never a CPU fallback)
+    two = (corpus.random_unit(41, 41) * 200)[:8000]
+    if zq.plan_block("56,180,1", two)["header"][6] > 32:
+        a2, o2, l2 = _arena([two])
+        with pytest.raises(zq.ZqError):
+            ctx.compress_blocks(a2, o2, l2, method="56,180,1")
+
+
 def test_unsupported_is_loud(ctx, zq):
     arena, offs, lens = _arena([corpus.text_unit(1, 5000)])
     with pytest.raises(zq.ZqError):

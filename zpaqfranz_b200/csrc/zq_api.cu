@@ -114,6 +114,31 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
   std::map<std::string, std::string> expand_cache;
   std::vector<ZqUnit> units(n);
   std::vector<uint8_t> blob;
+  // digit levels >= 5 pick their periodic models from the data: analysed on the device
+  std::vector<int> periods;
+  {
+    std::vector<int> need;
+    for (int u = 0; u < n; ++u) {
+      const char* m = method ? method[uniform ? 0 : u] : "1";
+      if (m && isdigit((unsigned char)m[0]) && m[0] >= '5') need.push_back(u);
+    }
+    if (!need.empty()) {
+      const int k = (int)need.size();
+      std::vector<uint64_t> o(k); std::vector<uint32_t> l(k);
+      for (int j = 0; j < k; ++j) { o[j] = in_off[need[j]]; l[j] = in_len[need[j]]; }
+      ZQ_CUDA(c, c->d_misc.ensure((size_t)k * 20 + 64));
+      u64* d_o = c->d_misc.as<u64>(); u32* d_l = (u32*)(d_o + k); int* d_p = (int*)(d_l + k);
+      ZQ_CUDA(c, cudaMemcpyAsync(d_o, o.data(), (size_t)k * 8, cudaMemcpyHostToDevice, c->stream));
+      ZQ_CUDA(c, cudaMemcpyAsync(d_l, l.data(), (size_t)k * 4, cudaMemcpyHostToDevice, c->stream));
+      k_gap_periods<<<std::min(k, c->num_sms * 8), 256, 0, c->stream>>>(d_in, d_o, d_l, k, d_p);
+      ++c->launches;
+      std::vector<int> pk((size_t)k * 2);
+      ZQ_CUDA(c, cudaMemcpyAsync(pk.data(), d_p, (size_t)k * 8, cudaMemcpyDeviceToHost, c->stream));
+      ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+      periods.assign((size_t)n * 2, 0);
+      for (int j = 0; j < k; ++j) { periods[2 * need[j]] = pk[2 * j]; periods[2 * need[j] + 1] = pk[2 * j + 1]; }
+    }
+  }
   try {
     for (int u = 0; u < n; ++u) {
       const char* m = method ? method[uniform ? 0 : u] : "1";
@@ -123,8 +148,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       const bool data_dependent = isdigit((unsigned char)m[0]) && m[0] >= '5';
       std::string expanded;
       if (data_dependent) {
-        if (!h_in) return fail(c, ZQ_E_UNSUPPORTED, "method level >= 5 needs host-visible input for its period analysis");
-        expanded = zq::expand_method(m, h_in + in_off[u], len);
+        expanded = zq::expand_method_periods(m, len, &periods[2 * u]);
       } else {
         const std::string ck = std::string(m) + "|" + std::to_string(arg0);
         auto it = expand_cache.find(ck);

@@ -538,7 +538,13 @@ std::string expand_method(const std::string& method_in, const uint8_t* data, uin
     default: break;
   }
   // levels 5..9: many-model CM; up to two periodic contexts from the byte-gap histogram
-  std::string mth = X + "," + num(e8) + ((type & 1) ? "w2c0,1010,255i1" : "w1i1") + "c256ci1,1,1,1,1,1,2a";
+  int periods[2] = {0, 0};
+  gap_periods(data, n, periods);
+  return expand_method_periods(method_in, n, periods);
+}
+
+void gap_periods(const uint8_t* data, uint32_t n, int periods[2]) {
+  periods[0] = periods[1] = 0;
   const int NR = 1 << 12;
   std::vector<int> gap(NR, 0);
   int last[256] = {0};
@@ -557,10 +563,29 @@ std::string expand_method(const std::string& method_in, const uint8_t* data, uin
       t += gap[j];
     }
     if (!(period > 4 && best > 0.1)) break;
-    mth += "c0,0," + num(999 + period) + ",255i1";
-    if (period <= 255) mth += "c0," + num(period) + "i1";
+    periods[rep] = period;
     n1 -= gap[period];
     gap[period] = 0;
+  }
+}
+
+std::string expand_method_periods(const std::string& method_in, uint32_t n, const int periods[2]) {
+  int arg0 = bitlen(n + 4095) - 20; if (arg0 < 0) arg0 = 0;
+  unsigned type = 512;
+  {
+    int commas = 0, f[4] = {0, 0, 0, 0};
+    for (size_t i = 1; i < method_in.size() && commas < 4; ++i) {
+      const char ch = method_in[i];
+      if (ch == ',' || ch == '.') ++commas;
+      else if (isdigit((unsigned char)ch)) f[commas] = f[commas] * 10 + (ch - '0');
+    }
+    if (commas) type = (unsigned)(f[1] * 4 + f[2]);
+  }
+  const int e8 = (type & 2) * 2;
+  std::string mth = "x" + num(arg0) + "," + num(e8) + ((type & 1) ? "w2c0,1010,255i1" : "w1i1") + "c256ci1,1,1,1,1,1,2a";
+  for (int rep = 0; rep < 2 && periods[rep] > 4; ++rep) {
+    mth += "c0,0," + num(999 + periods[rep]) + ",255i1";
+    if (periods[rep] <= 255) mth += "c0," + num(periods[rep]) + "i1";
   }
   return mth + "c0,2,0,255i1c0,3,0,0,255i1c0,4,0,0,0,255i1mm16ts19t0";
 }

@@ -36,6 +36,11 @@ struct Assembled {
 // `data`/`n` are only inspected for levels >= 5 (byte-gap period analysis, Z:20355-20388).
 // Non-digit methods are returned unchanged.
 std::string expand_method(const std::string& method, const uint8_t* data, uint32_t n);
+// Same for levels >= 5 when the two byte-gap periods were already found (e.g. on the device):
+// periods[k] == 0 means "none" (and stops, like the reference's loop).
+std::string expand_method_periods(const std::string& method, uint32_t n, const int periods[2]);
+// The period analysis alone (Z:20355-20388): fills periods[2].
+void gap_periods(const uint8_t* data, uint32_t n, int periods[2]);
 
 // Explicit method string -> ZPAQL config source text; fills args[0..8].
 std::string make_config(const std::string& method, int args[9]);

@@ -89,4 +89,55 @@ k_e8e9(u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const int* __
   }
 }
 
+// Byte-gap period analysis of compressBlock's levels >= 5 (Z:20355-20388): histogram of the distance
+// to the previous occurrence of the same byte value (first occurrences count from position 0, as the
+// reference's zero-initialised table does), then up to two periods picked by the same double
+// arithmetic.  One 256-thread CTA per block: thread b follows byte value b through the block (bytes are
+// staged in shared memory, every thread reads the same one = broadcast), histogram in shared memory.
+__global__ void __launch_bounds__(256)
+k_gap_periods(const u8* __restrict__ in_base, const u64* __restrict__ off, const u32* __restrict__ len, int n, int* __restrict__ periods) {
+  __shared__ u32 gap[4096];
+  __shared__ u8 tile[4096];
+  for (int t = blockIdx.x; t < n; t += gridDim.x) {
+    const u8* __restrict__ p = in_base + off[t];
+    const u32 L = len[t];
+    for (u32 k = threadIdx.x; k < 4096; k += blockDim.x) gap[k] = 0;
+    __syncthreads();
+    const u32 mine = threadIdx.x;
+    u32 last = 0;
+    for (u32 base = 0; base < L; base += 4096) {
+      const u32 cnt = min(4096u, L - base);
+      for (u32 k = threadIdx.x; k < cnt; k += blockDim.x) tile[k] = p[base + k];
+      __syncthreads();
+      for (u32 k = 0; k < cnt; ++k) {
+        if (tile[k] == mine) {
+          const u32 i = base + k, d = i - last;
+          if (d > 0 && d < 4096) atomicAdd(&gap[d], 1u);
+          last = i;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      int per[2] = {0, 0};
+      int n1 = (int)L - (int)gap[1] - (int)gap[2] - (int)gap[3];
+      for (int rep = 0; rep < 2; ++rep) {
+        int period = 0, tt = 0;
+        double best = 0;
+        for (int j = 5; j < 4096 && tt < n1; ++j) {
+          const double sc = (double)(int)gap[j] / (256.0 + n1 - tt);
+          if (sc > best) best = sc, period = j;
+          tt += (int)gap[j];
+        }
+        if (!(period > 4 && best > 0.1)) break;
+        per[rep] = period;
+        n1 -= (int)gap[period];
+        gap[period] = 0;
+      }
+      periods[2 * t] = per[0]; periods[2 * t + 1] = per[1];
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace zqdev
