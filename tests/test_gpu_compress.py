@@ -167,9 +167,11 @@ def test_config1_one_mib_of_zeros_m1(ctx, ref):
         assert out[: int(olen[0])].tobytes() == ref.compress_block(u, m, "", "")
 
 
-def test_parallel_parse_variant_is_bit_exact(zq, ref, monkeypatch):
-    # the candidates/chain/emit form of the SA parse (zq_lz77_par.cuh), selected with ZQ_LZ_PAR=1
-    monkeypatch.setenv("ZQ_LZ_PAR", "1")
+@pytest.mark.parametrize("knob", ["ZQ_LZ_PAR", "ZQ_LZ_HALF"])
+def test_parallel_parse_variant_is_bit_exact(zq, ref, monkeypatch, knob):
+    # alternative forms of the SA parse kept for comparison: candidates/chain/emit (zq_lz77_par.cuh, ZQ_LZ_PAR=1)
+    # and two blocks per warp (zq_lz77_half.cuh, ZQ_LZ_HALF=1)
+    monkeypatch.setenv(knob, "1")
     units = EDGE_UNITS[3:] + [corpus.text_unit(21, 65536), corpus.repeats_unit(22, 65536)]
     arena, offs, lens = _arena(units)
     with zq.Context(0) as c2:

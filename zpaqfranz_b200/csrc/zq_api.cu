@@ -21,6 +21,7 @@
 #include "zq_frame.cuh"
 #include "zq_hashes.cuh"
 #include "zq_lz77.cuh"
+#include "zq_lz77_half.cuh"
 #include "zq_lz77_par.cuh"
 #include "zq_sha1.cuh"
 #include "zq_sufsort.cuh"
@@ -63,6 +64,8 @@ struct zq_ctx {
   DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_ht, d_todo2, d_todo3, d_todo4, d_todo5, d_dec, d_tok, d_bitpos, d_lz, d_lzlen, d_sha, d_tables, d_cmplans, d_fills, d_model, d_coded, d_codedlen,
       d_kbuf, d_vbuf, d_err, d_misc;
   Timer tm[8];
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // h2d / d2h timing of the host-pointer entry point
+  bool attr_cm_enc = false, attr_cm_dec = false;
   float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   size_t wave_bytes = (size_t)12 << 30;  // sa|isa|lcp bytes per wave
   size_t model_budget = (size_t)120 << 30; // component-table bytes per wave (capped by free memory)
@@ -70,6 +73,7 @@ struct zq_ctx {
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 1;                         // 1: warp-per-block LZ77 parser (default, faster today); 0: candidates/chain/emit form (ZQ_LZ_PAR=1)
   int cm_occ = 2;                         // CTAs (16 warps) per SM of the CM coder
+  int lz_half = 0;                        // 1: SA parse with two blocks per warp (ZQ_LZ_HALF=1; bit-exact, slower today: the halves serialise)
   int lz_occ = 6;                         // CTAs (4 warps) per SM the LZ parse kernel is compiled for
 };
 
@@ -405,7 +409,17 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
     kern<<<pgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), c->d_lz.as<u8>(),           \
                                        c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);                       \
   } while (0)
-          if (v == 0) ZQ_LZ_LAUNCH(u16, true);
+          if ((v == 0 || v == 2) && c->lz_half) {   // two blocks per warp
+            const int hgrid = std::min((cnt + 7) / 8, c->num_sms * std::max(c->lz_occ, 6));
+            if (v == 0) {
+              auto kern = c->lz_occ >= 8 ? k_lz77_sa_half<u16, 8> : k_lz77_sa_half<u16, 6>;
+              kern<<<hgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);
+            } else {
+              auto kern = c->lz_occ >= 8 ? k_lz77_sa_half<u32, 8> : k_lz77_sa_half<u32, 6>;
+              kern<<<hgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);
+            }
+          }
+          else if (v == 0) ZQ_LZ_LAUNCH(u16, true);
           else if (v == 1) ZQ_LZ_LAUNCH(u16, false);
           else if (v == 2) ZQ_LZ_LAUNCH(u32, true);
           else ZQ_LZ_LAUNCH(u32, false);
@@ -446,11 +460,10 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       k_cm_init<<<nt * maxjobs, 256, 0, c->stream>>>(du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_fills.as<ZqCmFill>(), c->d_todo3.as<int>(), nt,
                                                      maxjobs, c->d_tables.as<CmTablesDev>(), c->d_model.as<u8>());
       ++c->launches;
-      static bool attr_set = false;
-      if (!attr_set) {
+      if (!c->attr_cm_enc) {   // per context (= per device): function attributes are per device
         cudaFuncSetAttribute(k_cm_encode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem));
         cudaFuncSetAttribute(k_cm_encode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem));
-        attr_set = true;
+        c->attr_cm_enc = true;
       }
       const int cgrid = std::min((nt + 15) / 16, c->num_sms * (c->cm_occ >= 2 ? 2 : 1));
       auto cmk = c->cm_occ >= 2 ? k_cm_encode<2> : k_cm_encode<1>;
@@ -565,9 +578,11 @@ zq_ctx* zq_create(int device) {
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream creation failed"; delete c; return nullptr; }
   c->stream = c->own_stream;
   for (int k = 0; k < 8; ++k) { cudaEventCreate(&c->tm[k].a); cudaEventCreate(&c->tm[k].b); }
+  for (int k = 0; k < 4; ++k) cudaEventCreate(&c->ev[k]);
   if (const char* s = getenv("ZQ_MODEL_BUDGET")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->model_budget = v; }
   if (const char* s = getenv("ZQ_FRAG_SEG")) { uint64_t v = strtoull(s, nullptr, 10); if (v >= 64) c->frag_seg = v; }
   if (const char* s = getenv("ZQ_LZ_OCC")) c->lz_occ = atoi(s);
+  if (const char* s = getenv("ZQ_LZ_HALF")) c->lz_half = atoi(s);
   if (const char* s = getenv("ZQ_CM_OCC")) c->cm_occ = atoi(s);
   if (const char* s = getenv("ZQ_LZ_PAR")) c->lz_old = atoi(s) ? 0 : 1;
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
@@ -588,6 +603,7 @@ void zq_destroy(zq_ctx* c) {
   DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_work, &c->d_ht, &c->d_todo2, &c->d_todo3, &c->d_todo4, &c->d_todo5, &c->d_dec, &c->d_tok, &c->d_bitpos, &c->d_tables, &c->d_cmplans, &c->d_fills, &c->d_model, &c->d_coded, &c->d_codedlen, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
   for (DevBuf* b : bufs) b->release();
   for (int k = 0; k < 8; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
+  for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -654,8 +670,7 @@ int zq_compress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t*
   const uint64_t span = hi - lo;
   ZQ_CUDA(c, c->d_in.ensure(span + 64));
   ZQ_CUDA(c, c->d_out.ensure(std::min<uint64_t>(bound, std::max<uint64_t>(out_cap, 1)) + 64));
-  cudaEvent_t e0, e1, e2, e3;
-  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+  cudaEvent_t e0 = c->ev[0], e1 = c->ev[1], e2 = c->ev[2], e3 = c->ev[3];
   cudaEventRecord(e0, c->stream);
   if (span) ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, in_base + lo, span, cudaMemcpyHostToDevice, c->stream));
   cudaEventRecord(e1, c->stream);
@@ -672,7 +687,6 @@ int zq_compress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t*
     if (e != cudaSuccess) rc = fail(c, ZQ_E_NODEVICE, std::string("CUDA error: ") + cudaGetErrorString(e));
     else { cudaEventElapsedTime(&c->last_ms[6], e0, e1); cudaEventElapsedTime(&c->last_ms[7], e2, e3); }
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
   return rc;
 }
 
@@ -762,8 +776,7 @@ int zq_decompress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_
   size_t budget = c->model_budget;
   { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); fr += c->d_model.cap; budget = std::min<size_t>(budget, fr > ((size_t)6 << 30) ? fr - ((size_t)6 << 30) : fr / 2); }
   std::vector<ZqDecResult> res(n);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_cm_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem)); attr_set = true; }
+  if (!c->attr_cm_dec) { cudaFuncSetAttribute(k_cm_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem)); c->attr_cm_dec = true; }
   int w0 = 0;
   while (w0 < n) {
     size_t model = 0; int w1 = w0, maxjobs = 1;
