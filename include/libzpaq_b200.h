@@ -8,9 +8,14 @@
 //   libzpaq::StringBuffer             Z:13362-13466       growable in-memory Reader+Writer
 //   libzpaq::compressBlock(...)       Z:13476 / Z:20255   one input buffer -> one ZPAQ block
 //
+//   libzpaq::SHA1 / SHA256            Z:12637 / Z:12828   streaming digests (hashed on the device at result())
+//   libzpaq::Compressor               Z:13325-13358       caller-driven block/segment writer
+//   libzpaq::Decompresser             Z:13241-13262       block/segment reader
+//   libzpaq::decompress(Reader*,Writer*) Z:13264 / Z:15536
+//
 // plus the batch form the GPU wants (compressBlocks), which is what a modified
-// CompressJob::appendz (Z:71364) would call, and decompress() for whole streams of such blocks
-// (the streaming Decompresser class with its per-segment callbacks stays the reference's own).
+// CompressJob::appendz (Z:71364) would call.  The byte-at-a-time classes buffer one segment and run it
+// on the device when the segment ends; a block holds ONE segment (what every zpaqfranz call site writes).
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -57,6 +62,96 @@ class StringBuffer : public Reader, public Writer {
   int read(char* b, int n) override;
 };
 
+inline int toU16(const char* p) { return (p[0] & 255) + 256 * (p[1] & 255); }   // Z:13479
+
+// == libzpaq::SHA1 (Z:12637): put/write accumulate, result() returns the 20-byte digest and resets.
+// The bytes are kept until result() and hashed there by the device kernel (zq_sha1).
+class SHA1 {
+  std::vector<unsigned char> buf_;
+  uint64_t len_ = 0;
+  char h_[20];
+ public:
+  void put(int c) { buf_.push_back((unsigned char)c); ++len_; }
+  void write(const char* b, int64_t n) { if (n > 0) { buf_.insert(buf_.end(), (const unsigned char*)b, (const unsigned char*)b + n); len_ += (uint64_t)n; } }
+  double size() const { return (double)len_; }
+  uint64_t usize() const { return len_; }
+  const char* result();
+};
+
+// == libzpaq::SHA256 (Z:12828)
+class SHA256 {
+  std::vector<unsigned char> buf_;
+  uint64_t len_ = 0;
+  char h_[32];
+ public:
+  void put(int c) { buf_.push_back((unsigned char)c); ++len_; }
+  void write(const char* b, int64_t n) { if (n > 0) { buf_.insert(buf_.end(), (const unsigned char*)b, (const unsigned char*)b + n); len_ += (uint64_t)n; } }
+  double size() const { return (double)len_; }
+  uint64_t usize() const { return len_; }
+  const char* result();
+};
+
+// == libzpaq::Compressor (Z:13325-13358, Z:15970-16187).  Same call sequence and the same bytes on the
+// Writer at the same calls: writeTag / startBlock / startSegment write at once; the segment's data is
+// collected by compress() and coded on the device in endSegment().
+class Compressor {
+ public:
+  Compressor() {}
+  void setOutput(Writer* out) { out_ = out; }
+  void writeTag();
+  void startBlock(int level);                     // built-in models 1 (min.cfg) and 2 (mid.cfg)
+  void startBlock(const char* hcomp);             // stored header: hsize[2] hh hm ph pm n comp.. 0 hcomp.. 0
+  void startBlock(const char* config, int* args, Writer* pcomp_cmd = 0);   // ZPAQL source (Compiler, Z:15904)
+  void startSegment(const char* filename = 0, const char* comment = 0);
+  void setInput(Reader* i) { in_ = i; }
+  void postProcess(const char* pcomp = 0, int len = 0);
+  bool compress(int n = -1);                      // n bytes, or to EOF if n < 0; false at EOF
+  void endSegment(const char* sha1string = 0);
+  void endBlock();
+  int stat(int) { return 0; }
+  void hcomp(Writer* out2) { if (out2) out2->write((const char*)header_.data(), (int)header_.size()); }
+  void setVerify(bool) {}                         // the device decoder is the verifier (zq_decompress_blocks)
+ private:
+  enum { INIT, BLOCK1, SEG1, BLOCK2, SEG2 } state_ = INIT;
+  Writer* out_ = 0;
+  Reader* in_ = 0;
+  std::vector<unsigned char> header_, pcomp_default_, pcomp_, data_;
+  std::string filename_, comment_;
+  bool have_pcomp_ = false;
+  void begin_block();
+};
+
+// == libzpaq::Decompresser (Z:13241-13262, Z:15418-15534).  Reads ahead to the next block locator tag
+// (or EOF) and restores the segment on the device at the first decompress()/readSegmentEnd().
+class Decompresser {
+ public:
+  Decompresser() {}
+  void setInput(Reader* in) { in_ = in; }
+  bool findBlock(double* memptr = 0);
+  void hcomp(Writer* out2);
+  bool findFilename(Writer* = 0);
+  void readComment(Writer* = 0);
+  void setOutput(Writer* out) { out_ = out; }
+  void setSHA1(SHA1* sha1ptr) { sha1_ = sha1ptr; }
+  bool decompress(int n = -1);                    // n bytes, -1 = all; true until the segment is done
+  void readSegmentEnd(char* sha1string = 0);
+  int stat(int) { return 0; }
+  int buffered() { return (int)(buf_.size() - pos_); }
+ private:
+  enum { BLOCK, FILENAME, COMMENT, DATA, SEGEND } state_ = BLOCK;
+  Reader* in_ = 0;
+  Writer* out_ = 0;
+  SHA1* sha1_ = 0;
+  std::vector<unsigned char> buf_, obuf_;
+  size_t pos_ = 0, blk_ = 0, hdr_ = 0, hdr_len_ = 0, opos_ = 0, seg_end_ = 0;
+  bool eof_ = false, decoded_ = false, first_seg_ = true;
+  unsigned char trailer_[21];
+  uint64_t expect_ = 0; bool have_expect_ = false;
+  bool fill(size_t need);
+  int byte();
+  void decode_segment();
+};
+
 // == libzpaq::compressBlock (Z:20255). Like the reference it may transform `in` in place (E8E9).
 // Runs as a batch of one on the calling thread's device context (created on first use, device
 // taken from ZQ_DEVICE or 0).  Throws via error() where the reference would.
@@ -67,8 +162,8 @@ void compressBlock(StringBuffer* in, Writer* out, const char* method, const char
 void compressBlocks(int n, StringBuffer* const* ins, Writer* const* outs, const char* const* methods,
                     const char* const* filenames, const char* const* comments, bool dosha1 = true);
 
-// == libzpaq::decompress(Reader*, Writer*) (Z:15536) for a stream of blocks as compressBlock writes
-// them (one segment per block): every block found in `in` is restored on the device and appended to out.
+// == libzpaq::decompress(Reader*, Writer*) (Z:15536): every block found in `in` is restored on the device
+// and appended to out (all blocks of the stream in one batch).
 void decompress(Reader* in, Writer* out);
 
 }  // namespace libzpaq_b200

@@ -73,6 +73,35 @@ int zq_compress_blocks_device(zq_ctx* ctx, int n,
                               uint8_t* d_out_base, uint64_t out_cap,
                               uint64_t* out_off, uint32_t* out_len);
 
+/* ---- caller-supplied models ---------------------------------------------------------------------
+ * == libzpaq::Compressor used directly (Z:15970-16187): writeTag / startBlock(hcomp) / startSegment(filename,
+ * comment) / postProcess(pcomp, len) / compress(-1) / endSegment(sha1string) / endBlock, once per unit.
+ *   header:  the block header exactly as it is stored (hsize[2] hh hm ph pm n comp.. 0 hcomp.. 0, Z:14084);
+ *   pcomp:   PCOMP bytecode to announce to the decoder (NULL/0: "0" = no post-processing);
+ *   the unit's bytes go to the coder AS THEY ARE (any pre-processing matching pcomp is the caller's);
+ *   comment: stored verbatim (compressBlock's "<n> " prefix is compressBlock's own, Z:20404);
+ *   sha1_digests: n x 20 bytes stored as the segments' checksums, or NULL for none;
+ *   write_tag: emit the 13-byte locator tag in front of each block.
+ * n == 0 components -> stored/unmodeled framing, else arithmetic coded with the given component chain. */
+int zq_compress_segments(zq_ctx* ctx, int n,
+                         const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                         const uint8_t* header, uint32_t header_len,
+                         const uint8_t* pcomp, uint32_t pcomp_len,
+                         const char* const* filename, const char* const* comment, int uniform,
+                         const uint8_t* sha1_digests, int write_tag,
+                         uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len);
+
+/* == libzpaq::Compiler (Z:15904) as Compressor::startBlock(config, args, pcomp_cmd) uses it: ZPAQL source ->
+ * stored block header + PCOMP bytecode (+ the text between "pcomp" and ";").  No GPU needed.
+ * header_len / pcomp_len: in = capacity, out = length. */
+int zq_assemble_config(const char* config, const int args9[9],
+                       uint8_t* header, uint32_t* header_len, uint8_t* pcomp, uint32_t* pcomp_len,
+                       char* pcomp_cmd, size_t pcomp_cmd_cap, char* errbuf, size_t errcap);
+
+/* ZPAQL source of the built-in models Compressor::startBlock(int level) selects (Z:15989): 1 = min.cfg,
+ * 2 = mid.cfg; NULL for other levels. */
+const char* zq_model_config(int level);
+
 /* ---- block decompression -------------------------------------------------------------------------
  * Element-wise == Decompresser::findBlock/findFilename/readComment/decompress/readSegmentEnd for one
  * block holding one segment (what compressBlock writes; Z:15418-15534) and libzpaq::decompress (Z:15536):
@@ -85,6 +114,16 @@ int zq_decompress_blocks(zq_ctx* ctx, int n,
                          const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
                          const uint32_t* expect_len /* may be NULL */,
                          uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len);
+
+/* Same, and additionally reports per block (either may be NULL): in_used[u] = offset, from the block's start, of
+ * the byte that follows the segment trailer (the end-of-block 0xFF), and sha1_out[u*21 ..] = readSegmentEnd()'s
+ * 21-byte answer (1 + stored SHA-1, or 0).  in_len[u] may run past the end of the block (e.g. to the end of
+ * the stream): decoding stops at the segment's end. */
+int zq_decompress_blocks_ex(zq_ctx* ctx, int n,
+                            const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                            const uint32_t* expect_len /* may be NULL */,
+                            uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
+                            uint32_t* in_used, uint8_t* sha1_out);
 
 /* Upper bound of one block's compressed size for an n-byte input (any method, names <= 255 bytes). */
 uint64_t zq_compress_bound(uint32_t n);

@@ -48,6 +48,31 @@ long long zref_compress_block(const unsigned char* in, unsigned n, const char* m
   } catch (std::exception& e) { g_lasterr = e.what(); return -1; }
 }
 
+// == libzpaq::Compressor driven directly (Z:15970-16187): one block, one segment, caller's model.
+// level > 0: startBlock(level) (built-in models); else header = stored block header bytes.
+// pcomp/plen: postProcess(pcomp, plen) when plen > 0, else postProcess() default.
+long long zref_compress_segment(int level, const unsigned char* header, const unsigned char* pcomp, int plen,
+                                const unsigned char* in, unsigned n, const char* filename, const char* comment,
+                                const unsigned char* sha1, int tag, unsigned char* out, unsigned long long cap) {
+  try {
+    MemReader r(in, n);
+    VecWriter w;
+    libzpaq::Compressor co;
+    co.setOutput(&w);
+    co.setInput(&r);
+    if (tag) co.writeTag();
+    if (level > 0) co.startBlock(level); else co.startBlock((const char*)header);
+    co.startSegment(filename, comment);
+    if (plen > 0) co.postProcess((const char*)pcomp, plen); else co.postProcess();
+    co.compress();
+    co.endSegment((const char*)sha1);
+    co.endBlock();
+    if (w.v.size() > cap) return -2;
+    memcpy(out, w.v.data(), w.v.size());
+    return (long long)w.v.size();
+  } catch (std::exception& e) { g_lasterr = e.what(); return -1; }
+}
+
 // == libzpaq::decompress (Z:15536) over a whole stream of blocks.
 long long zref_decompress(const unsigned char* in, unsigned long long n, unsigned char* out,
                           unsigned long long cap) {

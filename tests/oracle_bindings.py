@@ -88,7 +88,7 @@ class Ref:
 
     def __init__(self, lib):
         self.lib = lib
-        for f in ("zref_compress_block", "zref_decompress", "zref_lz_stream", "zref_fragment", "zref_compress_units_mt"):
+        for f in ("zref_compress_block", "zref_decompress", "zref_lz_stream", "zref_fragment", "zref_compress_units_mt", "zref_compress_segment"):
             getattr(lib, f).restype = C.c_longlong
         lib.zref_last_error.restype = C.c_char_p
 
@@ -102,6 +102,21 @@ class Ref:
                                          out, C.c_ulonglong(cap))
         if r < 0:
             raise RuntimeError("reference compressBlock failed: %s" % self.lib.zref_last_error().decode(errors="replace"))
+        return out.raw[:r]
+
+    def compress_segment(self, data, header=None, level=0, pcomp=b"", filename=None, comment=None, sha1=None, tag=True):
+        """libzpaq::Compressor driven directly: writeTag/startBlock(level | header)/startSegment/postProcess/compress/
+        endSegment(sha1)/endBlock."""
+        data = bytes(data)
+        cap = len(data) + len(data) // 8 + 200000
+        out = C.create_string_buffer(cap)
+        fn = filename.encode() if isinstance(filename, str) else filename
+        cm = comment.encode() if isinstance(comment, str) else comment
+        r = self.lib.zref_compress_segment(C.c_int(level), bytes(header) if header else None, bytes(pcomp) if pcomp else None,
+                                           C.c_int(len(pcomp)), data, C.c_uint(len(data)), fn, cm,
+                                           bytes(sha1) if sha1 is not None else None, C.c_int(1 if tag else 0), out, C.c_ulonglong(cap))
+        if r < 0:
+            raise RuntimeError("reference Compressor failed: %s" % self.lib.zref_last_error().decode(errors="replace"))
         return out.raw[:r]
 
     def decompress(self, blob, cap):

@@ -29,3 +29,20 @@ def test_no_device_fails_loudly(zq):
 def test_compress_bound_is_generous(zq):
     for n in (0, 1, 65536, 1 << 20):
         assert zq.lib.zq_compress_bound(n) >= n + n // 32 + 4 * (n // 65536 + 2) + 200
+
+
+def test_cpp_mirror_links_and_refuses_to_run_without_a_device(zq, tmp_path):
+    """include/libzpaq_b200.h (Reader/Writer/StringBuffer/SHA1/SHA256/Compressor/Decompresser/compressBlock/decompress)
+    compiles as a plain C++ caller and links against the shared library; without a GPU the first device call throws
+    (there is no CPU path to fall back to)."""
+    import subprocess
+    import torch
+    exe = tmp_path / "facade_driver"
+    subprocess.run(["g++", "-O0", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests/cpp/facade_driver.cpp"),
+                    "-o", str(exe), "-L" + os.path.join(ROOT, "zpaqfranz_b200"), "-lzqb200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "zpaqfranz_b200")], check=True)
+    if torch.cuda.is_available():
+        return
+    (tmp_path / "in.bin").write_bytes(b"hello")
+    r = subprocess.run([str(exe), str(tmp_path / "in.bin"), str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "FAILED" in r.stdout and "CUDA" in r.stdout

@@ -70,3 +70,36 @@ def test_cm_restatement_vs_reference(zq, oracle, ref, method):
         s = oracle.lz_stream(d, a) if (a[1] & 3) else d
         blk = oracle.block_modeled(p["header"], p["pcomp"], b"nm", ("%d cm" % len(d)).encode(), s, oracle.sha1(d))
         assert blk == ref.compress_block(d, method, "nm", "cm"), (method, len(d))
+
+
+def test_builtin_model_sources_assemble_to_the_reference_tables(zq, ref):
+    # Compressor::startBlock(int level) takes its header from a byte table (Z:15992-16026); ours assembles the
+    # published min.cfg / mid.cfg sources.  Same bytes, and the reference accepts ours as startBlock(hcomp).
+    for level in (1, 2):
+        header = zq.assemble_config(zq.model_config(level))["header"]
+        blk = ref.compress_segment(b"some data, some data", level=level, tag=False)
+        hs = blk[5] + 256 * blk[6] + 2
+        assert blk[5:5 + hs] == header
+        assert ref.compress_segment(b"some data, some data", header=header, tag=False) == blk
+    assert zq.model_config(3) is None
+
+
+HAND_MODELS = {
+    "cm_o1": "comp 2 2 0 0 1 0 cm 18 255 hcomp *d=a a<<= 8 *d=a halt end",
+    "all_types": ("comp 3 3 0 0 7 0 icm 12 1 isse 14 0 2 cm 16 32 3 match 14 16 4 mix2 8 1 2 20 255 5 sse 10 4 16 255 6 avg 4 5 96 "
+                  "hcomp c++ *c=a b=c a=0 d= 0 hash *d=a d++ b-- hash *d=a d++ a=*c a<<= 9 *d=a d++ "
+                  "b=c a=0 hash b-- hash b-- hash *d=a d++ a=*c *d=a d++ a=*c a>>= 3 *d=a halt end"),
+    "branches": ("comp 2 4 0 0 3 0 cm 14 8 1 cm 16 20 2 mix 8 0 2 30 255 "
+                 "hcomp *c=a c++ a== 32 if d= 0 *d=0 else d= 0 a+=*d a*= 73 *d=a endif "
+                 "d= 1 a=*c a^= 255 *d=a d= 2 a=c a&= 7 *d=a halt end"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(HAND_MODELS))
+def test_cm_restatement_on_hand_written_models(zq, oracle, ref, name):
+    # the Compressor class driven directly with a caller's model: comment verbatim, caller's checksum
+    a = zq.assemble_config(HAND_MODELS[name])
+    assert a["header"] == ref.compile(HAND_MODELS[name], [0] * 9)[0]
+    for d in (corpus.text_unit(1, 9000), corpus.random_unit(2, 1500), bytes(2000), b"", b"q"):
+        want = ref.compress_segment(d, header=a["header"], filename="f", comment="verbatim", sha1=oracle.sha1(d))
+        assert oracle.block_modeled(a["header"], b"", b"f", b"verbatim", d, oracle.sha1(d)) == want, (name, len(d))

@@ -48,6 +48,14 @@ def _load():
                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zq_decompress_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zq_decompress_blocks_ex.argtypes = lib.zq_decompress_blocks.argtypes + [C.c_void_p, C.c_void_p]
+    lib.zq_compress_segments.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32,
+                                         C.c_char_p, C.c_uint32, cpp, cpp, C.c_int, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zq_model_config.restype = C.c_char_p
+    lib.zq_model_config.argtypes = [C.c_int]
+    lib.zq_assemble_config.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_void_p, u32p, C.c_void_p, u32p, C.c_char_p, C.c_size_t,
+                                       C.c_char_p, C.c_size_t]
     for name in ("zq_sha1", "zq_sha256", "zq_xxh3_128", "zq_blake3", "zq_sha1_device"):
         getattr(lib, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.zq_fragment.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
@@ -78,6 +86,27 @@ def plan_block(method, data=b""):
     if rc:
         raise ZqError(rc, err.value.decode(errors="replace"))
     return dict(method=exp.value.decode(), args=list(args), header=hdr.raw[:hl.value], pcomp=pc.raw[:pl.value])
+
+
+def model_config(level):
+    """ZPAQL source of the built-in model Compressor::startBlock(level) selects (1 min.cfg, 2 mid.cfg) or None."""
+    r = lib.zq_model_config(int(level))
+    return r.decode() if r else None
+
+
+def assemble_config(config, args=None):
+    """== libzpaq::Compiler: ZPAQL source -> dict(header=bytes, pcomp=bytes, pcomp_cmd=str). No GPU needed."""
+    a = (C.c_int * 9)(*(list(args or []) + [0] * 9)[:9])
+    hdr = C.create_string_buffer(70000)
+    pc = C.create_string_buffer(70000)
+    cmd = C.create_string_buffer(4096)
+    hl, pl = C.c_uint32(70000), C.c_uint32(70000)
+    err = C.create_string_buffer(512)
+    rc = lib.zq_assemble_config(config.encode() if isinstance(config, str) else config, a, hdr, C.byref(hl), pc, C.byref(pl),
+                                cmd, 4096, err, 512)
+    if rc:
+        raise ZqError(rc, err.value.decode(errors="replace"))
+    return dict(header=hdr.raw[:hl.value], pcomp=pc.raw[:pl.value], pcomp_cmd=cmd.value.decode())
 
 
 def _cstr_array(v, n, uniform):
@@ -170,9 +199,31 @@ class Context:
         out, ooff, olen = self.compress_blocks(a if len(a) else np.zeros(1, np.uint8), [0], [len(data)], method, filename, comment, dosha1)
         return out[: int(olen[0])].tobytes()
 
-    def decompress_blocks(self, arena, offsets, lengths, expect_len=None, out_cap=None):
-        """Element-wise libzpaq::decompress of complete blocks arena[offsets[i]:+lengths[i]].
+    def compress_segments(self, arena, offsets, lengths, header, pcomp=b"", filename=None, comment=None, sha1=None, tag=True):
+        """libzpaq::Compressor driven directly, once per unit, with the caller's model: `header` is the stored block
+        header, `pcomp` the PCOMP bytecode to announce, `sha1` an (n,20) array of digests to store or None.
         Returns (out_array, out_off, out_len)."""
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+        n = len(off)
+        fn = _cstr_array(filename, n, True)
+        cm = _cstr_array(comment, n, True)
+        uniform = 1 if all(x is None or len(x) == 1 for x in (fn, cm)) else 0
+        dg = None if sha1 is None else np.ascontiguousarray(sha1, dtype=np.uint8).reshape(n, 20)
+        cap = int(sum(int(lib.zq_compress_bound(int(x))) for x in ln)) + n * (2 * len(pcomp) + len(header))
+        out = np.empty(cap, dtype=np.uint8)
+        ooff = np.zeros(n, dtype=np.uint64)
+        olen = np.zeros(n, dtype=np.uint32)
+        self._check(lib.zq_compress_segments(self._h, n, arena.ctypes.data, off.ctypes.data, ln.ctypes.data, bytes(header), len(header),
+                                             bytes(pcomp) if pcomp else None, len(pcomp), fn, cm, uniform,
+                                             dg.ctypes.data if dg is not None else None, 1 if tag else 0,
+                                             out.ctypes.data, out.size, ooff.ctypes.data, olen.ctypes.data))
+        return out, ooff, olen
+
+    def decompress_blocks(self, arena, offsets, lengths, expect_len=None, out_cap=None, details=False):
+        """Element-wise libzpaq::decompress of complete blocks arena[offsets[i]:+lengths[i]].
+        Returns (out_array, out_off, out_len); with details=True also (in_used, trailers[n,21])."""
         arena = np.ascontiguousarray(arena, dtype=np.uint8)
         off = np.ascontiguousarray(offsets, dtype=np.uint64)
         ln = np.ascontiguousarray(lengths, dtype=np.uint32)
@@ -183,6 +234,13 @@ class Context:
         out = np.empty(max(out_cap, 1), dtype=np.uint8)
         ooff = np.zeros(n, dtype=np.uint64)
         olen = np.zeros(n, dtype=np.uint32)
+        if details:
+            used = np.zeros(n, dtype=np.uint32)
+            tr = np.zeros((n, 21), dtype=np.uint8)
+            self._check(lib.zq_decompress_blocks_ex(self._h, n, arena.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                                    ex.ctypes.data if ex is not None else None, out.ctypes.data, out.size,
+                                                    ooff.ctypes.data, olen.ctypes.data, used.ctypes.data, tr.ctypes.data))
+            return out, ooff, olen, used, tr
         self._check(lib.zq_decompress_blocks(self._h, n, arena.ctypes.data, off.ctypes.data, ln.ctypes.data,
                                              ex.ctypes.data if ex is not None else None, out.ctypes.data, out.size,
                                              ooff.ctypes.data, olen.ctypes.data))

@@ -100,6 +100,14 @@ struct HostPlan {
   std::vector<uint8_t> payload;  // selector + pcomp
 };
 
+// A caller-supplied model (the Compressor class: startBlock(hcomp) / postProcess(pcomp) / endSegment(sha1)).
+struct RawModel {
+  zq::Assembled code;            // parsed COMP/HCOMP header
+  std::vector<uint8_t> pcomp;    // PCOMP bytecode announced in the first segment (may be empty)
+  bool tag = true;               // writeTag()
+  const uint8_t* digests = nullptr;  // n x 20 bytes to store as FD sha1, or null -> FE
+};
+
 static const unsigned char kTag[13] = {0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83, 0xd3, 0x8c, 0xb2, 0x28, 0xb0, 0xd3};
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -108,7 +116,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len,
                   const char* const* method, const char* const* filename, const char* const* comment,
                   int uniform, int dosha1, uint8_t* d_out, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
-                  const uint8_t* h_in /* host copy of the arena or null */) {
+                  const RawModel* raw = nullptr) {
   using namespace zqdev;
   if (n < 0 || (n > 0 && (!in_off || !in_len || !out_off || !out_len))) return fail(c, ZQ_E_ARG, "bad argument");
   if (n == 0) return ZQ_OK;
@@ -122,7 +130,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
   std::vector<int> periods;
   {
     std::vector<int> need;
-    for (int u = 0; u < n; ++u) {
+    for (int u = 0; u < n && !raw; ++u) {
       const char* m = method ? method[uniform ? 0 : u] : "1";
       if (m && isdigit((unsigned char)m[0]) && m[0] >= '5') need.push_back(u);
     }
@@ -145,13 +153,14 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
   }
   try {
     for (int u = 0; u < n; ++u) {
-      const char* m = method ? method[uniform ? 0 : u] : "1";
+      const char* m = raw ? "(caller's model)" : method ? method[uniform ? 0 : u] : "1";
       if (!m || !*m) return fail(c, ZQ_E_ARG, "empty method");
       const uint32_t len = in_len[u];
       int arg0 = zq::bitlen(len + 4095) - 20; if (arg0 < 0) arg0 = 0;
-      const bool data_dependent = isdigit((unsigned char)m[0]) && m[0] >= '5';
+      const bool data_dependent = !raw && isdigit((unsigned char)m[0]) && m[0] >= '5';
       std::string expanded;
-      if (data_dependent) {
+      if (raw) { expanded = m; arg0 = 0; }
+      else if (data_dependent) {
         expanded = zq::expand_method_periods(m, len, &periods[2 * u]);
       } else {
         const std::string ck = std::string(m) + "|" + std::to_string(arg0);
@@ -165,7 +174,11 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       if (it != plan_idx.end()) pi = it->second;
       else {
         HostPlan hp;
-        hp.bp = zq::plan_block(expanded, nullptr, len);
+        if (raw) {   // data goes to the coder as is; the caller did its own pre-processing
+          hp.bp.method = expanded; memset(hp.bp.args, 0, sizeof hp.bp.args);
+          hp.bp.code = raw->code; hp.bp.code.pcomp = raw->pcomp;
+          hp.bp.lz_level = 0; hp.bp.e8e9 = false; hp.bp.use_sa = false; hp.bp.stored = false;
+        } else hp.bp = zq::plan_block(expanded, nullptr, len);
         const auto& pc = hp.bp.code.pcomp;
         if (!pc.empty()) { hp.payload.push_back(1); hp.payload.push_back(pc.size() & 255); hp.payload.push_back(pc.size() >> 8); hp.payload.insert(hp.payload.end(), pc.begin(), pc.end()); }
         else hp.payload.push_back(0);
@@ -179,7 +192,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       zu.in_off = in_off[u]; zu.n = len; zu.plan = (u32)pi;
       // prefix: tag, "zPQ", level, 1, header, 1, filename, 0, "<n>[ comment]", 0, 0
       zu.prefix_off = (u32)blob.size();
-      blob.insert(blob.end(), kTag, kTag + 13);
+      if (!raw || raw->tag) blob.insert(blob.end(), kTag, kTag + 13);
       blob.push_back('z'); blob.push_back('P'); blob.push_back('Q');
       blob.push_back(1 + (hp.bp.code.ncomp == 0)); blob.push_back(1);
       blob.insert(blob.end(), hp.bp.code.header.begin(), hp.bp.code.header.end());
@@ -187,9 +200,9 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       const char* fn = filename ? filename[uniform ? 0 : u] : nullptr;
       if (fn) blob.insert(blob.end(), fn, fn + strlen(fn));
       blob.push_back(0);
-      std::string cs = std::to_string(len);
+      std::string cs = raw ? std::string() : std::to_string(len);   // startSegment() stores the comment verbatim (Z:16070)
       const char* cm = comment ? comment[uniform ? 0 : u] : nullptr;
-      if (cm) { cs += " "; cs += cm; }
+      if (cm) { if (!raw) cs += " "; cs += cm; }
       blob.insert(blob.end(), cs.begin(), cs.end());
       blob.push_back(0); blob.push_back(0);
       zu.prefix_len = (u32)blob.size() - zu.prefix_off;
@@ -302,7 +315,9 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
     ZQ_CUDA(c, cudaMemcpyAsync(c->d_units.p, units.data() + w0, (size_t)wn * sizeof(ZqUnit), cudaMemcpyHostToDevice, c->stream));
     const ZqUnit* du = c->d_units.as<ZqUnit>();
     const ZqPlan* dp = c->d_plans.as<ZqPlan>();
-    if (dosha1) {
+    if (dosha1 && raw && raw->digests) {   // endSegment(sha1string): the caller's digest of the original data
+      ZQ_CUDA(c, cudaMemcpyAsync(c->d_sha.p, raw->digests + (size_t)w0 * 20, (size_t)wn * 20, cudaMemcpyHostToDevice, c->stream));
+    } else if (dosha1) {
       tstart(c, 1);
       k_sha1_units<<<(wn + 127) / 128, 128, 0, c->stream>>>(d_in, du, wn, c->d_sha.as<u8>());
       ++c->launches;
@@ -653,9 +668,14 @@ int zq_compress_blocks_device(zq_ctx* c, int n, const uint8_t* d_in, const uint6
   return compress_core(c, n, d_in, in_off, in_len, method, filename, comment, uniform, dosha1, d_out, out_cap, out_off, out_len, nullptr);
 }
 
-int zq_compress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
-                       const char* const* method, const char* const* filename, const char* const* comment,
-                       int uniform, int dosha1, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len) {
+}  // extern "C"
+
+namespace {
+// host-pointer front end shared by zq_compress_blocks and zq_compress_segments
+int compress_host(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                  const char* const* method, const char* const* filename, const char* const* comment,
+                  int uniform, int dosha1, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
+                  const RawModel* raw) {
   if (!c) return ZQ_E_NODEVICE;
   if (n < 0 || (n > 0 && (!in_base || !in_off || !in_len || !out_base))) return fail(c, ZQ_E_ARG, "bad argument");
   if (n == 0) return ZQ_OK;
@@ -677,7 +697,7 @@ int zq_compress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t*
   std::vector<uint64_t> roff(n);
   for (int u = 0; u < n; ++u) roff[u] = in_off[u] - lo;
   int rc = compress_core(c, n, c->d_in.as<uint8_t>(), roff.data(), in_len, method, filename, comment, uniform, dosha1,
-                         c->d_out.as<uint8_t>(), std::min<uint64_t>(c->d_out.cap, out_cap), out_off, out_len, in_base + lo);
+                         c->d_out.as<uint8_t>(), std::min<uint64_t>(c->d_out.cap, out_cap), out_off, out_len, raw);
   if (rc == ZQ_OK) {
     const uint64_t total = out_off[n - 1] + out_len[n - 1];
     cudaEventRecord(e2, c->stream);
@@ -689,10 +709,83 @@ int zq_compress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t*
   }
   return rc;
 }
+}  // namespace
+
+extern "C" {
+
+int zq_compress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                       const char* const* method, const char* const* filename, const char* const* comment,
+                       int uniform, int dosha1, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len) {
+  return compress_host(c, n, in_base, in_off, in_len, method, filename, comment, uniform, dosha1, out_base, out_cap, out_off, out_len, nullptr);
+}
+
+int zq_compress_segments(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                         const uint8_t* header, uint32_t header_len, const uint8_t* pcomp, uint32_t pcomp_len,
+                         const char* const* filename, const char* const* comment, int uniform,
+                         const uint8_t* sha1_digests, int write_tag,
+                         uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len) {
+  if (!c) return ZQ_E_NODEVICE;
+  if (!header || header_len < 8) return fail(c, ZQ_E_ARG, "bad argument");
+  RawModel raw;
+  try {
+    size_t used = 0;
+    raw.code = zq::parse_block_header(header, header_len, &used);
+  } catch (const zq::Error& e) { return fail(c, ZQ_E_METHOD, e.msg); }
+  if (pcomp_len > 65535) return fail(c, ZQ_E_METHOD, "PCOMP too long");
+  if (pcomp && pcomp_len) raw.pcomp.assign(pcomp, pcomp + pcomp_len);
+  raw.tag = write_tag != 0;
+  raw.digests = sha1_digests;
+  return compress_host(c, n, in_base, in_off, in_len, nullptr, filename, comment, uniform, sha1_digests != nullptr,
+                       out_base, out_cap, out_off, out_len, &raw);
+}
+
+const char* zq_model_config(int level) {
+  // The two small standard models of the ZPAQ distribution as ZPAQL source (min.cfg, mid.cfg). The reference
+  // keeps their assembled bytes in a table (Compressor::startBlock(int), Z:15992-16026); assembling these
+  // sources reproduces those bytes (tests/test_oracle_pinned.py).
+  static const char* kMin =
+      "comp 1 2 0 0 2 0 icm 16 1 isse 19 0 "
+      "hcomp *b=a a=0 d=0 hash b-- hash *d=a d++ b-- hash b-- hash *d=a halt end ";
+  static const char* kMid =
+      "comp 3 3 0 0 8 0 icm 5 1 isse 13 0 2 isse 17 1 3 isse 18 2 4 isse 18 3 5 isse 19 4 "
+      "6 match 22 24 7 mix 16 0 7 24 255 "
+      "hcomp c++ *c=a b=c a=0 d= 1 hash *d=a b-- d++ hash *d=a b-- d++ hash *d=a b-- d++ hash *d=a "
+      "b-- d++ hash *d=a b-- d++ hash b-- hash *d=a d++ a=*c a<<= 8 *d=a halt end ";
+  return level == 1 ? kMin : level == 2 ? kMid : nullptr;
+}
+
+int zq_assemble_config(const char* config, const int args9[9], uint8_t* header, uint32_t* header_len,
+                       uint8_t* pcomp, uint32_t* pcomp_len, char* pcomp_cmd, size_t pcomp_cmd_cap, char* errbuf, size_t errcap) {
+  try {
+    if (!config) throw zq::Error("no config");
+    int args[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (args9) memcpy(args, args9, sizeof args);
+    zq::Assembled a = zq::assemble(config, args);
+    if (header_len) {
+      if (header && *header_len >= a.header.size()) memcpy(header, a.header.data(), a.header.size());
+      *header_len = (uint32_t)a.header.size();
+    }
+    if (pcomp_len) {
+      if (pcomp && *pcomp_len >= a.pcomp.size() && !a.pcomp.empty()) memcpy(pcomp, a.pcomp.data(), a.pcomp.size());
+      *pcomp_len = (uint32_t)a.pcomp.size();
+    }
+    if (pcomp_cmd && pcomp_cmd_cap) { strncpy(pcomp_cmd, a.pcomp_cmd.c_str(), pcomp_cmd_cap - 1); pcomp_cmd[pcomp_cmd_cap - 1] = 0; }
+    return ZQ_OK;
+  } catch (const zq::Error& e) {
+    if (errbuf && errcap) { strncpy(errbuf, e.msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
+    return ZQ_E_METHOD;
+  }
+}
 
 // ---- block decompression ---------------------------------------------------------------------------
 int zq_decompress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
                          const uint32_t* expect_len, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len) {
+  return zq_decompress_blocks_ex(c, n, in_base, in_off, in_len, expect_len, out_base, out_cap, out_off, out_len, nullptr, nullptr);
+}
+
+int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                            const uint32_t* expect_len, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
+                            uint32_t* in_used, uint8_t* sha1_out) {
   using namespace zqdev;
   if (!c) return ZQ_E_NODEVICE;
   if (n < 0 || (n > 0 && (!in_base || !in_off || !in_len || !out_base || !out_off || !out_len))) return fail(c, ZQ_E_ARG, "bad argument");
@@ -827,6 +920,8 @@ int zq_decompress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_
     } else if (b[p] != 254) return fail(c, ZQ_E_METHOD, "missing end of segment marker");
     const size_t e = p + (b[p] == 253 ? 21 : 1);
     if (e < in_len[u] && b[e] == 1) return fail(c, ZQ_E_UNSUPPORTED, "blocks with more than one segment have no device path yet");
+    if (in_used) in_used[u] = (uint32_t)e;       // offset of the end-of-block byte (255)
+    if (sha1_out) { sha1_out[(size_t)u * 21] = b[p] == 253; if (b[p] == 253) memcpy(sha1_out + (size_t)u * 21 + 1, b + p + 1, 20); }
   }
   if (!sidx.empty()) {
     const int k = (int)sidx.size();
