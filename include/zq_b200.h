@@ -150,6 +150,32 @@ int zq_fragment(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* of
                 uint32_t* frag_len, uint32_t* frag_hits, uint8_t* frag_sha1 /* may be NULL */,
                 uint64_t frag_cap, uint64_t* frag_first);
 
+/* Same, plus frag_o1 (256 bytes per fragment, may be NULL): the chunker's order-1 prediction table as it stands
+ * at the end of each fragment -- the input of the archiver's text/exe/redundancy heuristics (Z:122592-122634). */
+int zq_fragment_ex(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* off, const uint64_t* len,
+                   int fragment, uint32_t blocksize,
+                   uint32_t* frag_len, uint32_t* frag_hits, uint8_t* frag_sha1, uint8_t* frag_o1,
+                   uint64_t frag_cap, uint64_t* frag_first);
+
+/* ---- the archiver's add loop over files in memory ------------------------------------------------------
+ * == the body of Jidac::add between "for each file" and the index blocks (Z:122113-122911) for a fresh archive:
+ * fragment every file (device), look each fragment up by SHA-1, run the data-type heuristics on the new ones,
+ * pack them into blocks by the reference's new-block rule and compress every block (device).  Files are taken
+ * in the order given; the reference's order is ascending zq_file_sort_key(path, size), then path.
+ *   method:   -method as typed ("2", "14", "x..."); fragment: -fragment N; date14: the version's date as 14 digits
+ *   first_id: id of the first new fragment (1 for a new archive)
+ *   d_out:    the "d" blocks back to back, as they follow the version's header block in the archive
+ *   h_out:    the "h" blocks (compressed size + SHA-1/size per fragment of each data block), in order
+ *   file_frags[file_first[f] .. file_first[f+1]): fragment ids of file f (what its index entry lists).
+ * Not written here: the "c" header and "i" index blocks (file names, dates, attributes: the front end's). */
+int zq_add_files(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* off, const uint64_t* len,
+                 const char* method, int fragment, const char* date14, uint32_t first_id,
+                 uint8_t* d_out, uint64_t d_cap, uint64_t* d_len,
+                 uint8_t* h_out, uint64_t h_cap, uint64_t* h_len,
+                 uint32_t* file_frags, uint64_t file_frags_cap, uint64_t* file_first /* nfiles+1 */,
+                 uint32_t* nblocks);
+uint64_t zq_file_sort_key(const char* path, int64_t size);
+
 /* ---- introspection for tests / bench ---------------------------------------------------------- */
 /* number of kernel launches issued by this context since creation */
 uint64_t zq_launch_count(zq_ctx* ctx);

@@ -73,6 +73,10 @@ long long zref_compress_segment(int level, const unsigned char* header, const un
   } catch (std::exception& e) { g_lasterr = e.what(); return -1; }
 }
 
+// The reference's own command line (its main(), Z:78458), for archive-level comparisons: run it in a child
+// process -- it calls exit().
+int zref_main(int argc, const char** argv) { return zpaqfranz_reference_main(argc, argv); }
+
 // == libzpaq::decompress (Z:15536) over a whole stream of blocks.
 long long zref_decompress(const unsigned char* in, unsigned long long n, unsigned char* out,
                           unsigned long long cap) {

@@ -52,6 +52,13 @@ def _load():
     lib.zq_compress_segments.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32,
                                          C.c_char_p, C.c_uint32, cpp, cpp, C.c_int, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zq_fragment_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.zq_add_files.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_uint32,
+                                 C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                 C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zq_file_sort_key.restype = C.c_uint64
+    lib.zq_file_sort_key.argtypes = [C.c_char_p, C.c_int64]
     lib.zq_model_config.restype = C.c_char_p
     lib.zq_model_config.argtypes = [C.c_int]
     lib.zq_assemble_config.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_void_p, u32p, C.c_void_p, u32p, C.c_char_p, C.c_size_t,
@@ -86,6 +93,11 @@ def plan_block(method, data=b""):
     if rc:
         raise ZqError(rc, err.value.decode(errors="replace"))
     return dict(method=exp.value.decode(), args=list(args), header=hdr.raw[:hl.value], pcomp=pc.raw[:pl.value])
+
+
+def file_sort_key(path, size):
+    """The key Jidac::add sorts the files to add by (then by path): extension bytes, then descending size."""
+    return int(lib.zq_file_sort_key(path.encode() if isinstance(path, str) else path, int(size)))
 
 
 def model_config(level):
@@ -266,6 +278,30 @@ class Context:
 
     def blake3(self, arena, offsets, lengths):
         return self._hash(lib.zq_blake3, 32, arena, offsets, lengths)
+
+    def add_files(self, arena, offsets, lengths, method="1", fragment=6, date14="20260101000000", first_id=1):
+        """The archiver's add loop over files in memory (== Jidac::add's data path for a fresh archive): returns
+        dict(d=bytes of the data blocks, h=bytes of the fragment-table blocks, file_frags=[ids per file], nblocks)."""
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        n = len(off)
+        total = int(ln.sum())
+        dcap = total + total // 8 + (1 << 20) + 70000 * (total // 4096 + n + 4)
+        dcap = min(dcap, total * 2 + (64 << 20))
+        d = np.empty(dcap, dtype=np.uint8)
+        hcap = (total // 4096 + n + 16) * 64 + (1 << 20)
+        h = np.empty(hcap, dtype=np.uint8)
+        dl, hl = C.c_uint64(0), C.c_uint64(0)
+        idcap = total // 4096 + n + 16
+        ids = np.zeros(idcap, dtype=np.uint32)
+        first = np.zeros(n + 1, dtype=np.uint64)
+        nb = C.c_uint32(0)
+        self._check(lib.zq_add_files(self._h, n, arena.ctypes.data, off.ctypes.data, ln.ctypes.data, method.encode(), int(fragment),
+                                     date14.encode(), int(first_id), d.ctypes.data, d.size, C.byref(dl), h.ctypes.data, h.size,
+                                     C.byref(hl), ids.ctypes.data, ids.size, first.ctypes.data, C.byref(nb)))
+        return dict(d=d[: dl.value].tobytes(), h=h[: hl.value].tobytes(), nblocks=nb.value,
+                    file_frags=[ids[int(first[i]): int(first[i + 1])].tolist() for i in range(n)])
 
     # -- fragmenter ---------------------------------------------------------------------------------
     def fragment(self, arena, offsets, lengths, fragment=6, blocksize=(1 << 26) - 4096, want_sha1=True):

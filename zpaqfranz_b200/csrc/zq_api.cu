@@ -1024,6 +1024,12 @@ int zq_blake3(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const 
 int zq_fragment(zq_ctx* c, int nfiles, const uint8_t* base, const uint64_t* off, const uint64_t* len, int fragment,
                 uint32_t blocksize, uint32_t* frag_len, uint32_t* frag_hits, uint8_t* frag_sha1, uint64_t frag_cap,
                 uint64_t* frag_first) {
+  return zq_fragment_ex(c, nfiles, base, off, len, fragment, blocksize, frag_len, frag_hits, frag_sha1, nullptr, frag_cap, frag_first);
+}
+
+int zq_fragment_ex(zq_ctx* c, int nfiles, const uint8_t* base, const uint64_t* off, const uint64_t* len, int fragment,
+                   uint32_t blocksize, uint32_t* frag_len, uint32_t* frag_hits, uint8_t* frag_sha1, uint8_t* frag_o1,
+                   uint64_t frag_cap, uint64_t* frag_first) {
   using namespace zqdev;
   if (!c) return ZQ_E_NODEVICE;
   if (nfiles < 0 || (nfiles > 0 && (!base || !off || !len)) || !frag_first || fragment < 0 || blocksize < 64)
@@ -1113,6 +1119,12 @@ int zq_fragment(zq_ctx* c, int nfiles, const uint8_t* base, const uint64_t* off,
     k_sha1_many<<<(int)((total + 127) / 128), 128, 0, c->stream>>>(c->d_in.as<u8>(), d_fo, d_fl, nullptr, (int)total, c->d_sha.as<u8>());
     ++c->launches;
     ZQ_CUDA(c, cudaMemcpyAsync(frag_sha1, c->d_sha.p, total * 20, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (frag_o1) {
+    ZQ_CUDA(c, c->d_out.ensure(total * 256));
+    k_fragment_o1<<<(int)std::min<uint64_t>(total, (uint64_t)c->num_sms * 8), 256, 0, c->stream>>>(c->d_in.as<u8>(), d_fo, d_fl, (int)total, c->d_out.as<u8>());
+    ++c->launches;
+    ZQ_CUDA(c, cudaMemcpyAsync(frag_o1, c->d_out.p, total * 256, cudaMemcpyDeviceToHost, c->stream));
   }
   ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
   ZQ_CUDA(c, cudaGetLastError());

@@ -97,4 +97,28 @@ __global__ void k_fragment_gather(const ZqSeg* __restrict__ segs, int nseg, u32 
   }
 }
 
+// The fragmenter's order-1 table as it stands when a fragment ends (Z:122186: o1 starts at zero with every
+// fragment; o1[previous byte] = byte): entry v holds the byte that followed the LAST occurrence of v as
+// "previous byte" (the virtual byte in front of the fragment is 0), 0 if v never preceded anything.  The
+// archiver's type heuristics read it (Z:122608-122634).  One CTA per fragment, 256 threads.
+__global__ void __launch_bounds__(256)
+k_fragment_o1(const u8* __restrict__ base, const u64* __restrict__ frag_off, const u32* __restrict__ frag_len, int nfrag,
+              u8* __restrict__ o1_out) {
+  __shared__ int last[256];
+  for (int f = blockIdx.x; f < nfrag; f += gridDim.x) {
+    const u8* d = base + frag_off[f];
+    const int n = (int)frag_len[f];
+    last[threadIdx.x] = -1;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += 256) {
+      const u32 c1 = j ? d[j - 1] : 0u;
+      atomicMax(&last[c1], j);
+    }
+    __syncthreads();
+    const int l = last[threadIdx.x];
+    o1_out[(u64)f * 256 + threadIdx.x] = l >= 0 ? d[l] : (u8)0;
+    __syncthreads();
+  }
+}
+
 }  // namespace zqdev
