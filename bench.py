@@ -10,8 +10,13 @@ scaling); `value` = units of all ranks x 64 KiB / max-over-ranks device time.
   value : inputs and outputs resident in HBM (zq_compress_blocks_device)
   e2e   : the reference-facing call with HOST buffers (zq_compress_blocks): H2D of the batch and D2H
           of the compressed blocks inside the timed region.
-Timing: CUDA events on the stream the kernels are launched on (the context is switched onto torch's
-current stream), barrier + synchronize on both sides, max over ranks.  Inputs (655 MB/step) exceed L2.
+Both are measured with `--inflight` (default 2) steps outstanding through zq_pipe_* -- the counterpart of
+CompressJob's block queue: while the last units of step k are still being parsed, step k+1's copies and kernels
+already run (each lane has its own context and stream).  K steps are K complete batches; the bracket is
+barrier + device synchronize, CUDA event, K submits/waits, device synchronize, CUDA event, barrier; max over ranks.
+`stage_ms` / `roofline` come from a serial pass on ONE context whose stream is torch's current stream, so the
+per-kernel CUDA events there time exactly one kernel each (config.serial_ms_per_step is that pass).
+Inputs (655 MB/step) exceed L2.
 """
 import argparse
 import json
@@ -145,6 +150,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--units", type=int, default=10000, help="units per GPU per step (configs[1]: 10000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="batches in flight (zq_pipe lanes): the next step's copies/kernels fill the tail of the current one")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -171,14 +178,17 @@ def main():
     corpus.text_corpus(U, UNIT, seed0=rank, out=h_in.numpy())
     d_in = h_in.cuda()
     cap = int(zq.lib.zq_compress_bound(UNIT)) * U
-    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
-    h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    depth = max(1, min(args.inflight, 4))
+    d_outs = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(depth)]
+    h_outs = [torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
+    d_out, h_out = d_outs[0], h_outs[0]
     offs = (np.arange(U, dtype=np.uint64) * UNIT)
     lens = np.full(U, UNIT, dtype=np.uint32)
 
-    ctx = zq.Context(local)
+    ctx = zq.Context(local)          # serial pass: per-stage device times for the roofline, parity check
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    pipe = zq.Pipe(local, depth)     # the measured path: `depth` steps in flight (zq_pipe_*, CompressJob's queue)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -211,14 +221,45 @@ def main():
             ms = float(tt.item())
         return ms, stage / steps, ctx.launch_count() - l0
 
-    for _ in range(args.warmup):
+    def piped(steps, device):
+        """`steps` steps through the pipe, at most `depth` outstanding; returns device-clock ms (max over ranks)."""
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = pipe.launch_count()
+        e0.record(stream)
+        tickets = []
+        for k in range(steps):
+            if k >= depth:
+                pipe.wait(tickets[k - depth])
+            if device:
+                tickets.append(pipe.submit(d_in.data_ptr(), offs, lens, d_outs[k % depth].data_ptr(), cap, method=METHOD,
+                                           filename="", comment="", device=True))
+            else:
+                tickets.append(pipe.submit(h_in.data_ptr(), offs, lens, h_outs[k % depth].data_ptr(), cap, method=METHOD,
+                                           filename="", comment="", device=False))
+        for t in tickets[-depth:]:
+            pipe.wait(t)
+        torch.cuda.synchronize()
+        e1.record(stream)
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, pipe.launch_count() - l0
+
+    for _ in range(max(1, args.warmup - 2)):
         ooff, olen = step_device()
+    piped(max(args.warmup, depth), True)
     sampler = ClockSampler(local)
     sampler.start()
-    ms_dev, stage_dev, launches = timed(step_device, args.steps)
-    for _ in range(max(1, args.warmup - 1)):
-        step_host()
-    ms_e2e, stage_e2e, _ = timed(step_host, args.steps)
+    ms_dev, launches = piped(args.steps, True)
+    piped(max(args.warmup, depth), False)
+    ms_e2e, _ = piped(args.steps, False)
+    # serial pass on one context: device time of each stage (the roofline's kernel time)
+    ser_steps = min(args.steps, 3)
+    ms_ser, stage_dev, _ = timed(step_device, ser_steps)
     sampler.stop_flag = True
     sampler.join(timeout=3)
     out_bytes = int(ooff[-1]) + int(olen[-1])
@@ -267,6 +308,7 @@ def main():
         "config": {"workload": "%d x 64KiB synthetic text fragments per GPU, -m2 (x0,1,4,0,7,21,1), one compressBlock per unit" % U,
                    "method": METHOD, "units_per_gpu": U, "unit_bytes": UNIT, "parallelism": "units sharded, no collective",
                    "l2": "inputs %.0f MB per step > 126 MB L2 (no flush needed)" % (nbytes / MB), "parity": parity,
+                   "inflight": depth, "serial_ms_per_step": round(ms_ser / ser_steps, 3),
                    "compressed_ratio": round(out_bytes / nbytes, 4)},
         "e2e": {"value": round(e2e_v, 2), "unit": "MB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
@@ -287,6 +329,7 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     ctx.close()
+    pipe.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -73,6 +73,25 @@ int zq_compress_blocks_device(zq_ctx* ctx, int n,
                               uint8_t* d_out_base, uint64_t out_cap,
                               uint64_t* out_off, uint32_t* out_len);
 
+/* ---- batches in flight ---------------------------------------------------------------------------------
+ * The counterpart of CompressJob's block queue (appendz / compressThread / writeThread, Z:71364-71520): `depth`
+ * lanes, each with its own context, stream and worker thread, so the copies and kernels of the next batch fill the
+ * tail of the current one.  zq_pipe_submit takes the arguments of zq_compress_blocks (device_pointers = 0) or
+ * zq_compress_blocks_device (= 1) and returns a ticket >= 0; all argument arrays and buffers must stay valid and
+ * untouched until zq_pipe_wait(ticket) returns the call's result.  Batches run in submission order per lane;
+ * results are those of the synchronous calls. */
+typedef struct zq_pipe zq_pipe;
+zq_pipe* zq_pipe_create(int device, int depth);
+void zq_pipe_destroy(zq_pipe* pipe);
+int zq_pipe_submit(zq_pipe* pipe, int n,
+                   const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                   const char* const* method, const char* const* filename, const char* const* comment,
+                   int uniform, int dosha1, int device_pointers,
+                   uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len);
+int zq_pipe_wait(zq_pipe* pipe, int ticket);
+const char* zq_pipe_last_error(zq_pipe* pipe);
+uint64_t zq_pipe_launch_count(zq_pipe* pipe);
+
 /* ---- caller-supplied models ---------------------------------------------------------------------
  * == libzpaq::Compressor used directly (Z:15970-16187): writeTag / startBlock(hcomp) / startSegment(filename,
  * comment) / postProcess(pcomp, len) / compress(-1) / endSegment(sha1string) / endBlock, once per unit.

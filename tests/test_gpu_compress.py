@@ -203,3 +203,32 @@ def test_unsupported_is_loud(ctx, zq):
         ctx.compress_blocks(arena, offs, lens, method="x0,1,2,0,3,20")   # LZ77 min match too small
     with pytest.raises(zq.ZqError):
         ctx.compress_blocks(arena, offs, lens, method="q1")
+
+
+def test_pipe_matches_synchronous_calls(zq, ctx):
+    # batches in flight (zq_pipe_*): same bytes as the synchronous entry point, host and device pointers
+    import torch
+    units = [corpus.text_unit(s, 30000 + 977 * s) for s in range(24)]
+    lens = np.array([len(u) for u in units], dtype=np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens.astype(np.uint64))[:-1]]).astype(np.uint64)
+    arena = np.frombuffer(b"".join(units) + b"\0" * 16, dtype=np.uint8).copy()
+    want, woff, wlen = ctx.compress_blocks(arena, offs, lens, method="2", filename="f", comment="c")
+    want = want[: int(woff[-1]) + int(wlen[-1])].tobytes()
+    pipe = zq.Pipe(0, 2)
+    try:
+        cap = int(zq.lib.zq_compress_bound(int(lens.max()))) * len(units)
+        outs = [np.empty(cap, dtype=np.uint8) for _ in range(3)]
+        d_in = torch.from_numpy(arena).cuda()
+        d_outs = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        t = [pipe.submit(arena.ctypes.data, offs, lens, outs[k].ctypes.data, cap, method="2", filename="f", comment="c") for k in range(3)]
+        td = [pipe.submit(d_in.data_ptr(), offs, lens, d_outs[k].data_ptr(), cap, method="2", filename="f", comment="c", device=True)
+              for k in range(3)]
+        for k in range(3):
+            ooff, olen = pipe.wait(t[k])
+            assert outs[k][: int(ooff[-1]) + int(olen[-1])].tobytes() == want
+        for k in range(3):
+            ooff, olen = pipe.wait(td[k])
+            assert d_outs[k][: int(ooff[-1]) + int(olen[-1])].cpu().numpy().tobytes() == want
+        assert pipe.launch_count() > 0
+    finally:
+        pipe.close()

@@ -59,6 +59,16 @@ def _load():
                                  C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zq_file_sort_key.restype = C.c_uint64
     lib.zq_file_sort_key.argtypes = [C.c_char_p, C.c_int64]
+    lib.zq_pipe_create.restype = C.c_void_p
+    lib.zq_pipe_create.argtypes = [C.c_int, C.c_int]
+    lib.zq_pipe_destroy.argtypes = [C.c_void_p]
+    lib.zq_pipe_submit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, cpp, cpp, cpp, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zq_pipe_wait.argtypes = [C.c_void_p, C.c_int]
+    lib.zq_pipe_last_error.restype = C.c_char_p
+    lib.zq_pipe_last_error.argtypes = [C.c_void_p]
+    lib.zq_pipe_launch_count.restype = C.c_uint64
+    lib.zq_pipe_launch_count.argtypes = [C.c_void_p]
     lib.zq_model_config.restype = C.c_char_p
     lib.zq_model_config.argtypes = [C.c_int]
     lib.zq_assemble_config.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_void_p, u32p, C.c_void_p, u32p, C.c_char_p, C.c_size_t,
@@ -128,6 +138,47 @@ def _cstr_array(v, n, uniform):
         v = [v]
     arr = (C.c_char_p * len(v))(*[(s.encode() if isinstance(s, str) else s) for s in v])
     return arr
+
+
+class Pipe:
+    """`depth` batches in flight on one device (zq_pipe_*): submit() returns a ticket, wait(ticket) the
+    (out_off, out_len) of that batch.  Buffers passed to submit() must stay alive until wait()."""
+
+    def __init__(self, device=0, depth=2):
+        self._h = lib.zq_pipe_create(int(device), int(depth))
+        if not self._h:
+            raise ZqError(ZQ_E_NODEVICE, lib.zq_last_error(None).decode(errors="replace"))
+        self._keep = {}
+
+    def close(self):
+        if self._h:
+            lib.zq_pipe_destroy(self._h)
+            self._h = None
+
+    def submit(self, in_ptr, offsets, lengths, out_ptr, out_cap, method="2", filename=None, comment=None, dosha1=True, device=False):
+        """in_ptr/out_ptr: integer addresses (host, or device when device=True)."""
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+        n = len(off)
+        m, f, cm = _cstr_array(method, n, True), _cstr_array(filename, n, True), _cstr_array(comment, n, True)
+        ooff = np.zeros(n, dtype=np.uint64)
+        olen = np.zeros(n, dtype=np.uint32)
+        t = lib.zq_pipe_submit(self._h, n, in_ptr, off.ctypes.data, ln.ctypes.data, m, f, cm, 1, 1 if dosha1 else 0,
+                               1 if device else 0, out_ptr, out_cap, ooff.ctypes.data, olen.ctypes.data)
+        if t < 0:
+            raise ZqError(t, "submit failed")
+        self._keep[t] = (off, ln, m, f, cm, ooff, olen)
+        return t
+
+    def wait(self, ticket):
+        rc = lib.zq_pipe_wait(self._h, int(ticket))
+        keep = self._keep.pop(ticket)
+        if rc:
+            raise ZqError(rc, lib.zq_pipe_last_error(self._h).decode(errors="replace"))
+        return keep[5], keep[6]
+
+    def launch_count(self):
+        return int(lib.zq_pipe_launch_count(self._h))
 
 
 class Context:

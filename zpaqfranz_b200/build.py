@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzqb200.so")
-SOURCES = ["zq_api.cu", "zq_config.cpp", "zq_cm_host.cpp", "libzpaq_b200.cpp", "zq_archive.cpp"]
+SOURCES = ["zq_api.cu", "zq_config.cpp", "zq_cm_host.cpp", "libzpaq_b200.cpp", "zq_archive.cpp", "zq_pipe.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared", "-cudart", "static",
@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    extra = os.environ.get("ZQ_EXTRA_FLAGS", "").split()   # tuning builds, e.g. -DZQ_SORT_PROF
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

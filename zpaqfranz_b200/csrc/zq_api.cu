@@ -1131,6 +1131,17 @@ int zq_fragment_ex(zq_ctx* c, int nfiles, const uint8_t* base, const uint64_t* o
   return ZQ_OK;
 }
 
+#ifdef ZQ_SORT_PROF
+// tuning builds only (ZQ_EXTRA_FLAGS=-DZQ_SORT_PROF): read and clear the suffix sort's phase counters
+int zq_debug_sort_profile(unsigned long long out[8]) {
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, zqdev::g_sort_prof, sizeof z);
+  cudaMemcpyToSymbol(zqdev::g_sort_prof, z, sizeof z);
+  return 0;
+}
+#endif
+
 // ---- introspection -------------------------------------------------------------------------------
 uint64_t zq_launch_count(zq_ctx* c) { return c ? c->launches : 0; }
 int zq_last_timings(zq_ctx* c, float ms[8]) {

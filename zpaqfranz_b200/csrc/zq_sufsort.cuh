@@ -22,7 +22,21 @@
 
 namespace zqdev {
 
+#ifdef ZQ_SORT_PROF
+// phase cycle counters (thread 0 of every CTA): 0 initial keys+sort, 1 first rank, 2 round keys, 3 round sort,
+// 4 round rerank, 5 outputs (lcp/bwt/isa), 6 number of rounds, 7 sum of m over rounds
+__device__ unsigned long long g_sort_prof[8];
+#define ZQ_PROF_T0 long long prof_t = clock64();
+#define ZQ_PROF(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_sort_prof[k], (unsigned long long)(now_ - prof_t)); prof_t = now_; } } while (0)
+#define ZQ_PROF_ADD(k, v) do { if (threadIdx.x == 0) atomicAdd(&g_sort_prof[k], (unsigned long long)(v)); } while (0)
+#else
+#define ZQ_PROF_T0
+#define ZQ_PROF(k)
+#define ZQ_PROF_ADD(k, v)
+#endif
+
 constexpr int SORT_ITEMS = 8;
+constexpr int RANK_ITEMS = 4;            // consecutive elements per thread in the ranking loops
 constexpr int SORT_MAXD = 256;           // digits per radix pass (8 bits)
 constexpr u32 ZQ_LCP_CAP = 256;
 
@@ -32,6 +46,7 @@ struct SortSmem {
   u32 hist[SORT_MAXD];
   u32 base[SORT_MAXD];
   u32 wsum[32];
+  u32 wsum2[32];
   u32 misc[4];
   u32 hist_next[SORT_MAXD]; // digit histogram of the NEXT pass, gathered while this pass writes out
   u32 tot[SORT_MAXD];      // digit totals of the current tile
@@ -86,6 +101,33 @@ __device__ __forceinline__ u32 block_scan_incl_max(u32 v, SortSmem<NT>& sm, u32&
   total = sm.wsum[31];
   __syncthreads();
   return max(v, pre);
+}
+
+// Both scans of the ranking loops in one pass: inclusive max of `vmax` and inclusive sum of `vadd` over the
+// CTA's threads in thread order; totals of the whole CTA in tmax / tadd.
+template <int NT>
+__device__ __forceinline__ void block_scan_max_add(u32& vmax, u32& vadd, SortSmem<NT>& sm, u32& tmax, u32& tadd) {
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 a = __shfl_up_sync(ZQ_FULL, vmax, o), b = __shfl_up_sync(ZQ_FULL, vadd, o);
+    if (lane >= (u32)o) { vmax = max(vmax, a); vadd += b; }
+  }
+  if (lane == 31) { sm.wsum[warp] = vmax; sm.wsum2[warp] = vadd; }
+  __syncthreads();
+  if (warp == 0) {
+    u32 a = lane < NT / 32 ? sm.wsum[lane] : 0, b = lane < NT / 32 ? sm.wsum2[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 ta = __shfl_up_sync(ZQ_FULL, a, o), tb = __shfl_up_sync(ZQ_FULL, b, o);
+      if (lane >= (u32)o) { a = max(a, ta); b += tb; }
+    }
+    sm.wsum[lane] = a; sm.wsum2[lane] = b;
+  }
+  __syncthreads();
+  if (warp) { vmax = max(vmax, sm.wsum[warp - 1]); vadd += sm.wsum2[warp - 1]; }
+  tmax = sm.wsum[31]; tadd = sm.wsum2[31];
+  __syncthreads();
 }
 
 // lanes of the warp holding the same 8-bit digit (among active lanes): 8 ballots.  (match.any is
@@ -215,6 +257,108 @@ __device__ int radix_sort_bits(u64*& kA, u32*& vA, u64*& kB, u32*& vB, u32 m, in
   return 0;
 }
 
+// ---- doubling rounds: tile sort ------------------------------------------------------------------------
+// The compacted list of a round is already grouped by rank (it is in SA order), so only the order INSIDE
+// each group is open.  Instead of five global radix passes over (rank, rank2) the list is cut, at group
+// boundaries, into tiles of <= NT*SORT_ITEMS elements that are sorted in shared memory by one 64-bit word
+// (rank | rank2 | suffix) with a bitonic network: comparators whose partners lie inside one 256-element
+// region are run by the warp owning the region (warp-level sync only), the few wider ones block-wide.
+constexpr u32 TILE_REGION = 256;
+
+__device__ __forceinline__ void bitonic_cmpx(u64* __restrict__ S, u32 i, u32 j, u32 k) {
+  const u64 a = S[i], b = S[i + j];
+  const bool up = (i & k) == 0;
+  if ((a > b) == up) { S[i] = b; S[i + j] = a; }
+}
+
+template <int NT>
+__device__ void tile_sort(u64* __restrict__ kA, u32* __restrict__ vA, u32 s, u32 cnt, int bits2, int bitsv, SortSmem<NT>& sm) {
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64* __restrict__ S = sm.stage_k;
+  u32 P = 64;
+  while (P < cnt) P <<= 1;
+  const u64 vmask = (1ull << bitsv) - 1, k2mask = (1ull << bits2) - 1;
+  for (u32 t = tid; t < P; t += NT) {
+    u64 key = ~0ull;
+    if (t < cnt) { const u64 k = kA[s + t]; key = ((((k >> 32) << bits2) | (k & 0xffffffffull)) << bitsv) | vA[s + t]; }
+    S[t] = key;
+  }
+  __syncthreads();
+  for (u32 k = 2; k <= P; k <<= 1) {
+    for (u32 j = k >> 1; j > 0; j >>= 1) {
+      if (j >= TILE_REGION) {
+        for (u32 t = tid; t < P / 2; t += NT) bitonic_cmpx(S, 2 * t - (t & (j - 1)), j, k);
+        __syncthreads();
+      } else {
+        for (u32 base = warp * TILE_REGION; base < P; base += (NT / 32) * TILE_REGION) {
+          const u32 ncmp = min(TILE_REGION, P - base) / 2;
+          for (u32 t = lane; t < ncmp; t += 32) bitonic_cmpx(S, base + 2 * t - (t & (j - 1)), j, k);
+        }
+        __syncwarp();
+        if (j == 1 && k < P && k >= TILE_REGION) __syncthreads();   // the next merge starts with block-wide comparators
+      }
+    }
+  }
+  __syncthreads();
+  for (u32 t = tid; t < cnt; t += NT) {
+    const u64 key = S[t];
+    vA[s + t] = (u32)(key & vmask);
+    kA[s + t] = ((key >> (bitsv + bits2)) << 32) | ((key >> bitsv) & k2mask);
+  }
+  __syncthreads();
+}
+
+// Sorts the round's list kA/vA[0..m) (grouped by the high word) inside its groups by the low word.
+template <int NT>
+__device__ void sort_round_tiles(u64* kA, u32* vA, u64* kB, u32* vB, u32 m, int bits2, int bitsv, SortSmem<NT>& sm) {
+  const u32 tid = threadIdx.x, lane = tid & 31;
+  constexpr u32 TILE = NT * SORT_ITEMS;
+  u32 s = 0;
+  while (s < m) {
+    if (tid < 32) {   // warp 0 places the tile's end on a group boundary
+      u32 e = min(s + TILE, m), big_end = 0;
+      if (e < m) {
+        const u32 g = (u32)(kA[e] >> 32);
+        if ((u32)(kA[e - 1] >> 32) == g) {
+          const u32 back = e - 1 - s;   // how far a lane may look back
+          const bool same = lane <= back && (u32)(kA[e - 1 - min(lane, back)] >> 32) == g;
+          const u32 differ = ~__ballot_sync(ZQ_FULL, same);
+          u32 start;
+          if (differ) start = e - (u32)(__ffs(differ) - 1);
+          else {   // the group reaches further back than a warp sees: binary search its first element
+            u32 lo = s, hi = e - 32;
+            while (lo < hi) { const u32 mid = (lo + hi) >> 1; if ((u32)(kA[mid] >> 32) >= g) hi = mid; else lo = mid + 1; }
+            start = lo;
+          }
+          if (start > s) e = start;
+          else {   // one group larger than a tile: find where it ends
+            u32 a = e, b = m;
+            while (a < b) { const u32 mid = (a + b) >> 1; if ((u32)(kA[mid] >> 32) > g) b = mid; else a = mid + 1; }
+            big_end = a;
+          }
+        }
+      }
+      if (lane == 0) { sm.misc[1] = e; sm.misc[2] = big_end; }
+    }
+    __syncthreads();
+    const u32 e = sm.misc[1], big_end = sm.misc[2];
+    __syncthreads();
+    if (big_end) {   // all elements share the rank: LSD passes on the second key only, then back into place
+      const u32 len = big_end - s;
+      u64 *a = kA + s, *b = kB + s; u32 *va = vA + s, *vb = vB + s;
+      radix_sort_bits<NT>(a, va, b, vb, len, 0, bits2, sm);
+      if (a != kA + s) {
+        for (u32 t = tid; t < len; t += NT) { kA[s + t] = a[t]; vA[s + t] = va[t]; }
+        __syncthreads();
+      }
+      s = big_end;
+    } else {
+      tile_sort<NT>(kA, vA, s, e - s, bits2, bitsv, sm);
+      s = e;
+    }
+  }
+}
+
 // Builds the suffix array of T[0..n) in scratch (sa, rank = inverse SA) and writes sa | isa | lcp to
 // the unit's work region `w` with index width 2 (idx16) or 4 bytes.
 template <int NT>
@@ -224,6 +368,7 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
   const u32 tid = threadIdx.x;
   if (n == 0) return;
   u64 *kA = sc.kA, *kB = sc.kB; u32 *vA = sc.vA, *vB = sc.vB; u32 *pA = sc.pA, *pB = sc.pB;
+  ZQ_PROF_T0
   const u32 nshort = n < 3 ? n : 3;  // suffixes shorter than the 4-byte key: n-1, n-2, n-3
   // 1. keys = first 4 bytes (zero padded). Input order puts the short suffixes first, shortest
   //    first, so the stable sort leaves them ahead of equal-keyed longer suffixes (implicit
@@ -237,34 +382,62 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
   }
   __syncthreads();
   radix_sort_bits<NT>(kA, vA, kB, vB, n, 0, 32, sm);
+  ZQ_PROF(0);
   // 2. group heads -> rank, sa; compact the ambiguous positions
   u32 m = 0;
   {
     u32 carry_max = 0, carry_cnt = 0;
-    for (u32 b = 0; b < n; b += NT) {
-      const u32 x = b + tid;
-      const bool act = x < n;
-      u32 i = 0; bool head = false, nexthead = true;
-      if (act) {
-        i = vA[x];
-        const u64 kx = kA[x];
-        head = x == 0 || kA[x - 1] != kx || i + 4 > n || vA[x - 1] + 4 > n;
-        if (x + 1 < n) nexthead = kA[x + 1] != kx || i + 4 > n || vA[x + 1] + 4 > n;
+    for (u32 b = 0; b < n; b += NT * RANK_ITEMS) {
+      const u32 x0 = b + tid * RANK_ITEMS;
+      // keys/suffixes of x0-1 .. x0+RANK_ITEMS (the neighbours decide head / nexthead)
+      u64 kk[RANK_ITEMS + 2]; u32 vv[RANK_ITEMS + 2];
+#pragma unroll
+      for (int q = 0; q < RANK_ITEMS + 2; ++q) {
+        const u32 x = x0 + q - 1;
+        const bool ok = x0 + q >= 1 && x < n;
+        kk[q] = ok ? kA[x] : 0; vv[q] = ok ? vA[x] : 0;
       }
-      u32 tot;
-      u32 g = block_scan_incl_max<NT>(head ? x : 0u, sm, tot);
-      g = max(g, carry_max);
-      carry_max = max(carry_max, tot);
-      const bool amb = act && !(head && nexthead);
-      u32 tot2;
-      const u32 inc = block_scan_incl_add<NT>(amb ? 1u : 0u, sm, tot2);
-      if (act) { sa[x] = i; rank[i] = g; }
-      if (amb) pA[carry_cnt + inc - 1] = x;
-      carry_cnt += tot2;
+      bool headq[RANK_ITEMS + 1];
+#pragma unroll
+      for (int q = 0; q <= RANK_ITEMS; ++q) {   // headq[q]: element x0+q starts a group (elements past the end do)
+        const u32 x = x0 + q;
+        headq[q] = x >= n || x == 0 || kk[q] != kk[q + 1] || vv[q + 1] + 4 > n || vv[q] + 4 > n;
+      }
+      u32 lmax = 0, ladd = 0; u32 gq[RANK_ITEMS]; u32 aq[RANK_ITEMS];
+#pragma unroll
+      for (int q = 0; q < RANK_ITEMS; ++q) {
+        const u32 x = x0 + q;
+        const bool act = x < n;
+        if (act && headq[q]) lmax = max(lmax, x);
+        gq[q] = lmax;
+        const bool amb = act && !(headq[q] && headq[q + 1]);
+        ladd += amb ? 1u : 0u;
+        aq[q] = amb ? ladd : 0u;
+      }
+      u32 smax = lmax, sadd = ladd, tmax, tadd;
+      block_scan_max_add<NT>(smax, sadd, sm, tmax, tadd);
+      // exclusive prefixes of this thread
+      const u32 up = __shfl_up_sync(ZQ_FULL, smax, 1);
+      const u32 exmax = max(carry_max, (tid & 31) ? up : ((tid >> 5) ? sm.wsum[(tid >> 5) - 1] : 0u));
+      const u32 exadd = carry_cnt + sadd - ladd;
+#pragma unroll
+      for (int q = 0; q < RANK_ITEMS; ++q) {
+        const u32 x = x0 + q;
+        if (x < n) {
+          const u32 i = vv[q + 1];
+          sa[x] = i;
+          rank[i] = max(gq[q], exmax);
+          if (aq[q]) pA[exadd + aq[q] - 1] = x;
+        }
+      }
+      carry_max = max(carry_max, tmax);
+      carry_cnt += tadd;
+      __syncthreads();
     }
     m = carry_cnt;
   }
   __syncthreads();
+  ZQ_PROF(1);
   // 3. doubling rounds over the ambiguous suffixes only
   const int bits_rank = zq_bitlen(n - 1), bits_key2 = zq_bitlen(n);
   for (u32 h = 4; m > 0; h <<= 1) {
@@ -275,33 +448,61 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
       vA[j] = i;
     }
     __syncthreads();
-    radix_sort_bits<NT>(kA, vA, kB, vB, m, 0, bits_key2, sm);
-    radix_sort_bits<NT>(kA, vA, kB, vB, m, 32, 32 + bits_rank, sm);
+    ZQ_PROF(2); ZQ_PROF_ADD(6, 1); ZQ_PROF_ADD(7, m);
+    if (2 * bits_rank + bits_key2 <= 64) sort_round_tiles<NT>(kA, vA, kB, vB, m, bits_key2, bits_rank, sm);
+    else {
+      radix_sort_bits<NT>(kA, vA, kB, vB, m, 0, bits_key2, sm);
+      radix_sort_bits<NT>(kA, vA, kB, vB, m, 32, 32 + bits_rank, sm);
+    }
+    ZQ_PROF(3);
     u32 carry_max = 0, carry_cnt = 0;
-    for (u32 b = 0; b < m; b += NT) {
-      const u32 j = b + tid;
-      const bool act = j < m;
-      u32 i = 0, x = 0; bool head = false, nexthead = true;
-      if (act) {
-        i = vA[j]; x = pA[j];
-        const u64 kj = kA[j];
-        head = j == 0 || kA[j - 1] != kj;
-        if (j + 1 < m) nexthead = kA[j + 1] != kj;
+    for (u32 b = 0; b < m; b += NT * RANK_ITEMS) {
+      const u32 j0 = b + tid * RANK_ITEMS;
+      u64 kk[RANK_ITEMS + 2]; u32 ii[RANK_ITEMS], xx[RANK_ITEMS];
+#pragma unroll
+      for (int q = 0; q < RANK_ITEMS + 2; ++q) {
+        const u32 j = j0 + q - 1;
+        kk[q] = (j0 + q >= 1 && j < m) ? kA[j] : 0;
       }
-      u32 tot;
-      u32 g = block_scan_incl_max<NT>(head ? x : 0u, sm, tot);
-      g = max(g, carry_max);
-      carry_max = max(carry_max, tot);
-      const bool amb = act && !(head && nexthead);
-      u32 tot2;
-      const u32 inc = block_scan_incl_add<NT>(amb ? 1u : 0u, sm, tot2);
-      if (act) { sa[x] = i; rank[i] = g; }   // keys were materialised before: safe to update in place
-      if (amb) pB[carry_cnt + inc - 1] = x;
-      carry_cnt += tot2;
+#pragma unroll
+      for (int q = 0; q < RANK_ITEMS; ++q) {
+        const bool act = j0 + q < m;
+        ii[q] = act ? vA[j0 + q] : 0; xx[q] = act ? pA[j0 + q] : 0;
+      }
+      bool headq[RANK_ITEMS + 1];
+#pragma unroll
+      for (int q = 0; q <= RANK_ITEMS; ++q) { const u32 j = j0 + q; headq[q] = j >= m || j == 0 || kk[q] != kk[q + 1]; }
+      u32 lmax = 0, ladd = 0; u32 gq[RANK_ITEMS]; u32 aq[RANK_ITEMS];
+#pragma unroll
+      for (int q = 0; q < RANK_ITEMS; ++q) {
+        const bool act = j0 + q < m;
+        if (act && headq[q]) lmax = max(lmax, xx[q]);
+        gq[q] = lmax;
+        const bool amb = act && !(headq[q] && headq[q + 1]);
+        ladd += amb ? 1u : 0u;
+        aq[q] = amb ? ladd : 0u;
+      }
+      u32 smax = lmax, sadd = ladd, tmax, tadd;
+      block_scan_max_add<NT>(smax, sadd, sm, tmax, tadd);
+      const u32 up = __shfl_up_sync(ZQ_FULL, smax, 1);
+      const u32 exmax = max(carry_max, (tid & 31) ? up : ((tid >> 5) ? sm.wsum[(tid >> 5) - 1] : 0u));
+      const u32 exadd = carry_cnt + sadd - ladd;
+#pragma unroll
+      for (int q = 0; q < RANK_ITEMS; ++q) {
+        if (j0 + q < m) {   // keys were materialised before: safe to update rank in place
+          sa[xx[q]] = ii[q];
+          rank[ii[q]] = max(gq[q], exmax);
+          if (aq[q]) pB[exadd + aq[q] - 1] = xx[q];
+        }
+      }
+      carry_max = max(carry_max, tmax);
+      carry_cnt += tadd;
+      __syncthreads();
     }
     m = carry_cnt;
     { u32* t = pA; pA = pB; pB = t; }
     __syncthreads();
+    ZQ_PROF(4);
   }
   // 4. outputs: sa, isa (= rank) and the capped LCP of SA neighbours
   const u64 stride = zq_work_stride(n, idx16 ? 2 : 4);
@@ -320,6 +521,7 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
     if (idx16) { ((u16*)w)[x] = (u16)b; ((u16*)(w + stride))[x] = (u16)rank[x]; }
     else { ((u32*)w)[x] = b; ((u32*)(w + stride))[x] = rank[x]; }
   }
+  ZQ_PROF(5);
 }
 
 // Grid-stride over the units of a wave that need a suffix array; scratch is per CTA.
