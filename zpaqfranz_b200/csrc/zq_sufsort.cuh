@@ -359,6 +359,13 @@ __device__ void sort_round_tiles(u64* kA, u32* vA, u64* kB, u32* vB, u32 m, int 
   }
 }
 
+// 4 bytes at any address (little endian) from the two aligned words around it; reads up to 7 bytes past p.
+__device__ __forceinline__ u32 ld32_unaligned(const u8* p) {
+  const uintptr_t q = (uintptr_t)p;
+  const u32* w = (const u32*)(q & ~(uintptr_t)3);
+  return __funnelshift_r(w[0], w[1], (u32)(q & 3) * 8);
+}
+
 // Builds the suffix array of T[0..n) in scratch (sa, rank = inverse SA) and writes sa | isa | lcp to
 // the unit's work region `w` with index width 2 (idx16) or 4 bytes.
 template <int NT>
@@ -513,8 +520,16 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
     const u32 b = sa[x];
     if (x > 0) {
       const u32 a = sa[x - 1];
-      const u32 lim = min(ZQ_LCP_CAP, n - max(a, b));
-      while (l < lim && T[a + l] == T[b + l]) ++l;
+      const u32 hi = max(a, b);
+      const u32 lim = min(ZQ_LCP_CAP, n - hi);
+      // four bytes per step while both (re-aligned) word pairs stay inside the block, then bytewise
+      bool done = false;
+      while (l + 4 <= lim && hi + l + 8 <= n) {
+        const u32 d = ld32_unaligned(T + a + l) ^ ld32_unaligned(T + b + l);
+        if (d) { l += (u32)(__ffs(d) - 1) >> 3; done = true; break; }
+        l += 4;
+      }
+      if (!done) while (l < lim && T[a + l] == T[b + l]) ++l;
     }
     lcp[x] = (u16)l;
     bwt[x] = b > 0 ? T[b - 1] : (u8)0;
