@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libzqb200.so")
+_LIB_PATH = os.environ.get("ZQ_LIB", os.path.join(_HERE, "libzqb200.so"))   # ZQ_LIB: tuning builds (zpaqfranz_b200/build.py)
 
 ZQ_OK, ZQ_E_NODEVICE, ZQ_E_ARG, ZQ_E_METHOD, ZQ_E_NOMEM, ZQ_E_OUTPUT, ZQ_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 

@@ -35,7 +35,10 @@ __device__ unsigned long long g_sort_prof[8];
 #define ZQ_PROF_ADD(k, v)
 #endif
 
-constexpr int SORT_ITEMS = 8;
+#ifndef ZQ_SORT_ITEMS
+#define ZQ_SORT_ITEMS 8
+#endif
+constexpr int SORT_ITEMS = ZQ_SORT_ITEMS;
 constexpr int RANK_ITEMS = 4;            // consecutive elements per thread in the ranking loops
 constexpr int SORT_MAXD = 256;           // digits per radix pass (8 bits)
 constexpr u32 ZQ_LCP_CAP = 256;
