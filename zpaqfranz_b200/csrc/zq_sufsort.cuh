@@ -436,8 +436,9 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
         if (x < n) {
           const u32 i = vv[q + 1];
           sa[x] = i;
-          rank[i] = max(gq[q], exmax);
-          if (aq[q]) pA[exadd + aq[q] - 1] = x;
+          const u32 g = max(gq[q], exmax);
+          rank[i] = g;
+          if (aq[q]) { const u32 c = exadd + aq[q] - 1; pA[c] = x; kB[c] = (u64)g << 32; vB[c] = i; }   // next round's list
         }
       }
       carry_max = max(carry_max, tmax);
@@ -445,17 +446,23 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
       __syncthreads();
     }
     m = carry_cnt;
+    { u64* tk = kA; kA = kB; kB = tk; u32* tv = vA; vA = vB; vB = tv; }
   }
   __syncthreads();
   ZQ_PROF(1);
   // 3. doubling rounds over the ambiguous suffixes only
   const int bits_rank = zq_bitlen(n - 1), bits_key2 = zq_bitlen(n);
   for (u32 h = 4; m > 0; h <<= 1) {
-    for (u32 j = tid; j < m; j += NT) {
-      const u32 i = sa[pA[j]];
-      const u32 k2 = i + h < n ? rank[i + h] + 1u : 0u;
-      kA[j] = ((u64)rank[i] << 32) | k2;
-      vA[j] = i;
+    // the list (kA = rank << 32, vA = suffix, pA = SA slot) was written by the previous ranking pass: only the
+    // second key is gathered here, four independent elements per thread
+    for (u32 j0 = tid; j0 < m; j0 += NT * 4) {
+      u32 ii[4], k2[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const u32 j = j0 + q * NT; ii[q] = j < m ? vA[j] : 0xffffffffu; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) k2[q] = (ii[q] != 0xffffffffu && ii[q] + h < n) ? rank[ii[q] + h] + 1u : 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const u32 j = j0 + q * NT; if (j < m) kA[j] |= k2[q]; }
     }
     __syncthreads();
     ZQ_PROF(2); ZQ_PROF_ADD(6, 1); ZQ_PROF_ADD(7, m);
@@ -501,8 +508,9 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
       for (int q = 0; q < RANK_ITEMS; ++q) {
         if (j0 + q < m) {   // keys were materialised before: safe to update rank in place
           sa[xx[q]] = ii[q];
-          rank[ii[q]] = max(gq[q], exmax);
-          if (aq[q]) pB[exadd + aq[q] - 1] = xx[q];
+          const u32 g = max(gq[q], exmax);
+          rank[ii[q]] = g;
+          if (aq[q]) { const u32 c = exadd + aq[q] - 1; pB[c] = xx[q]; kB[c] = (u64)g << 32; vB[c] = ii[q]; }
         }
       }
       carry_max = max(carry_max, tmax);
@@ -510,7 +518,7 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
       __syncthreads();
     }
     m = carry_cnt;
-    { u32* t = pA; pA = pB; pB = t; }
+    { u32* t = pA; pA = pB; pB = t; u64* tk = kA; kA = kB; kB = tk; u32* tv = vA; vA = vB; vB = tv; }
     __syncthreads();
     ZQ_PROF(4);
   }
