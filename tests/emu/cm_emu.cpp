@@ -1,0 +1,68 @@
+// cm_emu.cpp -- TEST INFRASTRUCTURE ONLY: runs the device code of the context-mixing coder
+// (zpaqfranz_b200/csrc/zq_cm.cuh, compiled for the host through tests/emu/simt_emu.h) on one block and
+// returns the arithmetic coder's bytes, so tests/test_cm_emu.py can compare them with the oracle on CPU.
+// Build: g++ -O1 -std=c++17 -Itests/emu/shim -Izpaqfranz_b200/csrc -shared -fPIC tests/emu/cm_emu.cpp
+//        zpaqfranz_b200/csrc/zq_cm_host.cpp zpaqfranz_b200/csrc/zq_config.cpp
+#include <cuda_runtime.h>   // the shim
+
+#include "zq_cm.cuh"
+#include "zq_cm_host.h"
+
+using namespace zqdev;
+
+namespace {
+void host_fill(const ZqCmFill& f, const zq::CmTables& t, u8* region) {
+  u8* dst = region + f.off;
+  switch (f.kind) {
+    case ZQ_FILL_ZERO: memset(dst, 0, f.bytes); break;
+    case ZQ_FILL_MATCHBUF: memset(dst, 0, f.bytes); dst[0] = 1; break;
+    case ZQ_FILL_U32: for (u64 k = 0; k + 4 <= f.bytes; k += 4) memcpy(dst + k, &f.value, 4); break;
+    case ZQ_FILL_U16: { const u16 v = (u16)f.value; for (u64 k = 0; k + 2 <= f.bytes; k += 2) memcpy(dst + k, &v, 2); } break;
+    case ZQ_FILL_SSE:
+      for (u64 k = 0; k + 4 <= f.bytes; k += 4) {
+        const u32 j = (u32)(k / 4);
+        const u32 v = (u32)t.squash[(j & 31) * 64 - 992 + 2048] << 17 | f.value;
+        memcpy(dst + k, &v, 4);
+      }
+      break;
+    case ZQ_FILL_ICM: memcpy(dst, t.icm_init, f.bytes); break;
+    case ZQ_FILL_ISSE: memcpy(dst, t.isse_init, f.bytes); break;
+  }
+}
+}  // namespace
+
+// header: block header bytes (hsize .. hcomp 0); payload: selector (+PCOMP) bytes coded before the stream.
+// Returns the number of coded bytes written to out, or a negative error.
+extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_t* payload, uint32_t plen,
+                              const uint8_t* stream, uint32_t slen, uint8_t* out, uint32_t cap, int threads) {
+  try {
+    size_t used = 0;
+    zq::Assembled code = zq::parse_block_header(header, hlen, &used);
+    std::vector<ZqCmFill> fills;
+    ZqCmPlan cp = zq::make_cm_plan(code, fills);
+    const zq::CmTables& tab = zq::cm_tables();
+    std::vector<u8> blob(payload, payload + plen);
+    cp.hcomp_off = (u32)blob.size(); cp.hcomp_len = (u32)code.hcomp.size();
+    blob.insert(blob.end(), code.hcomp.begin(), code.hcomp.end());
+    u8* model = (u8*)aligned_alloc(256, (size_t)cp.model_bytes + 256);
+    for (u32 j = 0; j < cp.fill_count; ++j) host_fill(fills[cp.fill_first + j], tab, model);
+    ZqUnit u; memset(&u, 0, sizeof u);
+    u.n = slen; u.plan = 0; u.coded_cap = cap;
+    ZqPlan pl; memset(&pl, 0, sizeof pl);
+    pl.payload_off = 0; pl.payload_len = plen; pl.lz_level = 0; pl.modeled = 1; pl.cm_plan = 0;
+    int todo = 0;
+    u32 coded_len = 0, err = 0, next = 0, lzlen = slen;
+    static_assert(sizeof(CmTablesDev) == sizeof(zq::CmTables), "table layout");
+    const CmTablesDev* dtab = (const CmTablesDev*)&tab;
+    emu::launch(1, (unsigned)threads, sizeof(CmSmem), [&] {
+      k_cm_encode<1>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next);
+    });
+    free(model);
+    if (err) return -(long)err;
+    return (long)coded_len;
+  } catch (const zq::Error& e) {
+    fprintf(stderr, "emu_cm_encode: %s\n", e.msg.c_str());
+    return -100;
+  }
+}
+extern "C" unsigned long long emu_collectives() { return emu::collectives; }

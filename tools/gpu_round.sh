@@ -1,0 +1,32 @@
+#!/bin/bash
+# One gpurun call: bench lines (both arms), GPU parity tests, ncu launch list + full captures.
+# usage: gpurun --timeout 1000 -- 'bash tools/gpu_round.sh <tag> [steps...]'   (steps: bench tests launches ncu_m2 ncu_cm)
+TAG=${1:-r01h}; shift
+STEPS=${*:-bench tests launches ncu_m2 ncu_cm}
+O=gpurun_out; mkdir -p $O
+NCU="ncu --clock-control none"
+for s in $STEPS; do
+  t0=$(date +%s)
+  case $s in
+    bench)
+      timeout 300 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
+      timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err ;;
+    tests)
+      timeout 600 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1; tail -3 $O/${TAG}_pytest_gpu.log ;;
+    launches)
+      timeout 300 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/${TAG}_launches_bench_m2.csv \
+        python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${TAG}_launches_bench.log 2>&1 ;;
+    ncu_m2)
+      timeout 300 $NCU --set full --import-source on -k regex:'k_lz77_sa|k_suffix_sort' -c 2 -f -o $O/${TAG}_m2 \
+        python tools/prof_step.py --units 2000 --steps 1 > $O/${TAG}_ncu_m2.log 2>&1 ;;
+    ncu_cm)
+      timeout 300 $NCU --set full --import-source on -k regex:k_cm_encode -c 1 -f -o $O/${TAG}_cm_bwt \
+        python tools/prof_step.py --method 36,200,1 --units 592 --unit 16384 --steps 1 > $O/${TAG}_ncu_cm_bwt.log 2>&1
+      timeout 300 $NCU --set full --import-source on -k regex:k_cm_encode -c 1 -f -o $O/${TAG}_cm_m5 \
+        python tools/prof_step.py --method 5 --units 64 --unit 8192 --steps 1 > $O/${TAG}_ncu_cm_m5.log 2>&1 ;;
+    cmtime)
+      timeout 400 python tools/bench_configs.py --skip c4 --c5-units 1200 > $O/${TAG}_configs_c3_c5.json 2> $O/${TAG}_configs.err ;;
+    *) eval "$s" ;;
+  esac
+  echo "[$s] rc=$? $(( $(date +%s) - t0 )) s"
+done

@@ -384,7 +384,8 @@ __device__ void cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y, CmVm& vm)
   }
   X.c8 += X.c8 + y;
   if (X.c8 >= 256) {
-    cm_vm_run(vm, (u32)(X.c8 - 256));
+    if (lane == 0) cm_vm_run(vm, (u32)(X.c8 - 256));   // one lane owns the machine: no same-address races
+    __syncwarp();
     X.hmap4 = 1; X.c8 = 1;
     if ((int)lane < X.n) L.h = vm.h[lane & vm.hmask];
   } else if (X.c8 >= 16 && X.c8 < 32)
@@ -411,7 +412,7 @@ k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, co
             const CmTablesDev* __restrict__ tab, const u8* __restrict__ blob, const u8* __restrict__ lz_base,
             const u32* __restrict__ lz_len, u8* __restrict__ model_base, u8* __restrict__ coded_base,
             u32* __restrict__ coded_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ZQ_DYN_SMEM(smem_raw);
   CmSmem& T = *reinterpret_cast<CmSmem*>(smem_raw);
   {
     const uint4* src = (const uint4*)tab;

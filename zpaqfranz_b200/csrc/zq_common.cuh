@@ -43,10 +43,16 @@ __host__ __device__ inline u64 zq_work_stride(u32 n, u32 w) { return (((u64)n + 
 __host__ __device__ inline u64 zq_work_bytes(u32 n, u32 w) { return 2 * zq_work_stride(n, w) + zq_work_stride(n, 2) + zq_work_stride(n, 1); }
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+#ifdef ZQ_EMU   // host SIMT emulator build (tests/emu): no PTX, dynamic shared memory is a plain pointer
+__device__ __forceinline__ u32 lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+#define ZQ_DYN_SMEM(name) unsigned char* name = emu::dyn_smem
+#else
 __device__ __forceinline__ u32 lanemask_lt() {
   u32 m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
 }
+#define ZQ_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 // floor(log2(x))+1, 0 for 0 (== reference lg(), Z:19269)
 __device__ __forceinline__ int zq_bitlen(u32 x) { return 32 - __clz(x); }

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(512, 1)
 k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units, const ZqCmPlan* __restrict__ cmplans, int nunits,
             const CmTablesDev* __restrict__ tab, const u8* __restrict__ blob, u8* __restrict__ model_base,
             u8* __restrict__ out_base, ZqDecResult* __restrict__ results, u32* __restrict__ next_unit) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ZQ_DYN_SMEM(smem_raw);
   CmSmem& T = *reinterpret_cast<CmSmem*>(smem_raw);
   {
     const uint4* src = (const uint4*)tab;
