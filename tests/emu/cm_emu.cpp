@@ -5,7 +5,11 @@
 //        zpaqfranz_b200/csrc/zq_cm_host.cpp zpaqfranz_b200/csrc/zq_config.cpp
 #include <cuda_runtime.h>   // the shim
 
-#include "zq_cm.cuh"
+#ifdef ZQ_CM_V1
+#include "zq_decode_v1.cuh"
+#else
+#include "zq_decode.cuh"
+#endif
 #include "zq_cm_host.h"
 
 using namespace zqdev;
@@ -34,7 +38,8 @@ void host_fill(const ZqCmFill& f, const zq::CmTables& t, u8* region) {
 // header: block header bytes (hsize .. hcomp 0); payload: selector (+PCOMP) bytes coded before the stream.
 // Returns the number of coded bytes written to out, or a negative error.
 extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_t* payload, uint32_t plen,
-                              const uint8_t* stream, uint32_t slen, uint8_t* out, uint32_t cap, int threads) {
+                              const uint8_t* stream, uint32_t slen, uint8_t* out, uint32_t cap, int threads, int prefetch) {
+  (void)prefetch;
   try {
     size_t used = 0;
     zq::Assembled code = zq::parse_block_header(header, hlen, &used);
@@ -54,14 +59,56 @@ extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_
     u32 coded_len = 0, err = 0, next = 0, lzlen = slen;
     static_assert(sizeof(CmTablesDev) == sizeof(zq::CmTables), "table layout");
     const CmTablesDev* dtab = (const CmTablesDev*)&tab;
+#ifdef ZQ_CM_V1
     emu::launch(1, (unsigned)threads, sizeof(CmSmem), [&] {
       k_cm_encode<1>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next);
     });
+#else
+    const unsigned block = (unsigned)threads < 64 ? 64u : (unsigned)threads & ~63u;   // whole (coder, context) pairs
+    emu::launch(1, block, sizeof(CmSmem) + (block / 64) * sizeof(CmUnitSmem), [&] {
+      k_cm_encode(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch);
+    });
+#endif
     free(model);
     if (err) return -(long)err;
     return (long)coded_len;
   } catch (const zq::Error& e) {
     fprintf(stderr, "emu_cm_encode: %s\n", e.msg.c_str());
+    return -100;
+  }
+}
+// Decodes the coded data of one block (everything after the segment header) with the device decoder.
+// Returns the number of restored bytes or -(1000 + device error code).
+extern "C" long emu_cm_decode(const uint8_t* header, uint32_t hlen, const uint8_t* coded, uint32_t clen, uint8_t* out, uint32_t cap) {
+  try {
+    size_t used = 0;
+    zq::Assembled code = zq::parse_block_header(header, hlen, &used);
+    std::vector<ZqCmFill> fills;
+    ZqCmPlan cp;
+    if (code.ncomp > 0) cp = zq::make_cm_plan(code, fills);
+    else { memset(&cp, 0, sizeof cp); cp.hh = code.hh; cp.hm = code.hm; cp.fill_first = 0; }
+    zq::add_pcomp_region(cp, code.ph, code.pm, fills);
+    const zq::CmTables& tab = zq::cm_tables();
+    std::vector<u8> blob(code.hcomp.begin(), code.hcomp.end());
+    cp.hcomp_off = 0; cp.hcomp_len = (u32)code.hcomp.size();
+    u8* model = (u8*)aligned_alloc(256, (size_t)cp.model_bytes + 256);
+    for (u32 j = 0; j < cp.fill_count; ++j) host_fill(fills[cp.fill_first + j], tab, model);
+    ZqDecUnit u; memset(&u, 0, sizeof u);
+    u.data_off = 0; u.data_len = clen; u.out_off = 0; u.model_off = 0; u.out_cap = cap; u.plan = 0;
+    ZqDecResult res; memset(&res, 0, sizeof res);
+    u32 next = 0;
+    const CmTablesDev* dtab = (const CmTablesDev*)&tab;
+#ifdef ZQ_CM_V1
+    const size_t smem = sizeof(CmSmem);
+#else
+    const size_t smem = sizeof(CmSmem) + sizeof(CmUnitSmem);
+#endif
+    emu::launch(1, 32, smem, [&] { k_cm_decode(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next); });
+    free(model);
+    if (res.error) return -(1000 + (long)res.error);
+    return (long)res.out_len;
+  } catch (const zq::Error& e) {
+    fprintf(stderr, "emu_cm_decode: %s\n", e.msg.c_str());
     return -100;
   }
 }

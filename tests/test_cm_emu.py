@@ -1,0 +1,104 @@
+"""The context-mixing coder's DEVICE code (zpaqfranz_b200/csrc/zq_cm.cuh, zq_decode.cuh) compiled for the host
+through the SIMT emulator (tests/emu/simt_emu.h) and checked bit for bit against the oracle, no GPU needed.
+
+This pins the warp-level logic -- lane = component mapping, the (coder, context) warp pair and its ring, the
+flat-switch ZPAQL interpreter, shared-memory row cache -- on CPU; the GPU tests then only have to show the
+hardware runs the same program.  The emulator is test infrastructure: nothing on the product path uses it."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+import zpaqfranz_b200 as zq
+from zpaqfranz_b200 import corpus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "zpaqfranz_b200", "csrc")
+
+CONFIGS = {
+    "cm_o1": "comp 2 2 0 0 1 0 cm 18 255 hcomp *d=a a<<= 8 *d=a halt end",
+    "icm_chain_mix2_sse": ("comp 3 3 0 0 7 0 icm 12 1 isse 14 0 2 cm 16 32 3 match 14 16 4 mix2 8 1 2 20 255 "
+                           "5 sse 10 4 16 255 6 avg 4 5 96 "
+                           "hcomp c++ *c=a b=c a=0 d= 0 hash *d=a d++ b-- hash *d=a d++ a=*c a<<= 9 *d=a d++ "
+                           "b=c a=0 hash b-- hash b-- hash *d=a d++ a=*c *d=a d++ a=*c a>>= 3 *d=a halt end"),
+    "branches": ("comp 2 4 0 0 3 0 cm 14 8 1 cm 16 20 2 mix 8 0 2 30 255 "
+                 "hcomp *c=a c++ a== 32 if d= 0 *d=0 else d= 0 a+=*d a*= 73 *d=a endif "
+                 "d= 1 a=*c a^= 255 *d=a d= 2 a=c a&= 7 *d=a halt end"),
+    "const_only_mix": "comp 0 0 0 0 3 0 const 200 1 cm 10 4 2 mix 0 0 2 14 0 hcomp halt end",
+    # four mixers (the third and fourth take the generic weight path), a mixer feeding a mixer, H beyond shared memory
+    "four_mixers_big_h": ("comp 11 8 0 0 8 0 cm 12 16 1 icm 10 2 isse 10 1 3 mix 6 0 3 20 255 4 mix 0 0 4 24 0 "
+                          "5 mix 8 1 4 16 15 6 mix 4 0 6 28 255 7 mix2 6 5 6 12 255 "
+                          "hcomp *c=a c++ d= 0 *d=a d++ b=c b-- a=*b hash *d=a d++ hash *d=a d++ a=*c a<<= 4 *d=a d++ "
+                          "a=c *d=a d++ a=*c a>>= 2 *d=a d++ *d=0 d++ a=*c *d=a a= 3 a<<= 8 d=a *d=c halt end"),
+}
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libcmemu.so")
+    srcs = [os.path.join(EMU, "cm_emu.cpp"), os.path.join(CSRC, "zq_cm_host.cpp"), os.path.join(CSRC, "zq_config.cpp")]
+    deps = srcs + [os.path.join(EMU, "simt_emu.h"), os.path.join(CSRC, "zq_cm.cuh"), os.path.join(CSRC, "zq_decode.cuh"),
+                   os.path.join(CSRC, "zq_common.cuh")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC,
+                        "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-o", lib] + srcs, check=True)
+    h = C.CDLL(lib)
+    h.emu_cm_encode.restype = C.c_long
+    h.emu_cm_decode.restype = C.c_long
+    return h
+
+
+def _coded_by_oracle(oracle, header, pcomp, stream):
+    blk = oracle.block_modeled(header, pcomp, b"", b"", stream, None)
+    pre = 13 + 5 + len(header) + 4          # tag, zPQ level 1, header, 01 "" 00 "" 00 00
+    return blk[pre:-6]                       # ... coded ... 00 00 00 00 FE FF
+
+
+def _emu_encode(emu, header, pcomp, stream, threads=64, prefetch=1):
+    payload = (bytes([1, len(pcomp) & 255, len(pcomp) >> 8]) + pcomp) if pcomp else b"\0"
+    cap = len(stream) * 2 + len(payload) * 2 + 4096
+    out = (C.c_uint8 * cap)()
+    n = emu.emu_cm_encode(header, len(header), payload, len(payload), stream, len(stream), out, cap, threads, prefetch)
+    assert n >= 0, n
+    return bytes(out[:n])
+
+
+def _emu_decode(emu, header, coded, cap):
+    out = (C.c_uint8 * (cap + 16))()
+    n = emu.emu_cm_decode(header, len(header), coded, len(coded), out, cap + 16)
+    assert n >= 0, n
+    return bytes(out[:n])
+
+
+@pytest.mark.parametrize("method", ["36,200,1", "3", "4", "5", "46,200,1", "412,100,0"])
+def test_builtin_models_encode_and_decode(emu, oracle, method):
+    data = corpus.text_unit(3, 1200) if method != "412,100,0" else corpus.mixed_unit(5, 1200)
+    plan = zq.plan_block(method, data)
+    header, pcomp = bytes(plan["header"]), bytes(plan["pcomp"])
+    stream = oracle.lz_stream(data, plan["args"]) if (plan["args"][1] & 3) else data
+    want = _coded_by_oracle(oracle, header, pcomp, stream)
+    assert _emu_encode(emu, header, pcomp, stream) == want
+    # decoder: coded data + end-of-stream zeros -> post-processed original
+    assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data)) == data
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_custom_models_encode_and_decode(emu, oracle, name):
+    header = bytes(zq.assemble_config(CONFIGS[name])["header"])
+    for data in (b"", b"x", b"abracadabra" * 30, corpus.text_unit(9, 700), corpus.random_unit(5, 300)):
+        want = _coded_by_oracle(oracle, header, b"", data)
+        assert _emu_encode(emu, header, b"", data) == want, (name, len(data))
+        assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data)) == data, (name, len(data))
+
+
+def test_pairs_share_a_cta_and_prefetch_is_transparent(emu, oracle):
+    data = corpus.text_unit(11, 600)
+    plan = zq.plan_block("4", data)
+    header = bytes(plan["header"])
+    want = _coded_by_oracle(oracle, header, b"", data)
+    assert _emu_encode(emu, header, b"", data, threads=192, prefetch=0) == want   # idle pairs leave through the queue
+    assert _emu_encode(emu, header, b"", data, threads=64, prefetch=1) == want

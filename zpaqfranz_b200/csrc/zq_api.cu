@@ -12,11 +12,19 @@
 #include <vector>
 
 #include "../../include/zq_b200.h"
+#ifdef ZQ_CM_V1   // first CM engine (one warp per block, interpreter inline), kept for A/B builds
+#include "zq_cm_v1.cuh"
+#else
 #include "zq_cm.cuh"
+#endif
 #include "zq_cm_host.h"
 #include "zq_common.cuh"
 #include "zq_config.h"
+#ifdef ZQ_CM_V1
+#include "zq_decode_v1.cuh"
+#else
 #include "zq_decode.cuh"
+#endif
 #include "zq_fragment.cuh"
 #include "zq_frame.cuh"
 #include "zq_hashes.cuh"
@@ -72,7 +80,8 @@ struct zq_ctx {
   int sort_nt = 256, sort_minb = 4;       // suffix-sort CTA size and CTAs per SM (measured best: 95.9 ms vs 103.5 ms at 512x2)
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 1;                         // 1: warp-per-block LZ77 parser (default, faster today); 0: candidates/chain/emit form (ZQ_LZ_PAR=1)
-  int cm_occ = 2;                         // CTAs (16 warps) per SM of the CM coder
+  int cm_occ = 2;                         // first engine only: CTAs (16 warps) per SM of the CM coder
+  int cm_prefetch = 1;                    // context warp prefetches the coder's table lines (ZQ_CM_PREFETCH=0 to turn off)
   int lz_half = 0;                        // 1: SA parse with two blocks per warp (ZQ_LZ_HALF=1; bit-exact, slower today: the halves serialise)
   int lz_occ = 6;                         // CTAs (4 warps) per SM the LZ parse kernel is compiled for
 };
@@ -475,6 +484,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       k_cm_init<<<nt * maxjobs, 256, 0, c->stream>>>(du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_fills.as<ZqCmFill>(), c->d_todo3.as<int>(), nt,
                                                      maxjobs, c->d_tables.as<CmTablesDev>(), c->d_model.as<u8>());
       ++c->launches;
+#ifdef ZQ_CM_V1
       if (!c->attr_cm_enc) {   // per context (= per device): function attributes are per device
         cudaFuncSetAttribute(k_cm_encode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem));
         cudaFuncSetAttribute(k_cm_encode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem));
@@ -485,6 +495,19 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       cmk<<<cgrid, 512, sizeof(CmSmem), c->stream>>>(d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt,
                                                              c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(),
                                                              c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr);
+#else
+      // (coder, context) warp pairs: as many per CTA as spreads the wave over all SMs
+      const int pairs = std::max(1, std::min(ZQ_CM_MAX_PAIRS, (nt + c->num_sms - 1) / c->num_sms));
+      const size_t cm_smem = sizeof(CmSmem) + (size_t)pairs * sizeof(CmUnitSmem);
+      if (!c->attr_cm_enc) {   // per context (= per device): function attributes are per device
+        cudaFuncSetAttribute(k_cm_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CmSmem) + ZQ_CM_MAX_PAIRS * sizeof(CmUnitSmem)));
+        c->attr_cm_enc = true;
+      }
+      k_cm_encode<<<std::min((nt + pairs - 1) / pairs, c->num_sms), pairs * 64, cm_smem, c->stream>>>(
+          d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
+          c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr,
+          c->cm_prefetch);
+#endif
       ++c->launches;
       tstop(c, 5);
       ZQ_CUDA(c, cudaMemcpyAsync(coded_len_h.data() + w0, c->d_codedlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -599,6 +622,7 @@ zq_ctx* zq_create(int device) {
   if (const char* s = getenv("ZQ_LZ_OCC")) c->lz_occ = atoi(s);
   if (const char* s = getenv("ZQ_LZ_HALF")) c->lz_half = atoi(s);
   if (const char* s = getenv("ZQ_CM_OCC")) c->cm_occ = atoi(s);
+  if (const char* s = getenv("ZQ_CM_PREFETCH")) c->cm_prefetch = atoi(s);
   if (const char* s = getenv("ZQ_LZ_PAR")) c->lz_old = atoi(s) ? 0 : 1;
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
   if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);
@@ -869,7 +893,12 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
   size_t budget = c->model_budget;
   { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); fr += c->d_model.cap; budget = std::min<size_t>(budget, fr > ((size_t)6 << 30) ? fr - ((size_t)6 << 30) : fr / 2); }
   std::vector<ZqDecResult> res(n);
-  if (!c->attr_cm_dec) { cudaFuncSetAttribute(k_cm_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem)); c->attr_cm_dec = true; }
+#ifdef ZQ_CM_V1
+  const size_t dec_smem = sizeof(CmSmem);
+#else
+  const size_t dec_smem = sizeof(CmSmem) + 16 * sizeof(CmUnitSmem);
+#endif
+  if (!c->attr_cm_dec) { cudaFuncSetAttribute(k_cm_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem); c->attr_cm_dec = true; }
   int w0 = 0;
   while (w0 < n) {
     size_t model = 0; int w1 = w0, maxjobs = 1;
@@ -895,7 +924,7 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
     k_cm_init_pairs<<<wn * maxjobs, 256, 0, c->stream>>>(d_moff, d_pof, c->d_cmplans.as<ZqCmPlan>(), c->d_fills.as<ZqCmFill>(), wn, maxjobs,
                                                         c->d_tables.as<CmTablesDev>(), c->d_model.as<u8>());
     ++c->launches;
-    k_cm_decode<<<std::min((wn + 15) / 16, c->num_sms), 512, sizeof(CmSmem), c->stream>>>(
+    k_cm_decode<<<std::min((wn + 15) / 16, c->num_sms), 512, dec_smem, c->stream>>>(
         c->d_in.as<u8>(), c->d_units.as<ZqDecUnit>(), c->d_cmplans.as<ZqCmPlan>(), wn, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
         c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr);
     ++c->launches;

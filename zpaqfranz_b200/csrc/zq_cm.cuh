@@ -1,19 +1,29 @@
 // zq_cm.cuh -- the ZPAQ context-mixing compressor (methods -m3/-m4/-m5 and any explicit model of
 // <= 32 components): HCOMP virtual machine, component chain, logistic mixing and the binary
-// arithmetic coder.  One WARP per block, LANE i = COMPONENT i.
+// arithmetic coder.  Second engine (the first one is kept as zq_cm_v1.cuh, build flag -DZQ_CM_V1).
 //
 // Replaces (bit-exactly): ZPAQL::run0/execute Z:14232-14467, Predictor::predict0 Z:15041,
 // update0 Z:15139, find Z:15254, train Z:13161, Encoder::encode/compress Z:15557-15589.
 //
-// Why this mapping: coding is a strict per-bit recurrence (the next probability needs the previous
-// bit's updates), so a block cannot be split; but inside one bit every component does an independent
-// dependent-gather (hash row -> bit history -> adaptive probability) into its own tables.  On the
-// CPU those are n serial cache misses per bit; here the n lanes issue them at once and only the
-// final arithmetic (ISSE chains, MIX dot products, SSE interpolation) is resolved in dependency
-// levels with warp shuffles / one REDUX per mixer.  Component tables live in HBM (up to ~85 MB per
-// block for -m5); the 78 KB of model-independent tables (stretch, squash, dt, state table) are
-// staged into shared memory once per CTA.  ICM/ISSE hash rows (16 B) are held in registers for the
-// four bits of a nibble and written back on the next row switch.
+// Mapping.  Coding is a strict per-bit recurrence, so a block cannot be split along its bytes; what
+// can be separated is the block's two machines:
+//   * the CONTEXT machine (HCOMP, run once per byte) only ever looks at bytes that are already known
+//     to the compressor, so in the encoder it runs AHEAD of the coder on its own warp and hands the
+//     context hashes H[0..n) of each byte to the coder through a small shared-memory ring.  While it
+//     is there it also prefetches, for the byte the coder will reach a few bytes later, the hash rows
+//     / table lines every component is going to touch (their addresses depend on H and on the byte).
+//   * the CODER warp: LANE i = COMPONENT i.  Per bit all lanes gather from their own tables at once
+//     (hash row -> bit history -> adaptive probability; mixer weights are fetched in the same phase,
+//     their row does not depend on the predictions); ISSE chains / MIX2 / SSE / AVG are resolved in
+//     host-computed dependency levels with shuffles; each MIX is one multiply per input lane and one
+//     REDUX add.  ICM/ISSE 16-byte hash rows are cached in shared memory for the four bits of a nibble.
+// One (coder, context) warp pair per block; a CTA holds up to 12 pairs next to the 78 KB of
+// model-independent tables (stretch, squash, dt, state table).  The decoder cannot run the context
+// machine ahead (the byte is only known once decoded): there one warp does both, machine on lane 0.
+// ncu of the first engine (profiles/r01h_cm_*): 2 800 (-m3) to 14 500 (-m5) dependent warp
+// instructions per byte at IPC 0.1/warp, 30-60 % of them in the byte-code interpreter -- latency of
+// the instruction stream, not memory, was the limit; hence the flat-switch interpreter on shared-memory
+// byte code, the shared-memory row cache and the overlap of the two machines.
 #pragma once
 #include "zq_cm_types.h"
 #include "zq_common.cuh"
@@ -36,6 +46,29 @@ struct CmSmem {           // what the coder needs per bit
   int dt2k[256];
   u8 ns[1024];
 };
+
+#define ZQ_CM_RING 8          // context vectors in flight between the two warps of a pair
+#define ZQ_CM_CODE_CAP 1024   // HCOMP byte code staged to shared memory up to this size
+#define ZQ_CM_HBUF 512        // H[] lives in shared memory up to 2^9 words (every built-in model)
+struct CmUnitSmem {           // shared-memory working set of one block in flight
+  u32 ring[ZQ_CM_RING][32];   // H[lane] after byte k, slot k % ZQ_CM_RING
+  u8 rows[32][16];            // lane's current ICM/ISSE hash row
+  u32 hbuf[ZQ_CM_HBUF];
+  u8 code[ZQ_CM_CODE_CAP];
+  volatile u32 produced, consumed;   // context vectors written / taken
+  volatile int unit;
+  u32 pad;
+};
+
+#ifdef ZQ_EMU
+__device__ __forceinline__ void zq_pair_sync(u32 id) { emu::barrier((int)id, 64); }
+__device__ __forceinline__ void zq_prefetch_l1(const void*) {}
+__device__ __forceinline__ void zq_prefetch_l2(const void*) {}
+#else
+__device__ __forceinline__ void zq_pair_sync(u32 id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void zq_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void zq_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 
 // ---- model initialisation ------------------------------------------------------------------------
 // One CTA writes one fill job (a table's initial values, Z:14968-15032) of one unit's model region.
@@ -108,136 +141,136 @@ struct CmCoder {
   }
 };
 
-struct CmVm {   // HCOMP machine; registers are warp-uniform
+// ---- ZPAQL machine -------------------------------------------------------------------------------
+struct CmVm {   // registers live on the lane that owns the machine (lane 0)
   u32 a, b, c, d; int f;
   u8* m; u32* h; u32* r;
   u32 mmask, hmask;
   const u8* code; int len;
   int error;
 };
+struct VmOut { u8* out; u32 len, cap, error; };   // PCOMP's OUT sink (decoder)
 
-// One HCOMP run (Z:14232). Every lane executes the same instruction stream; stores are issued by all
-// lanes with identical address and value, so each lane later reads back what it wrote itself.
-__device__ void cm_vm_run(CmVm& v, u32 input) {
-  const u8* __restrict__ P = v.code;
-  int pc = 0;
+// One run of the program (ZPAQL::run0, Z:14232) by ONE lane.  A single switch over the opcode byte:
+// the two-operand group (opcode >= 64: operation = op>>3, source = op&7) is expanded case by case so the
+// dispatch is one indirect branch per instruction.
+#define ZQ_VM_X8(B, STMT)                                                  \
+  case (B) + 0: { const u32 x = a; STMT; } break;                          \
+  case (B) + 1: { const u32 x = b; STMT; } break;                          \
+  case (B) + 2: { const u32 x = c; STMT; } break;                          \
+  case (B) + 3: { const u32 x = d; STMT; } break;                          \
+  case (B) + 4: { const u32 x = M[b & mm]; STMT; } break;                  \
+  case (B) + 5: { const u32 x = M[c & mm]; STMT; } break;                  \
+  case (B) + 6: { const u32 x = H[d & hm]; STMT; } break;                  \
+  case (B) + 7: { const u32 x = P[pc++]; STMT; } break;
+template <bool WITH_OUT>
+__device__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) {
+  const u8* P = v.code;
+  u8* M = v.m; u32* H = v.h; u32* R = v.r;
+  const u32 mm = v.mmask, hm = v.hmask;
+  const int len = v.len;
+  int pc = 0, stop = 0;
   u32 a = input, b = v.b, c = v.c, d = v.d; int f = v.f;
-#define ZQ_MB v.m[b & v.mmask]
-#define ZQ_MC v.m[c & v.mmask]
-#define ZQ_HD v.h[d & v.hmask]
-  for (;;) {
-    if (pc >= v.len) { v.error = 1; break; }
-    const int op = P[pc++];
-    if (op == 56) break;
-    if (op >= 64) {
-      if (op == 255) { pc = P[pc] + 256 * P[pc + 1]; continue; }
-      const int src = op & 7, grp = op >> 3;
-      u32 x;
-      switch (src) {
-        case 0: x = a; break; case 1: x = b; break; case 2: x = c; break; case 3: x = d; break;
-        case 4: x = ZQ_MB; break; case 5: x = ZQ_MC; break; case 6: x = ZQ_HD; break;
-        default: x = P[pc++];
-      }
-      switch (grp) {
-        case 8: a = x; break; case 9: b = x; break; case 10: c = x; break; case 11: d = x; break;
-        case 12: ZQ_MB = (u8)x; break; case 13: ZQ_MC = (u8)x; break; case 14: ZQ_HD = x; break;
-        case 16: a += x; break; case 17: a -= x; break; case 18: a *= x; break;
-        case 19: a = x ? a / x : 0; break; case 20: a = x ? a % x : 0; break;
-        case 21: a &= x; break; case 22: a &= ~x; break; case 23: a |= x; break; case 24: a ^= x; break;
-        case 25: a <<= (x & 31); break; case 26: a >>= (x & 31); break;
-        case 27: f = a == x; break; case 28: f = a < x; break; case 29: f = a > x; break;
-        default: v.error = 1;
-      }
-      if (v.error) break;
-      continue;
-    }
+  while (!stop) {
+    if ((u32)pc >= (u32)len) { stop = 2; break; }
+    const u32 op = P[pc++];
     switch (op) {
       case 1: ++a; break; case 2: --a; break; case 3: a = ~a; break; case 4: a = 0; break;
-      case 7: a = v.r[P[pc++]]; break;
+      case 7: a = R[P[pc++]]; break;
       case 8: { const u32 t = a; a = b; b = t; } break;
       case 9: ++b; break; case 10: --b; break; case 11: b = ~b; break; case 12: b = 0; break;
-      case 15: b = v.r[P[pc++]]; break;
+      case 15: b = R[P[pc++]]; break;
       case 16: { const u32 t = a; a = c; c = t; } break;
       case 17: ++c; break; case 18: --c; break; case 19: c = ~c; break; case 20: c = 0; break;
-      case 23: c = v.r[P[pc++]]; break;
+      case 23: c = R[P[pc++]]; break;
       case 24: { const u32 t = a; a = d; d = t; } break;
       case 25: ++d; break; case 26: --d; break; case 27: d = ~d; break; case 28: d = 0; break;
-      case 31: d = v.r[P[pc++]]; break;
-      case 32: { const u8 t = ZQ_MB; ZQ_MB = (u8)a; a = (a & ~255u) | t; } break;
-      case 33: ZQ_MB = ZQ_MB + 1; break; case 34: ZQ_MB = ZQ_MB - 1; break; case 35: ZQ_MB = ~ZQ_MB; break; case 36: ZQ_MB = 0; break;
-      case 39: if (f) pc += ((P[pc] + 128) & 255) - 127; else ++pc; break;
-      case 40: { const u8 t = ZQ_MC; ZQ_MC = (u8)a; a = (a & ~255u) | t; } break;
-      case 41: ZQ_MC = ZQ_MC + 1; break; case 42: ZQ_MC = ZQ_MC - 1; break; case 43: ZQ_MC = ~ZQ_MC; break; case 44: ZQ_MC = 0; break;
-      case 47: if (!f) pc += ((P[pc] + 128) & 255) - 127; else ++pc; break;
-      case 48: { const u32 t = ZQ_HD; ZQ_HD = a; a = t; } break;
-      case 49: ZQ_HD = ZQ_HD + 1; break; case 50: ZQ_HD = ZQ_HD - 1; break; case 51: ZQ_HD = ~ZQ_HD; break; case 52: ZQ_HD = 0; break;
-      case 55: v.r[P[pc++]] = a; break;
-      case 57: break;   // OUT: HCOMP has no output
-      case 59: a = (a + ZQ_MB + 512) * 773; break;
-      case 60: ZQ_HD = (ZQ_HD + a + 512) * 773; break;
-      case 63: pc += ((P[pc] + 128) & 255) - 127; break;
-      default: v.error = 1;
+      case 31: d = R[P[pc++]]; break;
+      case 32: { const u32 t = M[b & mm]; M[b & mm] = (u8)a; a = (a & ~255u) | t; } break;
+      case 33: M[b & mm] = (u8)(M[b & mm] + 1); break; case 34: M[b & mm] = (u8)(M[b & mm] - 1); break;
+      case 35: M[b & mm] = (u8)~M[b & mm]; break; case 36: M[b & mm] = 0; break;
+      case 39: if (f) pc += (int)((P[pc] + 128u) & 255u) - 127; else ++pc; break;
+      case 40: { const u32 t = M[c & mm]; M[c & mm] = (u8)a; a = (a & ~255u) | t; } break;
+      case 41: M[c & mm] = (u8)(M[c & mm] + 1); break; case 42: M[c & mm] = (u8)(M[c & mm] - 1); break;
+      case 43: M[c & mm] = (u8)~M[c & mm]; break; case 44: M[c & mm] = 0; break;
+      case 47: if (!f) pc += (int)((P[pc] + 128u) & 255u) - 127; else ++pc; break;
+      case 48: { const u32 t = H[d & hm]; H[d & hm] = a; a = t; } break;
+      case 49: H[d & hm] = H[d & hm] + 1; break; case 50: H[d & hm] = H[d & hm] - 1; break;
+      case 51: H[d & hm] = ~H[d & hm]; break; case 52: H[d & hm] = 0; break;
+      case 55: R[P[pc++]] = a; break;
+      case 56: stop = 1; break;
+      case 57:
+        if (WITH_OUT) { if (o->len < o->cap) o->out[o->len] = (u8)a; else o->error = 3; ++o->len; }
+        break;
+      case 59: a = (a + M[b & mm] + 512u) * 773u; break;
+      case 60: H[d & hm] = (H[d & hm] + a + 512u) * 773u; break;
+      case 63: pc += (int)((P[pc] + 128u) & 255u) - 127; break;
+      ZQ_VM_X8(64, a = x) ZQ_VM_X8(72, b = x) ZQ_VM_X8(80, c = x) ZQ_VM_X8(88, d = x)
+      ZQ_VM_X8(96, M[b & mm] = (u8)x) ZQ_VM_X8(104, M[c & mm] = (u8)x) ZQ_VM_X8(112, H[d & hm] = x)
+      ZQ_VM_X8(128, a += x) ZQ_VM_X8(136, a -= x) ZQ_VM_X8(144, a *= x)
+      ZQ_VM_X8(152, a = x ? a / x : 0u) ZQ_VM_X8(160, a = x ? a % x : 0u)
+      ZQ_VM_X8(168, a &= x) ZQ_VM_X8(176, a &= ~x) ZQ_VM_X8(184, a |= x) ZQ_VM_X8(192, a ^= x)
+      ZQ_VM_X8(200, a <<= (x & 31u)) ZQ_VM_X8(208, a >>= (x & 31u))
+      ZQ_VM_X8(216, f = a == x) ZQ_VM_X8(224, f = a < x) ZQ_VM_X8(232, f = a > x)
+      case 255: pc = (int)P[pc] + 256 * (int)P[pc + 1]; break;
+      default: stop = 2;
     }
-    if (v.error || pc < 0) { v.error = 1; break; }
   }
+  if (stop == 2) v.error = 1;
   v.a = a; v.b = b; v.c = c; v.d = d; v.f = f;
-#undef ZQ_MB
-#undef ZQ_MC
-#undef ZQ_HD
 }
+#undef ZQ_VM_X8
 
 __device__ __forceinline__ int cm_clamp2k(int x) { return min(max(x, -2048), 2047); }
 __device__ __forceinline__ int cm_clamp512k(int x) { return min(max(x, -(1 << 19)), (1 << 19) - 1); }
 
-__device__ __forceinline__ u32 row_get(const uint4& r, u32 idx) {
-  const u32 w = idx < 8 ? (idx < 4 ? r.x : r.y) : (idx < 12 ? r.z : r.w);
-  return (w >> ((idx & 3) * 8)) & 255u;
-}
-__device__ __forceinline__ void row_set(uint4& r, u32 idx, u32 v) {
-  const u32 sh = (idx & 3) * 8, msk = ~(255u << sh), val = v << sh;
-  if (idx < 4) r.x = (r.x & msk) | val;
-  else if (idx < 8) r.y = (r.y & msk) | val;
-  else if (idx < 12) r.z = (r.z & msk) | val;
-  else r.w = (r.w & msk) | val;
-}
-
 // Everything one lane knows about its component.
 struct CmLane {
-  u32 type, a1, a2, a3, a4, a5, level;
+  u32 type, level;
+  u32 a2, a3, a4, a5;    // descriptor bytes cp[2..5]
   u32 in1, in2;          // lanes of the inputs (AVG j,k / MIX2 j,k / ISSE j / SSE j)
   u32* cm; u8* ht; u32 cm_mask, ht_mask;
+  u32 chkshift;          // ICM/ISSE: a1 + 2
   u32 h;                 // context hash H[i]
   int p;                 // stretched prediction of this component
   u32 cxt, limit, ca, cb, cc;
   u32 pn;                // table entry fetched for predict (trained in update)
   int w0, w1, pj, pk;    // ISSE weights / MIX2 weight in w0; inputs seen at predict time
-  uint4 row; u32 rowpos; bool rowok;
+  u32 rowpos, rowok;     // where the cached hash row came from
+  u8* row;               // this lane's 16 B row cache in shared memory
+  int* wp0; int* wp1;    // this lane's weight column in the first / second MIX it feeds (else null)
+  int wv0, wv1;          // those weights for the current bit
+  u32 mr0, mr1;          // and their row offsets
+  u32 mixinfo;           // MIX lanes: j0 | m << 8 | rate << 16
 };
 
-// Predictor::find (Z:15254) on this lane's hash table + switch of the register-cached row
+// Predictor::find (Z:15254) on this lane's hash table + switch of the shared-memory cached row.
+// The three candidate rows share one 64-byte block, fetched whole in one round trip.
 __device__ __forceinline__ void cm_row_switch(CmLane& L, u32 cxt) {
-  if (L.rowok) *(uint4*)(L.ht + L.rowpos) = L.row;
-  const int sizebits = (int)L.a1 + 2;
-  const u32 chk = (cxt >> sizebits) & 255u;
+  uint4* rc = (uint4*)L.row;
+  if (L.rowok) *(uint4*)(L.ht + L.rowpos) = *rc;
+  const u32 chk = (cxt >> L.chkshift) & 255u;
   const u32 h0 = (cxt * 16u) & (L.ht_mask - 15u), h1 = h0 ^ 16u, h2 = h0 ^ 32u;
-  const u32 w0 = *(const u32*)(L.ht + h0), w1 = *(const u32*)(L.ht + h1), w2 = *(const u32*)(L.ht + h2);
-  u32 r; bool fresh = false;
-  if ((w0 & 255u) == chk) r = h0;
-  else if ((w1 & 255u) == chk) r = h1;
-  else if ((w2 & 255u) == chk) r = h2;
+  const uint4 r0 = *(const uint4*)(L.ht + h0), r1 = *(const uint4*)(L.ht + h1), r2 = *(const uint4*)(L.ht + h2);
+  u32 r; uint4 row;
+  if ((r0.x & 255u) == chk) { r = h0; row = r0; }
+  else if ((r1.x & 255u) == chk) { r = h1; row = r1; }
+  else if ((r2.x & 255u) == chk) { r = h2; row = r2; }
   else {
-    const u32 p0 = (w0 >> 8) & 255u, p1 = (w1 >> 8) & 255u, p2 = (w2 >> 8) & 255u;
+    const u32 p0 = (r0.x >> 8) & 255u, p1 = (r1.x >> 8) & 255u, p2 = (r2.x >> 8) & 255u;
     if (p0 <= p1 && p0 <= p2) r = h0; else if (p1 < p2) r = h1; else r = h2;
-    fresh = true;
+    row = make_uint4(chk, 0, 0, 0);
   }
-  L.row = fresh ? make_uint4(chk, 0, 0, 0) : *(const uint4*)(L.ht + r);
-  L.rowpos = r; L.rowok = true; L.cc = r;
+  *rc = row;
+  L.rowpos = r; L.rowok = 1;
 }
 
 struct CmCtx {             // warp-uniform per-block state
   int n, nlevels, c8, hmap4;
   u32 mix_mask;            // lanes that are MIX components
   u32 mix_levels;          // bit L: some MIX sits at dependency level L
+  u32 two_levels;          // bit L: some two-input component (AVG, MIX2) sits at level L
+  int mix0, mix1;          // lanes of the first two MIX components (-1: none)
 };
 
 // p for the next bit: Predictor::predict0 (Z:15041)
@@ -245,6 +278,7 @@ __device__ int cm_predict(CmLane& L, const CmCtx& X, const CmSmem& T) {
   const u32 lane = lane_id();
   const int c8 = X.c8, hmap4 = X.hmap4;
   const bool nib = c8 == 1 || (c8 & 0xf0) == 16;
+  // phase 1: every table fetch whose address does not depend on another component's prediction
   switch (L.type) {
     case ZQ_CM:
       L.cxt = (L.h ^ (u32)hmap4) & L.cm_mask;
@@ -253,15 +287,17 @@ __device__ int cm_predict(CmLane& L, const CmCtx& X, const CmSmem& T) {
       break;
     case ZQ_ICM:
       if (nib) cm_row_switch(L, L.h + 16u * (u32)c8);
-      L.cxt = row_get(L.row, hmap4 & 15);
+      L.cxt = L.row[hmap4 & 15];
       L.pn = L.cm[L.cxt];
       L.p = T.stretch[L.pn >> 8];
       break;
-    case ZQ_ISSE:
+    case ZQ_ISSE: {
       if (nib) cm_row_switch(L, L.h + 16u * (u32)c8);
-      L.cxt = row_get(L.row, hmap4 & 15);
-      L.w0 = (int)L.cm[L.cxt * 2]; L.w1 = (int)L.cm[L.cxt * 2 + 1];
+      L.cxt = L.row[hmap4 & 15];
+      const int2 w = *(const int2*)(L.cm + L.cxt * 2);
+      L.w0 = w.x; L.w1 = w.y;
       break;
+    }
     case ZQ_MATCH:
       if (L.ca == 0) L.p = 0;
       else {
@@ -273,10 +309,20 @@ __device__ int cm_predict(CmLane& L, const CmCtx& X, const CmSmem& T) {
       L.cxt = (L.h + ((u32)c8 & L.a5)) & L.cm_mask;
       L.w0 = ((const u16*)L.cm)[L.cxt];
       break;
+    case ZQ_MIX:
+      L.cxt = ((L.h + ((u32)c8 & L.a5)) & L.cm_mask) * L.a3;   // first weight of this bit's row
+      break;
+    case ZQ_SSE:
+      zq_prefetch_l1(L.cm + (((L.h + (u32)c8) * 32u) & L.cm_mask));   // the bit's 32-bucket row = one 128 B line
+      break;
     default: break;
   }
+  if (X.mix0 >= 0) { L.mr0 = __shfl_sync(ZQ_FULL, L.cxt, X.mix0); if (L.wp0) L.wv0 = L.wp0[L.mr0]; }
+  if (X.mix1 >= 0) { L.mr1 = __shfl_sync(ZQ_FULL, L.cxt, X.mix1); if (L.wp1) L.wv1 = L.wp1[L.mr1]; }
+  // phase 2: dependency levels
   for (int lev = 1; lev < X.nlevels; ++lev) {
-    const int pj = __shfl_sync(ZQ_FULL, L.p, L.in1), pk = __shfl_sync(ZQ_FULL, L.p, L.in2);
+    const int pj = __shfl_sync(ZQ_FULL, L.p, L.in1);
+    const int pk = ((X.two_levels >> lev) & 1u) ? __shfl_sync(ZQ_FULL, L.p, L.in2) : 0;
     if ((int)L.level == lev) {
       switch (L.type) {
         case ZQ_AVG: L.p = (pj * (int)L.a3 + pk * (256 - (int)L.a3)) >> 8; break;
@@ -298,28 +344,30 @@ __device__ int cm_predict(CmLane& L, const CmCtx& X, const CmSmem& T) {
         default: break;
       }
     }
-    // mixers of this level: lanes j0..j0+m-1 each multiply their own p by their weight, one REDUX sums
+    // mixers of this level: every input lane multiplies its own p by its weight, one REDUX sums
     u32 mm = ((X.mix_levels >> lev) & 1u) ? __ballot_sync(ZQ_FULL, L.type == ZQ_MIX && (int)L.level == lev) : 0u;
     while (mm) {
       const int xl = __ffs(mm) - 1;
       mm &= mm - 1;
-      const u32 hX = __shfl_sync(ZQ_FULL, L.h, xl), j0 = __shfl_sync(ZQ_FULL, L.a2, xl), m = __shfl_sync(ZQ_FULL, L.a3, xl);
-      const u32 msk = __shfl_sync(ZQ_FULL, L.a5, xl), rmask = __shfl_sync(ZQ_FULL, L.cm_mask, xl);
-      const u64 base = __shfl_sync(ZQ_FULL, (u64)(uintptr_t)L.cm, xl);
-      const u32 row = ((hX + ((u32)c8 & msk)) & rmask) * m;
-      const bool mine = lane >= j0 && lane < j0 + m;
       int term = 0;
-      if (mine) term = (((const int*)(uintptr_t)base)[row + lane - j0] >> 8) * L.p;
+      if (xl == X.mix0) { if (L.wp0) term = (L.wv0 >> 8) * L.p; }
+      else if (xl == X.mix1) { if (L.wp1) term = (L.wv1 >> 8) * L.p; }
+      else {   // third and later mixers of a model: weight fetched here
+        const u32 info = __shfl_sync(ZQ_FULL, L.mixinfo, xl), row = __shfl_sync(ZQ_FULL, L.cxt, xl);
+        const u64 base = __shfl_sync(ZQ_FULL, (u64)(uintptr_t)L.cm, xl);
+        const u32 j0 = info & 255u, m = (info >> 8) & 255u;
+        if (lane >= j0 && lane < j0 + m) term = (((const int*)(uintptr_t)base)[row + lane - j0] >> 8) * L.p;
+      }
       const int sum = __reduce_add_sync(ZQ_FULL, term);
-      if ((int)lane == xl) { L.p = cm_clamp2k(sum >> 8); L.cxt = row; }
+      if ((int)lane == xl) L.p = cm_clamp2k(sum >> 8);
     }
   }
   return T.squash[__shfl_sync(ZQ_FULL, L.p, X.n - 1) + 2048];
 }
 
-// train all components on bit y, advance the bit context; Predictor::update0 (Z:15139).
-// Returns true when a byte was completed (HCOMP must run).
-__device__ void cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y, CmVm& vm) {
+// train all components on bit y and advance the bit context; Predictor::update0 (Z:15139).
+// Returns true when a byte was completed (the context machine's output for it is due).
+__device__ bool cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y) {
   const u32 lane = lane_id();
   // mixers first need every lane's p as seen at predict time: p is unchanged until the next predict
   u32 mm = X.mix_mask;
@@ -327,13 +375,18 @@ __device__ void cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y, CmVm& vm)
     const int xl = __ffs(mm) - 1;
     mm &= mm - 1;
     const int pX = __shfl_sync(ZQ_FULL, L.p, xl);
-    const u32 j0 = __shfl_sync(ZQ_FULL, L.a2, xl), m = __shfl_sync(ZQ_FULL, L.a3, xl), rate = __shfl_sync(ZQ_FULL, L.a4, xl);
-    const u32 row = __shfl_sync(ZQ_FULL, L.cxt, xl);
-    const u64 base = __shfl_sync(ZQ_FULL, (u64)(uintptr_t)L.cm, xl);
-    const int err = ((y * 32767 - (int)T.squash[pX + 2048]) * (int)rate) >> 4;
-    if (lane >= j0 && lane < j0 + m) {
-      int* wp = (int*)(uintptr_t)base + row + lane - j0;
-      *wp = cm_clamp512k(*wp + ((err * L.p + (1 << 12)) >> 13));
+    const u32 info = __shfl_sync(ZQ_FULL, L.mixinfo, xl);
+    const int err = ((y * 32767 - (int)T.squash[pX + 2048]) * (int)(info >> 16)) >> 4;
+    if (xl == X.mix0) { if (L.wp0) L.wp0[L.mr0] = cm_clamp512k(L.wv0 + ((err * L.p + (1 << 12)) >> 13)); }
+    else if (xl == X.mix1) { if (L.wp1) L.wp1[L.mr1] = cm_clamp512k(L.wv1 + ((err * L.p + (1 << 12)) >> 13)); }
+    else {
+      const u32 row = __shfl_sync(ZQ_FULL, L.cxt, xl);
+      const u64 base = __shfl_sync(ZQ_FULL, (u64)(uintptr_t)L.cm, xl);
+      const u32 j0 = info & 255u, m = (info >> 8) & 255u;
+      if (lane >= j0 && lane < j0 + m) {
+        int* wp = (int*)(uintptr_t)base + row + lane - j0;
+        *wp = cm_clamp512k(*wp + ((err * L.p + (1 << 12)) >> 13));
+      }
     }
   }
   switch (L.type) {
@@ -345,16 +398,18 @@ __device__ void cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y, CmVm& vm)
       break;
     }
     case ZQ_ICM: {
-      row_set(L.row, X.hmap4 & 15, T.ns[L.cxt * 4 + y]);
+      L.row[X.hmap4 & 15] = T.ns[L.cxt * 4 + y];
       L.pn += (u32)(((int)(y * 32767 - (int)(L.pn >> 8))) >> 2);
       L.cm[L.cxt] = L.pn;
       break;
     }
     case ZQ_ISSE: {
       const int err = y * 32767 - (int)T.squash[L.p + 2048];
-      L.cm[L.cxt * 2] = (u32)cm_clamp512k(L.w0 + ((err * L.pj + (1 << 12)) >> 13));
-      L.cm[L.cxt * 2 + 1] = (u32)cm_clamp512k(L.w1 + ((err + 16) >> 5));
-      row_set(L.row, X.hmap4 & 15, T.ns[L.cxt * 4 + y]);
+      int2 w;
+      w.x = cm_clamp512k(L.w0 + ((err * L.pj + (1 << 12)) >> 13));
+      w.y = cm_clamp512k(L.w1 + ((err + 16) >> 5));
+      *(int2*)(L.cm + L.cxt * 2) = w;
+      L.row[X.hmap4 & 15] = T.ns[L.cxt * 4 + y];
       break;
     }
     case ZQ_MIX2: {
@@ -365,10 +420,12 @@ __device__ void cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y, CmVm& vm)
       break;
     }
     case ZQ_MATCH: {
+      // The reference shifts y into ht[limit] bit by bit; the partial byte is never read (matches and the
+      // predicted bit look at earlier positions), so the finished byte is stored once.
       const u32 hm = L.ht_mask;
       if ((int)L.cc != y) L.ca = 0;
-      L.ht[L.limit & hm] = (u8)(L.ht[L.limit & hm] * 2 + y);
       if (++L.cxt == 8) {
+        L.ht[L.limit & hm] = (u8)(X.c8 * 2 + y);
         L.cxt = 0;
         L.limit = (L.limit + 1) & hm;
         if (L.ca == 0) {
@@ -383,35 +440,111 @@ __device__ void cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y, CmVm& vm)
     default: break;
   }
   X.c8 += X.c8 + y;
-  if (X.c8 >= 256) {
-    if (lane == 0) cm_vm_run(vm, (u32)(X.c8 - 256));   // one lane owns the machine: no same-address races
-    __syncwarp();
-    X.hmap4 = 1; X.c8 = 1;
-    if ((int)lane < X.n) L.h = vm.h[lane & vm.hmask];
-  } else if (X.c8 >= 16 && X.c8 < 32)
-    X.hmap4 = (X.hmap4 & 0xf) << 5 | y << 4 | 1;
-  else
-    X.hmap4 = (X.hmap4 & 0x1f0) | (((X.hmap4 & 0xf) * 2 + y) & 0xf);
+  if (X.c8 >= 256) { X.hmap4 = 1; X.c8 = 1; return true; }
+  if (X.c8 >= 16 && X.c8 < 32) X.hmap4 = (X.hmap4 & 0xf) << 5 | y << 4 | 1;
+  else X.hmap4 = (X.hmap4 & 0x1f0) | (((X.hmap4 & 0xf) * 2 + y) & 0xf);
+  return false;
 }
 
-__device__ __forceinline__ void cm_code_byte(CmCoder& E, CmLane& L, CmCtx& X, const CmSmem& T, CmVm& vm, u32 c) {
-  E.encode(0, 0);
-  for (int i = 7; i >= 0; --i) {
-    const u32 p16 = (u32)cm_predict(L, X, T) * 2 + 1;
-    const int y = (c >> i) & 1;
-    E.encode(y, p16);
-    cm_update(L, X, T, y, vm);
+// Lane state for a block: component `lane` of plan `cp`, tables in `model`, row cache in `S`.
+__device__ __forceinline__ void cm_setup(CmLane& L, CmCtx& X, const ZqCmPlan& cp, u8* model, CmUnitSmem& S) {
+  const u32 lane = lane_id();
+  X.n = cp.n; X.nlevels = cp.nlevels; X.c8 = 1; X.hmap4 = 1; X.mix_mask = cp.mix_mask;
+  const bool act = lane < (u32)cp.n;
+  const ZqCmComp c = cp.comp[act ? lane : 0];
+  L.type = act ? c.type : 0; L.level = act ? c.level : 255;
+  L.a2 = c.a2; L.a3 = c.a3; L.a4 = c.a4; L.a5 = c.a5;
+  X.mix_levels = __reduce_or_sync(ZQ_FULL, (act && c.type == ZQ_MIX) ? (1u << c.level) : 0u);
+  X.two_levels = __reduce_or_sync(ZQ_FULL, (act && (c.type == ZQ_AVG || c.type == ZQ_MIX2)) ? (1u << c.level) : 0u);
+  L.cm = (u32*)(model + c.cm_off); L.ht = model + c.ht_off; L.cm_mask = c.cm_mask; L.ht_mask = c.ht_mask;
+  L.chkshift = (u32)c.a1 + 2;
+  L.in1 = 0; L.in2 = 0;
+  if (L.type == ZQ_AVG) { L.in1 = c.a1; L.in2 = c.a2; }
+  else if (L.type == ZQ_MIX2) { L.in1 = c.a2; L.in2 = c.a3; }
+  else if (L.type == ZQ_ISSE || L.type == ZQ_SSE) L.in1 = c.a2;
+  L.h = 0; L.p = L.type == ZQ_CONS ? ((int)c.a1 - 128) * 4 : 0;
+  L.cxt = 0; L.ca = L.cb = L.cc = 0; L.pn = 0; L.w0 = L.w1 = L.pj = L.pk = 0;
+  L.limit = L.type == ZQ_CM ? c.a2 * 4u : L.type == ZQ_SSE ? c.a4 * 4u : L.type == ZQ_ICM ? 1023u : 0u;
+  L.rowpos = 0; L.rowok = 0; L.row = S.rows[lane];
+  L.mixinfo = (u32)c.a2 | (u32)c.a3 << 8 | (u32)c.a4 << 16;
+  // the first two mixers keep their weights in registers between predict and update
+  X.mix0 = X.mix_mask ? __ffs(X.mix_mask) - 1 : -1;
+  const u32 rest = X.mix_mask & (X.mix_mask - 1);
+  X.mix1 = rest ? __ffs(rest) - 1 : -1;
+  L.wp0 = nullptr; L.wp1 = nullptr; L.wv0 = L.wv1 = 0; L.mr0 = L.mr1 = 0;
+  if (X.mix0 >= 0) {
+    const ZqCmComp& m0 = cp.comp[X.mix0];
+    if (lane >= m0.a2 && lane < (u32)m0.a2 + m0.a3) L.wp0 = (int*)(model + m0.cm_off) + (lane - m0.a2);
+  }
+  if (X.mix1 >= 0) {
+    const ZqCmComp& m1 = cp.comp[X.mix1];
+    if (lane >= m1.a2 && lane < (u32)m1.a2 + m1.a3) L.wp1 = (int*)(model + m1.cm_off) + (lane - m1.a2);
   }
 }
 
-// grid of persistent 16-warp CTAs; warps pull modeled units from a counter
-template <int MINB>
-__global__ void __launch_bounds__(512, MINB)
+// Context machine of a block: memory M, R in the model region; H in shared memory when it fits.
+__device__ __forceinline__ void cm_vm_setup(CmVm& vm, const ZqCmPlan& cp, u8* model, const u8* blob, CmUnitSmem& S) {
+  const u32 lane = lane_id();
+  vm.a = vm.b = vm.c = vm.d = 0; vm.f = 0; vm.error = 0;
+  vm.m = model + cp.m_off; vm.r = (u32*)(model + cp.r_off);
+  vm.mmask = (1u << cp.hm) - 1; vm.hmask = (1u << cp.hh) - 1;
+  if ((1u << cp.hh) <= ZQ_CM_HBUF) {
+    vm.h = S.hbuf;
+    for (u32 k = lane; k < (1u << cp.hh); k += 32) S.hbuf[k] = 0;
+  } else vm.h = (u32*)(model + cp.h_off);
+  vm.len = (int)cp.hcomp_len;
+  if (cp.hcomp_len <= ZQ_CM_CODE_CAP) {
+    for (u32 k = lane; k < cp.hcomp_len; k += 32) S.code[k] = blob[cp.hcomp_off + k];
+    vm.code = S.code;
+  } else vm.code = blob + cp.hcomp_off;
+  __syncwarp();
+}
+
+// The context warp tells the memory system what the coder will touch while coding byte `nb` with the
+// contexts `h` (lane = component): ICM/ISSE hash-row blocks and CM lines of both nibbles, the 8 rows of
+// mixer weights / MIX2 weights / SSE buckets (one per bit: they are selected by the partial byte).
+__device__ __forceinline__ void cm_prefetch_byte(const ZqCmComp& c, u8* model, u32 h, u32 nb) {
+  const u32 hi = nb >> 4;
+  switch (c.type) {
+    case ZQ_ICM: case ZQ_ISSE: {
+      const u8* ht = model + c.ht_off;
+      zq_prefetch_l2(ht + (((h + 16u) * 16u) & (c.ht_mask - 63u)));
+      zq_prefetch_l2(ht + (((h + 16u * (16u + hi)) * 16u) & (c.ht_mask - 63u)));
+      break;
+    }
+    case ZQ_CM: {
+      const u32* cm = (const u32*)(model + c.cm_off);
+      const u32 x2 = ((8u + (hi >> 1)) << 5) | ((hi & 1u) << 4);
+      zq_prefetch_l2(cm + (h & c.cm_mask & ~15u));
+      zq_prefetch_l2(cm + ((h ^ x2) & c.cm_mask & ~15u));
+      break;
+    }
+    case ZQ_MIX: case ZQ_MIX2: case ZQ_SSE: {
+      const u8* base = model + c.cm_off;
+      for (u32 i = 0; i < 8; ++i) {
+        const u32 c8 = (1u << i) | (nb >> (8 - i));
+        if (c.type == ZQ_MIX) {
+          const u32 row = ((h + (c8 & c.a5)) & c.cm_mask) * c.a3;
+          zq_prefetch_l2(base + (u64)row * 4);
+          zq_prefetch_l2(base + (u64)(row + c.a3 - 1) * 4);
+        } else if (c.type == ZQ_MIX2) zq_prefetch_l2(base + (u64)((h + (c8 & c.a5)) & c.cm_mask) * 2);
+        else zq_prefetch_l2(base + (u64)(((h + c8) * 32u) & c.cm_mask) * 4);
+      }
+      break;
+    }
+    default: break;
+  }
+}
+
+// grid of persistent CTAs of `blockDim.x / 64` warp pairs (even warp: coder, odd warp: context machine);
+// pairs pull modeled units from a counter.  Dynamic shared memory: CmSmem + one CmUnitSmem per pair.
+#define ZQ_CM_MAX_PAIRS 12   // 768 threads: 85 registers per thread without spills; 1 776 blocks resident on 148 SMs
+__global__ void __launch_bounds__(64 * ZQ_CM_MAX_PAIRS, 1)
 k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
             const ZqCmPlan* __restrict__ cmplans, const int* __restrict__ todo, int ntodo,
             const CmTablesDev* __restrict__ tab, const u8* __restrict__ blob, const u8* __restrict__ lz_base,
             const u32* __restrict__ lz_len, u8* __restrict__ model_base, u8* __restrict__ coded_base,
-            u32* __restrict__ coded_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit) {
+            u32* __restrict__ coded_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit, int prefetch) {
   ZQ_DYN_SMEM(smem_raw);
   CmSmem& T = *reinterpret_cast<CmSmem*>(smem_raw);
   {
@@ -420,51 +553,70 @@ k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, co
     for (u32 k = threadIdx.x; k < sizeof(CmSmem) / 16; k += blockDim.x) dst[k] = src[k];
   }
   __syncthreads();
-  const u32 lane = lane_id();
+  const u32 lane = lane_id(), warp = threadIdx.x >> 5, pair = warp >> 1, role = warp & 1;
+  CmUnitSmem& S = reinterpret_cast<CmUnitSmem*>(smem_raw + sizeof(CmSmem))[pair];
   for (;;) {
-    int t = 0;
-    if (lane == 0) t = (int)atomicAdd(next_unit, 1u);
-    t = __shfl_sync(ZQ_FULL, t, 0);
+    if (role == 0 && lane == 0) { S.unit = (int)atomicAdd(next_unit, 1u); S.produced = 0; S.consumed = 0; }
+    zq_pair_sync(pair);
+    const int t = S.unit;
+    zq_pair_sync(pair);     // both warps hold t before the coder may publish the next one
     if (t >= ntodo) break;
     const int ui = todo[t];
     const ZqUnit u = units[ui];
     const ZqPlan pl = plans[u.plan];
     const ZqCmPlan& cp = cmplans[pl.cm_plan];
     u8* model = model_base + u.model_off;
-    CmCtx X; X.n = cp.n; X.nlevels = cp.nlevels; X.c8 = 1; X.hmap4 = 1; X.mix_mask = cp.mix_mask;
-    CmLane L;
-    {
-      const ZqCmComp c = cp.comp[lane < (u32)cp.n ? lane : 0];
-      const bool act = lane < (u32)cp.n;
-      L.type = act ? c.type : 0; L.a1 = c.a1; L.a2 = c.a2; L.a3 = c.a3; L.a4 = c.a4; L.a5 = c.a5; L.level = act ? c.level : 255;
-      X.mix_levels = __reduce_or_sync(ZQ_FULL, (act && c.type == ZQ_MIX) ? (1u << c.level) : 0u);
-      L.cm = (u32*)(model + c.cm_off); L.ht = model + c.ht_off; L.cm_mask = c.cm_mask; L.ht_mask = c.ht_mask;
-      L.in1 = 0; L.in2 = 0;
-      if (L.type == ZQ_AVG) { L.in1 = c.a1; L.in2 = c.a2; }
-      else if (L.type == ZQ_MIX2) { L.in1 = c.a2; L.in2 = c.a3; }
-      else if (L.type == ZQ_ISSE || L.type == ZQ_SSE) L.in1 = c.a2;
-      L.h = 0; L.p = L.type == ZQ_CONS ? ((int)c.a1 - 128) * 4 : 0;
-      L.cxt = 0; L.ca = L.cb = L.cc = 0; L.pn = 0; L.w0 = L.w1 = L.pj = L.pk = 0;
-      L.limit = L.type == ZQ_CM ? c.a2 * 4u : L.type == ZQ_SSE ? c.a4 * 4u : L.type == ZQ_ICM ? 1023u : 0u;
-      L.row = make_uint4(0, 0, 0, 0); L.rowpos = 0; L.rowok = false;
-    }
-    CmVm vm;
-    vm.a = vm.b = vm.c = vm.d = 0; vm.f = 0; vm.error = 0;
-    vm.m = model + cp.m_off; vm.h = (u32*)(model + cp.h_off); vm.r = (u32*)(model + cp.r_off);
-    vm.mmask = (1u << cp.hm) - 1; vm.hmask = (1u << cp.hh) - 1;
-    vm.code = blob + cp.hcomp_off; vm.len = (int)cp.hcomp_len;
-    CmCoder E; E.init(coded_base + u.coded_off, u.coded_cap);
     // the coded stream: post-processor selector (+ PCOMP bytes), then the (pre-processed) data
-    for (u32 k = 0; k < pl.payload_len; ++k) cm_code_byte(E, L, X, T, vm, blob[pl.payload_off + k]);
     const u8* __restrict__ stream; u32 slen;
     if (pl.lz_level) { stream = lz_base + u.lz_off; slen = lz_len[ui]; }
     else { stream = in_base + u.in_off; slen = u.n; }
-    for (u32 k = 0; k < slen; ++k) cm_code_byte(E, L, X, T, vm, stream[k]);
-    E.encode(1, 0);   // end of segment
-    if (lane == 0) {
-      coded_len[ui] = (u32)(E.out - (coded_base + u.coded_off));
-      if (E.overflow) atomicOr(err_flag, 1u);
-      if (vm.error) atomicOr(err_flag, 2u);
+    const u8* __restrict__ head = blob + pl.payload_off;
+    const u32 hlen = pl.payload_len, K = hlen + slen;
+    if (role == 1) {
+      // ---- context warp: HCOMP on byte k -> ring slot k, for every byte but the last
+      CmVm vm;
+      cm_vm_setup(vm, cp, model, blob, S);
+      const bool act = lane < (u32)cp.n;
+      const ZqCmComp comp = cp.comp[act ? lane : 0];
+      for (u32 k = 0; k + 1 < K; ++k) {
+        const u32 c = k < hlen ? head[k] : stream[k - hlen];
+        if (lane == 0) cm_vm_run<false>(vm, c, nullptr);
+        __syncwarp();
+        while (k - S.consumed >= ZQ_CM_RING) __nanosleep(64);
+        const u32 hv = act ? vm.h[lane & vm.hmask] : 0u;
+        S.ring[k % ZQ_CM_RING][lane] = hv;
+        if (prefetch && act) cm_prefetch_byte(comp, model, hv, k + 1 < hlen ? head[k + 1] : stream[k + 1 - hlen]);
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); S.produced = k + 1; }
+      }
+      if (lane == 0 && vm.error) atomicOr(err_flag, 2u);
+    } else {
+      // ---- coder warp
+      CmCtx X; CmLane L;
+      cm_setup(L, X, cp, model, S);
+      CmCoder E; E.init(coded_base + u.coded_off, u.coded_cap);
+      for (u32 k = 0; k < K; ++k) {
+        if (k > 0) {
+          while (S.produced < k) __nanosleep(32);
+          __threadfence_block();
+          L.h = S.ring[(k - 1) % ZQ_CM_RING][lane];
+          __syncwarp();
+          if (lane == 0) S.consumed = k;
+        }
+        const u32 c = k < hlen ? head[k] : stream[k - hlen];
+        E.encode(0, 0);
+        for (int i = 7; i >= 0; --i) {
+          const u32 p16 = (u32)cm_predict(L, X, T) * 2 + 1;
+          const int y = (c >> i) & 1;
+          E.encode(y, p16);
+          cm_update(L, X, T, y);
+        }
+      }
+      E.encode(1, 0);   // end of segment
+      if (lane == 0) {
+        coded_len[ui] = (u32)(E.out - (coded_base + u.coded_off));
+        if (E.overflow) atomicOr(err_flag, 1u);
+      }
     }
   }
 }
