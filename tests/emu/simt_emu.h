@@ -153,9 +153,12 @@ inline int __reduce_min_sync(unsigned m, int v) { ZQ_EMU_FULLMASK(m); const uint
 inline int __reduce_max_sync(unsigned m, int v) { ZQ_EMU_FULLMASK(m); const uint64_t* r = emu::rendezvous(emu_pack(v)); int s = -0x7fffffff - 1; for (int i = 0; i < 32; ++i) { const int x = emu_unpack<int>(r[i]); s = x > s ? x : s; } return s; }
 
 // single host thread runs every coroutine: plain read-modify-write is atomic
-template <class T> inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; return o; }
-template <class T> inline T atomicOr(T* p, T v) { const T o = *p; *p = o | v; return o; }
-template <class T> inline T atomicMax(T* p, T v) { const T o = *p; if (v > o) *p = v; return o; }
+template <class T, class V> inline T atomicAdd(T* p, V v) { const T o = *p; *p = (T)(o + (T)v); return o; }
+template <class T, class V> inline T atomicOr(T* p, V v) { const T o = *p; *p = (T)(o | (T)v); return o; }
+template <class T, class V> inline T atomicAnd(T* p, V v) { const T o = *p; *p = (T)(o & (T)v); return o; }
+template <class T, class V> inline T atomicMax(T* p, V v) { const T o = *p; if ((T)v > o) *p = (T)v; return o; }
+template <class T, class V> inline T atomicMin(T* p, V v) { const T o = *p; if ((T)v < o) *p = (T)v; return o; }
+template <class T, class V> inline T atomicExch(T* p, V v) { const T o = *p; *p = (T)v; return o; }
 inline void __threadfence_block() {}
 inline void __threadfence() {}
 inline void __nanosleep(unsigned) { emu::yield(); }

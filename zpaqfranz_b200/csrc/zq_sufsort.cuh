@@ -555,7 +555,7 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_suffix_sort(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const int* __restrict__ todo, int ntodo,
               u8* __restrict__ work_base, u64* kbuf, u32* vbuf, u64 scratch_elems) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ZQ_DYN_SMEM(smem_raw);
   SortSmem<NT>& sm = *reinterpret_cast<SortSmem<NT>*>(smem_raw);
   SortScratch sc;
   sc.kA = kbuf + (u64)blockIdx.x * 2 * scratch_elems; sc.kB = sc.kA + scratch_elems;
