@@ -66,7 +66,7 @@ extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_
 #else
     const unsigned block = (unsigned)threads < 64 ? 64u : (unsigned)threads & ~63u;   // whole (coder, context) pairs
     emu::launch(1, block, sizeof(CmSmem) + (block / 64) * sizeof(CmUnitSmem), [&] {
-      k_cm_encode(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch);
+      k_cm_encode(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1);
     });
 #endif
     free(model);

@@ -58,11 +58,11 @@ def _coded_by_oracle(oracle, header, pcomp, stream):
     return blk[pre:-6]                       # ... coded ... 00 00 00 00 FE FF
 
 
-def _emu_encode(emu, header, pcomp, stream, threads=64, prefetch=1):
+def _emu_encode(emu, header, pcomp, stream, threads=64, prefetch=1, fast=1):
     payload = (bytes([1, len(pcomp) & 255, len(pcomp) >> 8]) + pcomp) if pcomp else b"\0"
     cap = len(stream) * 2 + len(payload) * 2 + 4096
     out = (C.c_uint8 * cap)()
-    n = emu.emu_cm_encode(header, len(header), payload, len(payload), stream, len(stream), out, cap, threads, prefetch)
+    n = emu.emu_cm_encode(header, len(header), payload, len(payload), stream, len(stream), out, cap, threads, prefetch | fast << 1)
     assert n >= 0, n
     return bytes(out[:n])
 
@@ -82,6 +82,7 @@ def test_builtin_models_encode_and_decode(emu, oracle, method):
     stream = oracle.lz_stream(data, plan["args"]) if (plan["args"][1] & 3) else data
     want = _coded_by_oracle(oracle, header, pcomp, stream)
     assert _emu_encode(emu, header, pcomp, stream) == want
+    assert _emu_encode(emu, header, pcomp, stream, fast=0) == want     # chain models: the generic lane engine too
     # decoder: coded data + end-of-stream zeros -> post-processed original
     assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data)) == data
 

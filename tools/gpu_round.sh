@@ -24,6 +24,9 @@ for s in $STEPS; do
         python tools/prof_step.py --method 36,200,1 --units 296 --unit 16384 --steps 1 > $O/${TAG}_ncu_cm_bwt.log 2>&1
       timeout 300 $NCU --set full --import-source on -k regex:k_cm_encode -c 1 -f -o $O/${TAG}_cm_m5 \
         python tools/prof_step.py --method 5 --units 64 --unit 4096 --steps 1 > $O/${TAG}_ncu_cm_m5.log 2>&1 ;;
+    ncu_bwt)
+      timeout 300 $NCU --set full --import-source on -k regex:k_cm_encode -c 1 -f -o $O/${TAG}_cm_bwt \
+        python tools/prof_step.py --method 36,200,1 --units 296 --unit 16384 --steps 1 > $O/${TAG}_ncu_cm_bwt.log 2>&1 ;;
     cmtime)
       timeout 400 python tools/bench_configs.py --skip c4 --c5-units 1200 > $O/${TAG}_configs_c3_c5.json 2> $O/${TAG}_configs.err ;;
     cmtime_nopf)

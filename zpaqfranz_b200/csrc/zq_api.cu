@@ -81,6 +81,7 @@ struct zq_ctx {
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 1;                         // 1: warp-per-block LZ77 parser (default, faster today); 0: candidates/chain/emit form (ZQ_LZ_PAR=1)
   int cm_occ = 2;                         // first engine only: CTAs (16 warps) per SM of the CM coder
+  int cm_fast = 1;                        // encoder fast path for chain models (ZQ_CM_FAST=0: generic lanes)
   int cm_prefetch = 1;                    // context warp prefetches the coder's table lines (ZQ_CM_PREFETCH=0 to turn off)
   int lz_half = 0;                        // 1: SA parse with two blocks per warp (ZQ_LZ_HALF=1; bit-exact, slower today: the halves serialise)
   int lz_occ = 6;                         // CTAs (4 warps) per SM the LZ parse kernel is compiled for
@@ -506,7 +507,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       k_cm_encode<<<std::min((nt + pairs - 1) / pairs, c->num_sms), pairs * 64, cm_smem, c->stream>>>(
           d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
           c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr,
-          c->cm_prefetch);
+          c->cm_prefetch, c->cm_fast);
 #endif
       ++c->launches;
       tstop(c, 5);
@@ -623,6 +624,7 @@ zq_ctx* zq_create(int device) {
   if (const char* s = getenv("ZQ_LZ_HALF")) c->lz_half = atoi(s);
   if (const char* s = getenv("ZQ_CM_OCC")) c->cm_occ = atoi(s);
   if (const char* s = getenv("ZQ_CM_PREFETCH")) c->cm_prefetch = atoi(s);
+  if (const char* s = getenv("ZQ_CM_FAST")) c->cm_fast = atoi(s);
   if (const char* s = getenv("ZQ_LZ_PAR")) c->lz_old = atoi(s) ? 0 : 1;
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
   if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);

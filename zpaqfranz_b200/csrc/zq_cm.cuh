@@ -536,6 +536,119 @@ __device__ __forceinline__ void cm_prefetch_byte(const ZqCmComp& c, u8* model, u
   }
 }
 
+// ---- encoder fast path for the chain ICM -> ISSE (built-in level 3: "ci1" after BWT, "c0,0,511i2" after LZ77) ----
+// The compressor knows the whole byte before coding it, so the tree nodes (hash-row slots) of a nibble's
+// four bits are known up front: their bit-history states come out of the cached row at once and the four
+// probability / weight fetches are issued together; the bits are then pure arithmetic on registers (a later
+// bit that lands on the same state as an earlier one of the nibble takes the updated value instead of the
+// fetched one).  Nothing here depends on another lane: the coder warp runs it on lane 0, straight-line.
+struct ChainComp {
+  u32* cm; u8* ht;
+  u32 ht_mask, chkshift, rowpos, rowok;
+  uint4 row;
+};
+__device__ __forceinline__ void chain_setup(ChainComp& C, const ZqCmComp& c, u8* model) {
+  C.cm = (u32*)(model + c.cm_off); C.ht = model + c.ht_off; C.ht_mask = c.ht_mask; C.chkshift = (u32)c.a1 + 2;
+  C.rowpos = 0; C.rowok = 0; C.row = make_uint4(0, 0, 0, 0);
+}
+// Predictor::find (Z:15254) with the row held in registers
+__device__ __forceinline__ void chain_row_switch(ChainComp& C, u32 cxt) {
+  if (C.rowok) *(uint4*)(C.ht + C.rowpos) = C.row;
+  const u32 chk = (cxt >> C.chkshift) & 255u;
+  const u32 h0 = (cxt * 16u) & (C.ht_mask - 15u), h1 = h0 ^ 16u, h2 = h0 ^ 32u;
+  const uint4 r0 = *(const uint4*)(C.ht + h0), r1 = *(const uint4*)(C.ht + h1), r2 = *(const uint4*)(C.ht + h2);
+  u32 r; uint4 row;
+  if ((r0.x & 255u) == chk) { r = h0; row = r0; }
+  else if ((r1.x & 255u) == chk) { r = h1; row = r1; }
+  else if ((r2.x & 255u) == chk) { r = h2; row = r2; }
+  else {
+    const u32 p0 = (r0.x >> 8) & 255u, p1 = (r1.x >> 8) & 255u, p2 = (r2.x >> 8) & 255u;
+    if (p0 <= p1 && p0 <= p2) r = h0; else if (p1 < p2) r = h1; else r = h2;
+    row = make_uint4(chk, 0, 0, 0);
+  }
+  C.row = row; C.rowpos = r; C.rowok = 1;
+}
+__device__ __forceinline__ u32 chain_get(u32 word, u32 k) { return (word >> (8 * k)) & 255u; }
+__device__ __forceinline__ u32 chain_put(u32 word, u32 k, u32 v) { return (word & ~(255u << (8 * k))) | (v << (8 * k)); }
+
+// four bits (MSB first in `nib`) through ICM `A` -> ISSE `B`
+__device__ __forceinline__ void chain1_nibble(ChainComp& A, ChainComp& B, CmCoder& E, const CmSmem& T, u32 nib) {
+  const u32 y0 = (nib >> 3) & 1u, y1 = (nib >> 2) & 1u, y2 = (nib >> 1) & 1u, y3 = nib & 1u;
+  const u32 i1 = 2u + y0, i2 = (4u + 2u * y0 + y1) & 3u, i3 = 8u + 4u * y0 + 2u * y1 + y2;   // slots 1, i1, 4+i2, i3
+  const bool lo3 = i3 < 12u;
+  const u32 k3 = i3 & 3u;
+  // bit histories of the four nodes, both components
+  const u32 sa0 = chain_get(A.row.x, 1), sa1 = chain_get(A.row.x, i1), sa2 = chain_get(A.row.y, i2), sa3 = chain_get(lo3 ? A.row.z : A.row.w, k3);
+  const u32 sb0 = chain_get(B.row.x, 1), sb1 = chain_get(B.row.x, i1), sb2 = chain_get(B.row.y, i2), sb3 = chain_get(lo3 ? B.row.z : B.row.w, k3);
+  // their adaptive probabilities (ICM) and weight pairs (ISSE): eight independent fetches
+  u32 pn0 = A.cm[sa0], pn1 = A.cm[sa1], pn2 = A.cm[sa2], pn3 = A.cm[sa3];
+  int2 w0 = *(const int2*)(B.cm + sb0 * 2), w1 = *(const int2*)(B.cm + sb1 * 2), w2 = *(const int2*)(B.cm + sb2 * 2),
+       w3 = *(const int2*)(B.cm + sb3 * 2);
+#define ZQ_CHAIN_BIT(PN, W, SA, SB, YB)                                                         \
+  {                                                                                               \
+    const int pa = T.stretch[(PN) >> 8];                                                          \
+    const int pb = cm_clamp2k(((W).x * pa + (W).y * 64) >> 16);                                   \
+    const int pr = T.squash[pb + 2048];                                                           \
+    E.encode((int)(YB), (u32)pr * 2 + 1);                                                         \
+    (PN) += (u32)(((int)((YB) * 32767u) - (int)((PN) >> 8)) >> 2);                                \
+    A.cm[SA] = (PN);                                                                              \
+    const int err = (int)((YB) * 32767u) - pr;                                                    \
+    (W).x = cm_clamp512k((W).x + ((err * pa + (1 << 12)) >> 13));                                 \
+    (W).y = cm_clamp512k((W).y + ((err + 16) >> 5));                                              \
+    *(int2*)(B.cm + (SB) * 2) = (W);                                                              \
+  }
+  ZQ_CHAIN_BIT(pn0, w0, sa0, sb0, y0)
+  if (sa1 == sa0) pn1 = pn0;
+  if (sb1 == sb0) w1 = w0;
+  ZQ_CHAIN_BIT(pn1, w1, sa1, sb1, y1)
+  if (sa2 == sa0) pn2 = pn0;
+  if (sa2 == sa1) pn2 = pn1;
+  if (sb2 == sb0) w2 = w0;
+  if (sb2 == sb1) w2 = w1;
+  ZQ_CHAIN_BIT(pn2, w2, sa2, sb2, y2)
+  if (sa3 == sa0) pn3 = pn0;
+  if (sa3 == sa1) pn3 = pn1;
+  if (sa3 == sa2) pn3 = pn2;
+  if (sb3 == sb0) w3 = w0;
+  if (sb3 == sb1) w3 = w1;
+  if (sb3 == sb2) w3 = w2;
+  ZQ_CHAIN_BIT(pn3, w3, sa3, sb3, y3)
+#undef ZQ_CHAIN_BIT
+  // next states into the rows
+  A.row.x = chain_put(chain_put(A.row.x, 1, T.ns[sa0 * 4 + y0]), i1, T.ns[sa1 * 4 + y1]);
+  A.row.y = chain_put(A.row.y, i2, T.ns[sa2 * 4 + y2]);
+  B.row.x = chain_put(chain_put(B.row.x, 1, T.ns[sb0 * 4 + y0]), i1, T.ns[sb1 * 4 + y1]);
+  B.row.y = chain_put(B.row.y, i2, T.ns[sb2 * 4 + y2]);
+  const u32 na3 = T.ns[sa3 * 4 + y3], nb3 = T.ns[sb3 * 4 + y3];
+  if (lo3) { A.row.z = chain_put(A.row.z, k3, na3); B.row.z = chain_put(B.row.z, k3, nb3); }
+  else { A.row.w = chain_put(A.row.w, k3, na3); B.row.w = chain_put(B.row.w, k3, nb3); }
+}
+
+// whole block through the chain model, on the calling lane; contexts come from the pair's ring
+__device__ void cm_code_chain1(const ZqCmPlan& cp, u8* model, CmUnitSmem& S, const CmSmem& T, CmCoder& E,
+                               const u8* __restrict__ head, u32 hlen, const u8* __restrict__ stream, u32 K) {
+  ChainComp A, B;
+  chain_setup(A, cp.comp[0], model);
+  chain_setup(B, cp.comp[1], model);
+  u32 ha = 0, hb = 0;
+  for (u32 k = 0; k < K; ++k) {
+    if (k > 0) {
+      while (S.produced < k) __nanosleep(32);
+      __threadfence_block();
+      ha = S.ring[(k - 1) % ZQ_CM_RING][0]; hb = S.ring[(k - 1) % ZQ_CM_RING][1];
+      __threadfence_block();
+      S.consumed = k;
+    }
+    const u32 c = k < hlen ? head[k] : stream[k - hlen];
+    E.encode(0, 0);
+    chain_row_switch(A, ha + 16u); chain_row_switch(B, hb + 16u);
+    chain1_nibble(A, B, E, T, c >> 4);
+    const u32 c8 = 16u + (c >> 4);
+    chain_row_switch(A, ha + 16u * c8); chain_row_switch(B, hb + 16u * c8);
+    chain1_nibble(A, B, E, T, c & 15u);
+  }
+}
+
 // grid of persistent CTAs of `blockDim.x / 64` warp pairs (even warp: coder, odd warp: context machine);
 // pairs pull modeled units from a counter.  Dynamic shared memory: CmSmem + one CmUnitSmem per pair.
 #define ZQ_CM_MAX_PAIRS 12   // 768 threads: 85 registers per thread without spills; 1 776 blocks resident on 148 SMs
@@ -544,7 +657,7 @@ k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, co
             const ZqCmPlan* __restrict__ cmplans, const int* __restrict__ todo, int ntodo,
             const CmTablesDev* __restrict__ tab, const u8* __restrict__ blob, const u8* __restrict__ lz_base,
             const u32* __restrict__ lz_len, u8* __restrict__ model_base, u8* __restrict__ coded_base,
-            u32* __restrict__ coded_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit, int prefetch) {
+            u32* __restrict__ coded_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit, int prefetch, int fast) {
   ZQ_DYN_SMEM(smem_raw);
   CmSmem& T = *reinterpret_cast<CmSmem*>(smem_raw);
   {
@@ -592,9 +705,19 @@ k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, co
       if (lane == 0 && vm.error) atomicOr(err_flag, 2u);
     } else {
       // ---- coder warp
+      CmCoder E; E.init(coded_base + u.coded_off, u.coded_cap);
+      if (cp.chain == 1 && fast) {
+        if (lane == 0) {
+          cm_code_chain1(cp, model, S, T, E, head, hlen, stream, K);
+          E.encode(1, 0);   // end of segment
+          coded_len[ui] = (u32)(E.out - (coded_base + u.coded_off));
+          if (E.overflow) atomicOr(err_flag, 1u);
+        }
+        __syncwarp();
+        continue;
+      }
       CmCtx X; CmLane L;
       cm_setup(L, X, cp, model, S);
-      CmCoder E; E.init(coded_base + u.coded_off, u.coded_cap);
       for (u32 k = 0; k < K; ++k) {
         if (k > 0) {
           while (S.produced < k) __nanosleep(32);

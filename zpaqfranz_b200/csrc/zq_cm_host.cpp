@@ -202,6 +202,7 @@ ZqCmPlan make_cm_plan(const Assembled& code, std::vector<ZqCmFill>& fills) {
   }
   p.model_bytes = align256(off);
   p.fill_count = (uint32_t)fills.size() - p.fill_first;
+  p.chain = (p.n == 2 && p.comp[0].type == ZQ_ICM && p.comp[1].type == ZQ_ISSE && p.comp[1].a2 == 0) ? 1u : 0u;
   return p;
 }
 

@@ -23,7 +23,7 @@ struct ZqCmPlan {
   uint64_t m_off, h_off, r_off;      // VM memory inside the model region
   uint64_t model_bytes;              // size of one unit's model region (256 B aligned)
   uint32_t mix_mask;                 // lanes that are MIX components
-  uint32_t pad;
+  uint32_t chain;                    // 1: the model is ICM -> ISSE(0) (every built-in level-3 model): encoder fast path
   // decoder only: post-processor (PCOMP) machine of the block, Z:15358-15414
   int32_t ph, pm;                    // PCOMP H (2^ph u32) and M (2^pm bytes)
   uint64_t pm_off, ph_off, pr_off, pcode_off;
