@@ -79,7 +79,8 @@ extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_
 }
 // Decodes the coded data of one block (everything after the segment header) with the device decoder.
 // Returns the number of restored bytes or -(1000 + device error code).
-extern "C" long emu_cm_decode(const uint8_t* header, uint32_t hlen, const uint8_t* coded, uint32_t clen, uint8_t* out, uint32_t cap) {
+extern "C" long emu_cm_decode(const uint8_t* header, uint32_t hlen, const uint8_t* coded, uint32_t clen, uint8_t* out, uint32_t cap, int fast) {
+  (void)fast;
   try {
     size_t used = 0;
     zq::Assembled code = zq::parse_block_header(header, hlen, &used);
@@ -103,7 +104,11 @@ extern "C" long emu_cm_decode(const uint8_t* header, uint32_t hlen, const uint8_
 #else
     const size_t smem = sizeof(CmSmem) + sizeof(CmUnitSmem);
 #endif
+    #ifdef ZQ_CM_V1
     emu::launch(1, 32, smem, [&] { k_cm_decode(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next); });
+#else
+    emu::launch(1, 32, smem, [&] { k_cm_decode(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast); });
+#endif
     free(model);
     if (res.error) return -(1000 + (long)res.error);
     return (long)res.out_len;

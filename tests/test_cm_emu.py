@@ -67,9 +67,9 @@ def _emu_encode(emu, header, pcomp, stream, threads=64, prefetch=1, fast=1):
     return bytes(out[:n])
 
 
-def _emu_decode(emu, header, coded, cap):
+def _emu_decode(emu, header, coded, cap, fast=1):
     out = (C.c_uint8 * (cap + 16))()
-    n = emu.emu_cm_decode(header, len(header), coded, len(coded), out, cap + 16)
+    n = emu.emu_cm_decode(header, len(header), coded, len(coded), out, cap + 16, fast)
     assert n >= 0, n
     return bytes(out[:n])
 
@@ -85,6 +85,7 @@ def test_builtin_models_encode_and_decode(emu, oracle, method):
     assert _emu_encode(emu, header, pcomp, stream, fast=0) == want     # chain models: the generic lane engine too
     # decoder: coded data + end-of-stream zeros -> post-processed original
     assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data)) == data
+    assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data), fast=0) == data
 
 
 @pytest.mark.parametrize("name", sorted(CONFIGS))

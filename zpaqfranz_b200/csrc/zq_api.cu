@@ -928,7 +928,11 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
     ++c->launches;
     k_cm_decode<<<std::min((wn + 15) / 16, c->num_sms), 512, dec_smem, c->stream>>>(
         c->d_in.as<u8>(), c->d_units.as<ZqDecUnit>(), c->d_cmplans.as<ZqCmPlan>(), wn, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
+#ifdef ZQ_CM_V1
         c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr);
+#else
+        c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr, c->cm_fast);
+#endif
     ++c->launches;
     ZQ_CUDA(c, cudaMemcpyAsync(res.data() + w0, d_res, (size_t)wn * sizeof(ZqDecResult), cudaMemcpyDeviceToHost, c->stream));
     ZQ_CUDA(c, cudaStreamSynchronize(c->stream));

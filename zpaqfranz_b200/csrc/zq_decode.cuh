@@ -42,8 +42,10 @@ struct DecPost {
 
 // PostProcessor::write (Z:15368). Machine state and the output count live on lane 0; `outlen`/errors are
 // re-broadcast after every step so the warp's control flow stays uniform.
+// SOLO: the whole warp's work is being done by the calling lane alone (chain fast path): no lane tests, no shuffles.
+template <bool SOLO>
 __device__ __forceinline__ void dec_post_write(DecPost& pp, int c) {
-  const u32 lane = lane_id();
+  const u32 lane = SOLO ? 0u : lane_id();
   switch (pp.state) {
     case 0:
       if (c < 0) { pp.error = 2; break; }
@@ -71,19 +73,66 @@ __device__ __forceinline__ void dec_post_write(DecPost& pp, int c) {
       break;
     default:
       if (lane == 0) cm_vm_run<true>(pp.vm, (u32)c, &pp.o);   // c == -1 at end of segment -> a = 0xFFFFFFFF
-      pp.o.len = __shfl_sync(ZQ_FULL, pp.o.len, 0);
-      pp.o.error = __shfl_sync(ZQ_FULL, pp.o.error, 0);
-      pp.vm.error = __shfl_sync(ZQ_FULL, pp.vm.error, 0);
+      if (!SOLO) {
+        pp.o.len = __shfl_sync(ZQ_FULL, pp.o.len, 0);
+        pp.o.error = __shfl_sync(ZQ_FULL, pp.o.error, 0);
+        pp.vm.error = __shfl_sync(ZQ_FULL, pp.vm.error, 0);
+      }
       if (pp.o.error) pp.error = pp.o.error;
       break;
   }
+}
+
+// ---- decoder fast path for the chain ICM -> ISSE (see zq_cm.cuh): one lane, straight-line per bit ----------
+struct ChainDec {
+  u32 low, high, curr, err;
+  DecIn in;
+  __device__ __forceinline__ int bit(u32 p16) {   // Decoder::decode, Z:15282
+    if (curr < low || curr > high) { err = 1; return 0; }
+    const u32 mid = low + (u32)(((u64)(high - low) * p16) >> 16);
+    int y;
+    if (curr <= mid) { y = 1; high = mid; } else { y = 0; low = mid + 1; }
+    while ((high ^ low) < 0x1000000u) {
+      high = high << 8 | 255; low = low << 8; low += (low == 0);
+      curr = curr << 8 | (u32)in.get();
+    }
+    return y;
+  }
+};
+// one bit: node slot `k` of row words (wa of the ICM, wb of the ISSE); returns y and updates tables and rows
+__device__ __forceinline__ u32 chain1_dec_bit(ChainComp& A, ChainComp& B, u32& wa, u32& wb, u32 k, ChainDec& D, const CmSmem& T) {
+  const u32 sa = chain_get(wa, k), sb = chain_get(wb, k);
+  u32 pn = A.cm[sa];
+  int2 w = *(const int2*)(B.cm + sb * 2);
+  const int pa = T.stretch[pn >> 8];
+  const int pb = cm_clamp2k((w.x * pa + w.y * 64) >> 16);
+  const int pr = T.squash[pb + 2048];
+  const u32 y = (u32)D.bit((u32)pr * 2 + 1);
+  pn += (u32)(((int)(y * 32767u) - (int)(pn >> 8)) >> 2);
+  A.cm[sa] = pn;
+  const int err = (int)(y * 32767u) - pr;
+  w.x = cm_clamp512k(w.x + ((err * pa + (1 << 12)) >> 13));
+  w.y = cm_clamp512k(w.y + ((err + 16) >> 5));
+  *(int2*)(B.cm + sb * 2) = w;
+  wa = chain_put(wa, k, T.ns[sa * 4 + y]);
+  wb = chain_put(wb, k, T.ns[sb * 4 + y]);
+  return y;
+}
+__device__ __forceinline__ u32 chain1_dec_nibble(ChainComp& A, ChainComp& B, ChainDec& D, const CmSmem& T) {
+  const u32 y0 = chain1_dec_bit(A, B, A.row.x, B.row.x, 1u, D, T);
+  const u32 y1 = chain1_dec_bit(A, B, A.row.x, B.row.x, 2u + y0, D, T);
+  const u32 y2 = chain1_dec_bit(A, B, A.row.y, B.row.y, 2u * y0 + y1, D, T);
+  u32 y3;
+  if (y0 == 0) y3 = chain1_dec_bit(A, B, A.row.z, B.row.z, 2u * y1 + y2, D, T);
+  else y3 = chain1_dec_bit(A, B, A.row.w, B.row.w, 2u * y1 + y2, D, T);
+  return y0 << 3 | y1 << 2 | y2 << 1 | y3;
 }
 
 // 16 warps per CTA, one block per warp; dynamic shared memory: CmSmem + one CmUnitSmem per warp.
 __global__ void __launch_bounds__(512, 1)
 k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units, const ZqCmPlan* __restrict__ cmplans, int nunits,
             const CmTablesDev* __restrict__ tab, const u8* __restrict__ blob, u8* __restrict__ model_base,
-            u8* __restrict__ out_base, ZqDecResult* __restrict__ results, u32* __restrict__ next_unit) {
+            u8* __restrict__ out_base, ZqDecResult* __restrict__ results, u32* __restrict__ next_unit, int fast) {
   ZQ_DYN_SMEM(smem_raw);
   CmSmem& T = *reinterpret_cast<CmSmem*>(smem_raw);
   {
@@ -115,6 +164,34 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
     pp.vm.mmask = (1u << cp.pm) - 1; pp.vm.hmask = (1u << cp.ph) - 1; pp.vm.code = pp.code; pp.vm.len = 0;
     DecIn in; in.p = in_base + u.data_off; in.len = u.data_len; in.pos = 0; in.error = 0;
     u32 err = 0, vmerr = 0;
+    if (cp.chain == 1 && fast) {
+      if (lane == 0) {
+        ChainComp A, B;
+        chain_setup(A, cp.comp[0], model);
+        chain_setup(B, cp.comp[1], model);
+        ChainDec D; D.low = 1; D.high = 0xffffffffu; D.curr = 0; D.err = 0; D.in = in;
+        for (int k = 0; k < 4; ++k) D.curr = D.curr << 8 | (u32)D.in.get();
+        u32 ha = 0, hb = 0;
+        for (;;) {
+          if (D.bit(0)) { if (D.curr != 0 && !D.err) D.err = 1; break; }
+          chain_row_switch(A, ha + 16u); chain_row_switch(B, hb + 16u);
+          const u32 hi = chain1_dec_nibble(A, B, D, T);
+          chain_row_switch(A, ha + 16u * (16u + hi)); chain_row_switch(B, hb + 16u * (16u + hi));
+          const u32 c = hi << 4 | chain1_dec_nibble(A, B, D, T);
+          cm_vm_run<false>(vm, c, nullptr);
+          ha = vm.h[0]; hb = vm.h[1 & vm.hmask];
+          dec_post_write<true>(pp, (int)c);
+          if (D.err || D.in.error || pp.error || vm.error || pp.vm.error) break;
+        }
+        if (!D.err && !D.in.error && !pp.error && !vm.error && !pp.vm.error) dec_post_write<true>(pp, -1);
+        ZqDecResult r;
+        r.out_len = pp.o.len; r.consumed = (u32)D.in.pos; r.pad = 0;
+        r.error = D.err ? D.err : D.in.error ? D.in.error : pp.error ? pp.error : (vm.error || pp.vm.error) ? 4u : 0u;
+        results[t] = r;
+      }
+      __syncwarp();
+      continue;
+    }
     if (cp.n > 0) {
       u32 low = 1, high = 0xffffffffu, curr = 0;
       for (int k = 0; k < 4; ++k) curr = curr << 8 | (u32)in.get();
@@ -143,7 +220,7 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
             vmerr = (u32)__shfl_sync(ZQ_FULL, vm.error, 0);
           }
         }
-        dec_post_write(pp, c - 256);
+        dec_post_write<false>(pp, c - 256);
         if (err || in.error || pp.error || vmerr || pp.vm.error) break;
       }
     } else {
@@ -151,11 +228,11 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
         u32 cl = 0;
         for (int k = 0; k < 4; ++k) cl = cl << 8 | (u32)in.get();
         if (cl == 0 || in.error) break;
-        for (u32 k = 0; k < cl; ++k) dec_post_write(pp, in.get());
+        for (u32 k = 0; k < cl; ++k) dec_post_write<false>(pp, in.get());
         if (in.error || pp.error || pp.vm.error) break;
       }
     }
-    if (!err && !in.error && !pp.error && !vmerr && !pp.vm.error) dec_post_write(pp, -1);
+    if (!err && !in.error && !pp.error && !vmerr && !pp.vm.error) dec_post_write<false>(pp, -1);
     if (lane == 0) {
       ZqDecResult r;
       r.out_len = pp.o.len; r.consumed = (u32)in.pos; r.pad = 0;
