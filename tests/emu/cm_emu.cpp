@@ -49,6 +49,7 @@ extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_
     std::vector<u8> blob(payload, payload + plen);
     cp.hcomp_off = (u32)blob.size(); cp.hcomp_len = (u32)code.hcomp.size();
     blob.insert(blob.end(), code.hcomp.begin(), code.hcomp.end());
+    blob.resize(blob.size() + 16);   // like the device blob: slack after the last byte code
     u8* model = (u8*)aligned_alloc(256, (size_t)cp.model_bytes + 256);
     for (u32 j = 0; j < cp.fill_count; ++j) host_fill(fills[cp.fill_first + j], tab, model);
     ZqUnit u; memset(&u, 0, sizeof u);
@@ -92,6 +93,7 @@ extern "C" long emu_cm_decode(const uint8_t* header, uint32_t hlen, const uint8_
     const zq::CmTables& tab = zq::cm_tables();
     std::vector<u8> blob(code.hcomp.begin(), code.hcomp.end());
     cp.hcomp_off = 0; cp.hcomp_len = (u32)code.hcomp.size();
+    blob.resize(blob.size() + 16);
     u8* model = (u8*)aligned_alloc(256, (size_t)cp.model_bytes + 256);
     for (u32 j = 0; j < cp.fill_count; ++j) host_fill(fills[cp.fill_first + j], tab, model);
     ZqDecUnit u; memset(&u, 0, sizeof u);

@@ -27,6 +27,8 @@ for s in $STEPS; do
     ncu_bwt)
       timeout 300 $NCU --set full --import-source on -k regex:k_cm_encode -c 1 -f -o $O/${TAG}_cm_bwt \
         python tools/prof_step.py --method 36,200,1 --units 296 --unit 16384 --steps 1 > $O/${TAG}_ncu_cm_bwt.log 2>&1 ;;
+    configs)
+      timeout 500 python tools/bench_configs.py --c5-units 1200 > $O/${TAG}_configs_c3_c4_c5.json 2> $O/${TAG}_configs.err ;;
     cmtime)
       timeout 400 python tools/bench_configs.py --skip c4 --c5-units 1200 > $O/${TAG}_configs_c3_c5.json 2> $O/${TAG}_configs.err ;;
     cmtime_nopf)

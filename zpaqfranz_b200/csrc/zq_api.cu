@@ -1106,6 +1106,7 @@ int zq_fragment_ex(zq_ctx* c, int nfiles, const uint8_t* base, const uint64_t* o
   const size_t o_segs = take(sizeof(ZqSeg) * nseg), o_exA = take(8 * (size_t)nseg), o_exB = take(8 * (size_t)nseg), o_ent = take(8 * (size_t)nseg);
   const size_t o_bA = take(8 * per), o_bB = take(8 * per), o_hA = take(4 * per), o_hB = take(4 * per);
   const size_t o_cA = take(4 * (size_t)nseg), o_cB = take(4 * (size_t)nseg), o_fl = take(64), o_first = take(8 * (size_t)nseg);
+  const size_t o_cv = take(4 * (size_t)nseg), o_ce = take(8 * (size_t)nseg), o_lv = take(4 * 256), o_hv = take(4 * 256), o_rf = take(4 * (size_t)nseg);
   ZQ_CUDA(c, c->d_work.ensure(o));
   u8* W = c->d_work.as<u8>();
   ZQ_CUDA(c, cudaMemcpyAsync(W + o_segs, segs.data(), sizeof(ZqSeg) * nseg, cudaMemcpyHostToDevice, c->stream));
@@ -1118,9 +1119,29 @@ int zq_fragment_ex(zq_ctx* c, int nfiles, const uint8_t* base, const uint64_t* o
     k_fragment_round<<<(nseg + FRAG_THREADS - 1) / FRAG_THREADS, FRAG_THREADS, 0, c->stream>>>(
         c->d_in.as<u8>(), (const ZqSeg*)(W + o_segs), nseg, round, minf, maxf, thresh, cap, (const u64*)(W + exP), (u64*)(W + exN),
         (u64*)(W + o_ent), (const u64*)(W + bP), (const u32*)(W + hP), (const u32*)(W + cP), (u64*)(W + bN), (u32*)(W + hN),
-        (u32*)(W + cN), (u32*)(W + o_fl), (u32*)(W + o_fl + 4));
+        (u32*)(W + cN), (u32*)(W + o_fl), (u32*)(W + o_fl + 4), (u32*)(W + o_cv), (const u64*)(W + o_ce), (const u32*)(W + o_rf),
+        (const u32*)(W + o_lv), (const u32*)(W + o_hv));
     ++c->launches;
     cur ^= 1;
+    if (round == 0) {   // constant segments -> end of the constant run they belong to (same value, same file)
+      std::vector<uint32_t> cv(nseg);
+      ZQ_CUDA(c, cudaMemcpyAsync(cv.data(), W + o_cv, 4 * (size_t)nseg, cudaMemcpyDeviceToHost, c->stream));
+      ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+      std::vector<uint64_t> ce(nseg, 0);
+      std::vector<uint32_t> rf(nseg);
+      for (int k = nseg - 1; k >= 0; --k)
+        if (cv[k] < 256) ce[k] = (k + 1 < nseg && !segs[k + 1].first && cv[k + 1] == cv[k]) ? ce[k + 1] : segs[k].end;
+      for (int k = 0; k < nseg; ++k)
+        rf[k] = (cv[k] < 256 && k > 0 && !segs[k].first && cv[k - 1] == cv[k]) ? rf[k - 1] : (uint32_t)k;
+      ZQ_CUDA(c, cudaMemcpyAsync(W + o_ce, ce.data(), 8 * (size_t)nseg, cudaMemcpyHostToDevice, c->stream));
+      ZQ_CUDA(c, cudaMemcpyAsync(W + o_rf, rf.data(), 4 * (size_t)nseg, cudaMemcpyHostToDevice, c->stream));
+      bool any = false;
+      for (int k = 0; k < nseg && !any; ++k) any = cv[k] < 256;
+      if (any) {   // the fragment a fresh machine cuts from an endless run of each byte value
+        k_fragment_const_table<<<1, 256, 0, c->stream>>>(minf, maxf, thresh, (u32*)(W + o_lv), (u32*)(W + o_hv));
+        ++c->launches;
+      }
+    }
     uint32_t flags[2] = {0, 0};
     ZQ_CUDA(c, cudaMemcpyAsync(flags, W + o_fl, 8, cudaMemcpyDeviceToHost, c->stream));
     ZQ_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -151,18 +151,14 @@ struct CmVm {   // registers live on the lane that owns the machine (lane 0)
 };
 struct VmOut { u8* out; u32 len, cap, error; };   // PCOMP's OUT sink (decoder)
 
-// One run of the program (ZPAQL::run0, Z:14232) by ONE lane.  A single switch over the opcode byte:
-// the two-operand group (opcode >= 64: operation = op>>3, source = op&7) is expanded case by case so the
-// dispatch is one indirect branch per instruction.
-#define ZQ_VM_X8(B, STMT)                                                  \
-  case (B) + 0: { const u32 x = a; STMT; } break;                          \
-  case (B) + 1: { const u32 x = b; STMT; } break;                          \
-  case (B) + 2: { const u32 x = c; STMT; } break;                          \
-  case (B) + 3: { const u32 x = d; STMT; } break;                          \
-  case (B) + 4: { const u32 x = M[b & mm]; STMT; } break;                  \
-  case (B) + 5: { const u32 x = M[c & mm]; STMT; } break;                  \
-  case (B) + 6: { const u32 x = H[d & hm]; STMT; } break;                  \
-  case (B) + 7: { const u32 x = P[pc++]; STMT; } break;
+// One run of the program (ZPAQL::run0, Z:14232) by ONE lane.  The first interpreter dispatched through a
+// 256-way switch, which nvcc lowers to a nine-level compare/branch tree spread over 25 KB of code: ncu
+// (profiles/r01j) put ~290 of the ~380 cycles per ZPAQL instruction there (taken branches + instruction-cache
+// misses), and with the chain fast path the context warp had become the critical path.  ZPAQL's opcode byte is
+// regular -- two-operand group: operation = op>>3, source = op&7; one-operand groups: target = op>>3, action =
+// op&7 -- so each group is decoded arithmetically and executed as straight-line predicated code; only the
+// group choice and a handful of rare opcodes branch.  The opcode's operand byte is fetched together with it
+// (code buffers end with a spare byte).
 template <bool WITH_OUT>
 __device__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) {
   const u8* P = v.code;
@@ -173,53 +169,73 @@ __device__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) {
   u32 a = input, b = v.b, c = v.c, d = v.d; int f = v.f;
   while (!stop) {
     if ((u32)pc >= (u32)len) { stop = 2; break; }
-    const u32 op = P[pc++];
-    switch (op) {
-      case 1: ++a; break; case 2: --a; break; case 3: a = ~a; break; case 4: a = 0; break;
-      case 7: a = R[P[pc++]]; break;
-      case 8: { const u32 t = a; a = b; b = t; } break;
-      case 9: ++b; break; case 10: --b; break; case 11: b = ~b; break; case 12: b = 0; break;
-      case 15: b = R[P[pc++]]; break;
-      case 16: { const u32 t = a; a = c; c = t; } break;
-      case 17: ++c; break; case 18: --c; break; case 19: c = ~c; break; case 20: c = 0; break;
-      case 23: c = R[P[pc++]]; break;
-      case 24: { const u32 t = a; a = d; d = t; } break;
-      case 25: ++d; break; case 26: --d; break; case 27: d = ~d; break; case 28: d = 0; break;
-      case 31: d = R[P[pc++]]; break;
-      case 32: { const u32 t = M[b & mm]; M[b & mm] = (u8)a; a = (a & ~255u) | t; } break;
-      case 33: M[b & mm] = (u8)(M[b & mm] + 1); break; case 34: M[b & mm] = (u8)(M[b & mm] - 1); break;
-      case 35: M[b & mm] = (u8)~M[b & mm]; break; case 36: M[b & mm] = 0; break;
-      case 39: if (f) pc += (int)((P[pc] + 128u) & 255u) - 127; else ++pc; break;
-      case 40: { const u32 t = M[c & mm]; M[c & mm] = (u8)a; a = (a & ~255u) | t; } break;
-      case 41: M[c & mm] = (u8)(M[c & mm] + 1); break; case 42: M[c & mm] = (u8)(M[c & mm] - 1); break;
-      case 43: M[c & mm] = (u8)~M[c & mm]; break; case 44: M[c & mm] = 0; break;
-      case 47: if (!f) pc += (int)((P[pc] + 128u) & 255u) - 127; else ++pc; break;
-      case 48: { const u32 t = H[d & hm]; H[d & hm] = a; a = t; } break;
-      case 49: H[d & hm] = H[d & hm] + 1; break; case 50: H[d & hm] = H[d & hm] - 1; break;
-      case 51: H[d & hm] = ~H[d & hm]; break; case 52: H[d & hm] = 0; break;
-      case 55: R[P[pc++]] = a; break;
-      case 56: stop = 1; break;
-      case 57:
-        if (WITH_OUT) { if (o->len < o->cap) o->out[o->len] = (u8)a; else o->error = 3; ++o->len; }
-        break;
-      case 59: a = (a + M[b & mm] + 512u) * 773u; break;
-      case 60: H[d & hm] = (H[d & hm] + a + 512u) * 773u; break;
-      case 63: pc += (int)((P[pc] + 128u) & 255u) - 127; break;
-      ZQ_VM_X8(64, a = x) ZQ_VM_X8(72, b = x) ZQ_VM_X8(80, c = x) ZQ_VM_X8(88, d = x)
-      ZQ_VM_X8(96, M[b & mm] = (u8)x) ZQ_VM_X8(104, M[c & mm] = (u8)x) ZQ_VM_X8(112, H[d & hm] = x)
-      ZQ_VM_X8(128, a += x) ZQ_VM_X8(136, a -= x) ZQ_VM_X8(144, a *= x)
-      ZQ_VM_X8(152, a = x ? a / x : 0u) ZQ_VM_X8(160, a = x ? a % x : 0u)
-      ZQ_VM_X8(168, a &= x) ZQ_VM_X8(176, a &= ~x) ZQ_VM_X8(184, a |= x) ZQ_VM_X8(192, a ^= x)
-      ZQ_VM_X8(200, a <<= (x & 31u)) ZQ_VM_X8(208, a >>= (x & 31u))
-      ZQ_VM_X8(216, f = a == x) ZQ_VM_X8(224, f = a < x) ZQ_VM_X8(232, f = a > x)
-      case 255: pc = (int)P[pc] + 256 * (int)P[pc + 1]; break;
-      default: stop = 2;
+    const u32 op = P[pc], arg = P[pc + 1];
+    if (op >= 64) {
+      // ---- two operands: a/b/c/d/*b/*c/*d = x, a op= x, f = a cmp x
+      const u32 src = op & 7, grp = op >> 3;
+      u32 x = arg;
+      if (src < 4) x = src == 0 ? a : src == 1 ? b : src == 2 ? c : d;
+      else if (src == 4) x = M[b & mm];
+      else if (src == 5) x = M[c & mm];
+      else if (src == 6) x = H[d & hm];
+      pc += src == 7 ? 2 : 1;
+      if (grp < 15) {
+        if (grp == 8) a = x; else if (grp == 9) b = x; else if (grp == 10) c = x; else if (grp == 11) d = x;
+        else if (grp == 12) M[b & mm] = (u8)x; else if (grp == 13) M[c & mm] = (u8)x; else H[d & hm] = x;
+      } else if (grp >= 16 && grp <= 26 && grp != 19 && grp != 20) {
+        const u32 sh = x & 31u;
+        a = grp == 16 ? a + x : grp == 17 ? a - x : grp == 18 ? a * x : grp == 21 ? (a & x) : grp == 22 ? (a & ~x) :
+            grp == 23 ? (a | x) : grp == 24 ? (a ^ x) : grp == 25 ? (a << sh) : (a >> sh);
+      } else if (grp >= 27 && grp <= 29) f = grp == 27 ? a == x : grp == 28 ? a < x : a > x;
+      else if (grp == 19) a = x ? a / x : 0u;
+      else if (grp == 20) a = x ? a % x : 0u;
+      else if (op == 255) pc = (int)arg + 256 * (int)P[pc];   // LJ: pc already points at the third byte
+      else stop = 2;                                          // groups 15, 30, 31
+    } else if (op < 32) {
+      // ---- register target (a,b,c,d = op>>3): <>a, ++, --, !, =0, =r N
+      const u32 t = op >> 3, act = op & 7;
+      const u32 val = t == 0 ? a : t == 1 ? b : t == 2 ? c : d;
+      u32 nv;
+      if (act == 7) { nv = R[arg]; pc += 2; }
+      else { nv = act == 1 ? val + 1 : act == 2 ? val - 1 : act == 3 ? ~val : act == 4 ? 0u : a; pc += 1; }
+      if (act == 5 || act == 6 || op == 0) { stop = 2; break; }
+      if (act == 0) a = val;                 // swap: a takes the target's old value, the target takes a's
+      if (t == 0) a = nv; else if (t == 1) b = nv; else if (t == 2) c = nv; else d = nv;
+    } else if (op < 56 && (op & 7) <= 4) {
+      // ---- memory target (*b,*c,*d = (op>>3)-4): <>a, ++, --, !, =0
+      const u32 act = op & 7;
+      if (op >= 48) {
+        const u32 old = H[d & hm];
+        H[d & hm] = act == 0 ? a : act == 1 ? old + 1 : act == 2 ? old - 1 : act == 3 ? ~old : 0u;
+        if (act == 0) a = old;
+      } else {
+        const u32 idx = (op >= 40 ? c : b) & mm;
+        const u32 old = M[idx];
+        M[idx] = (u8)(act == 0 ? a : act == 1 ? old + 1 : act == 2 ? old - 1 : act == 3 ? ~old : 0u);
+        if (act == 0) a = (a & ~255u) | old;
+      }
+      pc += 1;
+    } else {
+      const int rel = (int)((arg + 128u) & 255u) - 127;   // jump distance counted from the operand byte
+      switch (op) {
+        case 39: pc = f ? pc + 1 + rel : pc + 2; break;
+        case 47: pc = !f ? pc + 1 + rel : pc + 2; break;
+        case 63: pc = pc + 1 + rel; break;
+        case 55: R[arg] = a; pc += 2; break;
+        case 56: stop = 1; break;
+        case 57:
+          if (WITH_OUT) { if (o->len < o->cap) o->out[o->len] = (u8)a; else o->error = 3; ++o->len; }
+          pc += 1;
+          break;
+        case 59: a = (a + M[b & mm] + 512u) * 773u; pc += 1; break;
+        case 60: H[d & hm] = (H[d & hm] + a + 512u) * 773u; pc += 1; break;
+        default: stop = 2;
+      }
     }
   }
   if (stop == 2) v.error = 1;
   v.a = a; v.b = b; v.c = c; v.d = d; v.f = f;
 }
-#undef ZQ_VM_X8
 
 __device__ __forceinline__ int cm_clamp2k(int x) { return min(max(x, -2048), 2047); }
 __device__ __forceinline__ int cm_clamp512k(int x) { return min(max(x, -(1 << 19)), (1 << 19) - 1); }
@@ -493,7 +509,7 @@ __device__ __forceinline__ void cm_vm_setup(CmVm& vm, const ZqCmPlan& cp, u8* mo
     for (u32 k = lane; k < (1u << cp.hh); k += 32) S.hbuf[k] = 0;
   } else vm.h = (u32*)(model + cp.h_off);
   vm.len = (int)cp.hcomp_len;
-  if (cp.hcomp_len <= ZQ_CM_CODE_CAP) {
+  if (cp.hcomp_len < ZQ_CM_CODE_CAP) {   // strictly: the interpreter reads the byte after an opcode
     for (u32 k = lane; k < cp.hcomp_len; k += 32) S.code[k] = blob[cp.hcomp_off + k];
     vm.code = S.code;
   } else vm.code = blob + cp.hcomp_off;

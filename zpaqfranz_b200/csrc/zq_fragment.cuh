@@ -13,6 +13,14 @@
 // fresh there, so the old tail is the true continuation).  Rounds repeat until no exit changes;
 // segment 0 of each file is true from the start, so the fix point is the reference's chain.
 // One thread per segment; the 256-byte o1 table of each thread lives in shared memory.
+//
+// Constant runs (zero pages, sparse files) never re-synchronise: every machine started inside the run cuts
+// fragments of the same length L(v) relative to ITS start, so a speculative chain is only right if its start is
+// congruent to the true one.  A fresh machine fed nothing but the byte v is a fixed sequence, so L(v) and its hit
+// count are tabulated once (k_fragment_const_table); round 0 marks the segments that hold a single byte value,
+// and from round 1 on a fragment that starts inside such a segment and fits before the end of the constant run is
+// emitted in closed form instead of being scanned; a segment deep inside a run takes its entry straight from the
+// run's entry (entry_run + j*L(v)), so a whole run settles in one round once its entry is final.
 #pragma once
 #include "zq_common.cuh"
 
@@ -26,6 +34,25 @@ struct ZqSeg {
 };
 
 constexpr int FRAG_THREADS = 128;
+constexpr u32 FRAG_NOT_CONST = 256;
+
+// L(v), hits(v): length and predictor hits of the fragment a fresh machine cuts from an endless run of byte v.
+// Only o1[0] (the virtual byte in front of the fragment is 0) and o1[v] are ever touched.
+__global__ void __launch_bounds__(256)
+k_fragment_const_table(u32 minf, u32 maxf, u32 thresh, u32* __restrict__ Lv, u32* __restrict__ Hv) {
+  const u32 v = threadIdx.x;
+  u32 o1_0 = 0, o1_v = 0, c1 = 0, h = 0, hits = 0, sz = 0;
+  for (;;) {
+    const u32 pred = (c1 == 0 || v == 0) ? o1_0 : o1_v;
+    const bool hit = v == pred;
+    h = (h + v + 1u) * (hit ? 314159265u : 271828182u);
+    hits += hit;
+    if (c1 == 0 || v == 0) o1_0 = v; else o1_v = v;
+    c1 = v; ++sz;
+    if (sz >= maxf || (thresh && h < thresh && sz >= minf)) break;
+  }
+  Lv[v] = sz; Hv[v] = hits;
+}
 
 __global__ void __launch_bounds__(FRAG_THREADS)
 k_fragment_round(const u8* __restrict__ base, const ZqSeg* __restrict__ segs, int nseg, int round,
@@ -33,13 +60,26 @@ k_fragment_round(const u8* __restrict__ base, const ZqSeg* __restrict__ segs, in
                  const u64* __restrict__ exit_prev, u64* __restrict__ exit_next,
                  u64* __restrict__ entry, const u64* __restrict__ bnd_prev, const u32* __restrict__ hits_prev,
                  const u32* __restrict__ cnt_prev, u64* __restrict__ bnd_next, u32* __restrict__ hits_next,
-                 u32* __restrict__ cnt_next, u32* __restrict__ changed, u32* __restrict__ overflow) {
+                 u32* __restrict__ cnt_next, u32* __restrict__ changed, u32* __restrict__ overflow,
+                 u32* __restrict__ constv /* round 0 writes, later rounds read */, const u64* __restrict__ const_end,
+                 const u32* __restrict__ run_first, const u32* __restrict__ Lv, const u32* __restrict__ Hv) {
   __shared__ u8 o1s[FRAG_THREADS][256 + 4];   // +4: stagger banks between threads
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nseg) return;
   u8* o1 = o1s[threadIdx.x];
   const ZqSeg sg = segs[k];
-  const u64 e = (round == 0 || sg.first) ? sg.begin : exit_prev[k - 1];
+  u64 e = (round == 0 || sg.first) ? sg.begin : exit_prev[k - 1];
+  const u32 cv = round ? constv[k] : FRAG_NOT_CONST;
+  const u64 cend = round ? const_end[k] : 0;
+  if (cv < FRAG_NOT_CONST && run_first[k] != (u32)k) {   // inside a constant run: boundaries are entry_run + j*L(v)
+    const u32 r = run_first[k];
+    const u64 er = segs[r].first ? segs[r].begin : exit_prev[r - 1];
+    const u64 L = Lv[cv];
+    if (er <= sg.begin) {
+      const u64 cand = er + (sg.begin - er + L - 1) / L * L;
+      if (cand <= cend) e = cand;
+    }
+  }
   const u64* oldb = bnd_prev + (u64)k * cap; const u32* oldh = hits_prev + (u64)k * cap;
   u64* nb = bnd_next + (u64)k * cap; u32* nh = hits_next + (u64)k * cap;
   const u32 oldn = round ? cnt_prev[k] : 0;
@@ -52,16 +92,27 @@ k_fragment_round(const u8* __restrict__ base, const ZqSeg* __restrict__ segs, in
   u32 cnt = 0, op = 0;
   u64 pos = e, ex = e;
   bool merged = false;
+  // round 0 (entry == begin): does the segment hold a single byte value?
+  const u64 seg_stop = min(sg.end, sg.file_end);
+  const u32 v0 = sg.begin < seg_stop ? (u32)base[sg.begin] : 0u;
+  bool same = round == 0;
   while (pos < sg.end && pos < sg.file_end) {   // a fragment starts inside this segment
-    for (int q = 0; q < 256; q += 4) *(u32*)(o1 + q) = 0;
-    u32 h = 0, hits = 0, sz = 0, c1 = 0;
-    for (;;) {
-      const u32 c = base[pos++];
-      const bool hit = c == o1[c1];
-      h = (h + c + 1u) * (hit ? 314159265u : 271828182u);
-      hits += hit;
-      o1[c1] = (u8)c; c1 = c; ++sz;
-      if (pos >= sg.file_end || sz >= maxf || (thresh && h < thresh && sz >= minf)) break;
+    u32 hits = 0;
+    if (cv < FRAG_NOT_CONST && pos + Lv[cv] <= cend) {   // wholly inside a constant run: closed form
+      pos += Lv[cv]; hits = Hv[cv];
+    } else {
+      for (int q = 0; q < 256; q += 4) *(u32*)(o1 + q) = 0;
+      u32 h = 0, sz = 0, c1 = 0;
+      for (;;) {
+        const u32 c = base[pos];
+        if (same && pos < seg_stop && c != v0) same = false;
+        ++pos;
+        const bool hit = c == o1[c1];
+        h = (h + c + 1u) * (hit ? 314159265u : 271828182u);
+        hits += hit;
+        o1[c1] = (u8)c; c1 = c; ++sz;
+        if (pos >= sg.file_end || sz >= maxf || (thresh && h < thresh && sz >= minf)) break;
+      }
     }
     if (cnt < cap) { nb[cnt] = pos; nh[cnt] = hits; } else atomicOr(overflow, 1u);
     ++cnt;
@@ -76,6 +127,7 @@ k_fragment_round(const u8* __restrict__ base, const ZqSeg* __restrict__ segs, in
     }
   }
   (void)merged;
+  if (round == 0) constv[k] = (same && sg.begin < seg_stop) ? v0 : FRAG_NOT_CONST;
   cnt_next[k] = min(cnt, cap);
   exit_next[k] = ex;
   if (!round || ex != exit_prev[k]) atomicOr(changed, 1u);
