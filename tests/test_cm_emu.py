@@ -58,43 +58,45 @@ def _coded_by_oracle(oracle, header, pcomp, stream):
     return blk[pre:-6]                       # ... coded ... 00 00 00 00 FE FF
 
 
-def _emu_encode(emu, header, pcomp, stream, threads=64, prefetch=1, fast=1):
+def _emu_encode(emu, header, pcomp, stream, threads=64, prefetch=1, fast=1, vm=0):
     payload = (bytes([1, len(pcomp) & 255, len(pcomp) >> 8]) + pcomp) if pcomp else b"\0"
     cap = len(stream) * 2 + len(payload) * 2 + 4096
     out = (C.c_uint8 * cap)()
-    n = emu.emu_cm_encode(header, len(header), payload, len(payload), stream, len(stream), out, cap, threads, prefetch | fast << 1)
+    n = emu.emu_cm_encode(header, len(header), payload, len(payload), stream, len(stream), out, cap, threads, prefetch | fast << 1 | vm << 2)
     assert n >= 0, n
     return bytes(out[:n])
 
 
-def _emu_decode(emu, header, coded, cap, fast=1):
+def _emu_decode(emu, header, coded, cap, fast=1, vm=0):
     out = (C.c_uint8 * (cap + 16))()
-    n = emu.emu_cm_decode(header, len(header), coded, len(coded), out, cap + 16, fast)
+    n = emu.emu_cm_decode(header, len(header), coded, len(coded), out, cap + 16, fast | vm << 2)
     assert n >= 0, n
     return bytes(out[:n])
 
 
+@pytest.mark.parametrize("vm", [0, 1])      # both ZPAQL interpreters (switch / arithmetic selects)
 @pytest.mark.parametrize("method", ["36,200,1", "3", "4", "5", "46,200,1", "412,100,0"])
-def test_builtin_models_encode_and_decode(emu, oracle, method):
+def test_builtin_models_encode_and_decode(emu, oracle, method, vm):
     data = corpus.text_unit(3, 1200) if method != "412,100,0" else corpus.mixed_unit(5, 1200)
     plan = zq.plan_block(method, data)
     header, pcomp = bytes(plan["header"]), bytes(plan["pcomp"])
     stream = oracle.lz_stream(data, plan["args"]) if (plan["args"][1] & 3) else data
     want = _coded_by_oracle(oracle, header, pcomp, stream)
-    assert _emu_encode(emu, header, pcomp, stream) == want
-    assert _emu_encode(emu, header, pcomp, stream, fast=0) == want     # chain models: the generic lane engine too
-    # decoder: coded data + end-of-stream zeros -> post-processed original
-    assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data)) == data
-    assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data), fast=0) == data
+    assert _emu_encode(emu, header, pcomp, stream, vm=vm) == want
+    assert _emu_encode(emu, header, pcomp, stream, fast=0, vm=vm) == want     # chain models: the generic lane engine too
+    # decoder: coded data + end-of-stream zeros -> post-processed original (PCOMP runs on the same interpreter)
+    assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data), vm=vm) == data
+    assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data), fast=0, vm=vm) == data
 
 
+@pytest.mark.parametrize("vm", [0, 1])
 @pytest.mark.parametrize("name", sorted(CONFIGS))
-def test_custom_models_encode_and_decode(emu, oracle, name):
+def test_custom_models_encode_and_decode(emu, oracle, name, vm):
     header = bytes(zq.assemble_config(CONFIGS[name])["header"])
     for data in (b"", b"x", b"abracadabra" * 30, corpus.text_unit(9, 700), corpus.random_unit(5, 300)):
         want = _coded_by_oracle(oracle, header, b"", data)
-        assert _emu_encode(emu, header, b"", data) == want, (name, len(data))
-        assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data)) == data, (name, len(data))
+        assert _emu_encode(emu, header, b"", data, vm=vm) == want, (name, len(data))
+        assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data), vm=vm) == data, (name, len(data))
 
 
 def test_pairs_share_a_cta_and_prefetch_is_transparent(emu, oracle):

@@ -29,6 +29,12 @@ for s in $STEPS; do
         python tools/prof_step.py --method 36,200,1 --units 296 --unit 16384 --steps 1 > $O/${TAG}_ncu_cm_bwt.log 2>&1 ;;
     configs)
       timeout 500 python tools/bench_configs.py --c5-units 1200 > $O/${TAG}_configs_c3_c4_c5.json 2> $O/${TAG}_configs.err ;;
+    tests_vm1)
+      ZQ_CM_VM=1 timeout 700 python -m pytest tests -m gpu -q > $O/${TAG}_pytest_gpu_vm1.log 2>&1; tail -4 $O/${TAG}_pytest_gpu_vm1.log ;;
+    tests_cm_vm0)
+      ZQ_CM_VM=0 timeout 500 python -m pytest tests/test_gpu_compress.py tests/test_gpu_decode.py tests/test_gpu_segments.py -m gpu -q > $O/${TAG}_pytest_gpu_cm_vm0.log 2>&1; tail -4 $O/${TAG}_pytest_gpu_cm_vm0.log ;;
+    cmtime_vm1)
+      ZQ_CM_VM=1 timeout 400 python tools/bench_configs.py --skip c4 --c5-units 1200 > $O/${TAG}_configs_c3_c5_vm1.json 2> $O/${TAG}_configs_vm1.err ;;
     cmtime)
       timeout 400 python tools/bench_configs.py --skip c4 --c5-units 1200 > $O/${TAG}_configs_c3_c5.json 2> $O/${TAG}_configs.err ;;
     cmtime_nopf)

@@ -81,6 +81,7 @@ struct zq_ctx {
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 1;                         // 1: warp-per-block LZ77 parser (default, faster today); 0: candidates/chain/emit form (ZQ_LZ_PAR=1)
   int cm_occ = 2;                         // first engine only: CTAs (16 warps) per SM of the CM coder
+  int cm_vm = 0;                          // ZPAQL interpreter: 0 switch, 1 arithmetic selects (ZQ_CM_VM)
   int cm_fast = 1;                        // encoder fast path for chain models (ZQ_CM_FAST=0: generic lanes)
   int cm_prefetch = 1;                    // context warp prefetches the coder's table lines (ZQ_CM_PREFETCH=0 to turn off)
   int lz_half = 0;                        // 1: SA parse with two blocks per warp (ZQ_LZ_HALF=1; bit-exact, slower today: the halves serialise)
@@ -501,10 +502,12 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       const int pairs = std::max(1, std::min(ZQ_CM_MAX_PAIRS, (nt + c->num_sms - 1) / c->num_sms));
       const size_t cm_smem = sizeof(CmSmem) + (size_t)pairs * sizeof(CmUnitSmem);
       if (!c->attr_cm_enc) {   // per context (= per device): function attributes are per device
-        cudaFuncSetAttribute(k_cm_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CmSmem) + ZQ_CM_MAX_PAIRS * sizeof(CmUnitSmem)));
+        cudaFuncSetAttribute(k_cm_encode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CmSmem) + ZQ_CM_MAX_PAIRS * sizeof(CmUnitSmem)));
+        cudaFuncSetAttribute(k_cm_encode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CmSmem) + ZQ_CM_MAX_PAIRS * sizeof(CmUnitSmem)));
         c->attr_cm_enc = true;
       }
-      k_cm_encode<<<std::min((nt + pairs - 1) / pairs, c->num_sms), pairs * 64, cm_smem, c->stream>>>(
+      auto cmk = c->cm_vm == 1 ? k_cm_encode<1> : k_cm_encode<0>;
+      cmk<<<std::min((nt + pairs - 1) / pairs, c->num_sms), pairs * 64, cm_smem, c->stream>>>(
           d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
           c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr,
           c->cm_prefetch, c->cm_fast);
@@ -625,6 +628,7 @@ zq_ctx* zq_create(int device) {
   if (const char* s = getenv("ZQ_CM_OCC")) c->cm_occ = atoi(s);
   if (const char* s = getenv("ZQ_CM_PREFETCH")) c->cm_prefetch = atoi(s);
   if (const char* s = getenv("ZQ_CM_FAST")) c->cm_fast = atoi(s);
+  if (const char* s = getenv("ZQ_CM_VM")) c->cm_vm = atoi(s);
   if (const char* s = getenv("ZQ_LZ_PAR")) c->lz_old = atoi(s) ? 0 : 1;
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
   if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);
@@ -900,7 +904,16 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
 #else
   const size_t dec_smem = sizeof(CmSmem) + 16 * sizeof(CmUnitSmem);
 #endif
+#ifdef ZQ_CM_V1
   if (!c->attr_cm_dec) { cudaFuncSetAttribute(k_cm_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem); c->attr_cm_dec = true; }
+#else
+  if (!c->attr_cm_dec) {
+    cudaFuncSetAttribute(k_cm_decode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
+    cudaFuncSetAttribute(k_cm_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
+    c->attr_cm_dec = true;
+  }
+  auto cmd = c->cm_vm == 1 ? k_cm_decode<1> : k_cm_decode<0>;
+#endif
   int w0 = 0;
   while (w0 < n) {
     size_t model = 0; int w1 = w0, maxjobs = 1;
@@ -926,11 +939,13 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
     k_cm_init_pairs<<<wn * maxjobs, 256, 0, c->stream>>>(d_moff, d_pof, c->d_cmplans.as<ZqCmPlan>(), c->d_fills.as<ZqCmFill>(), wn, maxjobs,
                                                         c->d_tables.as<CmTablesDev>(), c->d_model.as<u8>());
     ++c->launches;
+#ifdef ZQ_CM_V1
     k_cm_decode<<<std::min((wn + 15) / 16, c->num_sms), 512, dec_smem, c->stream>>>(
         c->d_in.as<u8>(), c->d_units.as<ZqDecUnit>(), c->d_cmplans.as<ZqCmPlan>(), wn, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
-#ifdef ZQ_CM_V1
         c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr);
 #else
+    cmd<<<std::min((wn + 15) / 16, c->num_sms), 512, dec_smem, c->stream>>>(
+        c->d_in.as<u8>(), c->d_units.as<ZqDecUnit>(), c->d_cmplans.as<ZqCmPlan>(), wn, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
         c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr, c->cm_fast);
 #endif
     ++c->launches;

@@ -151,16 +151,28 @@ struct CmVm {   // registers live on the lane that owns the machine (lane 0)
 };
 struct VmOut { u8* out; u32 len, cap, error; };   // PCOMP's OUT sink (decoder)
 
-// One run of the program (ZPAQL::run0, Z:14232) by ONE lane.  The first interpreter dispatched through a
-// 256-way switch, which nvcc lowers to a nine-level compare/branch tree spread over 25 KB of code: ncu
-// (profiles/r01j) put ~290 of the ~380 cycles per ZPAQL instruction there (taken branches + instruction-cache
-// misses), and with the chain fast path the context warp had become the critical path.  ZPAQL's opcode byte is
-// regular -- two-operand group: operation = op>>3, source = op&7; one-operand groups: target = op>>3, action =
-// op&7 -- so each group is decoded arithmetically and executed as straight-line predicated code; only the
-// group choice and a handful of rare opcodes branch.  The opcode's operand byte is fetched together with it
-// (code buffers end with a spare byte).
+// One run of the program (ZPAQL::run0, Z:14232) by ONE lane.  Two interpreters, chosen per launch (template
+// parameter VM of the kernels, ZQ_CM_VM):
+//  0  a single switch over the opcode byte, the two-operand group (opcode >= 64: operation = op>>3, source =
+//     op&7) expanded case by case.  nvcc lowers it to a nine-level compare/branch tree over 25 KB of code: ncu
+//     (profiles/r01j) puts ~290 of the ~380 cycles per ZPAQL instruction there, and with the chain fast path
+//     the context warp is the critical path.
+//  1  the opcode byte is decoded arithmetically (ZPAQL's encoding is regular) and each group runs as
+//     straight-line select code: all three possible memory operands are fetched (b&mm, c&mm, d&hm always index
+//     inside M / H) and one is picked, every ALU result is formed and one is picked, stores are predicated; only
+//     the group choice and the rare opcodes (division, long jump, jumps, hash) branch.  Selects are inline PTX
+//     selp: written as C conditionals nvcc turns them back into branch trees (measured slower, r01k).
+#define ZQ_VM_X8(B, STMT)                                                  \
+  case (B) + 0: { const u32 x = a; STMT; } break;                          \
+  case (B) + 1: { const u32 x = b; STMT; } break;                          \
+  case (B) + 2: { const u32 x = c; STMT; } break;                          \
+  case (B) + 3: { const u32 x = d; STMT; } break;                          \
+  case (B) + 4: { const u32 x = M[b & mm]; STMT; } break;                  \
+  case (B) + 5: { const u32 x = M[c & mm]; STMT; } break;                  \
+  case (B) + 6: { const u32 x = H[d & hm]; STMT; } break;                  \
+  case (B) + 7: { const u32 x = P[pc++]; STMT; } break;
 template <bool WITH_OUT>
-__device__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) {
+__device__ void cm_vm_run_switch(CmVm& v, u32 input, VmOut* o) {
   const u8* P = v.code;
   u8* M = v.m; u32* H = v.h; u32* R = v.r;
   const u32 mm = v.mmask, hm = v.hmask;
@@ -169,50 +181,138 @@ __device__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) {
   u32 a = input, b = v.b, c = v.c, d = v.d; int f = v.f;
   while (!stop) {
     if ((u32)pc >= (u32)len) { stop = 2; break; }
+    const u32 op = P[pc++];
+    switch (op) {
+      case 1: ++a; break; case 2: --a; break; case 3: a = ~a; break; case 4: a = 0; break;
+      case 7: a = R[P[pc++]]; break;
+      case 8: { const u32 t = a; a = b; b = t; } break;
+      case 9: ++b; break; case 10: --b; break; case 11: b = ~b; break; case 12: b = 0; break;
+      case 15: b = R[P[pc++]]; break;
+      case 16: { const u32 t = a; a = c; c = t; } break;
+      case 17: ++c; break; case 18: --c; break; case 19: c = ~c; break; case 20: c = 0; break;
+      case 23: c = R[P[pc++]]; break;
+      case 24: { const u32 t = a; a = d; d = t; } break;
+      case 25: ++d; break; case 26: --d; break; case 27: d = ~d; break; case 28: d = 0; break;
+      case 31: d = R[P[pc++]]; break;
+      case 32: { const u32 t = M[b & mm]; M[b & mm] = (u8)a; a = (a & ~255u) | t; } break;
+      case 33: M[b & mm] = (u8)(M[b & mm] + 1); break; case 34: M[b & mm] = (u8)(M[b & mm] - 1); break;
+      case 35: M[b & mm] = (u8)~M[b & mm]; break; case 36: M[b & mm] = 0; break;
+      case 39: if (f) pc += (int)((P[pc] + 128u) & 255u) - 127; else ++pc; break;
+      case 40: { const u32 t = M[c & mm]; M[c & mm] = (u8)a; a = (a & ~255u) | t; } break;
+      case 41: M[c & mm] = (u8)(M[c & mm] + 1); break; case 42: M[c & mm] = (u8)(M[c & mm] - 1); break;
+      case 43: M[c & mm] = (u8)~M[c & mm]; break; case 44: M[c & mm] = 0; break;
+      case 47: if (!f) pc += (int)((P[pc] + 128u) & 255u) - 127; else ++pc; break;
+      case 48: { const u32 t = H[d & hm]; H[d & hm] = a; a = t; } break;
+      case 49: H[d & hm] = H[d & hm] + 1; break; case 50: H[d & hm] = H[d & hm] - 1; break;
+      case 51: H[d & hm] = ~H[d & hm]; break; case 52: H[d & hm] = 0; break;
+      case 55: R[P[pc++]] = a; break;
+      case 56: stop = 1; break;
+      case 57:
+        if (WITH_OUT) { if (o->len < o->cap) o->out[o->len] = (u8)a; else o->error = 3; ++o->len; }
+        break;
+      case 59: a = (a + M[b & mm] + 512u) * 773u; break;
+      case 60: H[d & hm] = (H[d & hm] + a + 512u) * 773u; break;
+      case 63: pc += (int)((P[pc] + 128u) & 255u) - 127; break;
+      ZQ_VM_X8(64, a = x) ZQ_VM_X8(72, b = x) ZQ_VM_X8(80, c = x) ZQ_VM_X8(88, d = x)
+      ZQ_VM_X8(96, M[b & mm] = (u8)x) ZQ_VM_X8(104, M[c & mm] = (u8)x) ZQ_VM_X8(112, H[d & hm] = x)
+      ZQ_VM_X8(128, a += x) ZQ_VM_X8(136, a -= x) ZQ_VM_X8(144, a *= x)
+      ZQ_VM_X8(152, a = x ? a / x : 0u) ZQ_VM_X8(160, a = x ? a % x : 0u)
+      ZQ_VM_X8(168, a &= x) ZQ_VM_X8(176, a &= ~x) ZQ_VM_X8(184, a |= x) ZQ_VM_X8(192, a ^= x)
+      ZQ_VM_X8(200, a <<= (x & 31u)) ZQ_VM_X8(208, a >>= (x & 31u))
+      ZQ_VM_X8(216, f = a == x) ZQ_VM_X8(224, f = a < x) ZQ_VM_X8(232, f = a > x)
+      case 255: pc = (int)P[pc] + 256 * (int)P[pc + 1]; break;
+      default: stop = 2;
+    }
+  }
+  if (stop == 2) v.error = 1;
+  v.a = a; v.b = b; v.c = c; v.d = d; v.f = f;
+}
+#undef ZQ_VM_X8
+
+
+#ifdef ZQ_EMU
+__device__ __forceinline__ u32 zq_sel(bool p, u32 x, u32 y) { return p ? x : y; }
+__device__ __forceinline__ void zq_st8_if(bool p, u8* a, u32 v) { if (p) *a = (u8)v; }
+__device__ __forceinline__ void zq_st32_if(bool p, u32* a, u32 v) { if (p) *a = v; }
+#else
+__device__ __forceinline__ u32 zq_sel(bool p, u32 x, u32 y) {
+  u32 r;
+  asm("{ .reg .pred q; setp.ne.u32 q, %1, 0; selp.u32 %0, %2, %3, q; }" : "=r"(r) : "r"((u32)p), "r"(x), "r"(y));
+  return r;
+}
+__device__ __forceinline__ void zq_st8_if(bool p, u8* a, u32 v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.u8 [%1], %2; }" ::"r"((u32)p), "l"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void zq_st32_if(bool p, u32* a, u32 v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.u32 [%1], %2; }" ::"r"((u32)p), "l"(a), "r"(v) : "memory");
+}
+#endif
+template <bool WITH_OUT>
+__device__ void cm_vm_run_sel(CmVm& v, u32 input, VmOut* o) {
+  const u8* P = v.code;
+  u8* M = v.m; u32* H = v.h; u32* R = v.r;
+  const u32 mm = v.mmask, hm = v.hmask;
+  const int len = v.len;
+  int pc = 0, stop = 0;
+  u32 a = input, b = v.b, c = v.c, d = v.d; u32 f = (u32)v.f;
+  while (!stop) {
+    if ((u32)pc >= (u32)len) { stop = 2; break; }
     const u32 op = P[pc], arg = P[pc + 1];
-    if (op >= 64) {
-      // ---- two operands: a/b/c/d/*b/*c/*d = x, a op= x, f = a cmp x
-      const u32 src = op & 7, grp = op >> 3;
-      u32 x = arg;
-      if (src < 4) x = src == 0 ? a : src == 1 ? b : src == 2 ? c : d;
-      else if (src == 4) x = M[b & mm];
-      else if (src == 5) x = M[c & mm];
-      else if (src == 6) x = H[d & hm];
-      pc += src == 7 ? 2 : 1;
-      if (grp < 15) {
-        if (grp == 8) a = x; else if (grp == 9) b = x; else if (grp == 10) c = x; else if (grp == 11) d = x;
-        else if (grp == 12) M[b & mm] = (u8)x; else if (grp == 13) M[c & mm] = (u8)x; else H[d & hm] = x;
-      } else if (grp >= 16 && grp <= 26 && grp != 19 && grp != 20) {
-        const u32 sh = x & 31u;
-        a = grp == 16 ? a + x : grp == 17 ? a - x : grp == 18 ? a * x : grp == 21 ? (a & x) : grp == 22 ? (a & ~x) :
-            grp == 23 ? (a | x) : grp == 24 ? (a ^ x) : grp == 25 ? (a << sh) : (a >> sh);
-      } else if (grp >= 27 && grp <= 29) f = grp == 27 ? a == x : grp == 28 ? a < x : a > x;
-      else if (grp == 19) a = x ? a / x : 0u;
-      else if (grp == 20) a = x ? a % x : 0u;
-      else if (op == 255) pc = (int)arg + 256 * (int)P[pc];   // LJ: pc already points at the third byte
-      else stop = 2;                                          // groups 15, 30, 31
-    } else if (op < 32) {
-      // ---- register target (a,b,c,d = op>>3): <>a, ++, --, !, =0, =r N
-      const u32 t = op >> 3, act = op & 7;
-      const u32 val = t == 0 ? a : t == 1 ? b : t == 2 ? c : d;
-      u32 nv;
-      if (act == 7) { nv = R[arg]; pc += 2; }
-      else { nv = act == 1 ? val + 1 : act == 2 ? val - 1 : act == 3 ? ~val : act == 4 ? 0u : a; pc += 1; }
-      if (act == 5 || act == 6 || op == 0) { stop = 2; break; }
-      if (act == 0) a = val;                 // swap: a takes the target's old value, the target takes a's
-      if (t == 0) a = nv; else if (t == 1) b = nv; else if (t == 2) c = nv; else d = nv;
-    } else if (op < 56 && (op & 7) <= 4) {
-      // ---- memory target (*b,*c,*d = (op>>3)-4): <>a, ++, --, !, =0
-      const u32 act = op & 7;
-      if (op >= 48) {
+    const u32 lo = op & 7u, hi = op >> 3;
+    if (op >= 64u) {
+      // ---- two operands.  b&mm, c&mm, d&hm always index inside M / H, so all three are fetched and one is picked
+      const u32 xb = M[b & mm], xc = M[c & mm], xd = H[d & hm];
+      u32 x = zq_sel(lo & 4u, zq_sel(lo & 2u, zq_sel(lo & 1u, arg, xd), zq_sel(lo & 1u, xc, xb)),
+                     zq_sel(lo & 2u, zq_sel(lo & 1u, d, c), zq_sel(lo & 1u, b, a)));
+      pc += 1 + (int)(lo == 7u);
+      const u32 sh = x & 31u;
+      // a op= x, operation hi-16 in 0..10 (3: div, 4: mod handled below)
+      const u32 k = hi - 16u;
+      const u32 r0 = zq_sel(k & 1u, a - x, a + x);            // 0 add, 1 sub
+      const u32 r2 = zq_sel(k & 1u, a, a * x);                // 2 mul, (3 div)
+      const u32 r4 = zq_sel(k & 1u, a & x, a);                // (4 mod), 5 and
+      const u32 r6 = zq_sel(k & 1u, a | x, a & ~x);           // 6 andn, 7 or
+      const u32 r8 = zq_sel(k & 1u, a << sh, a ^ x);          // 8 xor, 9 shl
+      const u32 ra = a >> sh;                                  // 10 shr
+      const u32 lo8 = zq_sel(k & 4u, zq_sel(k & 2u, r6, r4), zq_sel(k & 2u, r2, r0));
+      const u32 alu = zq_sel(k & 8u, zq_sel(k & 2u, ra, r8), lo8);
+      const bool is_alu = k <= 10u;
+      const u32 cmp = zq_sel(hi == 27u, a == x, zq_sel(hi == 28u, a < x, a > x));
+      f = zq_sel(hi - 27u <= 2u, cmp, f);
+      const u32 na = zq_sel(is_alu, alu, zq_sel(hi == 8u, x, a));
+      const u32 a_old = a;
+      // stores use the registers as they were before this instruction
+      zq_st8_if(hi == 12u, M + (b & mm), x);
+      zq_st8_if(hi == 13u, M + (c & mm), x);
+      zq_st32_if(hi == 14u, H + (d & hm), x);
+      a = na;
+      b = zq_sel(hi == 9u, x, b); c = zq_sel(hi == 10u, x, c); d = zq_sel(hi == 11u, x, d);
+      if (k == 3u || k == 4u || hi == 15u || hi >= 30u) {   // rare: division, long jump, invalid
+        if (k == 3u) a = x ? a_old / x : 0u;
+        else if (k == 4u) a = x ? a_old % x : 0u;
+        else if (op == 255u) pc = (int)arg + 256 * (int)P[pc];
+        else stop = 2;
+      }
+    } else if (op < 32u) {
+      // ---- register target a/b/c/d = hi: <>a, ++, --, !, =0, =r N
+      const u32 val = zq_sel(hi & 2u, zq_sel(hi & 1u, d, c), zq_sel(hi & 1u, b, a));
+      const u32 rn = R[arg];                                   // always a valid slot (256 words)
+      const u32 nv = zq_sel(lo & 4u, zq_sel(lo & 2u, rn, 0u), zq_sel(lo & 2u, zq_sel(lo & 1u, ~val, val - 1u), zq_sel(lo & 1u, val + 1u, a)));
+      pc += 1 + (int)(lo == 7u);
+      if (lo == 5u || lo == 6u || op == 0u) { stop = 2; break; }
+      a = zq_sel(lo == 0u, val, a);
+      a = zq_sel(hi == 0u, nv, a); b = zq_sel(hi == 1u, nv, b); c = zq_sel(hi == 2u, nv, c); d = zq_sel(hi == 3u, nv, d);
+    } else if (op < 56u && lo <= 4u) {
+      // ---- memory target *b/*c/*d: <>a, ++, --, !, =0
+      if (op >= 48u) {
         const u32 old = H[d & hm];
-        H[d & hm] = act == 0 ? a : act == 1 ? old + 1 : act == 2 ? old - 1 : act == 3 ? ~old : 0u;
-        if (act == 0) a = old;
+        H[d & hm] = zq_sel(lo & 4u, 0u, zq_sel(lo & 2u, zq_sel(lo & 1u, ~old, old - 1u), zq_sel(lo & 1u, old + 1u, a)));
+        a = zq_sel(lo == 0u, old, a);
       } else {
-        const u32 idx = (op >= 40 ? c : b) & mm;
+        const u32 idx = zq_sel(op >= 40u, c, b) & mm;
         const u32 old = M[idx];
-        M[idx] = (u8)(act == 0 ? a : act == 1 ? old + 1 : act == 2 ? old - 1 : act == 3 ? ~old : 0u);
-        if (act == 0) a = (a & ~255u) | old;
+        M[idx] = (u8)zq_sel(lo & 4u, 0u, zq_sel(lo & 2u, zq_sel(lo & 1u, ~old, old - 1u), zq_sel(lo & 1u, old + 1u, a)));
+        a = zq_sel(lo == 0u, (a & ~255u) | old, a);
       }
       pc += 1;
     } else {
@@ -234,7 +334,12 @@ __device__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) {
     }
   }
   if (stop == 2) v.error = 1;
-  v.a = a; v.b = b; v.c = c; v.d = d; v.f = f;
+  v.a = a; v.b = b; v.c = c; v.d = d; v.f = (int)f;
+}
+
+template <int VM, bool WITH_OUT>
+__device__ __forceinline__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) {
+  if (VM == 1) cm_vm_run_sel<WITH_OUT>(v, input, o); else cm_vm_run_switch<WITH_OUT>(v, input, o);
 }
 
 __device__ __forceinline__ int cm_clamp2k(int x) { return min(max(x, -2048), 2047); }
@@ -285,7 +390,7 @@ struct CmCtx {             // warp-uniform per-block state
   int n, nlevels, c8, hmap4;
   u32 mix_mask;            // lanes that are MIX components
   u32 mix_levels;          // bit L: some MIX sits at dependency level L
-  u32 two_levels;          // bit L: some two-input component (AVG, MIX2) sits at level L
+  u32 other_levels;        // bit L: an AVG, MIX2 or SSE sits at level L (ISSE links need no flag)
   int mix0, mix1;          // lanes of the first two MIX components (-1: none)
 };
 
@@ -295,6 +400,11 @@ __device__ int cm_predict(CmLane& L, const CmCtx& X, const CmSmem& T) {
   const int c8 = X.c8, hmap4 = X.hmap4;
   const bool nib = c8 == 1 || (c8 & 0xf0) == 16;
   // phase 1: every table fetch whose address does not depend on another component's prediction
+  const bool hashed = L.type == ZQ_ICM || L.type == ZQ_ISSE;   // one pass over the hash rows for both kinds
+  if (hashed) {
+    if (nib) cm_row_switch(L, L.h + 16u * (u32)c8);
+    L.cxt = L.row[hmap4 & 15];
+  }
   switch (L.type) {
     case ZQ_CM:
       L.cxt = (L.h ^ (u32)hmap4) & L.cm_mask;
@@ -302,14 +412,10 @@ __device__ int cm_predict(CmLane& L, const CmCtx& X, const CmSmem& T) {
       L.p = T.stretch[L.pn >> 17];
       break;
     case ZQ_ICM:
-      if (nib) cm_row_switch(L, L.h + 16u * (u32)c8);
-      L.cxt = L.row[hmap4 & 15];
       L.pn = L.cm[L.cxt];
       L.p = T.stretch[L.pn >> 8];
       break;
     case ZQ_ISSE: {
-      if (nib) cm_row_switch(L, L.h + 16u * (u32)c8);
-      L.cxt = L.row[hmap4 & 15];
       const int2 w = *(const int2*)(L.cm + L.cxt * 2);
       L.w0 = w.x; L.w1 = w.y;
       break;
@@ -335,29 +441,35 @@ __device__ int cm_predict(CmLane& L, const CmCtx& X, const CmSmem& T) {
   }
   if (X.mix0 >= 0) { L.mr0 = __shfl_sync(ZQ_FULL, L.cxt, X.mix0); if (L.wp0) L.wv0 = L.wp0[L.mr0]; }
   if (X.mix1 >= 0) { L.mr1 = __shfl_sync(ZQ_FULL, L.cxt, X.mix1); if (L.wp1) L.wv1 = L.wp1[L.mr1]; }
-  // phase 2: dependency levels
+  // phase 2: dependency levels.  ISSE links are by far the most common inner node (chains of up to 7 in the
+  // built-in models): they are evaluated as predicated arithmetic by every lane, no branch; AVG / MIX2 / SSE only
+  // run at the levels the host flagged for them.
+  const bool isse = L.type == ZQ_ISSE;
   for (int lev = 1; lev < X.nlevels; ++lev) {
     const int pj = __shfl_sync(ZQ_FULL, L.p, L.in1);
-    const int pk = ((X.two_levels >> lev) & 1u) ? __shfl_sync(ZQ_FULL, L.p, L.in2) : 0;
-    if ((int)L.level == lev) {
-      switch (L.type) {
-        case ZQ_AVG: L.p = (pj * (int)L.a3 + pk * (256 - (int)L.a3)) >> 8; break;
-        case ZQ_MIX2: L.pj = pj; L.pk = pk; L.p = (L.w0 * pj + (65536 - L.w0) * pk) >> 16; break;
-        case ZQ_ISSE: L.pj = pj; L.p = cm_clamp2k((L.w0 * pj + L.w1 * 64) >> 16); break;
-        case ZQ_SSE: {
-          u32 cx = (L.h + (u32)c8) * 32u;
-          int pq = min(max(pj + 992, 0), 1983);
-          const int wt = pq & 63;
-          pq >>= 6;
-          cx += (u32)pq;
-          const u32 e0 = L.cm[cx & L.cm_mask], e1 = L.cm[(cx + 1) & L.cm_mask];
-          L.p = T.stretch[((e0 >> 10) * (u32)(64 - wt) + (e1 >> 10) * (u32)wt) >> 13];
-          cx += (u32)(wt >> 5);
-          L.cxt = cx & L.cm_mask;
-          L.pn = (wt >> 5) ? e1 : e0;
-          break;
+    const int pi = cm_clamp2k((L.w0 * pj + L.w1 * 64) >> 16);
+    if (isse && (int)L.level == lev) { L.pj = pj; L.p = pi; }
+    if ((X.other_levels >> lev) & 1u) {
+      const int pk = __shfl_sync(ZQ_FULL, L.p, L.in2);
+      if ((int)L.level == lev) {
+        switch (L.type) {
+          case ZQ_AVG: L.p = (pj * (int)L.a3 + pk * (256 - (int)L.a3)) >> 8; break;
+          case ZQ_MIX2: L.pj = pj; L.pk = pk; L.p = (L.w0 * pj + (65536 - L.w0) * pk) >> 16; break;
+          case ZQ_SSE: {
+            u32 cx = (L.h + (u32)c8) * 32u;
+            int pq = min(max(pj + 992, 0), 1983);
+            const int wt = pq & 63;
+            pq >>= 6;
+            cx += (u32)pq;
+            const u32 e0 = L.cm[cx & L.cm_mask], e1 = L.cm[(cx + 1) & L.cm_mask];
+            L.p = T.stretch[((e0 >> 10) * (u32)(64 - wt) + (e1 >> 10) * (u32)wt) >> 13];
+            cx += (u32)(wt >> 5);
+            L.cxt = cx & L.cm_mask;
+            L.pn = (wt >> 5) ? e1 : e0;
+            break;
+          }
+          default: break;
         }
-        default: break;
       }
     }
     // mixers of this level: every input lane multiplies its own p by its weight, one REDUX sums
@@ -405,6 +517,7 @@ __device__ bool cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y) {
       }
     }
   }
+  if (L.type == ZQ_ICM || L.type == ZQ_ISSE) L.row[X.hmap4 & 15] = T.ns[L.cxt * 4 + y];   // next bit history
   switch (L.type) {
     case ZQ_CM: case ZQ_SSE: {
       const u32 count = L.pn & 0x3ffu;
@@ -414,7 +527,6 @@ __device__ bool cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y) {
       break;
     }
     case ZQ_ICM: {
-      L.row[X.hmap4 & 15] = T.ns[L.cxt * 4 + y];
       L.pn += (u32)(((int)(y * 32767 - (int)(L.pn >> 8))) >> 2);
       L.cm[L.cxt] = L.pn;
       break;
@@ -425,7 +537,6 @@ __device__ bool cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y) {
       w.x = cm_clamp512k(L.w0 + ((err * L.pj + (1 << 12)) >> 13));
       w.y = cm_clamp512k(L.w1 + ((err + 16) >> 5));
       *(int2*)(L.cm + L.cxt * 2) = w;
-      L.row[X.hmap4 & 15] = T.ns[L.cxt * 4 + y];
       break;
     }
     case ZQ_MIX2: {
@@ -471,7 +582,7 @@ __device__ __forceinline__ void cm_setup(CmLane& L, CmCtx& X, const ZqCmPlan& cp
   L.type = act ? c.type : 0; L.level = act ? c.level : 255;
   L.a2 = c.a2; L.a3 = c.a3; L.a4 = c.a4; L.a5 = c.a5;
   X.mix_levels = __reduce_or_sync(ZQ_FULL, (act && c.type == ZQ_MIX) ? (1u << c.level) : 0u);
-  X.two_levels = __reduce_or_sync(ZQ_FULL, (act && (c.type == ZQ_AVG || c.type == ZQ_MIX2)) ? (1u << c.level) : 0u);
+  X.other_levels = __reduce_or_sync(ZQ_FULL, (act && (c.type == ZQ_AVG || c.type == ZQ_MIX2 || c.type == ZQ_SSE)) ? (1u << c.level) : 0u);
   L.cm = (u32*)(model + c.cm_off); L.ht = model + c.ht_off; L.cm_mask = c.cm_mask; L.ht_mask = c.ht_mask;
   L.chkshift = (u32)c.a1 + 2;
   L.in1 = 0; L.in2 = 0;
@@ -668,6 +779,7 @@ __device__ void cm_code_chain1(const ZqCmPlan& cp, u8* model, CmUnitSmem& S, con
 // grid of persistent CTAs of `blockDim.x / 64` warp pairs (even warp: coder, odd warp: context machine);
 // pairs pull modeled units from a counter.  Dynamic shared memory: CmSmem + one CmUnitSmem per pair.
 #define ZQ_CM_MAX_PAIRS 12   // 768 threads: 85 registers per thread without spills; 1 776 blocks resident on 148 SMs
+template <int VM>
 __global__ void __launch_bounds__(64 * ZQ_CM_MAX_PAIRS, 1)
 k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
             const ZqCmPlan* __restrict__ cmplans, const int* __restrict__ todo, int ntodo,
@@ -709,7 +821,7 @@ k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, co
       const ZqCmComp comp = cp.comp[act ? lane : 0];
       for (u32 k = 0; k + 1 < K; ++k) {
         const u32 c = k < hlen ? head[k] : stream[k - hlen];
-        if (lane == 0) cm_vm_run<false>(vm, c, nullptr);
+        if (lane == 0) cm_vm_run<VM, false>(vm, c, nullptr);
         __syncwarp();
         while (k - S.consumed >= ZQ_CM_RING) __nanosleep(64);
         const u32 hv = act ? vm.h[lane & vm.hmask] : 0u;

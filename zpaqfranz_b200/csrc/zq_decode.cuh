@@ -43,7 +43,7 @@ struct DecPost {
 // PostProcessor::write (Z:15368). Machine state and the output count live on lane 0; `outlen`/errors are
 // re-broadcast after every step so the warp's control flow stays uniform.
 // SOLO: the whole warp's work is being done by the calling lane alone (chain fast path): no lane tests, no shuffles.
-template <bool SOLO>
+template <int VM, bool SOLO>
 __device__ __forceinline__ void dec_post_write(DecPost& pp, int c) {
   const u32 lane = SOLO ? 0u : lane_id();
   switch (pp.state) {
@@ -72,7 +72,7 @@ __device__ __forceinline__ void dec_post_write(DecPost& pp, int c) {
       if (pp.loaded == pp.hsize) { pp.vm.code = pp.code; pp.vm.len = (int)pp.hsize; pp.state = 5; }
       break;
     default:
-      if (lane == 0) cm_vm_run<true>(pp.vm, (u32)c, &pp.o);   // c == -1 at end of segment -> a = 0xFFFFFFFF
+      if (lane == 0) cm_vm_run<VM, true>(pp.vm, (u32)c, &pp.o);   // c == -1 at end of segment -> a = 0xFFFFFFFF
       if (!SOLO) {
         pp.o.len = __shfl_sync(ZQ_FULL, pp.o.len, 0);
         pp.o.error = __shfl_sync(ZQ_FULL, pp.o.error, 0);
@@ -129,6 +129,7 @@ __device__ __forceinline__ u32 chain1_dec_nibble(ChainComp& A, ChainComp& B, Cha
 }
 
 // 16 warps per CTA, one block per warp; dynamic shared memory: CmSmem + one CmUnitSmem per warp.
+template <int VM>
 __global__ void __launch_bounds__(512, 1)
 k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units, const ZqCmPlan* __restrict__ cmplans, int nunits,
             const CmTablesDev* __restrict__ tab, const u8* __restrict__ blob, u8* __restrict__ model_base,
@@ -178,12 +179,12 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
           const u32 hi = chain1_dec_nibble(A, B, D, T);
           chain_row_switch(A, ha + 16u * (16u + hi)); chain_row_switch(B, hb + 16u * (16u + hi));
           const u32 c = hi << 4 | chain1_dec_nibble(A, B, D, T);
-          cm_vm_run<false>(vm, c, nullptr);
+          cm_vm_run<VM, false>(vm, c, nullptr);
           ha = vm.h[0]; hb = vm.h[1 & vm.hmask];
-          dec_post_write<true>(pp, (int)c);
+          dec_post_write<VM, true>(pp, (int)c);
           if (D.err || D.in.error || pp.error || vm.error || pp.vm.error) break;
         }
-        if (!D.err && !D.in.error && !pp.error && !vm.error && !pp.vm.error) dec_post_write<true>(pp, -1);
+        if (!D.err && !D.in.error && !pp.error && !vm.error && !pp.vm.error) dec_post_write<VM, true>(pp, -1);
         ZqDecResult r;
         r.out_len = pp.o.len; r.consumed = (u32)D.in.pos; r.pad = 0;
         r.error = D.err ? D.err : D.in.error ? D.in.error : pp.error ? pp.error : (vm.error || pp.vm.error) ? 4u : 0u;
@@ -214,13 +215,13 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
           const int y = decode(p16);
           c += c + y;
           if (cm_update(L, X, T, y)) {   // byte complete: contexts of the next one
-            if (lane == 0) cm_vm_run<false>(vm, (u32)(c - 256), nullptr);
+            if (lane == 0) cm_vm_run<VM, false>(vm, (u32)(c - 256), nullptr);
             __syncwarp();
             if (lane < (u32)X.n) L.h = vm.h[lane & vm.hmask];
             vmerr = (u32)__shfl_sync(ZQ_FULL, vm.error, 0);
           }
         }
-        dec_post_write<false>(pp, c - 256);
+        dec_post_write<VM, false>(pp, c - 256);
         if (err || in.error || pp.error || vmerr || pp.vm.error) break;
       }
     } else {
@@ -228,11 +229,11 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
         u32 cl = 0;
         for (int k = 0; k < 4; ++k) cl = cl << 8 | (u32)in.get();
         if (cl == 0 || in.error) break;
-        for (u32 k = 0; k < cl; ++k) dec_post_write<false>(pp, in.get());
+        for (u32 k = 0; k < cl; ++k) dec_post_write<VM, false>(pp, in.get());
         if (in.error || pp.error || pp.vm.error) break;
       }
     }
-    if (!err && !in.error && !pp.error && !vmerr && !pp.vm.error) dec_post_write<false>(pp, -1);
+    if (!err && !in.error && !pp.error && !vmerr && !pp.vm.error) dec_post_write<VM, false>(pp, -1);
     if (lane == 0) {
       ZqDecResult r;
       r.out_len = pp.o.len; r.consumed = (u32)in.pos; r.pad = 0;
