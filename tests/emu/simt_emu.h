@@ -21,6 +21,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __constant__ static
 #define __align__(x) alignas(x)
 #define __restrict__
 
@@ -174,6 +175,9 @@ inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
   return r;
 }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { const uint64_t v = (uint64_t)hi << 32 | lo; return (unsigned)(v >> (sh & 31)); }
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { const uint64_t v = (uint64_t)hi << 32 | lo; return (unsigned)((v << (sh & 31)) >> 32); }
+inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 #ifndef INT_MIN
 #include <climits>

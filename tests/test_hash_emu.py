@@ -1,0 +1,63 @@
+"""The digest kernels' DEVICE code (SHA-1, SHA-256, XXH3-128, BLAKE3: zq_sha1.cuh, zq_hashes.cuh) on the host through the
+SIMT emulator, against hashlib and the reference's own XXH3 / BLAKE3 (oracle/_ref) plus the reference's "ABCDE"
+known answers (Z:77129-77160).  Test infrastructure only."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from zpaqfranz_b200 import corpus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "zpaqfranz_b200", "csrc")
+SIZES = [0, 1, 3, 5, 55, 56, 63, 64, 65, 119, 128, 129, 240, 241, 1023, 1024, 1025, 2048, 3000, 4097, 9000, 70000]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libhashemu.so")
+    deps = [os.path.join(EMU, "hash_emu.cpp"), os.path.join(EMU, "simt_emu.h"), os.path.join(CSRC, "zq_sha1.cuh"),
+            os.path.join(CSRC, "zq_hashes.cuh"), os.path.join(CSRC, "zq_common.cuh")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC,
+                        "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-o", lib, deps[0]], check=True)
+    return C.CDLL(lib)
+
+
+def _run(emu, kind, width, bufs, shift=0):
+    blob = b"\0" * shift + b"".join(bufs) + b"\0" * 64          # shift: unaligned starts
+    lens = np.array([len(b) for b in bufs], dtype=np.uint64)
+    offs = (np.concatenate([[0], np.cumsum(lens)[:-1]]) + shift).astype(np.uint64)
+    out = (C.c_uint8 * (width * len(bufs)))()
+    emu.emu_hash(kind, blob, offs.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p), len(bufs), out)
+    raw = bytes(out)
+    return [raw[i * width:(i + 1) * width] for i in range(len(bufs))]
+
+
+BUFS = [bytes(corpus.random_unit(s + 1, s)) if s else b"" for s in SIZES] + [b"ABCDE", bytes(5000)]
+
+
+@pytest.mark.parametrize("shift", [0, 1, 7])
+def test_sha1_sha256(emu, shift):
+    assert _run(emu, 0, 20, BUFS, shift) == [hashlib.sha1(b).digest() for b in BUFS]
+    assert _run(emu, 1, 32, BUFS, shift) == [hashlib.sha256(b).digest() for b in BUFS]
+
+
+def test_xxh3_blake3_against_reference(emu, ref):
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    assert _run(emu, 2, 16, BUFS, 3) == [ref.xxh3_128(b) for b in BUFS]
+    assert _run(emu, 3, 32, BUFS, 5) == [ref.blake3(b) for b in BUFS]
+
+
+def test_reference_known_answers(emu):
+    abcde = [b"ABCDE"]
+    assert _run(emu, 0, 20, abcde)[0].hex().upper() == "7BE07AAF460D593A323D0DB33DA05B64BFDCB3A5"
+    assert _run(emu, 2, 16, abcde)[0].hex().upper() == "1C8288B6013152D97B4A5D7E6C7893D4"
+    assert _run(emu, 3, 32, abcde)[0].hex().upper().startswith("61274278")
