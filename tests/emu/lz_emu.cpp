@@ -34,3 +34,53 @@ extern "C" long emu_lz_sa(const uint8_t* data, uint32_t n, const int* args, uint
   if (err) return -(long)err;
   return (long)lzlen;
 }
+
+#include "zq_frame.cuh"
+
+// hash-table LZ77 parse (-m1 and the low-redundancy forms of -m2..-m4): k_lz77_hash over a zeroed 2^args[5] table
+extern "C" long emu_lz_hash(const uint8_t* data, uint32_t n, const int* args, uint8_t* out, uint32_t cap) {
+  std::vector<u8> in(data, data + n); in.resize(n + 64);
+  std::vector<u32> ht((size_t)1 << args[5], 0u);
+  ZqUnit u; memset(&u, 0, sizeof u);
+  u.n = n; u.lz_cap = cap;
+  ZqPlan pl; memset(&pl, 0, sizeof pl);
+  for (int k = 0; k < 9; ++k) pl.args[k] = args[k];
+  pl.lz_level = args[1] & 3;
+  int todo = 0;
+  u32 lzlen = 0, err = 0, next = 0;
+  emu::launch(1, 32, 0, [&] { k_lz77_hash<8>(in.data(), &u, &pl, &todo, 1, (u8*)ht.data(), out, &lzlen, &err, &next); });
+  if (err) return -(long)err;
+  return (long)lzlen;
+}
+
+// BWT pre-pass (level 3): k_suffix_sort then k_bwt_stream; n + 5 bytes
+extern "C" long emu_bwt(const uint8_t* data, uint32_t n, uint8_t* out) {
+  const bool idx16 = n <= 65536;
+  const u32 w = idx16 ? 2 : 4;
+  std::vector<u8> in(data, data + n); in.resize(n + 64);
+  std::vector<u8> work(zq_work_bytes(n, w) + 256);
+  ZqUnit u; memset(&u, 0, sizeof u);
+  u.n = n; u.idx16 = idx16;
+  int todo = 0;
+  const size_t scr = (((size_t)n + 1) + 63) & ~(size_t)63;
+  std::vector<u64> kbuf(2 * scr); std::vector<u32> vbuf(6 * scr);
+  emu::launch(1, 256, sizeof(SortSmem<256>), [&] { k_suffix_sort<256, 4>(in.data(), &u, &todo, 1, work.data(), kbuf.data(), vbuf.data(), scr); });
+  u32 lzlen = 0;
+  emu::launch(1, 256, 0, [&] { k_bwt_stream(in.data(), &u, &todo, 1, work.data(), out, &lzlen); });
+  return (long)lzlen;
+}
+
+// E8E9 filter in place (one thread per block); level >= 5 byte-gap period analysis (one CTA per block)
+extern "C" void emu_e8e9(uint8_t* data, uint32_t n) {
+  std::vector<u8> in(data, data + n); in.resize(n + 64);
+  ZqUnit u; memset(&u, 0, sizeof u);
+  u.n = n;
+  int todo = 0;
+  emu::launch(1, 64, 0, [&] { k_e8e9(in.data(), &u, &todo, 1); });
+  memcpy(data, in.data(), n);
+}
+extern "C" void emu_gap_periods(const uint8_t* data, uint32_t n, int* periods2) {
+  std::vector<u8> in(data, data + n); in.resize(n + 64);
+  const u64 off = 0;
+  emu::launch(1, 256, 0, [&] { k_gap_periods(in.data(), &off, &n, 1, periods2); });
+}

@@ -21,12 +21,14 @@ def emu():
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "liblzemu.so")
     deps = [os.path.join(EMU, "lz_emu.cpp"), os.path.join(EMU, "simt_emu.h")] + [os.path.join(CSRC, f) for f in
-                                                                                   ("zq_lz77.cuh", "zq_sufsort.cuh", "zq_common.cuh")]
+                                                                                   ("zq_lz77.cuh", "zq_sufsort.cuh", "zq_common.cuh", "zq_frame.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC,
                         "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-o", lib, deps[0]], check=True)
     h = C.CDLL(lib)
     h.emu_lz_sa.restype = C.c_long
+    h.emu_lz_hash.restype = C.c_long
+    h.emu_bwt.restype = C.c_long
     return h
 
 
@@ -49,3 +51,47 @@ def test_suffix_array_and_stream_match_oracle(emu, oracle, k):
     assert r >= 0
     assert list(sa[:n]) == list(oracle.suffix_array(data))
     assert bytes(out[:r]) == oracle.lz_stream(data, plan["args"])
+
+
+HASH_CASES = [("1", corpus.text_unit(3, 3000)), ("1", b"abracadabra" * 100), ("1", bytes(2000)), ("1", corpus.mixed_unit(4, 4000)),
+              ("1", corpus.random_unit(6, 1500)), ("1", b""), ("1", b"abc"), ("24,40,0", corpus.text_unit(2, 3000)),
+              ("14,200,3", corpus.text_unit(5, 2500))]
+
+
+@pytest.mark.parametrize("k", range(len(HASH_CASES)))
+def test_hash_table_parse_matches_oracle(emu, oracle, k):
+    method, data = HASH_CASES[k]
+    plan = zq.plan_block(method, data)
+    a = plan["args"]
+    if (a[1] & 3) not in (1, 2) or a[5] - a[0] >= 21:
+        pytest.skip("not the hash-table variant: " + plan["method"])
+    work = bytearray(data)
+    if a[1] & 4:
+        emu.emu_e8e9((C.c_uint8 * max(len(work), 1)).from_buffer(work), len(work)) if work else None
+        assert bytes(work) == oracle.e8e9(data)
+    cap = 2 * len(data) + 4096
+    out = (C.c_uint8 * cap)()
+    r = emu.emu_lz_hash(bytes(work), len(work), (C.c_int * 9)(*a), out, cap)
+    assert r >= 0
+    assert bytes(out[:r]) == oracle.lz_stream(data, a)     # the oracle filters E8E9 itself when args[1] says so
+
+
+@pytest.mark.parametrize("data", [corpus.text_unit(3, 3000), b"abracadabra" * 50, bytes(700), b"", b"z", corpus.random_unit(2, 999)])
+def test_bwt_stream_matches_oracle(emu, oracle, data):
+    plan = zq.plan_block("36,200,1", data)
+    assert (plan["args"][1] & 3) == 3
+    out = (C.c_uint8 * (len(data) + 16))()
+    r = emu.emu_bwt(data, len(data), out)
+    assert bytes(out[:r]) == oracle.lz_stream(data, plan["args"])
+
+
+def test_e8e9_filter_matches_oracle(emu, oracle):
+    import random
+    rnd = random.Random(5)
+    data = bytearray(corpus.random_unit(9, 6000))
+    for _ in range(300):                       # plant call/jump opcodes with small displacements
+        p = rnd.randrange(0, len(data) - 5)
+        data[p] = rnd.choice([0xE8, 0xE9]); data[p + 4] = rnd.choice([0, 255])
+    work = bytearray(data)
+    emu.emu_e8e9((C.c_uint8 * len(work)).from_buffer(work), len(work))
+    assert bytes(work) == oracle.e8e9(bytes(data))
