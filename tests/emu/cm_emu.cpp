@@ -67,7 +67,8 @@ extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_
 #else
     const unsigned block = (unsigned)threads < 64 ? 64u : (unsigned)threads & ~63u;   // whole (coder, context) pairs
     emu::launch(1, block, sizeof(CmSmem) + (block / 64) * sizeof(CmUnitSmem), [&] {
-      if (prefetch & 4) k_cm_encode<1>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1);
+      if (prefetch & 8) k_cm_encode<2>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1);
+      else if (prefetch & 4) k_cm_encode<1>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1);
       else k_cm_encode<0>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1);
     });
 #endif
@@ -111,7 +112,8 @@ extern "C" long emu_cm_decode(const uint8_t* header, uint32_t hlen, const uint8_
     emu::launch(1, 32, smem, [&] { k_cm_decode(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next); });
 #else
     emu::launch(1, 32, smem, [&] {
-      if (fast & 4) k_cm_decode<1>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
+      if (fast & 8) k_cm_decode<2>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
+      else if (fast & 4) k_cm_decode<1>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
       else k_cm_decode<0>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
     });
 #endif

@@ -74,7 +74,7 @@ def _emu_decode(emu, header, coded, cap, fast=1, vm=0):
     return bytes(out[:n])
 
 
-@pytest.mark.parametrize("vm", [0, 1])      # both ZPAQL interpreters (switch / arithmetic selects)
+@pytest.mark.parametrize("vm", [0, 1, 2])   # the ZPAQL interpreters (switch / selects / selects + predicated loads)
 @pytest.mark.parametrize("method", ["36,200,1", "3", "4", "5", "46,200,1", "412,100,0"])
 def test_builtin_models_encode_and_decode(emu, oracle, method, vm):
     data = corpus.text_unit(3, 1200) if method != "412,100,0" else corpus.mixed_unit(5, 1200)
@@ -89,7 +89,7 @@ def test_builtin_models_encode_and_decode(emu, oracle, method, vm):
     assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data), fast=0, vm=vm) == data
 
 
-@pytest.mark.parametrize("vm", [0, 1])
+@pytest.mark.parametrize("vm", [0, 1, 2])
 @pytest.mark.parametrize("name", sorted(CONFIGS))
 def test_custom_models_encode_and_decode(emu, oracle, name, vm):
     header = bytes(zq.assemble_config(CONFIGS[name])["header"])

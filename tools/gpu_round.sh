@@ -33,6 +33,12 @@ for s in $STEPS; do
       ZQ_CM_VM=1 timeout 700 python -m pytest tests -m gpu -q > $O/${TAG}_pytest_gpu_vm1.log 2>&1; tail -4 $O/${TAG}_pytest_gpu_vm1.log ;;
     tests_cm_vm0)
       ZQ_CM_VM=0 timeout 500 python -m pytest tests/test_gpu_compress.py tests/test_gpu_decode.py tests/test_gpu_segments.py -m gpu -q > $O/${TAG}_pytest_gpu_cm_vm0.log 2>&1; tail -4 $O/${TAG}_pytest_gpu_cm_vm0.log ;;
+    tests_cm_vm2)
+      ZQ_CM_VM=2 timeout 500 python -m pytest tests/test_gpu_compress.py tests/test_gpu_decode.py tests/test_gpu_segments.py -m gpu -q > $O/${TAG}_pytest_gpu_cm_vm2.log 2>&1; tail -4 $O/${TAG}_pytest_gpu_cm_vm2.log ;;
+    cmtime_vm2)
+      ZQ_CM_VM=2 timeout 400 python tools/bench_configs.py --skip c4 --c5-units 1200 > $O/${TAG}_configs_c3_c5_vm2.json 2> $O/${TAG}_configs_vm2.err ;;
+    smoke)
+      timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -2 $O/${TAG}_smoke.log ;;
     cmtime_vm1)
       ZQ_CM_VM=1 timeout 400 python tools/bench_configs.py --skip c4 --c5-units 1200 > $O/${TAG}_configs_c3_c5_vm1.json 2> $O/${TAG}_configs_vm1.err ;;
     cmtime)

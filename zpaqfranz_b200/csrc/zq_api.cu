@@ -81,7 +81,7 @@ struct zq_ctx {
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 1;                         // 1: warp-per-block LZ77 parser (default, faster today); 0: candidates/chain/emit form (ZQ_LZ_PAR=1)
   int cm_occ = 2;                         // first engine only: CTAs (16 warps) per SM of the CM coder
-  int cm_vm = 0;                          // ZPAQL interpreter: 0 switch, 1 arithmetic selects (ZQ_CM_VM)
+  int cm_vm = 0;                          // ZPAQL interpreter: 0 switch, 1 arithmetic selects, 2 selects + predicated loads (ZQ_CM_VM)
   int cm_fast = 1;                        // encoder fast path for chain models (ZQ_CM_FAST=0: generic lanes)
   int cm_prefetch = 1;                    // context warp prefetches the coder's table lines (ZQ_CM_PREFETCH=0 to turn off)
   int lz_half = 0;                        // 1: SA parse with two blocks per warp (ZQ_LZ_HALF=1; bit-exact, slower today: the halves serialise)
@@ -504,9 +504,10 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       if (!c->attr_cm_enc) {   // per context (= per device): function attributes are per device
         cudaFuncSetAttribute(k_cm_encode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CmSmem) + ZQ_CM_MAX_PAIRS * sizeof(CmUnitSmem)));
         cudaFuncSetAttribute(k_cm_encode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CmSmem) + ZQ_CM_MAX_PAIRS * sizeof(CmUnitSmem)));
+        cudaFuncSetAttribute(k_cm_encode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CmSmem) + ZQ_CM_MAX_PAIRS * sizeof(CmUnitSmem)));
         c->attr_cm_enc = true;
       }
-      auto cmk = c->cm_vm == 1 ? k_cm_encode<1> : k_cm_encode<0>;
+      auto cmk = c->cm_vm == 2 ? k_cm_encode<2> : c->cm_vm == 1 ? k_cm_encode<1> : k_cm_encode<0>;
       cmk<<<std::min((nt + pairs - 1) / pairs, c->num_sms), pairs * 64, cm_smem, c->stream>>>(
           d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
           c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr,
@@ -910,9 +911,10 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
   if (!c->attr_cm_dec) {
     cudaFuncSetAttribute(k_cm_decode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
     cudaFuncSetAttribute(k_cm_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
+    cudaFuncSetAttribute(k_cm_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
     c->attr_cm_dec = true;
   }
-  auto cmd = c->cm_vm == 1 ? k_cm_decode<1> : k_cm_decode<0>;
+  auto cmd = c->cm_vm == 2 ? k_cm_decode<2> : c->cm_vm == 1 ? k_cm_decode<1> : k_cm_decode<0>;
 #endif
   int w0 = 0;
   while (w0 < n) {

@@ -162,6 +162,9 @@ struct VmOut { u8* out; u32 len, cap, error; };   // PCOMP's OUT sink (decoder)
 //     inside M / H) and one is picked, every ALU result is formed and one is picked, stores are predicated; only
 //     the group choice and the rare opcodes (division, long jump, jumps, hash) branch.  Selects are inline PTX
 //     selp: written as C conditionals nvcc turns them back into branch trees (measured slower, r01k).
+//     Measured (r01l): decode a little faster, encode slower than 0 (BWT model 355 vs 236 ms) -- the two unwanted
+//     operand loads wait on lines the machine has just stored to (write-through, L1 line dropped).
+//  2  as 1, operand loads predicated (inline PTX @p ld): not measured yet, next round.
 #define ZQ_VM_X8(B, STMT)                                                  \
   case (B) + 0: { const u32 x = a; STMT; } break;                          \
   case (B) + 1: { const u32 x = b; STMT; } break;                          \
@@ -234,6 +237,8 @@ __device__ void cm_vm_run_switch(CmVm& v, u32 input, VmOut* o) {
 __device__ __forceinline__ u32 zq_sel(bool p, u32 x, u32 y) { return p ? x : y; }
 __device__ __forceinline__ void zq_st8_if(bool p, u8* a, u32 v) { if (p) *a = (u8)v; }
 __device__ __forceinline__ void zq_st32_if(bool p, u32* a, u32 v) { if (p) *a = v; }
+__device__ __forceinline__ u32 zq_ld8_if(bool p, const u8* a, u32 other) { return p ? (u32)*a : other; }
+__device__ __forceinline__ u32 zq_ld32_if(bool p, const u32* a, u32 other) { return p ? *a : other; }
 #else
 __device__ __forceinline__ u32 zq_sel(bool p, u32 x, u32 y) {
   u32 r;
@@ -246,8 +251,20 @@ __device__ __forceinline__ void zq_st8_if(bool p, u8* a, u32 v) {
 __device__ __forceinline__ void zq_st32_if(bool p, u32* a, u32 v) {
   asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.u32 [%1], %2; }" ::"r"((u32)p), "l"(a), "r"(v) : "memory");
 }
+// predicated loads: only the operand the instruction names is fetched (a load that is not wanted would still wait
+// for a line the machine has just written through to L2)
+__device__ __forceinline__ u32 zq_ld8_if(bool p, const u8* a, u32 other) {
+  u32 r = other;
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q ld.u8 %0, [%2]; }" : "+r"(r) : "r"((u32)p), "l"(a) : "memory");
+  return r;
+}
+__device__ __forceinline__ u32 zq_ld32_if(bool p, const u32* a, u32 other) {
+  u32 r = other;
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q ld.u32 %0, [%2]; }" : "+r"(r) : "r"((u32)p), "l"(a) : "memory");
+  return r;
+}
 #endif
-template <bool WITH_OUT>
+template <bool WITH_OUT, bool PRED_LD>
 __device__ void cm_vm_run_sel(CmVm& v, u32 input, VmOut* o) {
   const u8* P = v.code;
   u8* M = v.m; u32* H = v.h; u32* R = v.r;
@@ -261,7 +278,9 @@ __device__ void cm_vm_run_sel(CmVm& v, u32 input, VmOut* o) {
     const u32 lo = op & 7u, hi = op >> 3;
     if (op >= 64u) {
       // ---- two operands.  b&mm, c&mm, d&hm always index inside M / H, so all three are fetched and one is picked
-      const u32 xb = M[b & mm], xc = M[c & mm], xd = H[d & hm];
+      const u32 xb = PRED_LD ? zq_ld8_if(lo == 4u, M + (b & mm), 0u) : (u32)M[b & mm];
+      const u32 xc = PRED_LD ? zq_ld8_if(lo == 5u, M + (c & mm), 0u) : (u32)M[c & mm];
+      const u32 xd = PRED_LD ? zq_ld32_if(lo == 6u, H + (d & hm), 0u) : H[d & hm];
       u32 x = zq_sel(lo & 4u, zq_sel(lo & 2u, zq_sel(lo & 1u, arg, xd), zq_sel(lo & 1u, xc, xb)),
                      zq_sel(lo & 2u, zq_sel(lo & 1u, d, c), zq_sel(lo & 1u, b, a)));
       pc += 1 + (int)(lo == 7u);
@@ -296,7 +315,7 @@ __device__ void cm_vm_run_sel(CmVm& v, u32 input, VmOut* o) {
     } else if (op < 32u) {
       // ---- register target a/b/c/d = hi: <>a, ++, --, !, =0, =r N
       const u32 val = zq_sel(hi & 2u, zq_sel(hi & 1u, d, c), zq_sel(hi & 1u, b, a));
-      const u32 rn = R[arg];                                   // always a valid slot (256 words)
+      const u32 rn = PRED_LD ? zq_ld32_if(lo == 7u, R + arg, 0u) : R[arg];   // always a valid slot (256 words)
       const u32 nv = zq_sel(lo & 4u, zq_sel(lo & 2u, rn, 0u), zq_sel(lo & 2u, zq_sel(lo & 1u, ~val, val - 1u), zq_sel(lo & 1u, val + 1u, a)));
       pc += 1 + (int)(lo == 7u);
       if (lo == 5u || lo == 6u || op == 0u) { stop = 2; break; }
@@ -339,7 +358,9 @@ __device__ void cm_vm_run_sel(CmVm& v, u32 input, VmOut* o) {
 
 template <int VM, bool WITH_OUT>
 __device__ __forceinline__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) {
-  if (VM == 1) cm_vm_run_sel<WITH_OUT>(v, input, o); else cm_vm_run_switch<WITH_OUT>(v, input, o);
+  if (VM == 2) cm_vm_run_sel<WITH_OUT, true>(v, input, o);
+  else if (VM == 1) cm_vm_run_sel<WITH_OUT, false>(v, input, o);
+  else cm_vm_run_switch<WITH_OUT>(v, input, o);
 }
 
 __device__ __forceinline__ int cm_clamp2k(int x) { return min(max(x, -2048), 2047); }
