@@ -74,8 +74,12 @@ def _emu_decode(emu, header, coded, cap, fast=1, vm=0):
     return bytes(out[:n])
 
 
-@pytest.mark.parametrize("vm", [0, 1, 2])   # the ZPAQL interpreters (switch / selects / selects + predicated loads)
-@pytest.mark.parametrize("method", ["36,200,1", "3", "4", "5", "46,200,1", "412,100,0"])
+# every built-in model with the default interpreter; the other two ZPAQL interpreters (selects / selects + predicated
+# loads) on the models whose HCOMP/PCOMP programs branch, loop and jump the most
+BUILTIN = [(m, 0) for m in ["36,200,1", "3", "4", "5", "46,200,1", "412,100,0"]] + [(m, vm) for vm in (1, 2) for m in ["36,200,1", "3"]]
+
+
+@pytest.mark.parametrize("method,vm", BUILTIN)
 def test_builtin_models_encode_and_decode(emu, oracle, method, vm):
     data = corpus.text_unit(3, 1200) if method != "412,100,0" else corpus.mixed_unit(5, 1200)
     plan = zq.plan_block(method, data)
@@ -89,8 +93,10 @@ def test_builtin_models_encode_and_decode(emu, oracle, method, vm):
     assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data), fast=0, vm=vm) == data
 
 
-@pytest.mark.parametrize("vm", [0, 1, 2])
-@pytest.mark.parametrize("name", sorted(CONFIGS))
+CUSTOM = [(n, 0) for n in sorted(CONFIGS)] + [(n, vm) for vm in (1, 2) for n in ("branches", "icm_chain_mix2_sse")]
+
+
+@pytest.mark.parametrize("name,vm", CUSTOM)
 def test_custom_models_encode_and_decode(emu, oracle, name, vm):
     header = bytes(zq.assemble_config(CONFIGS[name])["header"])
     for data in (b"", b"x", b"abracadabra" * 30, corpus.text_unit(9, 700), corpus.random_unit(5, 300)):
