@@ -113,10 +113,11 @@ def run_reference(args):
         return 0
     from zpaqfranz_b200 import corpus
     ncpu = os.cpu_count() or 1
-    arena = corpus.text_corpus(max(ncpu * 12, 64))
+    arena = corpus.text_corpus(min(10000, max(ncpu * 48, 256)))
     threads = best_reference_threads(arena, len(arena) // UNIT)   # doubles as warm-up
-    # bounded sample per step: 12 units per thread (each unit costs ~7-80 ms of one core)
-    sample = min(len(arena) // UNIT, max(threads * 12, 64))
+    # bounded sample per step: 48 units per thread (each unit costs ~7-80 ms of one core): seconds of wall time,
+    # tens to hundreds of core-seconds per step
+    sample = min(len(arena) // UNIT, max(threads * 48, 256))
     times = []
     for _ in range(args.steps):
         r = cpu_reference_throughput(sample, threads, arena)
@@ -321,7 +322,7 @@ def main():
     }
     if rank == 0 and not args.no_cpu_baseline:
         threads = best_reference_threads(h_in.numpy(), U)
-        sample = min(U, max(threads * 12, 64))
+        sample = min(U, max(threads * 48, 256))
         r = cpu_reference_throughput(sample, threads, h_in.numpy())
         if r is not None:
             line["cpu_baseline"] = {"value": round(r[0], 2), "unit": "MB/s", "cores": threads, "kind": "reference",
