@@ -6,7 +6,7 @@
 // data part of Decompresser::decompress (Z:15481-15508); the host parses the block/segment framing
 // (Decompresser::findBlock/findFilename/readComment/readSegmentEnd, Z:15418-15534).
 #pragma once
-#include "zq_cm.cuh"
+#include "zq_cm_v1.cuh"
 
 namespace zqdev {
 
