@@ -205,6 +205,17 @@ int zq_last_timings(zq_ctx* ctx, float ms[8]);
 /* debugging aid for the parity tests: suffix array (u32[n]) of one buffer, computed on the device */
 int zq_suffix_array(zq_ctx* ctx, const uint8_t* data, uint32_t n, uint32_t* sa_out);
 
+/* ---- ZPAQL -> CUDA C translation (host only, no GPU needed) -------------------------------------
+ * libzpaq compiles a block's HCOMP/PCOMP to x86 when the block starts (ZPAQL::assemble, Z:16216 ff.).
+ * zq_jit_context_source does the source-to-source equivalent for the HCOMP of a block header (hsize ..
+ * hcomp 0, as zq_plan_block returns it): a translation unit with `zq_hcomp` (one run of the program) and the
+ * kernel `zq_ctx_kernel` (one thread per block, H[0..n) after every byte).  zq_jit_compile runs NVRTC on such a
+ * source for sm_100a and reports the cubin size.  Groundwork: the compress path still interprets.
+ * src may be NULL to query the length.  ZQ_E_UNSUPPORTED: program outside the translator's cover / no NVRTC. */
+int zq_jit_context_source(const uint8_t* header, uint32_t header_len, char* src, uint32_t src_cap, uint32_t* src_len,
+                          char* errbuf, size_t errcap);
+int zq_jit_compile(const char* src, uint32_t* cubin_size, char* log, size_t logcap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,60 @@
+"""ZPAQL -> CUDA C translation (zpaqfranz_b200/csrc/zq_jit.cpp): the generated code, compiled for the host, is stepped
+against the device interpreter over the same bytes (registers, H, R, M must agree after every byte), and NVRTC compiles
+the generated translation unit for sm_100a.  No GPU needed; the compress path does not use the translator yet."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+import zpaqfranz_b200 as zq
+from zpaqfranz_b200 import corpus
+from test_cm_emu import CONFIGS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "zpaqfranz_b200", "csrc")
+
+HEADERS = {("method " + m): lambda m=m: bytes(zq.plan_block(m, corpus.text_unit(1, 2000))["header"])
+           for m in ["36,200,1", "3", "4", "5", "412,100,0", "56,200,1"]}
+HEADERS.update({("config " + n): lambda n=n: bytes(zq.assemble_config(CONFIGS[n])["header"]) for n in sorted(CONFIGS)})
+# loops, backward jumps, division, register file, swaps, long jumps
+HEADERS["config loops"] = lambda: bytes(zq.assemble_config(
+    "comp 4 6 0 0 1 0 cm 12 8 hcomp *c=a c++ b=c a= 0 d= 0 do b-- a+=*b d++ a> 200 if a/= 3 a%= 101 endif d<>a a== 7 d<>a until "
+    "r=a 3 a=r 3 a*= 5 *d<>a b<>a c<>a *b<>a d= 0 *d=a a=c a<<= 3 a^=*d a|= 1 a&~ 6 *d=a halt end")["header"])
+
+
+def _source(header):
+    n, err = C.c_uint32(0), C.create_string_buffer(256)
+    rc = zq.lib.zq_jit_context_source(header, len(header), None, 0, C.byref(n), err, 256)
+    assert rc == 0, err.value
+    buf = C.create_string_buffer(n.value + 1)
+    assert zq.lib.zq_jit_context_source(header, len(header), buf, n.value + 1, C.byref(n), err, 256) == 0
+    return buf.value.decode()
+
+
+@pytest.mark.parametrize("name", sorted(HEADERS))
+def test_translation_matches_interpreter_and_compiles(name, tmp_path):
+    header = HEADERS[name]()
+    src = _source(header)
+    gen = tmp_path / "gen.h"
+    gen.write_text(src)
+    lib = tmp_path / "libjitcheck.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+                    '-DZQ_JIT_GENERATED="%s"' % gen, "-shared", "-fPIC", "-o", str(lib), os.path.join(EMU, "jit_check.cpp")], check=True)
+    chk = C.CDLL(str(lib))
+    # HCOMP byte code = header after the component list: hsize(2) hh hm ph pm n comp... 0 hcomp... 0
+    hh, hm, n = header[2], header[3], header[6]
+    sizes = [0, 2, 3, 2, 3, 4, 6, 6, 3, 5]
+    p = 7
+    for _ in range(n):
+        p += sizes[header[p]]
+    code = header[p + 1:]
+    for data in (corpus.text_unit(4, 3000), corpus.random_unit(5, 2000), bytes(600), b"abc" * 300 + bytes(range(256))):
+        errs = (C.c_int * 2)()
+        assert chk.jit_check(code, len(code), hh, hm, data, len(data), errs) == 0, (name, list(errs))
+    size, log = C.c_uint32(0), C.create_string_buffer(4096)
+    rc = zq.lib.zq_jit_compile(src.encode(), C.byref(size), log, 4096)
+    if rc == zq.ZQ_E_UNSUPPORTED:
+        pytest.skip("NVRTC not available: " + log.value.decode())
+    assert rc == 0 and size.value > 1000, log.value.decode()

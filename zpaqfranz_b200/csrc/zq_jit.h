@@ -1,0 +1,31 @@
+// zq_jit.h -- ZPAQL -> CUDA C translation of a block's context program (HCOMP), and run-time compilation with NVRTC.
+//
+// The reference does not interpret ZPAQL on its hot path either: libzpaq translates HCOMP/PCOMP to x86 machine code
+// when a block starts (ZPAQL::assemble, Z:16216 ff.; interpreter only under `flagnojit`).  The device counterpart is
+// source-to-source: one labelled C statement per ZPAQL instruction, jumps become gotos, M/H sizes are baked in as
+// constants, then NVRTC -> cubin for sm_100a.  ncu (profiles/r01j) has the interpreted context machine as the critical
+// path of the chain models (~380 cycles per ZPAQL instruction against a handful of SASS instructions translated).
+//
+// Status: translator + NVRTC compilation are exercised by the CPU tests (generated code is compiled for the host and
+// stepped against the interpreter; NVRTC compiles it for sm_100a without a GPU).  Loading the module and feeding the
+// coder from its output is the next round's work; nothing on the compress path calls this yet.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace zq {
+
+// C statements for one run of the program (registers a,b,c,d,f; memories M,H,R; masks MM,HM; `err` set on ZPAQL
+// errors).  Returns false (with `why`) for programs the translator does not cover: jumps into the middle of an
+// instruction.  `with_out`: PCOMP's OUT calls ZQ_JIT_OUT(a); HCOMP ignores it.
+bool jit_translate(const uint8_t* code, size_t len, bool with_out, std::string& body, std::string& why);
+
+// Complete translation unit: `zq_hcomp` (one run) and the kernel `zq_ctx_kernel` (one thread per block: runs the
+// program over the block's coded bytes and stores H[0..ncomp) after every byte but the last).
+bool jit_context_source(const uint8_t* hcomp, size_t len, int hh, int hm, int ncomp, std::string& src, std::string& why);
+
+// NVRTC (dlopen'ed, no link-time dependency): source -> cubin for sm_100a.  Returns 0 or a negative code with `log`.
+int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);
+
+}  // namespace zq
