@@ -206,7 +206,7 @@ int zq_last_timings(zq_ctx* ctx, float ms[8]);
 int zq_suffix_array(zq_ctx* ctx, const uint8_t* data, uint32_t n, uint32_t* sa_out);
 
 /* ---- ZPAQL -> CUDA C translation (host only, no GPU needed) -------------------------------------
- * libzpaq compiles a block's HCOMP/PCOMP to x86 when the block starts (ZPAQL::assemble, Z:16216 ff.).
+ * libzpaq compiles a block's HCOMP/PCOMP to x86 when the block starts (ZPAQL::assemble, Z:16358, called from ZPAQL::run Z:17677).
  * zq_jit_context_source does the source-to-source equivalent for the HCOMP of a block header (hsize ..
  * hcomp 0, as zq_plan_block returns it): a translation unit with `zq_hcomp` (one run of the program) and the
  * kernel `zq_ctx_kernel` (one thread per block, H[0..n) after every byte).  zq_jit_compile runs NVRTC on such a

@@ -1,7 +1,7 @@
 // zq_jit.h -- ZPAQL -> CUDA C translation of a block's context program (HCOMP), and run-time compilation with NVRTC.
 //
 // The reference does not interpret ZPAQL on its hot path either: libzpaq translates HCOMP/PCOMP to x86 machine code
-// when a block starts (ZPAQL::assemble, Z:16216 ff.; interpreter only under `flagnojit`).  The device counterpart is
+// when a block starts (ZPAQL::assemble, Z:16358, called from ZPAQL::run Z:17677; interpreter only under `flagnojit`).  The device counterpart is
 // source-to-source: one labelled C statement per ZPAQL instruction, jumps become gotos, M/H sizes are baked in as
 // constants, then NVRTC -> cubin for sm_100a.  ncu (profiles/r01j) has the interpreted context machine as the critical
 // path of the chain models (~380 cycles per ZPAQL instruction against a handful of SASS instructions translated).
