@@ -65,11 +65,30 @@ extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_
       k_cm_encode<1>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next);
     });
 #else
+    // bit 4 of the flags: contexts precomputed (the role the translated program plays on the device); here by the
+    // interpreter, byte-major H[0..n) after every byte but the last
+    std::vector<u32> ctxbuf;
+    const u32* ctxp = nullptr; const u64* ctxo = nullptr; u64 ctx_zero = 0;
+    if (prefetch & 16) {
+      const u32 K = plen + slen;
+      std::vector<u8> M((size_t)1 << cp.hm, 0), prog(code.hcomp); prog.resize(prog.size() + 16);
+      std::vector<u32> H((size_t)1 << cp.hh, 0), R(256, 0);
+      CmVm vm; memset(&vm, 0, sizeof vm);
+      vm.m = M.data(); vm.h = H.data(); vm.r = R.data(); vm.mmask = (u32)M.size() - 1; vm.hmask = (u32)H.size() - 1;
+      vm.code = prog.data(); vm.len = (int)code.hcomp.size();
+      ctxbuf.assign((size_t)(K ? K : 1) * (cp.n ? cp.n : 1), 0);
+      for (u32 k = 0; k + 1 < K; ++k) {
+        cm_vm_run_switch<false>(vm, k < plen ? payload[k] : stream[k - plen], nullptr);
+        for (int i = 0; i < cp.n; ++i) ctxbuf[(size_t)k * cp.n + i] = H[i & vm.hmask];
+      }
+      ctxp = ctxbuf.data(); ctxo = &ctx_zero;
+    }
     const unsigned block = (unsigned)threads < 64 ? 64u : (unsigned)threads & ~63u;   // whole (coder, context) pairs
     emu::launch(1, block, sizeof(CmSmem) + (block / 64) * sizeof(CmUnitSmem), [&] {
-      if (prefetch & 8) k_cm_encode<2>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1);
-      else if (prefetch & 4) k_cm_encode<1>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1);
-      else k_cm_encode<0>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1);
+      if (prefetch & 16) k_cm_encode<0, true>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1, ctxp, ctxo);
+      else if (prefetch & 8) k_cm_encode<2, false>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1, ctxp, ctxo);
+      else if (prefetch & 4) k_cm_encode<1, false>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1, ctxp, ctxo);
+      else k_cm_encode<0, false>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1, ctxp, ctxo);
     });
 #endif
     free(model);

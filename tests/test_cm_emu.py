@@ -58,11 +58,11 @@ def _coded_by_oracle(oracle, header, pcomp, stream):
     return blk[pre:-6]                       # ... coded ... 00 00 00 00 FE FF
 
 
-def _emu_encode(emu, header, pcomp, stream, threads=64, prefetch=1, fast=1, vm=0):
+def _emu_encode(emu, header, pcomp, stream, threads=64, prefetch=1, fast=1, vm=0, ctx=0):
     payload = (bytes([1, len(pcomp) & 255, len(pcomp) >> 8]) + pcomp) if pcomp else b"\0"
     cap = len(stream) * 2 + len(payload) * 2 + 4096
     out = (C.c_uint8 * cap)()
-    n = emu.emu_cm_encode(header, len(header), payload, len(payload), stream, len(stream), out, cap, threads, prefetch | fast << 1 | vm << 2)
+    n = emu.emu_cm_encode(header, len(header), payload, len(payload), stream, len(stream), out, cap, threads, prefetch | fast << 1 | vm << 2 | ctx << 4)
     assert n >= 0, n
     return bytes(out[:n])
 
@@ -112,3 +112,9 @@ def test_pairs_share_a_cta_and_prefetch_is_transparent(emu, oracle):
     want = _coded_by_oracle(oracle, header, b"", data)
     assert _emu_encode(emu, header, b"", data, threads=192, prefetch=0) == want   # idle pairs leave through the queue
     assert _emu_encode(emu, header, b"", data, threads=64, prefetch=1) == want
+    # contexts handed over precomputed (what the translated context program will provide): coder output unchanged
+    assert _emu_encode(emu, header, b"", data, ctx=1) == want
+    plan3 = zq.plan_block("3", data)
+    s3 = oracle.lz_stream(data, plan3["args"])
+    h3, p3 = bytes(plan3["header"]), bytes(plan3["pcomp"])
+    assert _emu_encode(emu, h3, p3, s3, ctx=1) == _coded_by_oracle(oracle, h3, p3, s3)

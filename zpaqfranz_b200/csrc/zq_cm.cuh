@@ -797,16 +797,32 @@ __device__ void cm_code_chain1(const ZqCmPlan& cp, u8* model, CmUnitSmem& S, con
   }
 }
 
+// Arguments of a translated context kernel (zq_jit.cpp: zq_ctx_kernel) for the listed units: where each block's
+// coded bytes start and how many there are (the LZ/BWT stream lengths only exist on the device), model region, slot
+// in the context buffer.
+__global__ void k_ctx_args(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, const int* __restrict__ ids, int n,
+                           const u32* __restrict__ lz_len, const u64* __restrict__ ctx_off_by_unit, u64* __restrict__ soff,
+                           u32* __restrict__ slen, u64* __restrict__ model_off, u64* __restrict__ ctx_off) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int ui = ids[t];
+  const ZqUnit u = units[ui];
+  if (plans[u.plan].lz_level) { soff[t] = u.lz_off; slen[t] = lz_len[ui]; } else { soff[t] = u.in_off; slen[t] = u.n; }
+  model_off[t] = u.model_off;
+  ctx_off[t] = ctx_off_by_unit[ui];
+}
+
 // grid of persistent CTAs of `blockDim.x / 64` warp pairs (even warp: coder, odd warp: context machine);
 // pairs pull modeled units from a counter.  Dynamic shared memory: CmSmem + one CmUnitSmem per pair.
 #define ZQ_CM_MAX_PAIRS 12   // 768 threads: 85 registers per thread without spills; 1 776 blocks resident on 148 SMs
-template <int VM>
+template <int VM, bool CTX>   // CTX: contexts of some blocks arrive precomputed (translated HCOMP, zq_jit.cpp)
 __global__ void __launch_bounds__(64 * ZQ_CM_MAX_PAIRS, 1)
 k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
             const ZqCmPlan* __restrict__ cmplans, const int* __restrict__ todo, int ntodo,
             const CmTablesDev* __restrict__ tab, const u8* __restrict__ blob, const u8* __restrict__ lz_base,
             const u32* __restrict__ lz_len, u8* __restrict__ model_base, u8* __restrict__ coded_base,
-            u32* __restrict__ coded_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit, int prefetch, int fast) {
+            u32* __restrict__ coded_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit, int prefetch, int fast,
+            const u32* __restrict__ ctx_base, const u64* __restrict__ ctx_off) {
   ZQ_DYN_SMEM(smem_raw);
   CmSmem& T = *reinterpret_cast<CmSmem*>(smem_raw);
   {
@@ -835,17 +851,21 @@ k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, co
     const u8* __restrict__ head = blob + pl.payload_off;
     const u32 hlen = pl.payload_len, K = hlen + slen;
     if (role == 1) {
-      // ---- context warp: HCOMP on byte k -> ring slot k, for every byte but the last
+      // ---- context warp: HCOMP on byte k -> ring slot k, for every byte but the last.  When the block's contexts
+      // were already computed by the translated program (zq_jit.cpp: ctx_off[ui] != ~0), they are only streamed in.
       CmVm vm;
       cm_vm_setup(vm, cp, model, blob, S);
       const bool act = lane < (u32)cp.n;
       const ZqCmComp comp = cp.comp[act ? lane : 0];
+      const u32* __restrict__ cx = (CTX && ctx_base && ctx_off[ui] != ~(u64)0) ? ctx_base + ctx_off[ui] : nullptr;
       for (u32 k = 0; k + 1 < K; ++k) {
-        const u32 c = k < hlen ? head[k] : stream[k - hlen];
-        if (lane == 0) cm_vm_run<VM, false>(vm, c, nullptr);
-        __syncwarp();
+        if (!CTX || !cx) {
+          const u32 c = k < hlen ? head[k] : stream[k - hlen];
+          if (lane == 0) cm_vm_run<VM, false>(vm, c, nullptr);
+          __syncwarp();
+        }
         while (k - S.consumed >= ZQ_CM_RING) __nanosleep(64);
-        const u32 hv = act ? vm.h[lane & vm.hmask] : 0u;
+        const u32 hv = !act ? 0u : (CTX && cx) ? cx[(u64)k * (u32)cp.n + lane] : vm.h[lane & vm.hmask];
         S.ring[k % ZQ_CM_RING][lane] = hv;
         if (prefetch && act) cm_prefetch_byte(comp, model, hv, k + 1 < hlen ? head[k + 1] : stream[k + 1 - hlen]);
         __syncwarp();
