@@ -26,10 +26,10 @@ HEADERS["config loops"] = lambda: bytes(zq.assemble_config(
 
 def _source(header):
     n, err = C.c_uint32(0), C.create_string_buffer(256)
-    rc = zq.lib.zq_jit_context_source(header, len(header), None, 0, C.byref(n), err, 256)
+    rc = zq.lib.zq_jit_context_source(header, len(header), None, 0, C.byref(n), err, C.c_size_t(256))
     assert rc == 0, err.value
     buf = C.create_string_buffer(n.value + 1)
-    assert zq.lib.zq_jit_context_source(header, len(header), buf, n.value + 1, C.byref(n), err, 256) == 0
+    assert zq.lib.zq_jit_context_source(header, len(header), buf, n.value + 1, C.byref(n), err, C.c_size_t(256)) == 0
     return buf.value.decode()
 
 
@@ -54,7 +54,42 @@ def test_translation_matches_interpreter_and_compiles(name, tmp_path):
         errs = (C.c_int * 2)()
         assert chk.jit_check(code, len(code), hh, hm, data, len(data), errs) == 0, (name, list(errs))
     size, log = C.c_uint32(0), C.create_string_buffer(4096)
-    rc = zq.lib.zq_jit_compile(src.encode(), C.byref(size), log, 4096)
+    rc = zq.lib.zq_jit_compile(src.encode(), C.byref(size), log, C.c_size_t(4096))
     if rc == zq.ZQ_E_UNSUPPORTED:
         pytest.skip("NVRTC not available: " + log.value.decode())
     assert rc == 0 and size.value > 1000, log.value.decode()
+
+
+def _raw_header(hcomp, hh=2, hm=4):
+    """hsize(2) hh hm ph pm n=0 | 0 | hcomp... (trailing 0 included in hcomp)"""
+    body = bytes([hh, hm, 0, 0, 0, 0]) + bytes(hcomp)
+    return bytes([len(body) & 255, len(body) >> 8]) + body
+
+
+@pytest.mark.parametrize("name,hcomp", [
+    ("invalid opcode", [1, 5, 56, 0]),                 # a++ ; undefined opcode 5
+    ("runs off the end", [1, 9, 0]),                   # no halt: the END marker is executed -> error
+    ("jump past the end", [1, 63, 100, 56, 0]),        # jmp +100
+    ("jump before the start", [1, 63, 156, 56, 0]),    # jmp -100
+    ("error only on some inputs", [219, 65, 39, 2, 56, 0, 5, 56, 0]),   # a== 65 ; jt +2 -> halt... / undefined
+])
+def test_zpaql_errors_agree(name, hcomp, tmp_path):
+    header = _raw_header(hcomp)
+    src = _source(header)
+    gen = tmp_path / "gen.h"
+    gen.write_text(src)
+    lib = tmp_path / "libjitcheck.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+                    '-DZQ_JIT_GENERATED="%s"' % gen, "-shared", "-fPIC", "-o", str(lib), os.path.join(EMU, "jit_check.cpp")], check=True)
+    chk = C.CDLL(str(lib))
+    code = bytes(hcomp)
+    for data in (b"AAAA", b"BABA", bytes(range(60, 70))):
+        errs = (C.c_int * 2)()
+        assert chk.jit_check(code, len(code), 2, 4, data, len(data), errs) == 0, (name, list(errs))
+
+
+def test_jump_into_an_operand_is_left_to_the_interpreter():
+    header = _raw_header([71, 63, 63, 253, 56, 0])     # a= 63 ; jmp -3 lands on the operand byte of "a= 63"
+    n, err = C.c_uint32(0), C.create_string_buffer(256)
+    assert zq.lib.zq_jit_context_source(header, len(header), None, 0, C.byref(n), err, C.c_size_t(256)) == zq.ZQ_E_UNSUPPORTED
+    assert b"middle of an instruction" in err.value

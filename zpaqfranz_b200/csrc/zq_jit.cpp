@@ -201,7 +201,7 @@ int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& l
 extern "C" int zq_jit_context_source(const uint8_t* header, uint32_t header_len, char* src, uint32_t src_cap, uint32_t* src_len,
                                      char* errbuf, size_t errcap) {
   auto fail = [&](int rc, const std::string& m) {
-    if (errbuf && errcap) { strncpy(errbuf, m.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
+    if (errbuf && errcap) snprintf(errbuf, errcap, "%s", m.c_str());
     return rc;
   };
   if (!header || !src_len) return fail(ZQ_E_ARG, "bad argument");
@@ -227,7 +227,7 @@ extern "C" int zq_jit_compile(const char* src, uint32_t* cubin_size, char* log, 
   std::vector<char> cubin;
   std::string l;
   const int rc = zq::jit_compile(src, cubin, l);
-  if (log && logcap) { strncpy(log, l.c_str(), logcap - 1); log[logcap - 1] = 0; }
+  if (log && logcap) snprintf(log, logcap, "%s", l.c_str());
   if (cubin_size) *cubin_size = (uint32_t)cubin.size();
   return rc == 0 ? ZQ_OK : rc == -1 ? ZQ_E_UNSUPPORTED : ZQ_E_METHOD;
 }
