@@ -215,6 +215,11 @@ int zq_suffix_array(zq_ctx* ctx, const uint8_t* data, uint32_t n, uint32_t* sa_o
 int zq_jit_context_source(const uint8_t* header, uint32_t header_len, char* src, uint32_t src_cap, uint32_t* src_len,
                           char* errbuf, size_t errcap);
 int zq_jit_compile(const char* src, uint32_t* cubin_size, char* log, size_t logcap);
+/* Same translation unit plus `zq_encode_block`: the block's model written out as straight-line code (every
+ * component in index order, sizes / masks / rates / table offsets as literals) -- Predictor::predict0/update0 and
+ * Encoder::encode specialised for this header, the generalisation of the chain fast path. */
+int zq_jit_coder_source(const uint8_t* header, uint32_t header_len, char* src, uint32_t src_cap, uint32_t* src_len,
+                        char* errbuf, size_t errcap);
 
 #ifdef __cplusplus
 }

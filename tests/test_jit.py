@@ -93,3 +93,61 @@ def test_jump_into_an_operand_is_left_to_the_interpreter():
     n, err = C.c_uint32(0), C.create_string_buffer(256)
     assert zq.lib.zq_jit_context_source(header, len(header), None, 0, C.byref(n), err, C.c_size_t(256)) == zq.ZQ_E_UNSUPPORTED
     assert b"middle of an instruction" in err.value
+
+
+def _coder_source(header):
+    n, err = C.c_uint32(0), C.create_string_buffer(256)
+    rc = zq.lib.zq_jit_coder_source(header, len(header), None, 0, C.byref(n), err, C.c_size_t(256))
+    assert rc == 0, err.value
+    buf = C.create_string_buffer(n.value + 1)
+    assert zq.lib.zq_jit_coder_source(header, len(header), buf, n.value + 1, C.byref(n), err, C.c_size_t(256)) == 0
+    return buf.value.decode()
+
+
+CODER_MODELS = ["method 36,200,1", "method 3", "method 4", "method 5", "method 412,100,0"] + ["config " + n for n in sorted(CONFIGS)]
+
+
+@pytest.mark.parametrize("name", CODER_MODELS)
+def test_generated_model_codes_like_the_oracle(name, oracle, tmp_path):
+    """The model written out as straight-line code (zq_encode_block) + the translated context program, compiled for the
+    host: coded bytes equal the oracle's; NVRTC compiles the same translation unit for sm_100a."""
+    from test_cm_emu import _coded_by_oracle
+    header = HEADERS[name]()
+    src = _coder_source(header)
+    gen = tmp_path / "gen.h"
+    gen.write_text(src)
+    lib = tmp_path / "libjitcoder.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + CSRC, "-I" + os.path.join(ROOT, "include"), '-DZQ_JIT_GENERATED="%s"' % gen,
+                    "-shared", "-fPIC", "-o", str(lib), os.path.join(EMU, "jit_coder_check.cpp"), os.path.join(CSRC, "zq_cm_host.cpp"),
+                    os.path.join(CSRC, "zq_config.cpp")], check=True)
+    chk = C.CDLL(str(lib))
+    chk.jit_encode.restype = C.c_long
+    if name.startswith("method "):
+        method = name.split(" ", 1)[1]
+        datas = [corpus.text_unit(1, 2000), corpus.text_unit(3, 2500), corpus.mixed_unit(5, 2000)]   # the first is the header's own unit
+    else:
+        method = None
+        datas = [b"", b"x", b"abracadabra" * 30, corpus.text_unit(9, 1200), corpus.random_unit(5, 500)]
+    ran = 0
+    for data in datas:
+        if method:
+            plan = zq.plan_block(method, data)
+            if bytes(plan["header"]) != header:
+                continue                                  # another type heuristics outcome -> different model
+            pcomp = bytes(plan["pcomp"])
+            stream = oracle.lz_stream(data, plan["args"]) if (plan["args"][1] & 3) else data
+        else:
+            pcomp, stream = b"", data
+        payload = (bytes([1, len(pcomp) & 255, len(pcomp) >> 8]) + pcomp) if pcomp else b"\0"
+        cap = 2 * len(stream) + 2 * len(payload) + 4096
+        out = (C.c_uint8 * cap)()
+        r = chk.jit_encode(header, len(header), payload, len(payload), stream, len(stream), out, cap)
+        assert r >= 0, r
+        assert bytes(out[:r]) == _coded_by_oracle(oracle, header, pcomp, stream), (name, len(data))
+        ran += 1
+    assert ran > 0
+    size, log = C.c_uint32(0), C.create_string_buffer(8192)
+    rc = zq.lib.zq_jit_compile(src.encode(), C.byref(size), log, C.c_size_t(8192))
+    if rc == zq.ZQ_E_UNSUPPORTED:
+        pytest.skip("NVRTC not available: " + log.value.decode())
+    assert rc == 0 and size.value > 1000, log.value.decode()

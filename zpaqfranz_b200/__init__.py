@@ -58,6 +58,7 @@ def _load():
                                  C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                  C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zq_jit_context_source.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, u32p, C.c_char_p, C.c_size_t]
+    lib.zq_jit_coder_source.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, u32p, C.c_char_p, C.c_size_t]
     lib.zq_jit_compile.argtypes = [C.c_char_p, u32p, C.c_char_p, C.c_size_t]
     lib.zq_file_sort_key.restype = C.c_uint64
     lib.zq_file_sort_key.argtypes = [C.c_char_p, C.c_int64]

@@ -3,6 +3,7 @@
 
 #include <dlfcn.h>
 
+#include <cstdarg>
 #include <cstdio>
 #include <set>
 
@@ -230,4 +231,239 @@ extern "C" int zq_jit_compile(const char* src, uint32_t* cubin_size, char* log, 
   if (log && logcap) snprintf(log, logcap, "%s", l.c_str());
   if (cubin_size) *cubin_size = (uint32_t)cubin.size();
   return rc == 0 ? ZQ_OK : rc == -1 ? ZQ_E_UNSUPPORTED : ZQ_E_METHOD;
+}
+
+// ---- model -> straight-line coder ---------------------------------------------------------------------------
+#include "zq_cm_types.h"
+
+namespace zq {
+namespace {
+
+std::string S(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+std::string S(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  return buf;
+}
+
+const char* kCoderPrelude = R"GEN(
+// ---- generated coder: helpers -------------------------------------------------------------------------------
+struct ZqGenCoder { unsigned low, high; unsigned char* out; unsigned char* end; int overflow; };
+ZQ_JIT_FN void zq_gen_encode(ZqGenCoder& E, unsigned y, unsigned p16) {            // Encoder::encode, Z:15557
+  const unsigned mid = E.low + (unsigned)(((unsigned long long)(E.high - E.low) * p16) >> 16);
+  if (y) E.high = mid; else E.low = mid + 1;
+  while ((E.high ^ E.low) < 0x1000000u) {
+    if (E.out < E.end) *E.out = (unsigned char)(E.high >> 24); else E.overflow = 1;
+    ++E.out;
+    E.high = E.high << 8 | 255; E.low = E.low << 8; E.low += (E.low == 0);
+  }
+}
+ZQ_JIT_FN int zq_gen_clamp2k(int x) { return x < -2048 ? -2048 : x > 2047 ? 2047 : x; }
+ZQ_JIT_FN int zq_gen_clamp512k(int x) { return x < -(1 << 19) ? -(1 << 19) : x > (1 << 19) - 1 ? (1 << 19) - 1 : x; }
+struct ZqGenRow { unsigned w[4]; unsigned pos, ok; };
+ZQ_JIT_FN unsigned zq_gen_get(const ZqGenRow& r, unsigned idx) { return (r.w[idx >> 2] >> ((idx & 3) * 8)) & 255u; }
+ZQ_JIT_FN void zq_gen_put(ZqGenRow& r, unsigned idx, unsigned v) {
+  const unsigned sh = (idx & 3) * 8;
+  r.w[idx >> 2] = (r.w[idx >> 2] & ~(255u << sh)) | (v << sh);
+}
+// Predictor::find (Z:15254) with the row held in variables; the previous row goes back to the table first
+ZQ_JIT_FN void zq_gen_find(ZqGenRow& r, unsigned char* ht, unsigned ht_mask, unsigned chkshift, unsigned cxt) {
+  if (r.ok) { unsigned* d = (unsigned*)(ht + r.pos); d[0] = r.w[0]; d[1] = r.w[1]; d[2] = r.w[2]; d[3] = r.w[3]; }
+  const unsigned chk = (cxt >> chkshift) & 255u;
+  const unsigned h0 = (cxt * 16u) & (ht_mask - 15u), h1 = h0 ^ 16u, h2 = h0 ^ 32u;
+  const unsigned* q0 = (const unsigned*)(ht + h0); const unsigned* q1 = (const unsigned*)(ht + h1); const unsigned* q2 = (const unsigned*)(ht + h2);
+  const unsigned a0 = q0[0], a1 = q1[0], a2 = q2[0];
+  const unsigned* q; unsigned pos; int fresh = 0;
+  if ((a0 & 255u) == chk) { q = q0; pos = h0; }
+  else if ((a1 & 255u) == chk) { q = q1; pos = h1; }
+  else if ((a2 & 255u) == chk) { q = q2; pos = h2; }
+  else {
+    const unsigned p0 = (a0 >> 8) & 255u, p1 = (a1 >> 8) & 255u, p2 = (a2 >> 8) & 255u;
+    if (p0 <= p1 && p0 <= p2) { q = q0; pos = h0; } else if (p1 < p2) { q = q1; pos = h1; } else { q = q2; pos = h2; }
+    fresh = 1;
+  }
+  if (fresh) { r.w[0] = chk; r.w[1] = r.w[2] = r.w[3] = 0; } else { r.w[0] = q[0]; r.w[1] = q[1]; r.w[2] = q[2]; r.w[3] = q[3]; }
+  r.pos = pos; r.ok = 1;
+}
+)GEN";
+
+}  // namespace
+
+bool jit_coder_source(const void* plan_ptr, std::string& src, std::string& why) {
+  const ZqCmPlan& cp = *(const ZqCmPlan*)plan_ptr;
+  const int n = cp.n;
+  if (n < 1) { why = "no components"; return false; }
+  std::string decl, pred, upd, byteend;
+  auto off = [](uint64_t o) { return std::to_string((unsigned long long)o) + "ull"; };
+  for (int i = 0; i < n; ++i) {
+    const ZqCmComp& c = cp.comp[i];
+    const std::string I = std::to_string(i);
+    const std::string cm = "((unsigned*)(model + " + off(c.cm_off) + "))", ht = "(model + " + off(c.ht_off) + ")";
+    switch (c.type) {
+      case ZQ_CONS:
+        decl += S("  const int p%d = %d;\n", i, ((int)c.a1 - 128) * 4);
+        break;
+      case ZQ_CM:
+        decl += S("  unsigned cx%d = 0, pn%d = 0; int p%d = 0;\n", i, i, i);
+        pred += S("      cx%d = (h%d ^ hmap4) & %uu; pn%d = %s[cx%d]; p%d = STRETCH[pn%d >> 17];\n", i, i, c.cm_mask, i, cm.c_str(), i, i, i);
+        upd += S("      { const unsigned cnt = pn%d & 0x3ffu; const int er = (int)(y * 32767u) - (int)(pn%d >> 17);\n"
+                 "        pn%d += (unsigned)((er * DT[cnt]) & -1024) + (cnt < %uu ? 1u : 0u); %s[cx%d] = pn%d; }\n",
+                 i, i, i, (unsigned)c.a2 * 4u, cm.c_str(), i, i);
+        break;
+      case ZQ_ICM:
+        decl += S("  ZqGenRow r%d; r%d.ok = 0; r%d.pos = 0; unsigned s%d = 0, pn%d = 0; int p%d = 0;\n", i, i, i, i, i, i);
+        pred += S("      if (nib) zq_gen_find(r%d, %s, %uu, %uu, h%d + 16u * c8);\n", i, ht.c_str(), c.ht_mask, (unsigned)c.a1 + 2u, i);
+        pred += S("      s%d = zq_gen_get(r%d, hmap4 & 15u); pn%d = %s[s%d]; p%d = STRETCH[pn%d >> 8];\n", i, i, i, cm.c_str(), i, i, i);
+        upd += S("      zq_gen_put(r%d, hmap4 & 15u, NS[s%d * 4 + y]); pn%d += (unsigned)(((int)(y * 32767u) - (int)(pn%d >> 8)) >> 2); %s[s%d] = pn%d;\n",
+                 i, i, i, i, cm.c_str(), i, i);
+        break;
+      case ZQ_ISSE:
+        decl += S("  ZqGenRow r%d; r%d.ok = 0; r%d.pos = 0; unsigned s%d = 0; int w0_%d = 0, w1_%d = 0, p%d = 0;\n", i, i, i, i, i, i, i);
+        pred += S("      if (nib) zq_gen_find(r%d, %s, %uu, %uu, h%d + 16u * c8);\n", i, ht.c_str(), c.ht_mask, (unsigned)c.a1 + 2u, i);
+        pred += S("      s%d = zq_gen_get(r%d, hmap4 & 15u); w0_%d = (int)%s[s%d * 2]; w1_%d = (int)%s[s%d * 2 + 1];\n", i, i, i, cm.c_str(), i, i, cm.c_str(), i);
+        pred += S("      p%d = zq_gen_clamp2k((w0_%d * p%d + w1_%d * 64) >> 16);\n", i, i, (int)c.a2, i);
+        upd += S("      { const int er = (int)(y * 32767u) - (int)SQUASH[p%d + 2048];\n"
+                 "        %s[s%d * 2] = (unsigned)zq_gen_clamp512k(w0_%d + ((er * p%d + (1 << 12)) >> 13));\n"
+                 "        %s[s%d * 2 + 1] = (unsigned)zq_gen_clamp512k(w1_%d + ((er + 16) >> 5));\n"
+                 "        zq_gen_put(r%d, hmap4 & 15u, NS[s%d * 4 + y]); }\n",
+                 i, cm.c_str(), i, i, (int)c.a2, cm.c_str(), i, i, i, i);
+        break;
+      case ZQ_MATCH:
+        decl += S("  unsigned ml%d = 0, mp%d = 0, mb%d = 0, mc%d = 0, lim%d = 0; int p%d = 0;\n", i, i, i, i, i, i);
+        pred += S("      if (ml%d == 0) p%d = 0; else { mb%d = (%s[(lim%d - mp%d) & %uu] >> (7 - mc%d)) & 1u;\n"
+                  "        p%d = STRETCH[(DT2K[ml%d] * (mb%d ? -1 : 1)) & 32767]; }\n",
+                  i, i, i, ht.c_str(), i, i, c.ht_mask, i, i, i, i);
+        upd += S("      if (mb%d != y) ml%d = 0;\n", i, i);
+        upd += S("      if (++mc%d == 8) { %s[lim%d & %uu] = (unsigned char)(c8 * 2 + y); mc%d = 0; lim%d = (lim%d + 1) & %uu;\n"
+                 "        if (ml%d == 0) { mp%d = lim%d - %s[h%d & %uu];\n"
+                 "          if (mp%d & %uu) while (ml%d < 255 && %s[(lim%d - ml%d - 1) & %uu] == %s[(lim%d - ml%d - mp%d - 1) & %uu]) ++ml%d; }\n"
+                 "        else ml%d += ml%d < 255;\n"
+                 "        %s[h%d & %uu] = lim%d; }\n",
+                 i, ht.c_str(), i, c.ht_mask, i, i, i, c.ht_mask,
+                 i, i, i, cm.c_str(), i, c.cm_mask,
+                 i, c.ht_mask, i, ht.c_str(), i, i, c.ht_mask, ht.c_str(), i, i, i, c.ht_mask, i,
+                 i, i,
+                 cm.c_str(), i, c.cm_mask, i);
+        break;
+      case ZQ_AVG:
+        decl += S("  int p%d = 0;\n", i);
+        pred += S("      p%d = (p%d * %d + p%d * %d) >> 8;\n", i, (int)c.a1, (int)c.a3, (int)c.a2, 256 - (int)c.a3);
+        break;
+      case ZQ_MIX2:
+        decl += S("  unsigned cx%d = 0; int w%d = 0, p%d = 0;\n", i, i, i);
+        pred += S("      cx%d = (h%d + (c8 & %uu)) & %uu; w%d = ((unsigned short*)%s)[cx%d];\n", i, i, (unsigned)c.a5, c.cm_mask, i, cm.c_str(), i);
+        pred += S("      p%d = (w%d * p%d + (65536 - w%d) * p%d) >> 16;\n", i, i, (int)c.a2, i, (int)c.a3);
+        upd += S("      { const int er = (((int)(y * 32767u) - (int)SQUASH[p%d + 2048]) * %d) >> 5;\n"
+                 "        int w = w%d + ((er * (p%d - p%d) + (1 << 12)) >> 13); w = w < 0 ? 0 : w > 65535 ? 65535 : w;\n"
+                 "        ((unsigned short*)%s)[cx%d] = (unsigned short)w; }\n",
+                 i, (int)c.a4, i, (int)c.a2, (int)c.a3, cm.c_str(), i);
+        break;
+      case ZQ_MIX: {
+        const int m = c.a3, j0 = c.a2;
+        decl += S("  unsigned row%d = 0; int p%d = 0;", i, i);
+        for (int k = 0; k < m; ++k) decl += S(" int wt%d_%d = 0;", i, k);
+        decl += "\n";
+        pred += S("      row%d = ((h%d + (c8 & %uu)) & %uu) * %uu;\n      { int* wp = (int*)%s + row%d; int sum = 0;\n", i, i, (unsigned)c.a5, c.cm_mask, (unsigned)m, cm.c_str(), i);
+        for (int k = 0; k < m; ++k) pred += S("        wt%d_%d = wp[%d]; sum += (wt%d_%d >> 8) * p%d;\n", i, k, k, i, k, j0 + k);
+        pred += S("        p%d = zq_gen_clamp2k(sum >> 8); }\n", i);
+        upd += S("      { int* wp = (int*)%s + row%d; const int er = (((int)(y * 32767u) - (int)SQUASH[p%d + 2048]) * %d) >> 4;\n", cm.c_str(), i, i, (int)c.a4);
+        for (int k = 0; k < m; ++k) upd += S("        wp[%d] = zq_gen_clamp512k(wt%d_%d + ((er * p%d + (1 << 12)) >> 13));\n", k, i, k, j0 + k);
+        upd += "      }\n";
+        break;
+      }
+      case ZQ_SSE:
+        decl += S("  unsigned cx%d = 0, pn%d = 0; int p%d = 0;\n", i, i, i);
+        pred += S("      { unsigned cx = (h%d + c8) * 32u; int pq = p%d + 992; pq = pq < 0 ? 0 : pq > 1983 ? 1983 : pq; const int wt = pq & 63; pq >>= 6; cx += (unsigned)pq;\n"
+                  "        const unsigned e0 = %s[cx & %uu], e1 = %s[(cx + 1) & %uu];\n"
+                  "        p%d = STRETCH[((e0 >> 10) * (unsigned)(64 - wt) + (e1 >> 10) * (unsigned)wt) >> 13];\n"
+                  "        cx += (unsigned)(wt >> 5); cx%d = cx & %uu; pn%d = (wt >> 5) ? e1 : e0; }\n",
+                  i, (int)c.a2, cm.c_str(), c.cm_mask, cm.c_str(), c.cm_mask, i, i, c.cm_mask, i);
+        upd += S("      { const unsigned cnt = pn%d & 0x3ffu; const int er = (int)(y * 32767u) - (int)(pn%d >> 17);\n"
+                 "        pn%d += (unsigned)((er * DT[cnt]) & -1024) + (cnt < %uu ? 1u : 0u); %s[cx%d] = pn%d; }\n",
+                 i, i, i, (unsigned)c.a4 * 4u, cm.c_str(), i, i);
+        break;
+      default: why = "unknown component type"; return false;
+    }
+  }
+  std::string s = kCoderPrelude;
+  s += S("// model: %d components; mixer updates come first, as in Predictor::update0 (Z:15139): they use every p as predicted\n", n);
+  s += "ZQ_JIT_FN unsigned zq_encode_block(const unsigned char* head, unsigned hlen, const unsigned char* stream, unsigned slen,\n"
+       "                                   const unsigned* ctx, unsigned char* model, const short* STRETCH, const unsigned short* SQUASH,\n"
+       "                                   const int* DT, const int* DT2K, const unsigned char* NS, unsigned char* out, unsigned cap, int* overflow) {\n";
+  s += "  ZqGenCoder E; E.low = 1; E.high = 0xffffffffu; E.out = out; E.end = out + cap; E.overflow = 0;\n";
+  s += decl;
+  for (int i = 0; i < n; ++i) s += S("  unsigned h%d = 0;\n", i);
+  s += "  const unsigned K = hlen + slen;\n  for (unsigned k = 0; k < K; ++k) {\n";
+  s += S("    if (k > 0) { const unsigned* cv = ctx + (unsigned long long)(k - 1) * %d;", n);
+  for (int i = 0; i < n; ++i) s += S(" h%d = cv[%d];", i, i);
+  s += " }\n";
+  s += "    const unsigned c = k < hlen ? head[k] : stream[k - hlen];\n    zq_gen_encode(E, 0, 0);\n    unsigned c8 = 1, hmap4 = 1;\n";
+  s += "    for (int bit = 7; bit >= 0; --bit) {\n      const unsigned y = (c >> bit) & 1u;\n      const int nib = c8 == 1 || (c8 & 0xf0u) == 16u;\n";
+  s += pred;
+  s += S("      zq_gen_encode(E, y, (unsigned)SQUASH[p%d + 2048] * 2 + 1);\n", n - 1);
+  // updates: no component's update reads another one's state (inputs are the p's of the prediction), so index order
+  s += upd;
+  s += "      c8 += c8 + y;\n"
+       "      if (c8 >= 256) { c8 = 1; hmap4 = 1; }\n"
+       "      else if (c8 >= 16 && c8 < 32) hmap4 = (hmap4 & 0xf) << 5 | y << 4 | 1;\n"
+       "      else hmap4 = (hmap4 & 0x1f0) | (((hmap4 & 0xf) * 2 + y) & 0xf);\n";
+  s += "    }\n  }\n  zq_gen_encode(E, 1, 0);\n  *overflow = E.overflow;\n  return (unsigned)(E.out - out);\n}\n";
+  s +=
+      "#ifdef __CUDACC__\n"
+      "// One block per `stride` threads (stride 32: lane 0 of every warp codes a block, the chain fast path's mapping;\n"
+      "// stride 1: one block per thread).  The model-independent tables (zq::CmTables order: stretch, squash, dt, dt2k, ns)\n"
+      "// are staged to dynamic shared memory first; contexts come from zq_ctx_kernel's buffer.\n"
+      "extern \"C\" __global__ void zq_code_kernel(const unsigned char* head, unsigned hlen, const unsigned char* sbase,\n"
+      "                                          const unsigned long long* soff, const unsigned* slen, int nunits, int stride,\n"
+      "                                          unsigned char* model_base, const unsigned long long* model_off,\n"
+      "                                          const unsigned* ctx_base, const unsigned long long* ctx_off, const unsigned char* tab,\n"
+      "                                          unsigned char* coded_base, const unsigned long long* coded_off, const unsigned* coded_cap,\n"
+      "                                          unsigned* coded_len, unsigned* err_flag) {\n"
+      "  extern __shared__ __align__(16) unsigned char zq_tab[];\n"
+      "  for (unsigned k = threadIdx.x; k < 79872u / 16u; k += blockDim.x) ((uint4*)zq_tab)[k] = ((const uint4*)tab)[k];\n"
+      "  __syncthreads();\n"
+      "  const int g = blockIdx.x * blockDim.x + threadIdx.x;\n"
+      "  if (g % stride) return;\n"
+      "  const int t = g / stride;\n"
+      "  if (t >= nunits) return;\n"
+      "  int overflow = 0;\n"
+      "  coded_len[t] = zq_encode_block(head, hlen, sbase + soff[t], slen[t], ctx_base + ctx_off[t], model_base + model_off[t],\n"
+      "                                 (const short*)zq_tab, (const unsigned short*)(zq_tab + 65536), (const int*)(zq_tab + 73728),\n"
+      "                                 (const int*)(zq_tab + 77824), zq_tab + 78848, coded_base + coded_off[t], coded_cap[t], &overflow);\n"
+      "  if (overflow) atomicOr(err_flag, 1u);\n"
+      "}\n"
+      "#endif\n";
+  src += s;
+  return true;
+}
+
+}  // namespace zq
+
+extern "C" int zq_jit_coder_source(const uint8_t* header, uint32_t header_len, char* src, uint32_t src_cap, uint32_t* src_len,
+                                   char* errbuf, size_t errcap) {
+  auto fail = [&](int rc, const std::string& m) {
+    if (errbuf && errcap) snprintf(errbuf, errcap, "%s", m.c_str());
+    return rc;
+  };
+  if (!header || !src_len) return fail(ZQ_E_ARG, "bad argument");
+  try {
+    size_t used = 0;
+    zq::Assembled code = zq::parse_block_header(header, header_len, &used);
+    std::vector<ZqCmFill> fills;
+    ZqCmPlan cp = zq::make_cm_plan(code, fills);
+    std::string s, why;
+    if (!zq::jit_context_source(code.hcomp.data(), code.hcomp.size(), code.hh, code.hm, code.ncomp, s, why)) return fail(ZQ_E_UNSUPPORTED, why);
+    if (!zq::jit_coder_source(&cp, s, why)) return fail(ZQ_E_UNSUPPORTED, why);
+    *src_len = (uint32_t)s.size();
+    if (src) {
+      if (src_cap < s.size() + 1) return fail(ZQ_E_OUTPUT, "source buffer too small");
+      memcpy(src, s.c_str(), s.size() + 1);
+    }
+    return ZQ_OK;
+  } catch (const zq::Error& e) {
+    return fail(ZQ_E_METHOD, e.msg);
+  }
 }

@@ -25,6 +25,14 @@ bool jit_translate(const uint8_t* code, size_t len, bool with_out, std::string& 
 // program over the block's coded bytes and stores H[0..ncomp) after every byte but the last).
 bool jit_context_source(const uint8_t* hcomp, size_t len, int hh, int hm, int ncomp, std::string& src, std::string& why);
 
+// The model itself as straight-line code: `zq_encode_block` codes a block's bytes with the component chain of `plan`
+// written out component by component (index order is a valid evaluation order: inputs always have lower indices),
+// every size, mask, limit, rate and table offset a literal, hash rows and mixer weights in local variables.  This is
+// the chain fast path of zq_cm.cuh generalised to any model; `plan` supplies the table offsets inside a block's
+// model region (make_cm_plan), so k_cm_init's initialisation applies unchanged.  Appended to `src`.
+struct ZqCmPlanRef;   // (ZqCmPlan from zq_cm_types.h; declared in the .cpp to keep this header light)
+bool jit_coder_source(const void* zq_cm_plan, std::string& src, std::string& why);
+
 // NVRTC (dlopen'ed, no link-time dependency): source -> cubin for sm_100a.  Returns 0 or a negative code with `log`.
 int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);
 
