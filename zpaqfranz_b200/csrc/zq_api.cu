@@ -82,8 +82,9 @@ struct zq_ctx {
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 1;                         // 1: warp-per-block LZ77 parser (default, faster today); 0: candidates/chain/emit form (ZQ_LZ_PAR=1)
   int cm_occ = 2;                         // first engine only: CTAs (16 warps) per SM of the CM coder
-  int cm_jit = 0;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter (ZQ_CM_JIT)
-  std::map<std::string, std::pair<cudaLibrary_t, cudaKernel_t>> jit_cache;   // translated context kernels by program
+  int cm_jit = 0;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter; 2: generated coder too (ZQ_CM_JIT)
+  struct JitProg { cudaLibrary_t lib = nullptr; cudaKernel_t ctx = nullptr, code = nullptr; };
+  std::map<std::string, JitProg> jit_cache;   // translated context program (+ generated coder) per model header
   DevBuf d_ctx, d_ctxoff, d_ctxargs;
   int cm_vm = 0;                          // ZPAQL interpreter: 0 switch, 1 arithmetic selects, 2 selects + predicated loads (ZQ_CM_VM)
   int cm_fast = 1;                        // encoder fast path for chain models (ZQ_CM_FAST=0: generic lanes)
@@ -502,31 +503,39 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
                                                              c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(),
                                                              c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr);
 #else
-      // ---- optional: contexts from the translated context program (one NVRTC-compiled kernel per HCOMP, cached)
+      // ---- optional: translated context program (ZQ_CM_JIT=1) and generated straight-line coder (ZQ_CM_JIT=2), one
+      // NVRTC-compiled module per model, cached.  Blocks whose program the translator does not cover stay with
+      // k_cm_encode's interpreter; with JIT=2 the others do not go through k_cm_encode at all.
       const u32* d_ctx = nullptr; const u64* d_ctxoff = nullptr;
+      std::vector<int> todo_rest = todo_cm;     // what k_cm_encode still has to code
       if (c->cm_jit) {
         std::vector<uint64_t> ctxoff(units.size(), ~(uint64_t)0);     // by unit id, in u32 elements; ~0: interpret
         std::map<u32, std::vector<int>> groups;                       // cm plan -> units of this wave
         for (int ui : todo_cm) groups[dplans[units[ui].plan].cm_plan].push_back(ui);
-        struct Launch { cudaKernel_t fn; std::vector<int> ids; u32 plan; };
+        struct Launch { zq_ctx::JitProg prog; std::vector<int> ids; u32 plan; };
         std::vector<Launch> launches;
         uint64_t ctx_elems = 0;
         for (auto& g : groups) {
           const ZqCmPlan& cp = cmplans[g.first];
           const u8* hc = blob.data() + cp.hcomp_off;
-          std::string key((const char*)hc, cp.hcomp_len);
-          key += (char)cp.hh; key += (char)cp.hm; key += (char)cp.n;
+          ZqCmPlan kp = cp; kp.hcomp_off = 0; kp.fill_first = 0;       // per-call positions are not part of the model
+          std::string key((const char*)&kp, sizeof(ZqCmPlan));          // components, sizes and table offsets
+          key.append((const char*)hc, cp.hcomp_len);
           auto it = c->jit_cache.find(key);
           if (it == c->jit_cache.end()) {
             std::string src, why, log; std::vector<char> cubin;
-            cudaLibrary_t lib = nullptr; cudaKernel_t fn = nullptr;
-            if (zq::jit_context_source(hc, cp.hcomp_len, cp.hh, cp.hm, cp.n, src, why) && zq::jit_compile(src, cubin, log) == 0 &&
-                cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
-                cudaLibraryGetKernel(&fn, lib, "zq_ctx_kernel") != cudaSuccess) fn = nullptr;
-            it = c->jit_cache.emplace(key, std::make_pair(lib, fn)).first;   // fn == nullptr: this program stays interpreted
+            zq_ctx::JitProg P;
+            if (zq::jit_context_source(hc, cp.hcomp_len, cp.hh, cp.hm, cp.n, src, why) && (c->cm_jit < 2 || zq::jit_coder_source(&cp, src, why)) &&
+                zq::jit_compile(src, cubin, log) == 0 &&
+                cudaLibraryLoadData(&P.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess) {
+              if (cudaLibraryGetKernel(&P.ctx, P.lib, "zq_ctx_kernel") != cudaSuccess) P.ctx = nullptr;
+              if (c->cm_jit < 2 || cudaLibraryGetKernel(&P.code, P.lib, "zq_code_kernel") != cudaSuccess) P.code = nullptr;
+            }
+            cudaGetLastError();   // a program that could not be built simply stays interpreted
+            it = c->jit_cache.emplace(key, P).first;
           }
-          if (!it->second.second) continue;
-          Launch L; L.fn = it->second.second; L.plan = g.first;
+          if (!it->second.ctx) continue;
+          Launch L; L.prog = it->second; L.plan = g.first;
           for (int ui : g.second) {
             const ZqUnit& zu = units[ui];
             const ZqPlan& p = dplans[zu.plan];
@@ -542,16 +551,19 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
           ZQ_CUDA(c, cudaMemcpyAsync(c->d_ctxoff.p, ctxoff.data(), units.size() * 8, cudaMemcpyHostToDevice, c->stream));
           size_t total = 0;
           for (auto& L : launches) total += L.ids.size();
-          // per launch: unit ids | soff | slen | model_off | ctx_off   (28 B per unit)
-          ZQ_CUDA(c, c->d_ctxargs.ensure(total * 32 + 256));
+          // per launch: unit ids | soff | model_off | ctx_off | coded_off | slen | coded_cap   (44 B per unit)
+          ZQ_CUDA(c, c->d_ctxargs.ensure(total * 48 + 256 * launches.size() + 256));
           u8* A = c->d_ctxargs.as<u8>();
-          size_t done = 0;
+          size_t at = 0;
           for (auto& L : launches) {
             const int gn = (int)L.ids.size();
-            int* d_ids = (int*)(A + done * 32);
-            u64* d_soff = (u64*)(d_ids + gn + (gn & 1)); u64* d_moff = d_soff + gn; u64* d_coff = d_moff + gn; u32* d_slen = (u32*)(d_coff + gn);
+            int* d_ids = (int*)(A + at);
+            u64* d_soff = (u64*)(A + at + align_up((size_t)gn * 4, 16)); u64* d_moff = d_soff + gn; u64* d_coff = d_moff + gn; u64* d_cdoff = d_coff + gn;
+            u32* d_slen = (u32*)(d_cdoff + gn); u32* d_cdcap = d_slen + gn;
+            at += align_up((size_t)gn * 48, 256);
             ZQ_CUDA(c, cudaMemcpyAsync(d_ids, L.ids.data(), (size_t)gn * 4, cudaMemcpyHostToDevice, c->stream));
-            k_ctx_args<<<(gn + 127) / 128, 128, 0, c->stream>>>(du, dp, d_ids, gn, c->d_lzlen.as<u32>(), c->d_ctxoff.as<u64>(), d_soff, d_slen, d_moff, d_coff);
+            k_ctx_args<<<(gn + 127) / 128, 128, 0, c->stream>>>(du, dp, d_ids, gn, c->d_lzlen.as<u32>(), c->d_ctxoff.as<u64>(), d_soff, d_slen, d_moff, d_coff,
+                                                                d_cdoff, d_cdcap);
             const ZqCmPlan& cp = cmplans[L.plan];
             const ZqPlan& p0 = dplans[units[L.ids[0]].plan];
             const u8* head = c->d_blob.as<u8>() + p0.payload_off; unsigned hlen = p0.payload_len;
@@ -559,15 +571,30 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
             u8* mbase = c->d_model.as<u8>(); unsigned long long mo = cp.m_off, ho = cp.h_off, ro = cp.r_off;
             u32* cbase = c->d_ctx.as<u32>(); u32* eflag = c->d_err.as<u32>(); int gnn = gn;
             void* args[] = {&head, &hlen, &sbase, &d_soff, &d_slen, &gnn, &mbase, &d_moff, &mo, &ho, &ro, &cbase, &d_coff, &eflag};
-            ZQ_CUDA(c, cudaLaunchKernel((const void*)L.fn, dim3((gn + 63) / 64), dim3(64), args, 0, c->stream));
+            ZQ_CUDA(c, cudaLaunchKernel((const void*)L.prog.ctx, dim3((gn + 63) / 64), dim3(64), args, 0, c->stream));
             c->launches += 2;
-            done += gn;
+            if (L.prog.code) {
+              // the generated coder: lane 0 of every warp codes one block (stride 32), four warps per CTA
+              int stride = 32;
+              const u8* tabp = c->d_tables.as<u8>(); u8* cdbase = c->d_coded.as<u8>(); u32* cdlen = c->d_codedlen.as<u32>();
+              const u32* cbase_c = cbase;
+              void* cargs[] = {&head, &hlen, &sbase, &d_soff, &d_slen, &gnn, &stride, &mbase, &d_moff, &cbase_c, &d_coff, &tabp,
+                               &cdbase, &d_cdoff, &d_cdcap, &d_ids, &cdlen, &eflag};
+              ZQ_CUDA(c, cudaLaunchKernel((const void*)L.prog.code, dim3((gn * stride + 127) / 128), dim3(128), cargs, 0, c->stream));
+              ++c->launches;
+              for (int ui : L.ids) ctxoff[ui] = ~(uint64_t)0 - 1;   // coded: not k_cm_encode's business
+            }
           }
           d_ctx = c->d_ctx.as<u32>(); d_ctxoff = c->d_ctxoff.as<u64>();
+          todo_rest.clear();
+          for (int ui : todo_cm) if (ctxoff[ui] != ~(uint64_t)0 - 1) todo_rest.push_back(ui);
+          if (todo_rest.size() != todo_cm.size() && !todo_rest.empty())
+            ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo3.p, todo_rest.data(), todo_rest.size() * 4, cudaMemcpyHostToDevice, c->stream));
         }
       }
+      const int nt_enc = (int)todo_rest.size();
       // (coder, context) warp pairs: as many per CTA as spreads the wave over all SMs
-      const int pairs = std::max(1, std::min(ZQ_CM_MAX_PAIRS, (nt + c->num_sms - 1) / c->num_sms));
+      const int pairs = std::max(1, std::min(ZQ_CM_MAX_PAIRS, (nt_enc + c->num_sms - 1) / c->num_sms));
       const size_t cm_smem = sizeof(CmSmem) + (size_t)pairs * sizeof(CmUnitSmem);
       if (!c->attr_cm_enc) {   // per context (= per device): function attributes are per device
         const int cm_smem_max = (int)(sizeof(CmSmem) + ZQ_CM_MAX_PAIRS * sizeof(CmUnitSmem));
@@ -578,8 +605,9 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
         c->attr_cm_enc = true;
       }
       auto cmk = d_ctx ? k_cm_encode<0, true> : c->cm_vm == 2 ? k_cm_encode<2, false> : c->cm_vm == 1 ? k_cm_encode<1, false> : k_cm_encode<0, false>;
-      cmk<<<std::min((nt + pairs - 1) / pairs, c->num_sms), pairs * 64, cm_smem, c->stream>>>(
-          d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
+      if (nt_enc > 0)
+      cmk<<<std::min((nt_enc + pairs - 1) / pairs, c->num_sms), pairs * 64, cm_smem, c->stream>>>(
+          d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt_enc, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
           c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr,
           c->cm_prefetch, c->cm_fast, d_ctx, d_ctxoff);
 #endif
@@ -720,7 +748,7 @@ void zq_destroy(zq_ctx* c) {
   DevBuf* bufs[] = {&c->d_in, &c->d_out, &c->d_units, &c->d_plans, &c->d_blob, &c->d_todo, &c->d_outoff, &c->d_work, &c->d_ht, &c->d_todo2, &c->d_todo3, &c->d_todo4, &c->d_todo5, &c->d_dec, &c->d_tok, &c->d_bitpos, &c->d_tables, &c->d_cmplans, &c->d_fills, &c->d_model, &c->d_coded, &c->d_codedlen, &c->d_lz, &c->d_lzlen, &c->d_sha, &c->d_kbuf, &c->d_vbuf, &c->d_err, &c->d_misc};
   for (DevBuf* b : bufs) b->release();
   c->d_ctx.release(); c->d_ctxoff.release(); c->d_ctxargs.release();
-  for (auto& kv : c->jit_cache) if (kv.second.first) cudaLibraryUnload(kv.second.first);
+  for (auto& kv : c->jit_cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
   for (int k = 0; k < 8; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   cudaStreamDestroy(c->own_stream);

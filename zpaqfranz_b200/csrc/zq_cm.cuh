@@ -802,7 +802,8 @@ __device__ void cm_code_chain1(const ZqCmPlan& cp, u8* model, CmUnitSmem& S, con
 // in the context buffer.
 __global__ void k_ctx_args(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, const int* __restrict__ ids, int n,
                            const u32* __restrict__ lz_len, const u64* __restrict__ ctx_off_by_unit, u64* __restrict__ soff,
-                           u32* __restrict__ slen, u64* __restrict__ model_off, u64* __restrict__ ctx_off) {
+                           u32* __restrict__ slen, u64* __restrict__ model_off, u64* __restrict__ ctx_off,
+                           u64* __restrict__ coded_off, u32* __restrict__ coded_cap) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int ui = ids[t];
@@ -810,6 +811,7 @@ __global__ void k_ctx_args(const ZqUnit* __restrict__ units, const ZqPlan* __res
   if (plans[u.plan].lz_level) { soff[t] = u.lz_off; slen[t] = lz_len[ui]; } else { soff[t] = u.in_off; slen[t] = u.n; }
   model_off[t] = u.model_off;
   ctx_off[t] = ctx_off_by_unit[ui];
+  coded_off[t] = u.coded_off; coded_cap[t] = u.coded_cap;
 }
 
 // grid of persistent CTAs of `blockDim.x / 64` warp pairs (even warp: coder, odd warp: context machine);

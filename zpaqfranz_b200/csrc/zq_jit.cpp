@@ -414,25 +414,22 @@ bool jit_coder_source(const void* plan_ptr, std::string& src, std::string& why) 
   s +=
       "#ifdef __CUDACC__\n"
       "// One block per `stride` threads (stride 32: lane 0 of every warp codes a block, the chain fast path's mapping;\n"
-      "// stride 1: one block per thread).  The model-independent tables (zq::CmTables order: stretch, squash, dt, dt2k, ns)\n"
-      "// are staged to dynamic shared memory first; contexts come from zq_ctx_kernel's buffer.\n"
+      "// stride 1: one block per thread).  `tab` is the device copy of zq::CmTables (stretch, squash, dt, dt2k, ns in that\n"
+      "// order), read through L1; contexts come from zq_ctx_kernel's buffer; ids[t] is the unit the t-th block belongs to.\n"
       "extern \"C\" __global__ void zq_code_kernel(const unsigned char* head, unsigned hlen, const unsigned char* sbase,\n"
       "                                          const unsigned long long* soff, const unsigned* slen, int nunits, int stride,\n"
       "                                          unsigned char* model_base, const unsigned long long* model_off,\n"
       "                                          const unsigned* ctx_base, const unsigned long long* ctx_off, const unsigned char* tab,\n"
       "                                          unsigned char* coded_base, const unsigned long long* coded_off, const unsigned* coded_cap,\n"
-      "                                          unsigned* coded_len, unsigned* err_flag) {\n"
-      "  extern __shared__ __align__(16) unsigned char zq_tab[];\n"
-      "  for (unsigned k = threadIdx.x; k < 79872u / 16u; k += blockDim.x) ((uint4*)zq_tab)[k] = ((const uint4*)tab)[k];\n"
-      "  __syncthreads();\n"
+      "                                          const int* ids, unsigned* coded_len, unsigned* err_flag) {\n"
       "  const int g = blockIdx.x * blockDim.x + threadIdx.x;\n"
       "  if (g % stride) return;\n"
       "  const int t = g / stride;\n"
       "  if (t >= nunits) return;\n"
       "  int overflow = 0;\n"
-      "  coded_len[t] = zq_encode_block(head, hlen, sbase + soff[t], slen[t], ctx_base + ctx_off[t], model_base + model_off[t],\n"
-      "                                 (const short*)zq_tab, (const unsigned short*)(zq_tab + 65536), (const int*)(zq_tab + 73728),\n"
-      "                                 (const int*)(zq_tab + 77824), zq_tab + 78848, coded_base + coded_off[t], coded_cap[t], &overflow);\n"
+      "  coded_len[ids[t]] = zq_encode_block(head, hlen, sbase + soff[t], slen[t], ctx_base + ctx_off[t], model_base + model_off[t],\n"
+      "                                      (const short*)tab, (const unsigned short*)(tab + 65536), (const int*)(tab + 73728),\n"
+      "                                      (const int*)(tab + 77824), tab + 78848, coded_base + coded_off[t], coded_cap[t], &overflow);\n"
       "  if (overflow) atomicOr(err_flag, 1u);\n"
       "}\n"
       "#endif\n";
