@@ -151,3 +151,47 @@ def test_generated_model_codes_like_the_oracle(name, oracle, tmp_path):
     if rc == zq.ZQ_E_UNSUPPORTED:
         pytest.skip("NVRTC not available: " + log.value.decode())
     assert rc == 0 and size.value > 1000, log.value.decode()
+
+
+@pytest.mark.parametrize("name,stride", [("method 36,200,1", 32), ("method 3", 1), ("config icm_chain_mix2_sse", 32), ("config four_mixers_big_h", 1)])
+def test_generated_kernels_under_the_emulator(name, stride, oracle, tmp_path):
+    """zq_ctx_kernel + zq_code_kernel themselves (indexing of the per-group argument arrays, one block per thread or per
+    warp, several blocks of different lengths per launch) under the SIMT emulator."""
+    import numpy as np
+    from test_cm_emu import _coded_by_oracle
+    header = HEADERS[name]()
+    src = _coder_source(header)
+    gen = tmp_path / "gen.h"
+    gen.write_text(src)
+    lib = tmp_path / "libjitkernels.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+                    '-DZQ_JIT_GENERATED="%s"' % gen, "-shared", "-fPIC", "-o", str(lib), os.path.join(EMU, "jit_kernel_check.cpp"),
+                    os.path.join(CSRC, "zq_cm_host.cpp"), os.path.join(CSRC, "zq_config.cpp")], check=True)
+    chk = C.CDLL(str(lib))
+    if name.startswith("method "):
+        method = name.split(" ", 1)[1]
+        datas = [corpus.text_unit(1, 2000), corpus.text_unit(1, 2000)[:700], corpus.text_unit(3, 1500), corpus.text_unit(4, 40), corpus.text_unit(5, 1100)]
+        streams, pcomp = [], b""
+        for d in datas:
+            plan = zq.plan_block(method, d)
+            if bytes(plan["header"]) != header:
+                continue
+            pcomp = bytes(plan["pcomp"])
+            streams.append(oracle.lz_stream(d, plan["args"]) if (plan["args"][1] & 3) else d)
+    else:
+        pcomp = b""
+        streams = [b"abracadabra" * 30, b"", corpus.text_unit(9, 900), b"x", corpus.random_unit(5, 400)]
+    assert len(streams) >= 3
+    payload = (bytes([1, len(pcomp) & 255, len(pcomp) >> 8]) + pcomp) if pcomp else b"\0"
+    blob = b"".join(streams) + b"\0" * 16
+    slen = np.array([len(s) for s in streams], dtype=np.uint32)
+    soff = np.concatenate([[0], np.cumsum(slen.astype(np.uint64))[:-1]]).astype(np.uint64)
+    cap = 2 * int(slen.max()) + 2 * len(payload) + 4096
+    out = (C.c_uint8 * (cap * len(streams)))()
+    olen = (C.c_uint32 * len(streams))()
+    rc = chk.jit_kernels(header, len(header), payload, len(payload), blob, soff.ctypes.data_as(C.c_void_p), slen.ctypes.data_as(C.c_void_p),
+                         len(streams), stride, out, cap, olen)
+    assert rc == 0
+    raw = bytes(out)
+    for t, s in enumerate(streams):
+        assert raw[t * cap: t * cap + olen[t]] == _coded_by_oracle(oracle, header, pcomp, s), (name, t, len(s))
