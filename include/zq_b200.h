@@ -205,6 +205,12 @@ int zq_last_timings(zq_ctx* ctx, float ms[8]);
 /* debugging aid for the parity tests: suffix array (u32[n]) of one buffer, computed on the device */
 int zq_suffix_array(zq_ctx* ctx, const uint8_t* data, uint32_t n, uint32_t* sa_out);
 
+/* CRC-32 (crc32_16bytes, Z:30299: always on in Jidac::updatehash, Z:85948) and XXH64 seed 0 (the archiver's default
+ * file hash, XXH64 Z:24688) of n buffers: digests = 4 / 8 bytes per buffer, little-endian.  Emulator-verified against
+ * zlib and the reference's XXH64; not yet run on hardware. */
+int zq_crc32(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests);
+int zq_xxh64(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests);
+
 /* ---- ZPAQL -> CUDA C translation (host only, no GPU needed) -------------------------------------
  * libzpaq compiles a block's HCOMP/PCOMP to x86 when the block starts (ZPAQL::assemble, Z:16358, called from ZPAQL::run Z:17677).
  * zq_jit_context_source does the source-to-source equivalent for the HCOMP of a block header (hsize ..

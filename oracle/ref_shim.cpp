@@ -96,6 +96,18 @@ void zref_sha1(const unsigned char* in, unsigned long long n, unsigned char* out
 void zref_sha256(const unsigned char* in, unsigned long long n, unsigned char* out32) {
   libzpaq::SHA256 s; s.write((const char*)in, (int64_t)n); memcpy(out32, s.result(), 32);
 }
+// XXH64, seed 0 (the archiver's default file hash), little-endian u64
+void zref_xxh64(const unsigned char* in, unsigned long long n, unsigned char* out8) {
+  XXHash64 x(0);            // the archiver's own wrapper (Z:27039) around XXH64_reset/update/digest
+  x.add(in, n);
+  const unsigned long long h = x.hash();
+  for (int k = 0; k < 8; ++k) out8[k] = (unsigned char)(h >> (8 * k));
+}
+// CRC-32 as Jidac::updatehash computes it (crc32_16bytes, Z:30299), little-endian u32
+void zref_crc32(const unsigned char* in, unsigned long long n, unsigned char* out4) {
+  const unsigned int c = crc32_16bytes(in, n, 0);
+  for (int k = 0; k < 4; ++k) out4[k] = (unsigned char)(c >> (8 * k));
+}
 // XXH3-128, seed 0; out = high64 then low64, big-endian hex order as the reference prints it
 void zref_xxh3_128(const unsigned char* in, unsigned long long n, unsigned char* out16) {
   XXH3_state_t st; (void)XXH3_128bits_reset(&st);

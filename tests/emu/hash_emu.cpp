@@ -6,10 +6,11 @@
 
 #include "zq_sha1.cuh"
 #include "zq_hashes.cuh"
+#include "zq_hashes2.cuh"
 
 using namespace zqdev;
 
-// kind: 0 SHA-1 (20 B), 1 SHA-256 (32 B), 2 XXH3-128 (16 B), 3 BLAKE3 (32 B); buffers base+off[i], len[i]
+// kind: 0 SHA-1 (20 B), 1 SHA-256 (32 B), 2 XXH3-128 (16 B), 3 BLAKE3 (32 B), 4 CRC-32 (4 B), 5 XXH64 (8 B)
 extern "C" int emu_hash(int kind, const uint8_t* base, const uint64_t* off, const uint64_t* len, int n, uint8_t* digests) {
   if (n <= 0) return 0;
   if (kind == 0) {
@@ -18,6 +19,21 @@ extern "C" int emu_hash(int kind, const uint8_t* base, const uint64_t* off, cons
     emu::launch((n + 127) / 128, 128, 0, [&] { k_sha256_many(base, off, len, n, digests); });
   } else if (kind == 2) {
     emu::launch((n + 3) / 4, 128, 0, [&] { k_xxh3_128_many(base, off, len, n, digests); });
+  } else if (kind == 4) {
+    // tables exactly as crc_tables() in zq_api.cu builds them
+    static CrcTables t;
+    for (u32 v = 0; v < 256; ++v) { u32 c = v; for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u))); t.T[0][v] = c; }
+    for (u32 v = 0; v < 256; ++v) for (int k = 1; k < 4; ++k) t.T[k][v] = (t.T[k - 1][v] >> 8) ^ t.T[0][t.T[k - 1][v] & 255];
+    for (int k = 0; k < 4; ++k) for (u32 v = 0; v < 256; ++v) { u32 s = v << (8 * k); for (u32 z = 0; z < CRC_CHUNK; ++z) s = t.T[0][s & 255] ^ (s >> 8); t.Z[k][v] = s; }
+    std::vector<u64> first(n + 1);
+    u64 tot = 0;
+    for (int i = 0; i < n; ++i) { first[i] = tot; tot += (len[i] + CRC_CHUNK - 1) / CRC_CHUNK; }
+    first[n] = tot;
+    std::vector<u32> part(tot + 1);
+    if (tot) emu::launch((unsigned)((tot + 127) / 128), 128, 0, [&] { k_crc32_chunks(base, off, len, first.data(), n, tot, &t, part.data()); });
+    emu::launch((n + 127) / 128, 128, 0, [&] { k_crc32_fold(len, first.data(), n, &t, part.data(), (u32*)digests); });
+  } else if (kind == 5) {
+    emu::launch((n + 127) / 128, 128, 0, [&] { k_xxh64_many(base, off, len, n, (u64*)digests); });
   } else {
     std::vector<u64> first(n + 1);
     std::vector<int> multi;

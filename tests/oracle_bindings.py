@@ -143,6 +143,12 @@ class Ref:
     def blake3(self, d):
         return self._digest(self.lib.zref_blake3, 32, d)
 
+    def xxh64(self, d):
+        return self._digest(self.lib.zref_xxh64, 8, d)
+
+    def crc32(self, d):
+        return self._digest(self.lib.zref_crc32, 4, d)
+
     def divsufsort(self, data):
         data = bytes(data)
         sa = np.zeros(max(len(data), 1), dtype=np.int32)

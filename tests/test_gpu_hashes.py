@@ -1,5 +1,7 @@
 """Parity of the hash and fragmenter kernels with the reference's own implementations (oracle/_ref)
 and its known-answer vectors (autotest "ABCDE" values, Z:77129-77160)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -56,3 +58,20 @@ def test_fragmenter_matches_oracle_and_reference(ctx, oracle, ref):
             for k in range(a, min(b, a + 40)):
                 assert fs[k].tobytes() == oracle.sha1(data[pos:pos + int(fl[k])]), (frag, f, k)
                 pos += int(fl[k])
+
+
+@pytest.mark.skipif(not os.environ.get("ZQ_TEST_UNVERIFIED"), reason="CRC-32 / XXH64 kernels are emulator-verified only so far; set "
+                    "ZQ_TEST_UNVERIFIED=1 to run them on hardware (round 2)")
+def test_crc32_xxh64_match_reference(ctx, ref):
+    import zlib
+    bufs = [b"", b"ABCDE", bytes(5000), corpus.random_unit(3, 4096).tobytes() if hasattr(corpus.random_unit(3, 4096), "tobytes") else bytes(corpus.random_unit(3, 4096)),
+            bytes(corpus.text_unit(4, 70001)), bytes(corpus.random_unit(5, 1 << 20))]
+    lens = np.array([len(b) for b in bufs], dtype=np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    arena = np.frombuffer(b"".join(bufs) + b"\0", dtype=np.uint8)
+    crc = ctx.crc32(arena, offs, lens)
+    xx = ctx.xxh64(arena, offs, lens)
+    for i, b in enumerate(bufs):
+        assert crc[i].tobytes() == zlib.crc32(b).to_bytes(4, "little")
+        if ref is not None:
+            assert xx[i].tobytes() == ref.xxh64(b)

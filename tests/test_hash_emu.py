@@ -23,7 +23,7 @@ def emu():
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "libhashemu.so")
     deps = [os.path.join(EMU, "hash_emu.cpp"), os.path.join(EMU, "simt_emu.h"), os.path.join(CSRC, "zq_sha1.cuh"),
-            os.path.join(CSRC, "zq_hashes.cuh"), os.path.join(CSRC, "zq_common.cuh")]
+            os.path.join(CSRC, "zq_hashes.cuh"), os.path.join(CSRC, "zq_hashes2.cuh"), os.path.join(CSRC, "zq_common.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC,
                         "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-o", lib, deps[0]], check=True)
@@ -61,3 +61,13 @@ def test_reference_known_answers(emu):
     assert _run(emu, 0, 20, abcde)[0].hex().upper() == "7BE07AAF460D593A323D0DB33DA05B64BFDCB3A5"
     assert _run(emu, 2, 16, abcde)[0].hex().upper() == "1C8288B6013152D97B4A5D7E6C7893D4"
     assert _run(emu, 3, 32, abcde)[0].hex().upper().startswith("61274278")
+
+
+@pytest.mark.parametrize("shift", [0, 1, 2, 3])
+def test_crc32_xxh64(emu, ref, shift):
+    import zlib
+    bufs = BUFS + [bytes(corpus.random_unit(77, 4096)), bytes(corpus.random_unit(78, 8192)), bytes(corpus.random_unit(79, 12289))]
+    assert _run(emu, 4, 4, bufs, shift) == [zlib.crc32(b).to_bytes(4, "little") for b in bufs]
+    if ref is not None:
+        assert _run(emu, 4, 4, bufs, shift) == [ref.crc32(b) for b in bufs]
+        assert _run(emu, 5, 8, bufs, shift) == [ref.xxh64(b) for b in bufs]

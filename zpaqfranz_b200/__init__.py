@@ -76,7 +76,7 @@ def _load():
     lib.zq_model_config.argtypes = [C.c_int]
     lib.zq_assemble_config.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_void_p, u32p, C.c_void_p, u32p, C.c_char_p, C.c_size_t,
                                        C.c_char_p, C.c_size_t]
-    for name in ("zq_sha1", "zq_sha256", "zq_xxh3_128", "zq_blake3", "zq_sha1_device"):
+    for name in ("zq_sha1", "zq_sha256", "zq_xxh3_128", "zq_blake3", "zq_sha1_device", "zq_crc32", "zq_xxh64"):
         getattr(lib, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.zq_fragment.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -332,6 +332,14 @@ class Context:
 
     def blake3(self, arena, offsets, lengths):
         return self._hash(lib.zq_blake3, 32, arena, offsets, lengths)
+
+    def crc32(self, arena, offsets, lengths):
+        """CRC-32 per buffer as little-endian bytes (4 per row)."""
+        return self._hash(lib.zq_crc32, 4, arena, offsets, lengths)
+
+    def xxh64(self, arena, offsets, lengths):
+        """XXH64 (seed 0) per buffer as little-endian bytes (8 per row)."""
+        return self._hash(lib.zq_xxh64, 8, arena, offsets, lengths)
 
     def add_files(self, arena, offsets, lengths, method="1", fragment=6, date14="20260101000000", first_id=1):
         """The archiver's add loop over files in memory (== Jidac::add's data path for a fresh archive): returns

@@ -29,6 +29,7 @@
 #include "zq_fragment.cuh"
 #include "zq_frame.cuh"
 #include "zq_hashes.cuh"
+#include "zq_hashes2.cuh"
 #include "zq_lz77.cuh"
 #include "zq_lz77_half.cuh"
 #include "zq_lz77_par.cuh"
@@ -1170,6 +1171,61 @@ int zq_blake3(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const 
       ++c->launches;
     }
     ZQ_CUDA(c, cudaStreamSynchronize(c->stream));   // host vectors go out of scope
+    return ZQ_OK;
+  });
+}
+
+// CRC-32 slice tables and the "advance through 4 KiB of zeros" operator (see zq_hashes2.cuh)
+static const zqdev::CrcTables& crc_tables() {
+  static zqdev::CrcTables t;
+  static bool done = false;
+  if (!done) {
+    for (uint32_t v = 0; v < 256; ++v) {
+      uint32_t c = v;
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+      t.T[0][v] = c;
+    }
+    for (uint32_t v = 0; v < 256; ++v)
+      for (int k = 1; k < 4; ++k) t.T[k][v] = (t.T[k - 1][v] >> 8) ^ t.T[0][t.T[k - 1][v] & 255];
+    for (int k = 0; k < 4; ++k)
+      for (uint32_t v = 0; v < 256; ++v) {
+        uint32_t s = v << (8 * k);
+        for (uint32_t z = 0; z < zqdev::CRC_CHUNK; ++z) s = t.T[0][s & 255] ^ (s >> 8);
+        t.Z[k][v] = s;
+      }
+    done = true;
+  }
+  return t;
+}
+
+int zq_crc32(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
+  return hash_many(c, n, base, off, len, digests, 4, [&](u64* d_off, u64* d_len, std::vector<uint64_t>&) -> int {
+    std::vector<uint64_t> first(n + 1);
+    uint64_t tot = 0;
+    for (int i = 0; i < n; ++i) { first[i] = tot; tot += (len[i] + zqdev::CRC_CHUNK - 1) / zqdev::CRC_CHUNK; }
+    first[n] = tot;
+    ZQ_CUDA(c, c->d_work.ensure(tot * 4 + (size_t)(n + 1) * 8 + sizeof(zqdev::CrcTables) + 1024));
+    u8* W = c->d_work.as<u8>();
+    zqdev::CrcTables* d_tab = (zqdev::CrcTables*)W;
+    u64* d_first = (u64*)(W + sizeof(zqdev::CrcTables)); u32* d_part = (u32*)(d_first + n + 1);
+    const zqdev::CrcTables& t = crc_tables();
+    ZQ_CUDA(c, cudaMemcpyAsync(d_tab, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
+    ZQ_CUDA(c, cudaMemcpyAsync(d_first, first.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (tot) {
+      zqdev::k_crc32_chunks<<<(unsigned)((tot + 127) / 128), 128, 0, c->stream>>>(c->d_in.as<u8>(), d_off, d_len, d_first, n, tot, d_tab, d_part);
+      ++c->launches;
+    }
+    zqdev::k_crc32_fold<<<(n + 127) / 128, 128, 0, c->stream>>>(d_len, d_first, n, d_tab, d_part, c->d_sha.as<u32>());
+    ++c->launches;
+    ZQ_CUDA(c, cudaStreamSynchronize(c->stream));   // host vectors go out of scope
+    return ZQ_OK;
+  });
+}
+
+int zq_xxh64(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
+  return hash_many(c, n, base, off, len, digests, 8, [&](u64* d_off, u64* d_len, std::vector<uint64_t>&) {
+    zqdev::k_xxh64_many<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_in.as<u8>(), d_off, d_len, n, c->d_sha.as<u64>());
+    ++c->launches;
     return ZQ_OK;
   });
 }
