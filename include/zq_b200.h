@@ -202,6 +202,9 @@ uint64_t zq_launch_count(zq_ctx* ctx);
  * zq_compress_blocks* call: [0] total, [1] sha1, [2] suffix sort + lcp, [3] lz parse, [4] framing/
  * gather, [5] modeling/coding, [6] h2d, [7] d2h.  Unused stages are 0. */
 int zq_last_timings(zq_ctx* ctx, float ms[8]);
+/* the same plus the stages of the LZ77 parse pipeline: [8] look-ahead-0 scan, [9] look-ahead-1 scan, [10] walk,
+ * [11] emit; n <= 16 values are written. */
+int zq_last_timings_ex(zq_ctx* ctx, float* ms, int n);
 /* debugging aid for the parity tests: suffix array (u32[n]) of one buffer, computed on the device */
 int zq_suffix_array(zq_ctx* ctx, const uint8_t* data, uint32_t n, uint32_t* sa_out);
 

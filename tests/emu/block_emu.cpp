@@ -63,8 +63,8 @@ extern "C" long emu_block(const uint8_t* data, uint32_t n, const int* args, cons
       emu::launch(1, 256, sizeof(SortSmem<256>), [&] { k_suffix_sort<256, 4>(in.data(), &u, &todo, 1, work.data(), kbuf.data(), vbuf.data(), scr); });
       if (lz_level == 3) emu::launch(1, 256, 0, [&] { k_bwt_stream(in.data(), &u, &todo, 1, work.data(), lz.data(), &lzlen); });
       else emu::launch(1, 32, 0, [&] {
-        if (u.idx16) k_lz77_sa<u16, true, 6>(in.data(), &u, &pl, &todo, 1, work.data(), lz.data(), &lzlen, &err, &next);
-        else k_lz77_sa<u32, true, 6>(in.data(), &u, &pl, &todo, 1, work.data(), lz.data(), &lzlen, &err, &next);
+        if (u.idx16) k_lz77_sa<u16>(in.data(), &u, &pl, &todo, 1, work.data(), lz.data(), &lzlen, &err, &next);
+        else k_lz77_sa<u32>(in.data(), &u, &pl, &todo, 1, work.data(), lz.data(), &lzlen, &err, &next);
       });
     } else if (lz_level) {
       std::vector<u32> ht((size_t)1 << args[5], 0u);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>   // the shim
 
 #include "zq_lz77.cuh"
+#include "zq_lz77_scan.cuh"
 
 using namespace zqdev;
 
@@ -28,11 +29,54 @@ extern "C" long emu_lz_sa(const uint8_t* data, uint32_t n, const int* args, uint
     for (u32 i = 0; i < n; ++i) sa_out[i] = idx16 ? ((const u16*)work.data())[i] : ((const u32*)work.data())[i];
   u32 lzlen = 0, err = 0, next = 0;
   emu::launch(1, 32, 0, [&] {
-    if (idx16) k_lz77_sa<u16, true, 6>(in.data(), &u, &pl, &todo, 1, work.data(), out, &lzlen, &err, &next);
-    else k_lz77_sa<u32, true, 6>(in.data(), &u, &pl, &todo, 1, work.data(), out, &lzlen, &err, &next);
+    if (idx16) k_lz77_sa<u16>(in.data(), &u, &pl, &todo, 1, work.data(), out, &lzlen, &err, &next);
+    else k_lz77_sa<u32>(in.data(), &u, &pl, &todo, 1, work.data(), out, &lzlen, &err, &next);
   });
   if (err) return -(long)err;
   return (long)lzlen;
+}
+
+
+// The position-parallel form of the same parse (zq_lz77_scan.cuh): k_suffix_sort -> k_lz_scan<0> -> k_lz_scan<1> ->
+// k_lz_walk -> k_lz_emit, with the grid / block shapes the host uses.  Returns stream length or <0.
+template <typename IdxT>
+static long run_scan_pipeline(std::vector<u8>& in, ZqUnit& u, ZqPlan& pl, std::vector<u8>& work, uint8_t* out, uint32_t* ntok_out) {
+  int todo = 0;
+  u32 tile_first[2] = {0, lzs_tiles(u.n)};
+  u32 ctr = 0;
+  emu::launch(2, LZS_NT, sizeof(LzsSmem<IdxT>), [&] { k_lz_scan<IdxT, 0>(&u, &pl, &todo, tile_first, 1, work.data(), &ctr); });
+  ctr = 0;
+  emu::launch(2, LZS_NT, sizeof(LzsSmem<IdxT>), [&] { k_lz_scan<IdxT, 1>(&u, &pl, &todo, tile_first, 1, work.data(), &ctr); });
+  const size_t tokcap = u.n / std::max(pl.args[2], 1) + u.n / 4096 + 4 + 32;
+  std::vector<LzToken> tok(tokcap);
+  std::vector<u64> bitpos(tokcap);
+  u64 tok_off = 0; u32 ntok = 0, next = 0, lzlen = 0, err = 0;
+  emu::launch(1, 128, 0, [&] { k_lz_walk<IdxT>(in.data(), &u, &pl, &todo, 1, work.data(), &tok_off, tok.data(), &ntok, &next); });
+  if (ntok_out) *ntok_out = ntok;
+  std::vector<u8> lz(((size_t)u.lz_cap + 15) / 16 * 16 + 16, 0);   // malloc'ed: 16-byte aligned like the device arena
+  emu::launch(1, LZE_NT, sizeof(LzeSmem), [&] { k_lz_emit(in.data(), &u, &pl, &todo, 1, &tok_off, tok.data(), &ntok, bitpos.data(), lz.data(), &lzlen, &err); });
+  if (err) return -(long)err;
+  memcpy(out, lz.data(), lzlen);
+  return (long)lzlen;
+}
+
+extern "C" long emu_lz_scan(const uint8_t* data, uint32_t n, const int* args, uint8_t* out, uint32_t cap, uint32_t* ntok_out) {
+  const bool idx16 = n <= 65536;
+  const u32 w = idx16 ? 2 : 4;
+  std::vector<u8> in(data, data + n); in.resize(n + 64);
+  std::vector<u8> work(zq_work_bytes_scan(n, w) + 256);
+  ZqUnit u; memset(&u, 0, sizeof u);
+  u.n = n; u.idx16 = idx16; u.lz_cap = cap;
+  ZqPlan pl; memset(&pl, 0, sizeof pl);
+  for (int k = 0; k < 9; ++k) pl.args[k] = args[k];
+  pl.lz_level = args[1] & 3; pl.use_sa = 1;
+  int todo = 0;
+  const size_t scr = (((size_t)n + 1) + 63) & ~(size_t)63;
+  std::vector<u64> kbuf(2 * scr); std::vector<u32> vbuf(6 * scr);
+  emu::launch(1, 256, sizeof(SortSmem<256>), [&] {
+    k_suffix_sort<256, 4>(in.data(), &u, &todo, 1, work.data(), kbuf.data(), vbuf.data(), scr);
+  });
+  return idx16 ? run_scan_pipeline<u16>(in, u, pl, work, out, ntok_out) : run_scan_pipeline<u32>(in, u, pl, work, out, ntok_out);
 }
 
 #include "zq_frame.cuh"

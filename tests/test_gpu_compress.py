@@ -167,11 +167,10 @@ def test_config1_one_mib_of_zeros_m1(ctx, ref):
         assert out[: int(olen[0])].tobytes() == ref.compress_block(u, m, "", "")
 
 
-@pytest.mark.parametrize("knob", ["ZQ_LZ_PAR", "ZQ_LZ_HALF"])
-def test_parallel_parse_variant_is_bit_exact(zq, ref, monkeypatch, knob):
-    # alternative forms of the SA parse kept for comparison: candidates/chain/emit (zq_lz77_par.cuh, ZQ_LZ_PAR=1)
-    # and two blocks per warp (zq_lz77_half.cuh, ZQ_LZ_HALF=1)
-    monkeypatch.setenv(knob, "1")
+def test_general_parser_is_bit_exact(zq, ref, monkeypatch):
+    # the warp-per-block form of the SA parse (k_lz77_sa): serves methods the scan pipeline does not cover (bucket > 127,
+    # look-ahead > 1) and, with ZQ_LZ_OLD=1, every block -- same bytes either way
+    monkeypatch.setenv("ZQ_LZ_OLD", "1")
     units = EDGE_UNITS[3:] + [corpus.text_unit(21, 65536), corpus.repeats_unit(22, 65536)]
     arena, offs, lens = _arena(units)
     with zq.Context(0) as c2:
@@ -179,6 +178,20 @@ def test_parallel_parse_variant_is_bit_exact(zq, ref, monkeypatch, knob):
             out, ooff, olen = c2.compress_blocks(arena, offs, lens, method=method, filename="", comment="")
             for i, u in enumerate(units):
                 assert out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes() == ref.compress_block(u, method, "", ""), (method, i)
+
+
+def test_scan_pipeline_shapes(ctx, ref):
+    # the position-parallel parse (k_lz_scan -> k_lz_walk -> k_lz_emit) across its code paths: several tiles per block,
+    # 16- and 32-bit indices, look-ahead 0 and 1, both code formats, capped LCPs (exact slow path in the walk), streams
+    # assembled in shared memory (<= 64 KiB blocks) and in global memory (larger), plus a method it hands to k_lz77_sa
+    units = [corpus.text_unit(31, 65536), corpus.text_unit(32, 70001), corpus.repeats_unit(33, 65536), bytes(66000),
+             corpus.random_unit(34, 40000), corpus.mixed_unit(6, 100000), b"ab" * 3000 + b"c" + b"ab" * 3000,
+             corpus.text_unit(35, 4096), corpus.text_unit(36, 4097), corpus.text_unit(37, 8191), b"", b"x", bytes(range(256)) * 300]
+    arena, offs, lens = _arena(units)
+    for method in ("2", "x0,2,12,0,7,21,1", "x0,1,4,0,3,21,0", "x0,2,5,0,6,21,1", "x0,1,6,0,7,21,1", "x0,1,4,0,8,21,1", "x0,1,4,0,5,21,2"):
+        out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method=method, filename="", comment="")
+        for i, u in enumerate(units):
+            assert out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes() == ref.compress_block(u, method, "", ""), (method, i)
 
 
 def test_level5_period_models_on_device(ctx, zq, ref):

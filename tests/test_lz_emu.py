@@ -21,12 +21,13 @@ def emu():
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "liblzemu.so")
     deps = [os.path.join(EMU, "lz_emu.cpp"), os.path.join(EMU, "simt_emu.h")] + [os.path.join(CSRC, f) for f in
-                                                                                   ("zq_lz77.cuh", "zq_sufsort.cuh", "zq_common.cuh", "zq_frame.cuh")]
+                                                                                   ("zq_lz77.cuh", "zq_lz77_scan.cuh", "zq_sufsort.cuh", "zq_common.cuh", "zq_frame.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC,
                         "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-o", lib, deps[0]], check=True)
     h = C.CDLL(lib)
     h.emu_lz_sa.restype = C.c_long
+    h.emu_lz_scan.restype = C.c_long
     h.emu_lz_hash.restype = C.c_long
     h.emu_bwt.restype = C.c_long
     return h
@@ -51,6 +52,41 @@ def test_suffix_array_and_stream_match_oracle(emu, oracle, k):
     assert r >= 0
     assert list(sa[:n]) == list(oracle.suffix_array(data))
     assert bytes(out[:r]) == oracle.lz_stream(data, plan["args"])
+
+
+# the position-parallel pipeline (zq_lz77_scan.cuh: k_lz_scan<0> -> k_lz_scan<1> -> k_lz_walk -> k_lz_emit) on the same
+# cases plus: several tiles, look-ahead 0, small buckets, byte codes with matches, capped LCPs (deferred to the walk)
+SCAN_CASES = CASES + [("x0,1,4,0,3,21,0", corpus.text_unit(3, 6000)), ("x0,2,5,0,6,21,1", corpus.text_unit(4, 7000)),
+                      ("x0,2,5,0,6,21,1", corpus.repeats_unit(3, 14000)), ("x0,1,6,0,7,21,1", corpus.repeats_unit(3, 9000)),
+                      ("x0,1,4,0,5,21,0", corpus.mixed_unit(6, 8000)),
+                      ("2", corpus.text_unit(11, 9000) + bytes(3000) + corpus.text_unit(11, 5000)), ("2", bytes(range(256)) * 40)]
+
+
+@pytest.mark.parametrize("k", range(len(SCAN_CASES)))
+def test_scan_pipeline_matches_oracle(emu, oracle, k):
+    method, data = SCAN_CASES[k]
+    plan = zq.plan_block(method, data)
+    a = plan["args"]
+    assert (a[1] & 3) in (1, 2) and a[5] - a[0] >= 21 and a[4] <= 7 and a[6] <= 1, plan["method"]
+    n = len(data)
+    cap = n + n // 32 + 64
+    out = (C.c_uint8 * (cap + 64))()
+    ntok = C.c_uint32(0)
+    r = emu.emu_lz_scan(data, n, (C.c_int * 9)(*a), out, cap, C.byref(ntok))
+    assert r >= 0
+    assert bytes(out[:r]) == oracle.lz_stream(data, a)
+
+
+@pytest.mark.parametrize("n", [65536, 66000])
+def test_scan_pipeline_full_block(emu, oracle, n):
+    # a whole 64 KiB text block (16 tiles, 16-bit indices) and one just past it (32-bit indices, stream OR-ed in place)
+    data = corpus.text_unit(21, n)
+    a = zq.plan_block("2", data)["args"]
+    cap = n + n // 32 + 64
+    out = (C.c_uint8 * (cap + 64))()
+    ntok = C.c_uint32(0)
+    r = emu.emu_lz_scan(data, n, (C.c_int * 9)(*a), out, cap, C.byref(ntok))
+    assert r >= 0 and bytes(out[:r]) == oracle.lz_stream(data, a)
 
 
 HASH_CASES = [("1", corpus.text_unit(3, 3000)), ("1", b"abracadabra" * 100), ("1", bytes(2000)), ("1", corpus.mixed_unit(4, 4000)),

@@ -83,6 +83,7 @@ def _load():
     lib.zq_launch_count.restype = C.c_uint64
     lib.zq_launch_count.argtypes = [C.c_void_p]
     lib.zq_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.zq_last_timings_ex.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
     lib.zq_suffix_array.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     return lib
 
@@ -90,6 +91,7 @@ def _load():
 lib = _load()
 
 TIMING_KEYS = ("total", "sha1", "sufsort", "lzparse", "frame", "model", "h2d", "d2h")
+TIMING_KEYS_EX = TIMING_KEYS + ("lz_scan0", "lz_scan1", "lz_walk", "lz_emit")
 
 
 def plan_block(method, data=b""):
@@ -387,7 +389,11 @@ class Context:
     def launch_count(self):
         return int(lib.zq_launch_count(self._h))
 
-    def last_timings(self):
+    def last_timings(self, ex=False):
+        if ex:
+            ms = (C.c_float * 12)()
+            lib.zq_last_timings_ex(self._h, ms, 12)
+            return dict(zip(TIMING_KEYS_EX, [float(x) for x in ms]))
         ms = (C.c_float * 8)()
         lib.zq_last_timings(self._h, ms)
         return dict(zip(TIMING_KEYS, [float(x) for x in ms]))

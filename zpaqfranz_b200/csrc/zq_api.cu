@@ -31,8 +31,7 @@
 #include "zq_hashes.cuh"
 #include "zq_hashes2.cuh"
 #include "zq_lz77.cuh"
-#include "zq_lz77_half.cuh"
-#include "zq_lz77_par.cuh"
+#include "zq_lz77_scan.cuh"
 #include "zq_sha1.cuh"
 #include "zq_sufsort.cuh"
 
@@ -72,16 +71,17 @@ struct zq_ctx {
   std::string err;
   uint64_t launches = 0;
   DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_ht, d_todo2, d_todo3, d_todo4, d_todo5, d_dec, d_tok, d_bitpos, d_lz, d_lzlen, d_sha, d_tables, d_cmplans, d_fills, d_model, d_coded, d_codedlen,
-      d_kbuf, d_vbuf, d_err, d_misc;
-  Timer tm[8];
+      d_kbuf, d_vbuf, d_err, d_misc, d_lzs;
+  Timer tm[16];
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // h2d / d2h timing of the host-pointer entry point
   bool attr_cm_enc = false, attr_cm_dec = false;
-  float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  size_t wave_bytes = (size_t)12 << 30;  // sa|isa|lcp bytes per wave
+  float last_ms[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  size_t wave_bytes = (size_t)24 << 30;  // sa|isa|lcp|bwt|scan-table bytes per wave
   size_t model_budget = (size_t)120 << 30; // component-table bytes per wave (capped by free memory)
   int sort_nt = 256, sort_minb = 4;       // suffix-sort CTA size and CTAs per SM (measured best: 95.9 ms vs 103.5 ms at 512x2)
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
-  int lz_old = 1;                         // 1: warp-per-block LZ77 parser (default, faster today); 0: candidates/chain/emit form (ZQ_LZ_PAR=1)
+  int lz_old = 0;                         // 1: warp-per-block LZ77 parser for every block (ZQ_LZ_OLD=1); 0: position-parallel scan/walk/emit (zq_lz77_scan.cuh)
+  int scan_occ[2] = {0, 0};               // resident CTAs per SM of k_lz_scan<u16/u32, *> (queried once)
   int cm_occ = 2;                         // first engine only: CTAs (16 warps) per SM of the CM coder
   int cm_jit = 0;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter; 2: generated coder too (ZQ_CM_JIT)
   struct JitProg { cudaLibrary_t lib = nullptr; cudaKernel_t ctx = nullptr, code = nullptr; };
@@ -90,8 +90,6 @@ struct zq_ctx {
   int cm_vm = 0;                          // ZPAQL interpreter: 0 switch, 1 arithmetic selects, 2 selects + predicated loads (ZQ_CM_VM)
   int cm_fast = 1;                        // encoder fast path for chain models (ZQ_CM_FAST=0: generic lanes)
   int cm_prefetch = 1;                    // context warp prefetches the coder's table lines (ZQ_CM_PREFETCH=0 to turn off)
-  int lz_half = 0;                        // 1: SA parse with two blocks per warp (ZQ_LZ_HALF=1; bit-exact, slower today: the halves serialise)
-  int lz_occ = 6;                         // CTAs (4 warps) per SM the LZ parse kernel is compiled for
 };
 
 namespace {
@@ -263,7 +261,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
     } catch (const zq::Error& e) { return fail(c, ZQ_E_METHOD, e.msg); }
   }
   // ---- device tables -----------------------------------------------------------------------------
-  for (int k = 0; k < 8; ++k) c->tm[k].used = false;
+  for (int k = 0; k < 16; ++k) c->tm[k].used = false;
   tstart(c, 0);
   ZQ_CUDA(c, c->d_plans.ensure(dplans.size() * sizeof(ZqPlan)));
   ZQ_CUDA(c, c->d_blob.ensure(blob.size() + 16));
@@ -304,7 +302,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       zu.idx16 = zu.n <= 65536 ? 1 : 0;
       const bool hashlz = p.lz_level && !p.use_sa;
       if (p.e8e9) todo_e8.push_back(w1 - w0);
-      const size_t e = p.use_sa ? (size_t)zq_work_bytes(zu.n, zu.idx16 ? 2 : 4) : 0;
+      const size_t e = !p.use_sa ? 0 : p.lz_level == 3 ? (size_t)zq_work_bytes(zu.n, zu.idx16 ? 2 : 4) : (size_t)zq_work_bytes_scan(zu.n, zu.idx16 ? 2 : 4);
       const size_t hb = hashlz ? ((size_t)4 << p.args[5]) : 0;
       const size_t mb = p.modeled ? (size_t)cmplans[p.cm_plan].model_bytes : 0;
       if (w1 > w0 && (work + e + htbytes + hb > c->wave_bytes || model + mb > model_budget)) break;
@@ -376,86 +374,103 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       tstop(c, 2);
       tstart(c, 3);
       {
-        // LZ77 parse: one launch per (index width, parse flavour) present; BWT units go to their own kernel
-        std::vector<int> lists[4];
+        // LZ77 parse.  Blocks the scan pipeline covers (bucket <= 127, look-ahead <= 1: every built-in method) go
+        // through k_lz_scan<0/1> -> k_lz_walk -> k_lz_emit, per index width; the rest through the warp-per-block
+        // parser.  BWT units go to their own kernel.
+        std::vector<int> lists[4];   // 0/1: scan pipeline u16/u32; 2/3: warp-per-block parser u16/u32
         for (int t : todo_sa) {
           const ZqUnit& zu = units[w0 + t];
-          if (dplans[zu.plan].lz_level == 3) continue;
-          const bool pipe = dplans[zu.plan].args[6] <= 1;
-          lists[(zu.idx16 ? 0 : 2) + (pipe ? 0 : 1)].push_back(t);
+          const ZqPlan& p = dplans[zu.plan];
+          if (p.lz_level == 3) continue;
+          const bool scan_ok = !c->lz_old && p.args[4] <= 7 && p.args[6] <= 1;
+          lists[(scan_ok ? 0 : 2) + (zu.idx16 ? 0 : 1)].push_back(t);
         }
         size_t lo = 0;
         std::vector<int> flat;
         for (auto& l : lists) flat.insert(flat.end(), l.begin(), l.end());
-        const size_t nlz = flat.size();
+        const size_t nscan = lists[0].size() + lists[1].size();
         flat.insert(flat.end(), todo_bwt.begin(), todo_bwt.end());
         ZQ_CUDA(c, c->d_todo2.ensure(flat.size() * 4 + 4));
         ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo2.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        if (!c->lz_old && nlz) {
-          // parallel form: candidates per position -> sequential chain per block -> parallel bit emission
-          std::vector<uint64_t> dec_off(nlz), tok_off(nlz);
-          uint64_t npos = 0, ntokcap = 0; uint32_t maxlen = 0;
-          for (size_t k = 0; k < nlz; ++k) {
+        ZQ_CUDA(c, cudaMemsetAsync(c->d_err.as<u32>() + 4, 0, 48, c->stream));   // the work-queue counters of this wave
+        if (nscan) {
+          // per list: tile_first[cnt+1] (u32); over both lists: tok_off[nscan] (u64), ntok[nscan] (u32)
+          std::vector<uint64_t> tok_off(nscan);
+          std::vector<uint32_t> tile_first[2];
+          uint64_t ntokcap = 0; bool big = false;
+          for (size_t k = 0; k < nscan; ++k) {
             const ZqUnit& zu = units[w0 + flat[k]];
             const ZqPlan& p = dplans[zu.plan];
-            dec_off[k] = npos; npos += zu.n;
             tok_off[k] = ntokcap; ntokcap += zu.n / std::max(p.args[2], 1) + zu.n / 4096 + 4;
-            maxlen = std::max(maxlen, zu.n);
+            big = big || zu.lz_cap > LZE_SMEM_STREAM;
           }
-          ZQ_CUDA(c, c->d_dec.ensure(npos * 16 + 64));
+          for (int v = 0; v < 2; ++v) {
+            tile_first[v].push_back(0);
+            for (int t : lists[v]) tile_first[v].push_back(tile_first[v].back() + lzs_tiles(units[w0 + t].n));
+          }
+          const size_t tf_bytes = align_up((lists[0].size() + lists[1].size() + 2) * 4, 16);
+          ZQ_CUDA(c, c->d_lzs.ensure(tf_bytes + nscan * 12 + 64));
+          u32* d_tf0 = c->d_lzs.as<u32>(); u32* d_tf1 = d_tf0 + lists[0].size() + 1;
+          u64* d_tokoff = (u64*)(c->d_lzs.as<u8>() + tf_bytes); u32* d_ntok = (u32*)(d_tokoff + nscan);
+          ZQ_CUDA(c, cudaMemcpyAsync(d_tf0, tile_first[0].data(), tile_first[0].size() * 4, cudaMemcpyHostToDevice, c->stream));
+          ZQ_CUDA(c, cudaMemcpyAsync(d_tf1, tile_first[1].data(), tile_first[1].size() * 4, cudaMemcpyHostToDevice, c->stream));
+          ZQ_CUDA(c, cudaMemcpyAsync(d_tokoff, tok_off.data(), nscan * 8, cudaMemcpyHostToDevice, c->stream));
           ZQ_CUDA(c, c->d_tok.ensure(ntokcap * 16 + 64));
           ZQ_CUDA(c, c->d_bitpos.ensure(ntokcap * 8 + 64));
-          ZQ_CUDA(c, c->d_misc.ensure(nlz * 20 + 64));
-          u64* d_decoff = c->d_misc.as<u64>(); u64* d_tokoff = d_decoff + nlz; u32* d_ntok = (u32*)(d_tokoff + nlz);
-          ZQ_CUDA(c, cudaMemcpyAsync(d_decoff, dec_off.data(), nlz * 8, cudaMemcpyHostToDevice, c->stream));
-          ZQ_CUDA(c, cudaMemcpyAsync(d_tokoff, tok_off.data(), nlz * 8, cudaMemcpyHostToDevice, c->stream));
-          ZQ_CUDA(c, cudaMemsetAsync(c->d_lz.p, 0, lzbytes, c->stream));
-          if (maxlen) {
-            dim3 g((maxlen + LZC_CHUNK - 1) / LZC_CHUNK, (unsigned)nlz);
-            k_lz_candidates<<<g, 256, 0, c->stream>>>(d_in, du, dp, c->d_todo2.as<int>(), c->d_work.as<u8>(), d_decoff, c->d_dec.as<u64>());
-            ++c->launches;
+          if (big) ZQ_CUDA(c, cudaMemsetAsync(c->d_lz.p, 0, lzbytes, c->stream));   // streams too large for shared memory are OR-ed in place
+          if (!c->scan_occ[0]) {
+            cudaFuncSetAttribute(k_lz_scan<u16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzsSmem<u16>));
+            cudaFuncSetAttribute(k_lz_scan<u16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzsSmem<u16>));
+            cudaFuncSetAttribute(k_lz_scan<u32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzsSmem<u32>));
+            cudaFuncSetAttribute(k_lz_scan<u32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzsSmem<u32>));
+            cudaFuncSetAttribute(k_lz_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzeSmem));
+            int o16 = 1, o32 = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o16, k_lz_scan<u16, 1>, LZS_NT, sizeof(LzsSmem<u16>));
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, k_lz_scan<u32, 1>, LZS_NT, sizeof(LzsSmem<u32>));
+            c->scan_occ[0] = std::max(o16, 1); c->scan_occ[1] = std::max(o32, 1);
           }
-          k_lz_chain<<<(unsigned)((nlz + 63) / 64), 64, 0, c->stream>>>(d_in, du, dp, c->d_todo2.as<int>(), (int)nlz, c->d_work.as<u8>(), d_decoff,
-                                                                        c->d_dec.as<u64>(), d_tokoff, c->d_tok.as<LzToken>(), d_ntok);
-          ++c->launches;
-          k_lz_emit<<<(unsigned)std::min<size_t>(nlz, (size_t)c->num_sms * 8), 256, 0, c->stream>>>(
-              d_in, du, dp, c->d_todo2.as<int>(), (int)nlz, d_tokoff, c->d_tok.as<LzToken>(), d_ntok, c->d_bitpos.as<u64>(), c->d_lz.as<u8>(),
+          u32* ctr = c->d_err.as<u32>() + 10;   // [10..15]: tile / unit counters of this wave
+          size_t first = 0;
+          for (int v = 0; v < 2; ++v) {
+            const int cnt = (int)lists[v].size();
+            if (!cnt) continue;
+            const int* tl = c->d_todo2.as<int>() + first;
+            const u32* tf = v == 0 ? d_tf0 : d_tf1;
+            const u32 ntiles = tile_first[v].back();
+            const unsigned sgrid = (unsigned)std::max<u32>(1, std::min<u32>(ntiles, (u32)(c->num_sms * c->scan_occ[v])));
+            const unsigned wgrid = (unsigned)std::min((cnt + 3) / 4, c->num_sms * 16);
+            tstart(c, 8 + 0);
+            if (v == 0) k_lz_scan<u16, 0><<<sgrid, LZS_NT, sizeof(LzsSmem<u16>), c->stream>>>(du, dp, tl, tf, cnt, c->d_work.as<u8>(), ctr + 3 * v);
+            else k_lz_scan<u32, 0><<<sgrid, LZS_NT, sizeof(LzsSmem<u32>), c->stream>>>(du, dp, tl, tf, cnt, c->d_work.as<u8>(), ctr + 3 * v);
+            tstop(c, 8 + 0);
+            tstart(c, 8 + 1);
+            if (v == 0) k_lz_scan<u16, 1><<<sgrid, LZS_NT, sizeof(LzsSmem<u16>), c->stream>>>(du, dp, tl, tf, cnt, c->d_work.as<u8>(), ctr + 3 * v + 1);
+            else k_lz_scan<u32, 1><<<sgrid, LZS_NT, sizeof(LzsSmem<u32>), c->stream>>>(du, dp, tl, tf, cnt, c->d_work.as<u8>(), ctr + 3 * v + 1);
+            tstop(c, 8 + 1);
+            tstart(c, 8 + 2);
+            if (v == 0) k_lz_walk<u16><<<wgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), d_tokoff + first, c->d_tok.as<LzToken>(), d_ntok + first, ctr + 3 * v + 2);
+            else k_lz_walk<u32><<<wgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), d_tokoff + first, c->d_tok.as<LzToken>(), d_ntok + first, ctr + 3 * v + 2);
+            tstop(c, 8 + 2);
+            c->launches += 3;
+            first += cnt;
+          }
+          tstart(c, 8 + 3);
+          k_lz_emit<<<(unsigned)std::min<size_t>(nscan, (size_t)c->num_sms * 3), LZE_NT, sizeof(LzeSmem), c->stream>>>(
+              d_in, du, dp, c->d_todo2.as<int>(), (int)nscan, d_tokoff, c->d_tok.as<LzToken>(), d_ntok, c->d_bitpos.as<u64>(), c->d_lz.as<u8>(),
               c->d_lzlen.as<u32>(), c->d_err.as<u32>());
+          tstop(c, 8 + 3);
           ++c->launches;
-          lo = nlz;
-        } else
-        for (int v = 0; v < 4; ++v) {
+          lo = nscan;
+        }
+        for (int v = 2; v < 4; ++v) {
           const int cnt = (int)lists[v].size();
           if (!cnt) continue;
           const int* tl = c->d_todo2.as<int>() + lo;
           lo += cnt;
-          const int pgrid = std::min((cnt + 3) / 4, c->num_sms * std::max(c->lz_occ, 6));
+          const int pgrid = std::min((cnt + 3) / 4, c->num_sms * 6);
           u32* ctr = c->d_err.as<u32>() + 4 + v;
-          ZQ_CUDA(c, cudaMemsetAsync(ctr, 0, 4, c->stream));
-#define ZQ_LZ_LAUNCH(IDX, PIPE)                                                                              \
-  do {                                                                                                       \
-    auto kern = k_lz77_sa<IDX, PIPE, 6>;                                                                     \
-    if (c->lz_occ >= 12) kern = k_lz77_sa<IDX, PIPE, 12>;                                                    \
-    else if (c->lz_occ >= 10) kern = k_lz77_sa<IDX, PIPE, 10>;                                               \
-    else if (c->lz_occ >= 8) kern = k_lz77_sa<IDX, PIPE, 8>;                                                 \
-    kern<<<pgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), c->d_lz.as<u8>(),           \
-                                       c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);                       \
-  } while (0)
-          if ((v == 0 || v == 2) && c->lz_half) {   // two blocks per warp
-            const int hgrid = std::min((cnt + 7) / 8, c->num_sms * std::max(c->lz_occ, 6));
-            if (v == 0) {
-              auto kern = c->lz_occ >= 8 ? k_lz77_sa_half<u16, 8> : k_lz77_sa_half<u16, 6>;
-              kern<<<hgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);
-            } else {
-              auto kern = c->lz_occ >= 8 ? k_lz77_sa_half<u32, 8> : k_lz77_sa_half<u32, 6>;
-              kern<<<hgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);
-            }
-          }
-          else if (v == 0) ZQ_LZ_LAUNCH(u16, true);
-          else if (v == 1) ZQ_LZ_LAUNCH(u16, false);
-          else if (v == 2) ZQ_LZ_LAUNCH(u32, true);
-          else ZQ_LZ_LAUNCH(u32, false);
-#undef ZQ_LZ_LAUNCH
+          if (v == 2) k_lz77_sa<u16><<<pgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);
+          else k_lz77_sa<u32><<<pgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_err.as<u32>(), ctr);
           ++c->launches;
         }
         if (!todo_bwt.empty()) {
@@ -654,7 +669,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
   ZQ_CUDA(c, cudaGetLastError());
   if (errflag & 2) return fail(c, ZQ_E_METHOD, "ZPAQL execution error");
   if (errflag) return fail(c, ZQ_E_OUTPUT, "internal: intermediate stream exceeded its bound");
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < 16; ++k) {
     c->last_ms[k] = 0;
     if (c->tm[k].used) cudaEventElapsedTime(&c->last_ms[k], c->tm[k].a, c->tm[k].b);
   }
@@ -719,18 +734,16 @@ zq_ctx* zq_create(int device) {
   c->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "stream creation failed"; delete c; return nullptr; }
   c->stream = c->own_stream;
-  for (int k = 0; k < 8; ++k) { cudaEventCreate(&c->tm[k].a); cudaEventCreate(&c->tm[k].b); }
+  for (int k = 0; k < 16; ++k) { cudaEventCreate(&c->tm[k].a); cudaEventCreate(&c->tm[k].b); }
   for (int k = 0; k < 4; ++k) cudaEventCreate(&c->ev[k]);
   if (const char* s = getenv("ZQ_MODEL_BUDGET")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->model_budget = v; }
   if (const char* s = getenv("ZQ_FRAG_SEG")) { uint64_t v = strtoull(s, nullptr, 10); if (v >= 64) c->frag_seg = v; }
-  if (const char* s = getenv("ZQ_LZ_OCC")) c->lz_occ = atoi(s);
-  if (const char* s = getenv("ZQ_LZ_HALF")) c->lz_half = atoi(s);
   if (const char* s = getenv("ZQ_CM_OCC")) c->cm_occ = atoi(s);
   if (const char* s = getenv("ZQ_CM_PREFETCH")) c->cm_prefetch = atoi(s);
   if (const char* s = getenv("ZQ_CM_FAST")) c->cm_fast = atoi(s);
   if (const char* s = getenv("ZQ_CM_VM")) c->cm_vm = atoi(s);
   if (const char* s = getenv("ZQ_CM_JIT")) c->cm_jit = atoi(s);
-  if (const char* s = getenv("ZQ_LZ_PAR")) c->lz_old = atoi(s) ? 0 : 1;
+  if (const char* s = getenv("ZQ_LZ_OLD")) c->lz_old = atoi(s) ? 1 : 0;
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
   if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);
   if (c->sort_nt != 1024 && c->sort_nt != 512 && c->sort_nt != 256 && c->sort_nt != 128) c->sort_nt = 256;
@@ -750,7 +763,7 @@ void zq_destroy(zq_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   c->d_ctx.release(); c->d_ctxoff.release(); c->d_ctxargs.release();
   for (auto& kv : c->jit_cache) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
-  for (int k = 0; k < 8; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
+  for (int k = 0; k < 16; ++k) { cudaEventDestroy(c->tm[k].a); cudaEventDestroy(c->tm[k].b); }
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   cudaStreamDestroy(c->own_stream);
   delete c;
@@ -1376,7 +1389,13 @@ int zq_debug_sort_profile(unsigned long long out[8]) {
 uint64_t zq_launch_count(zq_ctx* c) { return c ? c->launches : 0; }
 int zq_last_timings(zq_ctx* c, float ms[8]) {
   if (!c) return ZQ_E_NODEVICE;
-  memcpy(ms, c->last_ms, sizeof c->last_ms);
+  memcpy(ms, c->last_ms, 8 * sizeof(float));
+  return ZQ_OK;
+}
+
+int zq_last_timings_ex(zq_ctx* c, float* ms, int n) {
+  if (!c) return ZQ_E_NODEVICE;
+  for (int k = 0; k < n; ++k) ms[k] = k < 16 ? c->last_ms[k] : 0.f;
   return ZQ_OK;
 }
 

@@ -56,3 +56,60 @@ __device__ __forceinline__ u32 lanemask_lt() {
 #endif
 // floor(log2(x))+1, 0 for 0 (== reference lg(), Z:19269)
 __device__ __forceinline__ int zq_bitlen(u32 x) { return 32 - __clz(x); }
+
+// ---- bulk async copies (TMA, cp.async.bulk) + mbarrier -------------------------------------------------------
+// One elected thread arms the barrier with the byte count and issues the copies; everyone waits on the phase
+// parity.  Addresses and sizes must be multiples of 16 bytes.  Under the host emulator the copy is a memcpy and
+// the barrier a phase counter, so the kernels' control flow is identical.
+#ifdef ZQ_EMU
+struct ZqMbar { u32 phase; u32 pending; };
+__device__ __forceinline__ void zq_mbar_init(ZqMbar* b, u32) { b->phase = 0; b->pending = 0; }
+__device__ __forceinline__ void zq_mbar_expect_tx(ZqMbar* b, u32 bytes) { b->pending += bytes; if (b->pending == 0) ++b->phase; }
+__device__ __forceinline__ void zq_bulk_g2s(void* dst, const void* src, u32 bytes, ZqMbar* b) {
+  if (((uintptr_t)dst | (uintptr_t)src | bytes) & 15) { fprintf(stderr, "emu: misaligned bulk copy\n"); abort(); }
+  memcpy(dst, src, bytes);
+  b->pending -= bytes;
+  if (b->pending == 0) ++b->phase;
+}
+__device__ __forceinline__ void zq_mbar_wait(ZqMbar* b, u32 parity) { while ((b->phase & 1u) == parity) emu::yield(); }
+__device__ __forceinline__ void zq_bulk_s2g(void* dst, const void* src, u32 bytes) {
+  if (((uintptr_t)dst | (uintptr_t)src | bytes) & 15) { fprintf(stderr, "emu: misaligned bulk store\n"); abort(); }
+  memcpy(dst, src, bytes);
+}
+__device__ __forceinline__ void zq_bulk_commit_wait() {}
+__device__ __forceinline__ void zq_fence_async_smem() {}
+#else
+typedef u64 ZqMbar;
+__device__ __forceinline__ u32 zq_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void zq_mbar_init(ZqMbar* b, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(zq_smem_addr(b)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void zq_mbar_expect_tx(ZqMbar* b, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zq_smem_addr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void zq_bulk_g2s(void* dst, const void* src, u32 bytes, ZqMbar* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(zq_smem_addr(dst)), "l"(src), "r"(bytes), "r"(zq_smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ void zq_mbar_wait(ZqMbar* b, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "ZQ_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra ZQ_DONE;\n"
+      "bra ZQ_WAIT;\n"
+      "ZQ_DONE:\n"
+      "}" ::"r"(zq_smem_addr(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void zq_bulk_s2g(void* dst, const void* src, u32 bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(zq_smem_addr(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void zq_bulk_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void zq_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif

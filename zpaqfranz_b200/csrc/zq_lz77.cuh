@@ -351,50 +351,6 @@ __device__ void lz77_sa_parse(const u8* __restrict__ in, u32 n, const IdxT* __re
   sk.flush();
 }
 
-// Same parse for look-ahead <= 1 (every built-in method), software pipelined: the neighbourhood of
-// position i+1 is requested before position i is evaluated; it serves the h=1 look-ahead of this
-// step and, when the step ends as a literal, IS the h=0 neighbourhood of the next step.  That takes
-// the isa -> sa/lcp dependent-load chain off the critical path of literal steps.
-template <typename IdxT>
-__device__ void lz77_sa_parse_pipe(const u8* __restrict__ in, u32 n, const IdxT* __restrict__ sa, const IdxT* __restrict__ isa,
-                                   const u16* __restrict__ lcp, const u8* __restrict__ bwt, const LzParams P, WarpSink& sk) {
-  const u32 maxMatch = 3u << 14;
-  const u32 lane = lane_id();
-  u32 i = 0, lit = 0;
-  if (n == 0) { sk.flush(); return; }
-  // rows of i, i+1 (lane0/lane1 fetch adjacent isa entries in one request)
-  u32 qv = (lane < 2 && i + lane < n) ? (u32)isa[i + lane] : 0u;
-  u32 qA = __shfl_sync(ZQ_FULL, qv, 0), qB = __shfl_sync(ZQ_FULL, qv, 1);
-  LzChunk A = lz_chunk_issue(sa, lcp, bwt, n, qA, P.bucket, true);
-  while (i < n) {
-    const bool haveB = i + 1 < n;
-    LzChunk B = lz_chunk_issue(sa, lcp, bwt, n, qB, P.bucket, haveB);
-    const u32 qC = i + 2 < n ? (u32)isa[i + 2] : 0u;
-    LzBest b; b.blen = P.minMatch - 1; b.bp = 0; b.blit = 0; b.bscore = 0;
-    const u32 lmax = min(maxMatch, n - i);
-    // If neither SA neighbour of row qA shares minMatch bytes with suffix i, no candidate can reach
-    // minMatch: whatever the scan accepts (a shorter, positive-score match) ends as a literal with no
-    // other effect on the parse state (Z:19428, Z:19476-19486), so the scan is skipped.
-    const u32 adj = max(__shfl_sync(ZQ_FULL, A.inr ? A.e : 0u, 0), __shfl_sync(ZQ_FULL, A.inr ? A.e : 0u, 16));
-    if (adj >= P.minMatch)
-      lz_scan_pos(in, n, sa, lcp, bwt, P, i, 0, lit, lmax, qA, A, b);
-    if (P.lookahead >= 1 && !(b.bscore <= 0 || b.blen < P.minMatch) && haveB &&
-        ((i + 1) >> P.checkbits) == (i >> P.checkbits)) {
-      lz_scan_pos(in, n, sa, lcp, bwt, P, i, 1, lit, lmax, qB, B, b);
-    }
-    const u32 adv = lz_emit_step(sk, P, in, i, b, lit);
-    i += adv;
-    if (adv == 1) { A = B; qA = qB; qB = qC; }
-    else if (i < n) {
-      qv = (lane < 2 && i + lane < n) ? (u32)isa[i + lane] : 0u;
-      qA = __shfl_sync(ZQ_FULL, qv, 0); qB = __shfl_sync(ZQ_FULL, qv, 1);
-      A = lz_chunk_issue(sa, lcp, bwt, n, qA, P.bucket, true);
-    }
-  }
-  lz_write_literal(sk, P, in, n, lit);
-  sk.flush();
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Hash-table search variant of the same parse (LZBuffer::fill, Z:19434-19471, index update
 // Z:19490-19515): methods with args[5]-args[0] < 21, i.e. -m1 and the low-redundancy forms of -m2..-m4.
@@ -579,12 +535,14 @@ k_bwt_stream(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, c
   }
 }
 
-// One warp per unit (grid-stride over the listed units). Instantiated per index width and per
-// parse flavour so each variant gets its own register allocation; the host sorts units into lists.
+// One warp per unit (persistent warps pull units from a counter).  The general form of the parse: any look-ahead
+// and bucket size.  The built-in methods go through the position-parallel pipeline of zq_lz77_scan.cuh instead;
+// this kernel serves what that one does not cover, and its per-position evaluator (lz_scan_pos) is the exact
+// slow path of the pipeline's walk.
 // work layout per unit (bytes from work_base + work_off): sa | isa | lcp | bwt, index width 2 B when
 // n <= 65536 (ZqUnit::idx16) else 4 B, each array padded to 128 B.
-template <typename IdxT, bool PIPE, int MINB>
-__global__ void __launch_bounds__(128, MINB)
+template <typename IdxT>
+__global__ void __launch_bounds__(128, 6)
 k_lz77_sa(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
           const int* __restrict__ todo, int ntodo, const u8* __restrict__ work_base,
           u8* __restrict__ lz_base, u32* __restrict__ lz_len, u32* __restrict__ err_flag, u32* __restrict__ next_unit) {
@@ -606,8 +564,7 @@ k_lz77_sa(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, cons
     const u16* lcp = (const u16*)(w + 2 * stride);
     const u8* bwt = w + 2 * stride + zq_work_stride(u.n, 2);
     const u8* in = in_base + u.in_off;
-    if (PIPE) lz77_sa_parse_pipe<IdxT>(in, u.n, (const IdxT*)w, (const IdxT*)(w + stride), lcp, bwt, P, sk);
-    else lz77_sa_parse<IdxT>(in, u.n, (const IdxT*)w, (const IdxT*)(w + stride), lcp, bwt, P, sk);
+    lz77_sa_parse<IdxT>(in, u.n, (const IdxT*)w, (const IdxT*)(w + stride), lcp, bwt, P, sk);
     if (lane_id() == 0) {
       lz_len[ui] = (u32)(sk.out - (lz_base + u.lz_off));
       if (sk.overflow) atomicOr(err_flag, 1u);
