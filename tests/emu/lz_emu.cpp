@@ -44,9 +44,9 @@ static long run_scan_pipeline(std::vector<u8>& in, ZqUnit& u, ZqPlan& pl, std::v
   int todo = 0;
   u32 tile_first[2] = {0, lzs_tiles(u.n)};
   u32 ctr = 0;
-  emu::launch(2, LZS_NT, sizeof(LzsSmem<IdxT>), [&] { k_lz_scan<IdxT, 0>(&u, &pl, &todo, tile_first, 1, work.data(), &ctr); });
+  emu::launch(2, LZS_NT, sizeof(LzsSmem<IdxT>) + (LZS_NT / 32) * sizeof(LzsQueue<IdxT>), [&] { k_lz_scan<IdxT, 0>(&u, &pl, &todo, tile_first, 1, 0u, work.data(), &ctr); });
   ctr = 0;
-  emu::launch(2, LZS_NT, sizeof(LzsSmem<IdxT>), [&] { k_lz_scan<IdxT, 1>(&u, &pl, &todo, tile_first, 1, work.data(), &ctr); });
+  emu::launch(2, LZS_NT, sizeof(LzsSmem<IdxT>) + (LZS_NT / 32) * sizeof(LzsQueue<IdxT>), [&] { k_lz_scan<IdxT, 1>(&u, &pl, &todo, tile_first, 1, lzs_tiles(u.n), work.data(), &ctr); });
   const size_t tokcap = u.n / std::max(pl.args[2], 1) + u.n / 4096 + 4 + 32;
   std::vector<LzToken> tok(tokcap);
   std::vector<u64> bitpos(tokcap);
@@ -66,7 +66,7 @@ extern "C" long emu_lz_scan(const uint8_t* data, uint32_t n, const int* args, ui
   std::vector<u8> in(data, data + n); in.resize(n + 64);
   std::vector<u8> work(zq_work_bytes_scan(n, w) + 256);
   ZqUnit u; memset(&u, 0, sizeof u);
-  u.n = n; u.idx16 = idx16; u.lz_cap = cap;
+  u.n = n; u.idx16 = idx16; u.lz_cap = cap; u.want_pk = 1;
   ZqPlan pl; memset(&pl, 0, sizeof pl);
   for (int k = 0; k < 9; ++k) pl.args[k] = args[k];
   pl.lz_level = args[1] & 3; pl.use_sa = 1;

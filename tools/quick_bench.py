@@ -30,7 +30,7 @@ ctx = zq.Context(0)
 acc = None
 for s in range(a.steps + 2):
     oo, ol = ctx.compress_blocks_device(arena.data_ptr(), offs, lens, out.data_ptr(), cap, method=a.method, filename="", comment="")
-    t = ctx.last_timings()
+    t = ctx.last_timings(ex=True)
     if s >= 2:
         acc = t if acc is None else {k: acc[k] + t[k] for k in t}
 print({k: round(v / a.steps, 2) for k, v in acc.items()}, "MB/s=%.0f" % (a.units * a.unit / 1e6 / (acc["total"] / a.steps / 1e3)),

@@ -81,7 +81,7 @@ struct zq_ctx {
   int sort_nt = 256, sort_minb = 4;       // suffix-sort CTA size and CTAs per SM (measured best: 95.9 ms vs 103.5 ms at 512x2)
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 0;                         // 1: warp-per-block LZ77 parser for every block (ZQ_LZ_OLD=1); 0: position-parallel scan/walk/emit (zq_lz77_scan.cuh)
-  int scan_occ[2] = {0, 0};               // resident CTAs per SM of k_lz_scan<u16/u32, *> (queried once)
+  int scan_occ[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of k_lz_scan<u16/u32, pass> (queried once)
   int cm_occ = 2;                         // first engine only: CTAs (16 warps) per SM of the CM coder
   int cm_jit = 0;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter; 2: generated coder too (ZQ_CM_JIT)
   struct JitProg { cudaLibrary_t lib = nullptr; cudaKernel_t ctx = nullptr, code = nullptr; };
@@ -302,7 +302,9 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       zu.idx16 = zu.n <= 65536 ? 1 : 0;
       const bool hashlz = p.lz_level && !p.use_sa;
       if (p.e8e9) todo_e8.push_back(w1 - w0);
-      const size_t e = !p.use_sa ? 0 : p.lz_level == 3 ? (size_t)zq_work_bytes(zu.n, zu.idx16 ? 2 : 4) : (size_t)zq_work_bytes_scan(zu.n, zu.idx16 ? 2 : 4);
+      const bool scan_ok = p.use_sa && p.lz_level != 3 && !c->lz_old && p.args[4] <= 7 && p.args[6] <= 1;   // covered by the scan pipeline
+      zu.want_pk = scan_ok ? 1 : 0;
+      const size_t e = !p.use_sa ? 0 : scan_ok ? (size_t)zq_work_bytes_scan(zu.n, zu.idx16 ? 2 : 4) : (size_t)zq_work_bytes(zu.n, zu.idx16 ? 2 : 4);
       const size_t hb = hashlz ? ((size_t)4 << p.args[5]) : 0;
       const size_t mb = p.modeled ? (size_t)cmplans[p.cm_plan].model_bytes : 0;
       if (w1 > w0 && (work + e + htbytes + hb > c->wave_bytes || model + mb > model_budget)) break;
@@ -382,8 +384,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
           const ZqUnit& zu = units[w0 + t];
           const ZqPlan& p = dplans[zu.plan];
           if (p.lz_level == 3) continue;
-          const bool scan_ok = !c->lz_old && p.args[4] <= 7 && p.args[6] <= 1;
-          lists[(scan_ok ? 0 : 2) + (zu.idx16 ? 0 : 1)].push_back(t);
+          lists[(zu.want_pk ? 0 : 2) + (zu.idx16 ? 0 : 1)].push_back(t);
         }
         size_t lo = 0;
         std::vector<int> flat;
@@ -394,6 +395,8 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
         ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo2.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, c->stream));
         ZQ_CUDA(c, cudaMemsetAsync(c->d_err.as<u32>() + 4, 0, 48, c->stream));   // the work-queue counters of this wave
         if (nscan) {
+          const size_t LZS_SMEM16 = sizeof(LzsSmem<u16>) + (LZS_NT / 32) * sizeof(LzsQueue<u16>);
+          const size_t LZS_SMEM32 = sizeof(LzsSmem<u32>) + (LZS_NT / 32) * sizeof(LzsQueue<u32>);
           // per list: tile_first[cnt+1] (u32); over both lists: tok_off[nscan] (u64), ntok[nscan] (u32)
           std::vector<uint64_t> tok_off(nscan);
           std::vector<uint32_t> tile_first[2];
@@ -418,16 +421,18 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
           ZQ_CUDA(c, c->d_tok.ensure(ntokcap * 16 + 64));
           ZQ_CUDA(c, c->d_bitpos.ensure(ntokcap * 8 + 64));
           if (big) ZQ_CUDA(c, cudaMemsetAsync(c->d_lz.p, 0, lzbytes, c->stream));   // streams too large for shared memory are OR-ed in place
-          if (!c->scan_occ[0]) {
-            cudaFuncSetAttribute(k_lz_scan<u16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzsSmem<u16>));
-            cudaFuncSetAttribute(k_lz_scan<u16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzsSmem<u16>));
-            cudaFuncSetAttribute(k_lz_scan<u32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzsSmem<u32>));
-            cudaFuncSetAttribute(k_lz_scan<u32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzsSmem<u32>));
+          if (!c->scan_occ[0][0]) {
+            cudaFuncSetAttribute(k_lz_scan<u16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZS_SMEM16);
+            cudaFuncSetAttribute(k_lz_scan<u16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZS_SMEM16);
+            cudaFuncSetAttribute(k_lz_scan<u32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZS_SMEM32);
+            cudaFuncSetAttribute(k_lz_scan<u32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZS_SMEM32);
             cudaFuncSetAttribute(k_lz_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzeSmem));
-            int o16 = 1, o32 = 1;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o16, k_lz_scan<u16, 1>, LZS_NT, sizeof(LzsSmem<u16>));
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o32, k_lz_scan<u32, 1>, LZS_NT, sizeof(LzsSmem<u32>));
-            c->scan_occ[0] = std::max(o16, 1); c->scan_occ[1] = std::max(o32, 1);
+            int o[2][2] = {{1, 1}, {1, 1}};
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[0][0], k_lz_scan<u16, 0>, LZS_NT, LZS_SMEM16);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[0][1], k_lz_scan<u16, 1>, LZS_NT, LZS_SMEM16);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[1][0], k_lz_scan<u32, 0>, LZS_NT, LZS_SMEM32);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o[1][1], k_lz_scan<u32, 1>, LZS_NT, LZS_SMEM32);
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) c->scan_occ[a][b] = std::max(o[a][b], 1);
           }
           u32* ctr = c->d_err.as<u32>() + 10;   // [10..15]: tile / unit counters of this wave
           size_t first = 0;
@@ -437,15 +442,20 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
             const int* tl = c->d_todo2.as<int>() + first;
             const u32* tf = v == 0 ? d_tf0 : d_tf1;
             const u32 ntiles = tile_first[v].back();
-            const unsigned sgrid = (unsigned)std::max<u32>(1, std::min<u32>(ntiles, (u32)(c->num_sms * c->scan_occ[v])));
+            u32 tpu = lzs_tiles(units[w0 + lists[v][0]].n);      // all blocks of the list cut into the same number of tiles?
+            for (int t : lists[v]) if (lzs_tiles(units[w0 + t].n) != tpu) { tpu = 0; break; }
+            // a CTA keeps LZS_NB tiles resident: fewer CTAs than that many tiles would leave SMs empty
+            const u32 want_ctas = std::max<u32>(1, (ntiles + LZS_NB - 1) / LZS_NB);
+            const unsigned sgrid0 = (unsigned)std::min<u32>(want_ctas, (u32)(c->num_sms * c->scan_occ[v][0]));
+            const unsigned sgrid1 = (unsigned)std::min<u32>(want_ctas, (u32)(c->num_sms * c->scan_occ[v][1]));
             const unsigned wgrid = (unsigned)std::min((cnt + 3) / 4, c->num_sms * 16);
             tstart(c, 8 + 0);
-            if (v == 0) k_lz_scan<u16, 0><<<sgrid, LZS_NT, sizeof(LzsSmem<u16>), c->stream>>>(du, dp, tl, tf, cnt, c->d_work.as<u8>(), ctr + 3 * v);
-            else k_lz_scan<u32, 0><<<sgrid, LZS_NT, sizeof(LzsSmem<u32>), c->stream>>>(du, dp, tl, tf, cnt, c->d_work.as<u8>(), ctr + 3 * v);
+            if (v == 0) k_lz_scan<u16, 0><<<sgrid0, LZS_NT, LZS_SMEM16, c->stream>>>(du, dp, tl, tf, cnt, tpu, c->d_work.as<u8>(), ctr + 3 * v);
+            else k_lz_scan<u32, 0><<<sgrid0, LZS_NT, LZS_SMEM32, c->stream>>>(du, dp, tl, tf, cnt, tpu, c->d_work.as<u8>(), ctr + 3 * v);
             tstop(c, 8 + 0);
             tstart(c, 8 + 1);
-            if (v == 0) k_lz_scan<u16, 1><<<sgrid, LZS_NT, sizeof(LzsSmem<u16>), c->stream>>>(du, dp, tl, tf, cnt, c->d_work.as<u8>(), ctr + 3 * v + 1);
-            else k_lz_scan<u32, 1><<<sgrid, LZS_NT, sizeof(LzsSmem<u32>), c->stream>>>(du, dp, tl, tf, cnt, c->d_work.as<u8>(), ctr + 3 * v + 1);
+            if (v == 0) k_lz_scan<u16, 1><<<sgrid1, LZS_NT, LZS_SMEM16, c->stream>>>(du, dp, tl, tf, cnt, tpu, c->d_work.as<u8>(), ctr + 3 * v + 1);
+            else k_lz_scan<u32, 1><<<sgrid1, LZS_NT, LZS_SMEM32, c->stream>>>(du, dp, tl, tf, cnt, tpu, c->d_work.as<u8>(), ctr + 3 * v + 1);
             tstop(c, 8 + 1);
             tstart(c, 8 + 2);
             if (v == 0) k_lz_walk<u16><<<wgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), d_tokoff + first, c->d_tok.as<LzToken>(), d_ntok + first, ctr + 3 * v + 2);

@@ -23,7 +23,7 @@ struct ZqUnit {
   u32 prefix_off, prefix_len;  // block prefix (tag .. segment header) in the blob
   u32 idx16;     // 1: sa/isa stored as u16 (n <= 65536), 0: u32
   u32 coded_cap; // capacity reserved at coded_off
-  u32 pad;
+  u32 want_pk;   // 1: the suffix sort also writes the packed rows the LZ77 scan kernels read (work region sized by zq_work_bytes_scan)
 };
 
 // Per (method, block size class) constants (== makeConfig's args, Z:19620-19628).
@@ -41,6 +41,15 @@ struct ZqPlan {
 // per-unit work region: sa | isa (index width w = 2 or 4) | lcp (u16) | bwt (u8), each padded to 128 B
 __host__ __device__ inline u64 zq_work_stride(u32 n, u32 w) { return (((u64)n + 1) * w + 127) & ~(u64)127; }
 __host__ __device__ inline u64 zq_work_bytes(u32 n, u32 w) { return 2 * zq_work_stride(n, w) + zq_work_stride(n, 2) + zq_work_stride(n, 1); }
+
+// The LZ77 scan pipeline (zq_lz77_scan.cuh) keeps three more arrays behind them: pk (one packed word per SA row:
+// suffix start | LCP with the row above saturated at 255 | BWT byte; 4 bytes for 16-bit indices, 8 otherwise; padded so
+// that whole 64-row groups can be bulk-copied), r0[n+1] and f[n][2].
+__host__ __device__ inline u64 zq_align128(u64 x) { return (x + 127) & ~(u64)127; }
+__host__ __device__ inline u64 zq_pk_bytes(u32 n, u32 w) { return zq_align128((((u64)n + 63) & ~(u64)63) * (w == 2 ? 4 : 8)); }
+__host__ __device__ inline u64 zq_work_bytes_scan(u32 n, u32 w) {
+  return zq_work_bytes(n, w) + zq_pk_bytes(n, w) + zq_align128(((u64)n + 1) * (w == 2 ? 4 : 8)) + zq_align128((u64)n * (w == 2 ? 8 : 16));
+}
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 #ifdef ZQ_EMU   // host SIMT emulator build (tests/emu): no PTX, dynamic shared memory is a plain pointer
@@ -72,6 +81,7 @@ __device__ __forceinline__ void zq_bulk_g2s(void* dst, const void* src, u32 byte
   if (b->pending == 0) ++b->phase;
 }
 __device__ __forceinline__ void zq_mbar_wait(ZqMbar* b, u32 parity) { while ((b->phase & 1u) == parity) emu::yield(); }
+__device__ __forceinline__ bool zq_mbar_test(ZqMbar* b, u32 parity) { return (b->phase & 1u) != parity; }
 __device__ __forceinline__ void zq_bulk_s2g(void* dst, const void* src, u32 bytes) {
   if (((uintptr_t)dst | (uintptr_t)src | bytes) & 15) { fprintf(stderr, "emu: misaligned bulk store\n"); abort(); }
   memcpy(dst, src, bytes);
@@ -102,6 +112,17 @@ __device__ __forceinline__ void zq_mbar_wait(ZqMbar* b, u32 parity) {
       "bra ZQ_WAIT;\n"
       "ZQ_DONE:\n"
       "}" ::"r"(zq_smem_addr(b)), "r"(parity) : "memory");
+}
+// has the phase with this parity completed?  (non-blocking: safe inside divergent code)
+__device__ __forceinline__ bool zq_mbar_test(ZqMbar* b, u32 parity) {
+  u32 ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}" : "=r"(ok) : "r"(zq_smem_addr(b)), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void zq_bulk_s2g(void* dst, const void* src, u32 bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(zq_smem_addr(src)), "r"(bytes) : "memory");

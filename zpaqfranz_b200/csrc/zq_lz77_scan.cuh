@@ -31,11 +31,16 @@ namespace zqdev {
 
 constexpr u32 LZS_HALO = 128;    // rows of context on either side of a tile (bucket <= 127)
 constexpr u32 LZS_TILE = 4096;   // rows per tile
+constexpr u32 LZS_ROWS = LZS_TILE + 2 * LZS_HALO;
+constexpr int LZS_NB = 4;        // tiles resident per CTA (ring of bulk-copy buffers)
 constexpr int LZS_NT = 512;      // threads per CTA of the scan kernels
-constexpr int LZS_ROUND = 6;     // scan steps between two refills
-constexpr u32 LZS_IDLE = 0xffffffffu;
+constexpr int LZS_ROUND = 4;     // scan steps between two event rounds
+#ifndef LZS_OCC1
+#define LZS_OCC1 2      // CTAs per SM the look-ahead-1 pass is compiled for
+#endif
+constexpr u32 LZS_CAP = 255;     // saturated LCP of a packed row: the position goes to the exact evaluator
 
-// per-unit arrays behind sa | isa | lcp | bwt in the work region: r0[n] then f[n][2]
+// per-unit arrays behind sa | isa | lcp | bwt | pk in the work region: r0[n+1] (indexed by CONSUMER row) then f[n][2]
 template <typename IdxT> struct LzsFmt;
 template <> struct LzsFmt<u16> {
   typedef u32 R0T; typedef u32 FT;
@@ -62,16 +67,11 @@ template <> struct LzsFmt<u32> {
   static __device__ __forceinline__ u32 f_blit(u64 d) { return (u32)(d >> 48) & 1u; }
 };
 
-__host__ __device__ inline u64 zq_align128(u64 x) { return (x + 127) & ~(u64)127; }
-// bytes of the extended work region (sa | isa | lcp | bwt | r0 | f) of a block of n bytes with index width w
-__host__ __device__ inline u64 zq_work_bytes_scan(u32 n, u32 w) {
-  return zq_work_bytes(n, w) + zq_align128((u64)n * (w == 2 ? 4 : 8)) + zq_align128((u64)n * (w == 2 ? 8 : 16));
-}
 __host__ __device__ inline u32 lzs_tiles(u32 n) { return (n + LZS_TILE - 1) / LZS_TILE; }
 
 template <typename IdxT>
 struct LzsView {
-  const IdxT* sa; const IdxT* isa; const u16* lcp; const u8* bwt;
+  const IdxT* sa; const IdxT* isa; const u16* lcp; const u8* bwt; const typename LzsPack<IdxT>::T* pk;
   typename LzsFmt<IdxT>::R0T* r0; typename LzsFmt<IdxT>::FT* f;
 };
 template <typename IdxT>
@@ -82,50 +82,63 @@ __device__ __forceinline__ LzsView<IdxT> lzs_view(u8* work_base, u64 work_off, u
   v.sa = (const IdxT*)w; v.isa = (const IdxT*)(w + stride); v.lcp = (const u16*)(w + 2 * stride);
   v.bwt = w + 2 * stride + zq_work_stride(n, 2);
   u8* r = w + zq_work_bytes(n, sizeof(IdxT));
+  v.pk = (const typename LzsPack<IdxT>::T*)r;
+  r += zq_pk_bytes(n, sizeof(IdxT));
   v.r0 = (typename LzsFmt<IdxT>::R0T*)r;
-  v.f = (typename LzsFmt<IdxT>::FT*)(r + zq_align128((u64)n * sizeof(typename LzsFmt<IdxT>::R0T)));
+  v.f = (typename LzsFmt<IdxT>::FT*)(r + zq_align128(((u64)n + 1) * sizeof(typename LzsFmt<IdxT>::R0T)));
   return v;
 }
 
-struct LzsDesc {   // one tile in flight
-  u32 valid, n, lo, t0, t1, plan;
-  u64 work_off;
+struct LzsDesc {   // one resident tile; everything the event round needs, so that it costs a few shared-memory loads
+  u32 valid, n, t1, adj;          // adj: shared-memory index of row r is r + adj
+  u32 minMatch, bucket, lookahead, checkbits, level, pad;
+  const void* isa; void* r0; void* f;
 };
 
 template <typename IdxT>
 struct LzsSmem {
-  ZqMbar bar[2];
-  LzsDesc d[2];
-  u32 next_row[2];
-  u32 pad[2];
-  alignas(128) IdxT sa[2][LZS_TILE + 2 * LZS_HALO];
-  alignas(128) u16 lcp[2][LZS_TILE + 2 * LZS_HALO];
-  alignas(128) u8 bwt[2][LZS_TILE + 2 * LZS_HALO];
+  ZqMbar full[LZS_NB];      // bulk copy of the tile in this buffer has landed (one phase per reuse)
+  u32 next_row[LZS_NB];     // next unclaimed row of the tile
+  u32 exited[LZS_NB];       // lanes that have left the tile; the last one out refills the buffer
+  LzsDesc d[LZS_NB];
+  alignas(128) typename LzsPack<IdxT>::T pk[LZS_NB][LZS_ROWS];
 };
 
-// thread 0: claim the next tile of the launch, describe it in slot `sl` and start its bulk copies
-template <typename IdxT, bool WITH_BWT>
-__device__ void lzs_fetch(LzsSmem<IdxT>& sm, int sl, const ZqUnit* __restrict__ units, const int* __restrict__ todo,
-                          const u32* __restrict__ tile_first, int ntodo, u8* work_base, u32* tile_ctr) {
+// One lane: claim the next tile of the launch for buffer `sl` and start its bulk copy (or mark the buffer invalid
+// when the launch has no tiles left; the barrier phase completes either way).
+template <typename IdxT>
+__device__ void lzs_fetch(LzsSmem<IdxT>& sm, u32 sl, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
+                          const int* __restrict__ todo, const u32* __restrict__ tile_first, int ntodo, u32 uniform_tpu,
+                          u8* work_base, u32* tile_ctr) {
   LzsDesc& d = sm.d[sl];
   const u32 tile = atomicAdd(tile_ctr, 1u);
-  if (tile >= tile_first[ntodo]) { d.valid = 0; return; }
-  int lo = 0, hi = ntodo - 1;      // last t with tile_first[t] <= tile
-  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile_first[mid] <= tile) lo = mid; else hi = mid - 1; }
+  sm.exited[sl] = 0;
+  const u32 total = uniform_tpu ? uniform_tpu * (u32)ntodo : tile_first[ntodo];
+  if (tile >= total) { d.valid = 0; d.t1 = 0; sm.next_row[sl] = 0; zq_mbar_expect_tx(&sm.full[sl], 0); return; }
+  int lo = 0;
+  u32 first_tile;
+  if (uniform_tpu) { lo = (int)(tile / uniform_tpu); first_tile = (u32)lo * uniform_tpu; }   // every block has the same number of tiles
+  else {
+    int hi = ntodo - 1;      // last t with tile_first[t] <= tile
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile_first[mid] <= tile) lo = mid; else hi = mid - 1; }
+    first_tile = tile_first[lo];
+  }
   const ZqUnit u = units[todo[lo]];
+  const ZqPlan& pl = plans[u.plan];
   const u32 n = u.n;
-  d.valid = 1; d.n = n; d.plan = u.plan; d.work_off = u.work_off;
-  d.t0 = (tile - tile_first[lo]) * LZS_TILE;
-  d.t1 = min(n, d.t0 + LZS_TILE);
-  d.lo = d.t0 >= LZS_HALO ? d.t0 - LZS_HALO : 0u;
-  const u32 rhi = min(d.t1 + LZS_HALO, (n + 63u) & ~63u);
-  const u32 rows = rhi - d.lo;
-  sm.next_row[sl] = d.t0;
   const LzsView<IdxT> v = lzs_view<IdxT>(work_base, u.work_off, n);
-  zq_mbar_expect_tx(&sm.bar[sl], rows * (u32)(sizeof(IdxT) + 2 + (WITH_BWT ? 1 : 0)));
-  zq_bulk_g2s(sm.sa[sl], v.sa + d.lo, rows * (u32)sizeof(IdxT), &sm.bar[sl]);
-  zq_bulk_g2s(sm.lcp[sl], v.lcp + d.lo, rows * 2u, &sm.bar[sl]);
-  if (WITH_BWT) zq_bulk_g2s(sm.bwt[sl], v.bwt + d.lo, rows, &sm.bar[sl]);
+  d.valid = 1; d.n = n;
+  d.minMatch = pl.args[2]; d.bucket = (1u << pl.args[4]) - 1; d.lookahead = pl.args[6]; d.checkbits = 17 + pl.args[0]; d.level = pl.lz_level;
+  d.isa = v.isa; d.r0 = v.r0; d.f = v.f;
+  const u32 t0 = (tile - first_tile) * LZS_TILE;
+  d.t1 = min(n, t0 + LZS_TILE);
+  const u32 first = t0 >= LZS_HALO ? t0 - LZS_HALO : 0u;
+  d.adj = sl * LZS_ROWS - first;
+  const u32 rhi = min(d.t1 + LZS_HALO, (n + 63u) & ~63u);
+  const u32 bytes = (rhi - first) * (u32)sizeof(typename LzsPack<IdxT>::T);
+  sm.next_row[sl] = t0;
+  zq_mbar_expect_tx(&sm.full[sl], bytes);
+  zq_bulk_g2s(sm.pk[sl], v.pk + first, bytes, &sm.full[sl]);
 }
 
 struct LzsParams { u32 minMatch, bucket, lookahead, checkbits, level; };
@@ -138,190 +151,228 @@ __device__ __forceinline__ LzsParams lzs_params(const ZqPlan& pl) {
 
 // final decision (Z:19474-19477) from a best candidate; off = i - bp
 template <typename IdxT>
-__device__ __forceinline__ typename LzsFmt<IdxT>::FT lzs_decide(const LzsParams& P, u32 off, u32 blen, u32 blit, int bscore) {
+__device__ __forceinline__ typename LzsFmt<IdxT>::FT lzs_decide(u32 minMatch, u32 level, u32 off, u32 blen, u32 blit, int bscore) {
   typedef LzsFmt<IdxT> F;
   const bool match = off > 0 && bscore > 0 &&
-                     blen - blit >= P.minMatch + (P.level == 2 ? (u32)(off >= (1u << 16)) + (u32)(off >= (1u << 24)) : 0u);
+                     blen - blit >= minMatch + (level == 2 ? (u32)(off >= (1u << 16)) + (u32)(off >= (1u << 24)) : 0u);
   return match ? F::f_pack(off, blen, blit) : (typename F::FT)0;
 }
-
-// ---- pass 1: look-ahead 0 -----------------------------------------------------------------------------------
-template <typename IdxT>
-__device__ void lzs_scan0_tile(const IdxT* __restrict__ s_sa, const u16* __restrict__ s_lcp, const LzsDesc& d, const LzsParams P,
-                               u32* next_row, typename LzsFmt<IdxT>::R0T* __restrict__ r0) {
-  typedef LzsFmt<IdxT> F;
-  const u32 lane = lane_id(), n = d.n, lo = d.lo, t1 = d.t1;
-  u32 q = LZS_IDLE, s = 0, k = 0, runmin = 0, blen = 0, bp = 0, dir = 0;
-  int bscore = 0;
-  for (;;) {
-    const u32 need = __ballot_sync(ZQ_FULL, q == LZS_IDLE);
-    if (need) {
-      u32 base = 0;
-      if (lane == 0) base = atomicAdd(next_row, (u32)__popc(need));
-      base = __shfl_sync(ZQ_FULL, base, 0);
-      if (q == LZS_IDLE) {
-        const u32 r = base + (u32)__popc(need & lanemask_lt());
-        if (r < t1) { q = r; s = s_sa[q - lo]; dir = 0; k = 1; runmin = 0xffffffffu; blen = P.minMatch - 1; bp = 0; bscore = 0; }
-      }
-      if (__all_sync(ZQ_FULL, q == LZS_IDLE)) break;
-    }
-#pragma unroll
-    for (int r = 0; r < LZS_ROUND; ++r) {
-      if (q != LZS_IDLE) {
-        bool end_dir = false, fin = false;
-        typename F::R0T res = 0;
-        const bool inr = k <= P.bucket && (dir == 0 ? q >= k : q + k < n);
-        if (!inr) end_dir = true;
-        else {
-          const u32 x = dir == 0 ? q - k : q + k;
-          runmin = min(runmin, (u32)s_lcp[(dir == 0 ? x + 1 : x) - lo]);
-          if ((int)(runmin * 8u) - 12 <= bscore) end_dir = true;   // exact pruning (a capped LCP never prunes: 8*256-12 > any score)
-          else {
-            const u32 p = s_sa[x - lo];
-            ++k;
-            if (p < s) {
-              if (runmin >= ZQ_LCP_CAP) { fin = true; res = F::R0_DEFER; }   // exact length needed (Z:19419): the walk does it
-              else {
-                const int sc = (int)(runmin * 8u) - zq_bitlen(s - p) - 11;
-                if (sc > bscore) { blen = runmin; bp = p; bscore = sc; }
-                if (runmin < blen || runmin < P.minMatch) end_dir = true;
-              }
-            }
-          }
-        }
-        if (end_dir) {
-          if (dir == 0) { dir = 1; k = 1; runmin = 0xffffffffu; }
-          else { fin = true; res = bscore > 0 ? F::r0_pack(blen, bp) : (typename F::R0T)0; }
-        }
-        if (fin) { r0[s] = res; q = LZS_IDLE; }
-      }
-    }
-  }
-}
-
-// ---- pass 2: look-ahead 1, both literal states ---------------------------------------------------------------
 __device__ __forceinline__ int lzs_scale58(int sc) { return sc * 5 / 8; }   // C division: truncates toward zero like the reference
 
+// Both passes.  Per-lane state machine, the scan step written without branches so the warp stays converged: `left`
+// counts the steps the lane may still take in its current direction (0 = row done / no row), x is the shared-memory
+// index of the next neighbour; the switch from the backward to the forward direction is part of the step.
+// Every LZS_ROUND steps an event round runs, warp-converged except for the result stores:
+//   * lanes whose row is done store its result;
+//   * free lanes take rows from the warp's queue; when the queue is empty the warp SWEEPS: it claims 32 rows of its
+//     current tile with one atomic, evaluates all of them at once (PASS 1: coalesced load of r0, rows the look-ahead
+//     cannot improve are decided on the spot) and queues the ones that need a scan.
+// Warps move through the tiles of the CTA's ring on their own: nobody waits at a tile boundary for a lane that is
+// still on a 254-step row.  A warp leaves a tile when it has swept past it and all its rows from that tile are
+// finished; the last warp out refills the buffer (next tile of the launch, bulk copy).  A warp that finds the next
+// tile not landed yet keeps scanning what it has and tests the barrier again next round.
+//   PASS 0: look-ahead 0 of position s (row q); the result is scattered to r0[isa[s+1]], the row that continues it.
+//   PASS 1: row q continues position s-1 with look-ahead 1 for both literal states -> f[s-1][0..1].
 template <typename IdxT>
-__device__ void lzs_scan1_tile(const IdxT* __restrict__ s_sa, const u16* __restrict__ s_lcp, const u8* __restrict__ s_bwt,
-                               const LzsDesc& d, const LzsParams P, u32* next_row,
-                               const typename LzsFmt<IdxT>::R0T* __restrict__ r0, typename LzsFmt<IdxT>::FT* __restrict__ f) {
-  typedef LzsFmt<IdxT> F;
-  typedef typename F::FT FT;
-  const u32 lane = lane_id(), n = d.n, lo = d.lo, t1 = d.t1;
-  u32 q = LZS_IDLE, s = 0, k = 0, runmin = 0, dir = 0, ci = 0;
-  u32 blen0 = 0, bp0 = 0, blit0 = 0, blen1 = 0, bp1 = 0, blit1 = 0;
-  int bs0 = 0, bs1 = 0;
-  bool stop0 = false, stop1 = false;
-  for (;;) {
-    bool exhausted = false;
-    for (int tries = 0; tries < 4; ++tries) {   // rows that need no look-ahead scan finish at once: fill the lanes again
-      const u32 need = __ballot_sync(ZQ_FULL, q == LZS_IDLE);
-      if (__popc(need) < (tries ? 8 : 1)) break;
-      u32 base = 0;
-      if (lane == 0) base = atomicAdd(next_row, (u32)__popc(need));
-      base = __shfl_sync(ZQ_FULL, base, 0);
-      if (base >= t1) { exhausted = true; break; }
-      if (q == LZS_IDLE) {
-        const u32 r = base + (u32)__popc(need & lanemask_lt());
-        if (r < t1) {
-          s = s_sa[r - lo];
-          // this row's job: position i = s-1 (row of suffix i+1); the row of suffix 0 takes position n-1, which has no look-ahead
-          const u32 i = s > 0 ? s - 1 : n - 1;
-          const typename F::R0T a = r0[i];
-          if (a == F::R0_DEFER) { f[2 * (u64)i] = F::F_DEFER; f[2 * (u64)i + 1] = F::F_DEFER; }
-          else {
-            const u32 bl = a ? F::r0_blen(a) : P.minMatch - 1, bpp = a ? F::r0_bp(a) : 0u;
-            const int bsc = a ? (int)(bl * 8u) - zq_bitlen(i - bpp) - 11 : 0;
-            const bool cont = s > 0 && P.lookahead >= 1 && bsc > 0 && bl >= P.minMatch && (s >> P.checkbits) == (i >> P.checkbits);
-            if (!cont) { const FT dd = lzs_decide<IdxT>(P, i - bpp, bl, 0, bsc); f[2 * (u64)i] = dd; f[2 * (u64)i + 1] = dd; }
-            else {
-              q = r; dir = 0; k = 1; runmin = 0xffffffffu; ci = s_bwt[r - lo];
-              blen0 = blen1 = bl; bp0 = bp1 = bpp; blit0 = blit1 = 0; bs0 = bs1 = bsc; stop0 = stop1 = false;
-            }
-          }
-        }
-      }
-    }
-    if (exhausted && __all_sync(ZQ_FULL, q == LZS_IDLE)) break;
-#pragma unroll
-    for (int r = 0; r < LZS_ROUND; ++r) {
-      if (q != LZS_IDLE) {
-        bool end_dir = false, defer = false;
-        const bool inr = k <= P.bucket && (dir == 0 ? q >= k : q + k < n);
-        if (!inr) end_dir = true;
-        else {
-          const u32 x = dir == 0 ? q - k : q + k;
-          runmin = min(runmin, (u32)s_lcp[(dir == 0 ? x + 1 : x) - lo]);
-          const int ub = lzs_scale58((int)((1u + runmin) * 8u) - 12);
-          if (ub <= bs0) stop0 = true;
-          if (ub <= bs1) stop1 = true;
-          if (stop0 && stop1) end_dir = true;
-          else {
-            const u32 p1 = s_sa[x - lo];
-            const u32 bw = s_bwt[x - lo];
-            ++k;
-            if (p1 != 0 && p1 < s) {            // p = p1 - 1 < i
-              if (runmin >= ZQ_LCP_CAP) defer = true;
-              else {
-                const u32 l = 1u + runmin;
-                const u32 l1 = bw == ci ? 0u : 1u;
-                const int base = (int)((l - l1) * 8u) - zq_bitlen(s - p1) - 11;
-                const bool brk = l < P.minMatch || l > 255;
-                if (!stop0) {
-                  const int sc = lzs_scale58(base - (l1 ? 4 : 0));
-                  if (sc > bs0) { blen0 = l; bp0 = p1 - 1; blit0 = l1; bs0 = sc; }
-                  if (l < blen0 || brk) stop0 = true;
-                }
-                if (!stop1) {
-                  const int sc = lzs_scale58(base);
-                  if (sc > bs1) { blen1 = l; bp1 = p1 - 1; blit1 = l1; bs1 = sc; }
-                  if (l < blen1 || brk) stop1 = true;
-                }
-                if (stop0 && stop1) end_dir = true;
-              }
-            }
-          }
-        }
-        const u32 i = s - 1;
-        if (defer) { f[2 * (u64)i] = F::F_DEFER; f[2 * (u64)i + 1] = F::F_DEFER; q = LZS_IDLE; }
-        else if (end_dir) {
-          if (dir == 0) { dir = 1; k = 1; runmin = 0xffffffffu; stop0 = stop1 = false; }
-          else {
-            f[2 * (u64)i] = lzs_decide<IdxT>(P, i - bp0, blen0, blit0, bs0);
-            f[2 * (u64)i + 1] = lzs_decide<IdxT>(P, i - bp1, blen1, blit1, bs1);
-            q = LZS_IDLE;
-          }
-        }
-      }
-    }
-  }
-}
+struct LzsQueue { u32 q0[32]; typename LzsFmt<IdxT>::R0T a[32]; };
 
-// PASS 0: k_lz_scan0, PASS 1: k_lz_scan1.  Persistent CTAs pull tiles (unit, first row) from a counter.
 template <typename IdxT, int PASS>
-__global__ void __launch_bounds__(LZS_NT)
+__global__ void __launch_bounds__(LZS_NT, PASS == 0 ? 3 : LZS_OCC1)
 k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, const int* __restrict__ todo,
-          const u32* __restrict__ tile_first, int ntodo, u8* __restrict__ work_base, u32* tile_ctr) {
+          const u32* __restrict__ tile_first, int ntodo, u32 uniform_tpu, u8* __restrict__ work_base, u32* tile_ctr) {
+  typedef LzsFmt<IdxT> F;
+  typedef LzsPack<IdxT> K;
+  typedef typename K::T PT;
+  typedef typename F::R0T R0T;
+  typedef typename F::FT FT;
   ZQ_DYN_SMEM(smem_raw);
   LzsSmem<IdxT>& sm = *reinterpret_cast<LzsSmem<IdxT>*>(smem_raw);
-  const u32 tid = threadIdx.x;
-  if (tid == 0) {
-    zq_mbar_init(&sm.bar[0], 1); zq_mbar_init(&sm.bar[1], 1);
-    lzs_fetch<IdxT, PASS == 1>(sm, 0, units, todo, tile_first, ntodo, work_base, tile_ctr);
-  }
+  LzsQueue<IdxT>* wqs = reinterpret_cast<LzsQueue<IdxT>*>(smem_raw + sizeof(LzsSmem<IdxT>));
+  const u32 tid = threadIdx.x, lane = tid & 31;
+  LzsQueue<IdxT>& wq = wqs[tid >> 5];
+  constexpr u32 NWARPS = LZS_NT / 32;
+  if (tid == 0) for (int b = 0; b < LZS_NB; ++b) zq_mbar_init(&sm.full[b], 1);
   __syncthreads();
-  u32 use0 = 0, use1 = 0;
-  for (int cur = 0;; cur ^= 1) {
-    if (tid == 0) lzs_fetch<IdxT, PASS == 1>(sm, cur ^ 1, units, todo, tile_first, ntodo, work_base, tile_ctr);
-    const LzsDesc d = sm.d[cur];
-    if (!d.valid) break;
-    if (cur == 0) { zq_mbar_wait(&sm.bar[0], use0 & 1u); ++use0; } else { zq_mbar_wait(&sm.bar[1], use1 & 1u); ++use1; }
-    const LzsParams P = lzs_params(plans[d.plan]);
-    const LzsView<IdxT> v = lzs_view<IdxT>(work_base, d.work_off, d.n);
-    if (PASS == 0) lzs_scan0_tile<IdxT>(sm.sa[cur], sm.lcp[cur], d, P, &sm.next_row[cur], v.r0);
-    else lzs_scan1_tile<IdxT>(sm.sa[cur], sm.lcp[cur], sm.bwt[cur], d, P, &sm.next_row[cur], v.r0, v.f);
-    __syncthreads();
+  if (tid < (u32)LZS_NB) lzs_fetch<IdxT>(sm, tid, units, plans, todo, tile_first, ntodo, uniform_tpu, work_base, tile_ctr);
+  __syncthreads();
+  const PT* __restrict__ s_pk = &sm.pk[0][0];
+  // warp-uniform: tile being swept, its barrier still to be tested, launch out of tiles, queue, rows out per buffer
+  u32 wseq = 0, qhead = 0, qlen = 0, pend = 0, swept = 0, held = 0, dead = 0;
+  bool wwait = true, wdone = false;
+  // per lane
+  bool have = false, defer = false, stop0 = false, stop1 = false;
+  u32 qq = 0, s = 0, x = 0, carry = 0, runmin = 0, aux = 0, lb = 0;   // aux: PASS 0 consumer row, PASS 1 own BWT byte
+  u32 blen0 = 0, bp0 = 0, blit0 = 0, blen1 = 0, bp1 = 0, blit1 = 0;
+  int left = 0, fwd_left = 0, dstep = 1, bs0 = 0, bs1 = 0, mm = 0;
+  for (;;) {
+    // ---- event round ----
+    const bool fin = have && left == 0;
+    if (fin) {
+      const LzsDesc& d = sm.d[lb];
+      if (PASS == 0) ((R0T*)d.r0)[aux] = defer ? F::R0_DEFER : (bs0 > 0 ? F::r0_pack(blen0, bp0) : (R0T)0);
+      else {
+        const u32 i = s - 1;
+        FT* fo = (FT*)d.f + 2 * (u64)i;
+        fo[0] = defer ? F::F_DEFER : lzs_decide<IdxT>(d.minMatch, d.level, i - bp0, blen0, blit0, bs0);
+        fo[1] = defer ? F::F_DEFER : lzs_decide<IdxT>(d.minMatch, d.level, i - bp1, blen1, blit1, bs1);
+      }
+      have = false;
+    }
+    pend -= __reduce_add_sync(ZQ_FULL, fin ? 1u << (8 * lb) : 0u);
+    // leave the tiles this warp is through with
+    for (u32 m = swept & held; m; m &= m - 1) {
+      const u32 b = (u32)__ffs(m) - 1;
+      if ((pend >> (8 * b)) & 255u) continue;
+      held &= ~(1u << b); swept &= ~(1u << b);
+      if (lane == 0 && atomicAdd(&sm.exited[b], 1u) == NWARPS - 1)
+        lzs_fetch<IdxT>(sm, b, units, plans, todo, tile_first, ntodo, uniform_tpu, work_base, tile_ctr);
+      __syncwarp();
+    }
+    // hand rows to the free lanes
+    u32 freemask = __ballot_sync(ZQ_FULL, !have);
+    while (freemask) {
+      if (qlen == 0) {
+        if (wdone) break;
+        const u32 b = wseq % LZS_NB;
+        if (dead & (1u << b)) { ++wseq; continue; }                          // this buffer got no tile any more
+        if (wwait) {
+          // (one lane looks, everyone gets the same answer: the warp's bookkeeping must not diverge)
+          const bool landed = __shfl_sync(ZQ_FULL, (lane == 0 && zq_mbar_test(&sm.full[b], (wseq / LZS_NB) & 1u)) ? 1 : 0, 0) != 0;
+          if (!landed) break;                                                 // not landed yet: try again next round
+          wwait = false;
+          if (!sm.d[b].valid) {   // the launch ran out of tiles when this buffer was to be refilled; others may still hold some
+            dead |= 1u << b; ++wseq; wwait = true;
+            wdone = dead == (1u << LZS_NB) - 1;
+            continue;
+          }
+          held |= 1u << b;
+        }
+        const LzsDesc& d = sm.d[b];
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(&sm.next_row[b], 32u);
+        base = __shfl_sync(ZQ_FULL, base, 0);
+        if (base >= d.t1) { swept |= 1u << b; ++wseq; wwait = true; continue; }   // (left at the next event round)
+        const u32 r = base + lane;
+        bool push = r < d.t1;
+        const u32 q0 = r + d.adj;
+        R0T a = 0;
+        if (PASS == 1 && push) {
+          const u32 n = d.n;
+          const PT w = s_pk[q0];
+          const u32 ss = K::sa(w);
+          // this row's job: position i = s-1 (it is the row of suffix i+1); the row of suffix 0 takes position n-1,
+          // which has no look-ahead
+          const u32 i = ss > 0 ? ss - 1 : n - 1;
+          a = ((const R0T*)d.r0)[ss > 0 ? r : n];
+          FT* fo = (FT*)d.f + 2 * (u64)i;
+          if (a == F::R0_DEFER) { fo[0] = F::F_DEFER; fo[1] = F::F_DEFER; push = false; }
+          else {
+            const u32 bl = a ? F::r0_blen(a) : d.minMatch - 1, bpp = a ? F::r0_bp(a) : 0u;
+            const int bsc = a ? (int)(bl * 8u) - zq_bitlen(i - bpp) - 11 : 0;
+            const bool cont = ss > 0 && d.lookahead >= 1 && bsc > 0 && bl >= d.minMatch && (ss >> d.checkbits) == (i >> d.checkbits);
+            // nothing to gain from the look-ahead either when the rows next to q share too little with it: the
+            // first step of each direction would already be pruned (ub <= best score)
+            const u32 lcf = r + 1 < n ? K::lcp(s_pk[q0 + 1]) : 0u;
+            const bool nogain = lzs_scale58((int)(max(K::lcp(w), lcf) * 8u) - 4) <= bsc;
+            if (!cont || nogain) { const FT dd = lzs_decide<IdxT>(d.minMatch, d.level, i - bpp, bl, 0, bsc); fo[0] = dd; fo[1] = dd; push = false; }
+          }
+        }
+        const u32 pm = __ballot_sync(ZQ_FULL, push);
+        if (push) { const u32 slot = (qhead + (u32)__popc(pm & lanemask_lt())) & 31u; wq.q0[slot] = q0; if (PASS == 1) wq.a[slot] = a; }
+        qlen = (u32)__popc(pm);
+        pend += qlen << (8 * b);
+        __syncwarp();
+        if (qlen == 0) continue;
+      }
+      const u32 take = min((u32)__popc(freemask), qlen);
+      const u32 rank = (u32)__popc(freemask & lanemask_lt());
+      if (!have && rank < take) {
+        const u32 slot = (qhead + rank) & 31u;
+        const u32 q0 = wq.q0[slot];
+        lb = q0 / LZS_ROWS;
+        const LzsDesc& d = sm.d[lb];
+        const u32 n = d.n, r = q0 - d.adj;
+        const PT w = s_pk[q0];
+        const u32 ss = K::sa(w);
+        if (PASS == 0) {
+          aux = ss + 1 < n ? (u32)((const IdxT*)d.isa)[ss + 1] : n;   // in flight during the scan, needed when the row is done
+          blen0 = d.minMatch - 1; bp0 = 0; bs0 = 0;
+        } else {
+          const R0T a = wq.a[slot];
+          const u32 i = ss - 1;
+          const u32 bl = F::r0_blen(a), bpp = F::r0_bp(a);
+          const int bsc = (int)(bl * 8u) - zq_bitlen(i - bpp) - 11;
+          aux = K::bwt(w);
+          blen0 = blen1 = bl; bp0 = bp1 = bpp; blit0 = blit1 = 0; bs0 = bs1 = bsc; stop0 = stop1 = false;
+        }
+        qq = q0; s = ss; carry = K::lcp(w);
+        have = true; x = qq - 1; dstep = -1; runmin = 0xffffffffu; defer = false;
+        left = (int)min(d.bucket, r);
+        fwd_left = (int)min(d.bucket, n - 1 - r);
+        mm = (int)d.minMatch;
+        if (left == 0) { x = qq + 1; dstep = 1; left = fwd_left; }   // first row of the block: forward only
+        // (a block of one row has nothing to scan: left stays 0 and the row is stored at the next event round)
+      }
+      __syncwarp();
+      qhead = (qhead + take) & 31u; qlen -= take;
+      freemask = __ballot_sync(ZQ_FULL, !have);
+    }
+    if (wdone && held == 0 && freemask == ZQ_FULL) break;
+    if (__all_sync(ZQ_FULL, left == 0)) {   // nobody has a step to take: a tile is landing, or rows finished at once
+      if (freemask == ZQ_FULL) __nanosleep(100);
+      continue;
+    }
+    // ---- LZS_ROUND scan steps ----
+#pragma unroll
+    for (int r = 0; r < LZS_ROUND; ++r) {
+      const bool inr = left > 0;
+      const PT w = s_pk[inr ? x : qq];
+      const u32 p = K::sa(w), lc = K::lcp(w);
+      const u32 e = dstep < 0 ? carry : lc;
+      carry = lc;
+      const u32 rm = min(runmin, e);
+      const bool capped = rm >= LZS_CAP;
+      bool go;          // keep going in this direction
+      bool dnow;        // this candidate needs the exact evaluator
+      if (PASS == 0) {
+        const int t8 = (int)(rm * 8u) - 12;
+        const bool live = inr && t8 > bs0;                   // exact pruning: nothing left can beat the best score
+        const bool valid = live && p < s;
+        const int sc = t8 - (31 - __clz(s - p));             // 8*l - lg(s-p) - 11
+        const bool take = valid && !capped && sc > bs0;
+        blen0 = take ? rm : blen0; bp0 = take ? p : bp0; bs0 = take ? sc : bs0;
+        dnow = valid && capped;
+        go = live && !dnow && !(valid && (int)rm < max((int)blen0, mm));
+      } else {
+        const u32 bw = K::bwt(w);
+        const int ub = lzs_scale58((int)(rm * 8u) - 4);      // ((1+rm)*8 - 12) * 5/8
+        stop0 = stop0 || ub <= bs0;
+        stop1 = stop1 || ub <= bs1;
+        const bool live = inr && !(stop0 && stop1);
+        const bool valid = live && p != 0 && p < s;          // candidate p-1 < i
+        const u32 l = 1u + rm;
+        const u32 l1 = bw == aux ? 0u : 1u;
+        const int base = (int)((l - l1) * 8u) - (32 - __clz(s - p)) - 11;
+        const int sc0 = lzs_scale58(base - (l1 ? 4 : 0)), sc1 = lzs_scale58(base);
+        const bool ok = valid && !capped;
+        const bool t0 = ok && !stop0 && sc0 > bs0, t1b = ok && !stop1 && sc1 > bs1;
+        blen0 = t0 ? l : blen0; bp0 = t0 ? p - 1 : bp0; blit0 = t0 ? l1 : blit0; bs0 = t0 ? sc0 : bs0;
+        blen1 = t1b ? l : blen1; bp1 = t1b ? p - 1 : bp1; blit1 = t1b ? l1 : blit1; bs1 = t1b ? sc1 : bs1;
+        const bool brk = (int)l < mm;                        // (l > 255 cannot happen below the cap)
+        stop0 = stop0 || (ok && (l < blen0 || brk));
+        stop1 = stop1 || (ok && (l < blen1 || brk));
+        dnow = valid && capped;
+        go = live && !dnow && !(stop0 && stop1);
+      }
+      defer = defer || dnow;
+      // next step: same direction, or the first forward neighbour once the backward direction has ended
+      const bool sw = inr && !dnow && dstep < 0 && (!go || left == 1);   // ended by the rules, or out of backward neighbours
+      x = sw ? qq + 1 : x + dstep;
+      runmin = sw ? 0xffffffffu : rm;
+      left = sw ? fwd_left : (go ? left - 1 : 0);
+      dstep = sw ? 1 : dstep;
+      if (PASS == 1) { stop0 = stop0 && !sw; stop1 = stop1 && !sw; }
+    }
   }
 }
 

@@ -43,6 +43,23 @@ constexpr int RANK_ITEMS = 4;            // consecutive elements per thread in t
 constexpr int SORT_MAXD = 256;           // digits per radix pass (8 bits)
 constexpr u32 ZQ_LCP_CAP = 256;
 
+// packed SA row for the LZ77 scan kernels: one shared-memory load per scan step
+template <typename IdxT> struct LzsPack;
+template <> struct LzsPack<u16> {
+  typedef u32 T;
+  static __device__ __forceinline__ u32 make(u32 sa, u32 lcp, u32 bw) { return sa | (min(lcp, 255u) << 16) | (bw << 24); }
+  static __device__ __forceinline__ u32 sa(u32 w) { return w & 0xffffu; }
+  static __device__ __forceinline__ u32 lcp(u32 w) { return (w >> 16) & 255u; }
+  static __device__ __forceinline__ u32 bwt(u32 w) { return w >> 24; }
+};
+template <> struct LzsPack<u32> {
+  typedef u64 T;
+  static __device__ __forceinline__ u64 make(u32 sa, u32 lcp, u32 bw) { return sa | ((u64)min(lcp, 255u) << 32) | ((u64)bw << 40); }
+  static __device__ __forceinline__ u32 sa(u64 w) { return (u32)w; }
+  static __device__ __forceinline__ u32 lcp(u64 w) { return (u32)(w >> 32) & 255u; }
+  static __device__ __forceinline__ u32 bwt(u64 w) { return (u32)(w >> 40) & 255u; }
+};
+
 template <int NT>
 struct SortSmem {
   u32 wcount[(NT / 32) * SORT_MAXD];  // per-warp digit counters, then per-warp scatter bases
@@ -373,7 +390,7 @@ __device__ __forceinline__ u32 ld32_unaligned(const u8* p) {
 // the unit's work region `w` with index width 2 (idx16) or 4 bytes.
 template <int NT>
 __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restrict__ w, bool idx16,
-                                  SortScratch sc, SortSmem<NT>& sm) {
+                                  SortScratch sc, SortSmem<NT>& sm, bool want_pk) {
   u32* __restrict__ sa = sc.sa; u32* __restrict__ rank = sc.rank;
   const u32 tid = threadIdx.x;
   if (n == 0) return;
@@ -544,8 +561,14 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
     }
     lcp[x] = (u16)l;
     bwt[x] = b > 0 ? T[b - 1] : (u8)0;
-    if (idx16) { ((u16*)w)[x] = (u16)b; ((u16*)(w + stride))[x] = (u16)rank[x]; }
-    else { ((u32*)w)[x] = b; ((u32*)(w + stride))[x] = rank[x]; }
+    const u32 bw = b > 0 ? (u32)T[b - 1] : 0u;
+    if (idx16) {
+      ((u16*)w)[x] = (u16)b; ((u16*)(w + stride))[x] = (u16)rank[x];
+      if (want_pk) ((u32*)(w + zq_work_bytes(n, 2)))[x] = LzsPack<u16>::make(b, l, bw);
+    } else {
+      ((u32*)w)[x] = b; ((u32*)(w + stride))[x] = rank[x];
+      if (want_pk) ((u64*)(w + zq_work_bytes(n, 4)))[x] = LzsPack<u32>::make(b, l, bw);
+    }
   }
   ZQ_PROF(5);
 }
@@ -564,7 +587,7 @@ k_suffix_sort(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, 
   sc.sa = vb + 4 * scratch_elems; sc.rank = vb + 5 * scratch_elems;
   for (int t = blockIdx.x; t < ntodo; t += gridDim.x) {
     const ZqUnit u = units[todo[t]];
-    suffix_sort_block<NT>(in_base + u.in_off, u.n, work_base + u.work_off, u.idx16 != 0, sc, sm);
+    suffix_sort_block<NT>(in_base + u.in_off, u.n, work_base + u.work_off, u.idx16 != 0, sc, sm, u.want_pk != 0);
     __syncthreads();
   }
 }
