@@ -9,6 +9,7 @@
 #include "/root/reference/zpaqfranz.cpp"
 #undef main
 #include <pthread.h>
+#include <atomic>
 
 namespace {
 struct VecWriter : public libzpaq::Writer {
@@ -26,6 +27,9 @@ struct MemReader : public libzpaq::Reader {
   }
 };
 thread_local std::string g_lasterr;
+// built with -DHWSHA2 like the reference's own Makefile on x86: use the SHA extensions where the host has them, as the
+// command line does (Z:68513)
+struct HwInit { HwInit() { flaghw = ihavehw(); } } g_hwinit;
 }  // namespace
 
 extern "C" {
@@ -214,6 +218,79 @@ long long zref_compress_units_mt(const unsigned char* base, unsigned unit, int n
   long long tot = 0;
   for (int t = 0; t < threads; ++t) { pthread_join(th[t], 0); if (args[t].out < 0) tot = -1; else if (tot >= 0) tot += args[t].out; }
   return tot;
+}
+
+
+// Same pool over an arbitrary list of buffers (offset, length), handed out dynamically; optionally the SHA-256 and the
+// length of every compressed block (bench.py's whole-batch parity check) and, with `roundtrip`, each block is also
+// decompressed again by the reference's own decoder and compared with its input (configs[2]).
+struct ListJob {
+  const unsigned char* base; const unsigned long long* off; const unsigned* len; int n; const char* method;
+  unsigned char* digests; unsigned* outlen; int roundtrip; std::atomic<int> next; std::atomic<long long> total; std::atomic<int> bad;
+};
+static void* list_worker(void* p) {
+  ListJob* j = (ListJob*)p;
+  for (;;) {
+    const int u = j->next.fetch_add(1);
+    if (u >= j->n) break;
+    libzpaq::StringBuffer sb; sb.write((const char*)j->base + j->off[u], j->len[u]);
+    VecWriter w;
+    try { libzpaq::compressBlock(&sb, &w, j->method, "", "", true); } catch (...) { j->bad.fetch_add(1); continue; }
+    j->total.fetch_add((long long)w.v.size());
+    if (j->outlen) j->outlen[u] = (unsigned)w.v.size();
+    if (j->digests) {
+      libzpaq::SHA256 h; for (size_t k = 0; k < w.v.size(); ++k) h.put(w.v[k]);
+      memcpy(j->digests + (size_t)u * 32, h.result(), 32);
+    }
+    if (j->roundtrip) {
+      MemReader r(w.v.data(), w.v.size()); VecWriter back;
+      try { libzpaq::decompress(&r, &back); } catch (...) { j->bad.fetch_add(1); continue; }
+      if (back.v.size() != j->len[u] || memcmp(back.v.data(), j->base + j->off[u], j->len[u]) != 0) j->bad.fetch_add(1);
+    }
+  }
+  return 0;
+}
+long long zref_compress_list_mt(const unsigned char* base, const unsigned long long* off, const unsigned* len, int n,
+                                const char* method, int threads, unsigned char* digests, unsigned* outlen, int roundtrip) {
+  if (threads < 1) threads = 1;
+  ListJob j; j.base = base; j.off = off; j.len = len; j.n = n; j.method = method; j.digests = digests; j.outlen = outlen;
+  j.roundtrip = roundtrip; j.next = 0; j.total = 0; j.bad = 0;
+  std::vector<pthread_t> th(threads);
+  for (int t = 0; t < threads; ++t) pthread_create(&th[t], 0, list_worker, &j);
+  for (int t = 0; t < threads; ++t) pthread_join(th[t], 0);
+  return j.bad.load() ? -1 : j.total.load();
+}
+
+
+// The chunker path on `threads` host threads, files handed out dynamically: fragment boundaries (zref_fragment's loop),
+// libzpaq::SHA1 of every fragment, BLAKE3 of every file -- what Jidac::add + updatehash do per file (Z:122457-122573,
+// Z:85948).  Returns the number of fragments (bench.py's CPU baseline of configs[3]).
+struct FragJob { const unsigned char* base; const unsigned long long* off; const unsigned long long* len; int n, fragment; std::atomic<int> next; std::atomic<long long> frags; };
+static void* frag_worker(void* p) {
+  FragJob* j = (FragJob*)p;
+  std::vector<unsigned> fl, fh;
+  for (;;) {
+    const int f = j->next.fetch_add(1);
+    if (f >= j->n) break;
+    const unsigned char* d = j->base + j->off[f]; const unsigned long long n = j->len[f];
+    const unsigned long long cap = n / 4096 + 16;
+    fl.resize(cap); fh.resize(cap);
+    const long long k = zref_fragment(d, n, j->fragment, fl.data(), fh.data(), cap);
+    unsigned long long o = 0; unsigned char dg[32];
+    for (long long q = 0; q < k; ++q) { zref_sha1(d + o, fl[q], dg); o += fl[q]; }
+    zref_blake3(d, n, dg);
+    j->frags.fetch_add(k > 0 ? k : 0);
+  }
+  return 0;
+}
+long long zref_fragment_hash_mt(const unsigned char* base, const unsigned long long* off, const unsigned long long* len, int nfiles,
+                                int fragment, int threads) {
+  if (threads < 1) threads = 1;
+  FragJob j; j.base = base; j.off = off; j.len = len; j.n = nfiles; j.fragment = fragment; j.next = 0; j.frags = 0;
+  std::vector<pthread_t> th(threads);
+  for (int t = 0; t < threads; ++t) pthread_create(&th[t], 0, frag_worker, &j);
+  for (int t = 0; t < threads; ++t) pthread_join(th[t], 0);
+  return j.frags.load();
 }
 
 }  // extern "C"

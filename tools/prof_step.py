@@ -17,7 +17,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--method", default="2")
 ap.add_argument("--unit", type=int, default=65536)
 a = ap.parse_args()
-arena = torch.from_numpy(corpus.text_corpus(a.units, a.unit)).cuda()
+arena = torch.from_numpy(corpus.text_corpus(a.units, a.unit) if a.method in ("1", "2") else np.frombuffer(b"".join(corpus.mixed_unit(s, a.unit) for s in range(a.units)), dtype=np.uint8).copy() if a.method == "5" else corpus.text_corpus(a.units, a.unit)).cuda()
 cap = int(zq.lib.zq_compress_bound(a.unit)) * a.units
 out = torch.empty(cap, dtype=torch.uint8, device="cuda")
 offs = np.arange(a.units, dtype=np.uint64) * a.unit

@@ -34,7 +34,10 @@ constexpr u32 LZS_TILE = 4096;   // rows per tile
 constexpr u32 LZS_ROWS = LZS_TILE + 2 * LZS_HALO;
 constexpr int LZS_NB = 4;        // tiles resident per CTA (ring of bulk-copy buffers)
 constexpr int LZS_NT = 512;      // threads per CTA of the scan kernels
-constexpr int LZS_ROUND = 4;     // scan steps between two event rounds
+#ifndef LZS_ROUND_STEPS
+#define LZS_ROUND_STEPS 4
+#endif
+constexpr int LZS_ROUND = LZS_ROUND_STEPS;   // scan steps between two event rounds
 #ifndef LZS_OCC1
 #define LZS_OCC1 2      // CTAs per SM the look-ahead-1 pass is compiled for
 #endif
@@ -405,7 +408,7 @@ __device__ LzsDecision lzs_decide_exact(const u8* __restrict__ in, u32 n, const 
 
 // One warp per block.  tok_off[t] = first token slot of todo entry t; ntok[t] = tokens written.
 template <typename IdxT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 k_lz_walk(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
           const int* __restrict__ todo, int ntodo, u8* __restrict__ work_base, const u64* __restrict__ tok_off,
           LzToken* __restrict__ tok_base, u32* __restrict__ ntok, u32* next_unit) {
