@@ -65,7 +65,11 @@ int zq_compress_blocks(zq_ctx* ctx, int n,
                        uint64_t* out_off, uint32_t* out_len);
 
 /* Device variant: in_base/out_base are device pointers on ctx's device; offsets/lengths stay on the
- * host.  Used for HBM-resident measurement and by callers that already staged data. */
+ * host.  Used for HBM-resident measurement and by callers that already staged data.
+ * Like libzpaq::compressBlock, which filters its StringBuffer in place (E8E9, Z:19363 / Z:20414), a method whose type
+ * has the exe bit set (args[1] & 4) REWRITES the unit's bytes in d_in_base: units of such a call must not overlap and
+ * the buffer cannot be submitted a second time without being refilled.  (The host variant filters its staged copy;
+ * the caller's bytes stay untouched.) */
 int zq_compress_blocks_device(zq_ctx* ctx, int n,
                               const uint8_t* d_in_base, const uint64_t* in_off, const uint32_t* in_len,
                               const char* const* method, const char* const* filename,

@@ -5,11 +5,7 @@
 //        zpaqfranz_b200/csrc/zq_cm_host.cpp zpaqfranz_b200/csrc/zq_config.cpp
 #include <cuda_runtime.h>   // the shim
 
-#ifdef ZQ_CM_V1
-#include "zq_decode_v1.cuh"
-#else
 #include "zq_decode.cuh"
-#endif
 #include "zq_cm_host.h"
 
 using namespace zqdev;
@@ -60,11 +56,6 @@ extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_
     u32 coded_len = 0, err = 0, next = 0, lzlen = slen;
     static_assert(sizeof(CmTablesDev) == sizeof(zq::CmTables), "table layout");
     const CmTablesDev* dtab = (const CmTablesDev*)&tab;
-#ifdef ZQ_CM_V1
-    emu::launch(1, (unsigned)threads, sizeof(CmSmem), [&] {
-      k_cm_encode<1>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next);
-    });
-#else
     // bit 4 of the flags: contexts precomputed (the role the translated program plays on the device); here by the
     // interpreter, byte-major H[0..n) after every byte but the last
     std::vector<u32> ctxbuf;
@@ -90,7 +81,6 @@ extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_
       else if (prefetch & 4) k_cm_encode<1, false>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1, ctxp, ctxo);
       else k_cm_encode<0, false>(stream, &u, &pl, &cp, &todo, 1, dtab, blob.data(), stream, &lzlen, model, out, &coded_len, &err, &next, prefetch & 1, (prefetch >> 1) & 1, ctxp, ctxo);
     });
-#endif
     free(model);
     if (err) return -(long)err;
     return (long)coded_len;
@@ -122,20 +112,12 @@ extern "C" long emu_cm_decode(const uint8_t* header, uint32_t hlen, const uint8_
     ZqDecResult res; memset(&res, 0, sizeof res);
     u32 next = 0;
     const CmTablesDev* dtab = (const CmTablesDev*)&tab;
-#ifdef ZQ_CM_V1
-    const size_t smem = sizeof(CmSmem);
-#else
     const size_t smem = sizeof(CmSmem) + sizeof(CmUnitSmem);
-#endif
-    #ifdef ZQ_CM_V1
-    emu::launch(1, 32, smem, [&] { k_cm_decode(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next); });
-#else
     emu::launch(1, 32, smem, [&] {
       if (fast & 8) k_cm_decode<2>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
       else if (fast & 4) k_cm_decode<1>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
       else k_cm_decode<0>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
     });
-#endif
     free(model);
     if (res.error) return -(1000 + (long)res.error);
     return (long)res.out_len;

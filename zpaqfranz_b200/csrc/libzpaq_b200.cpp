@@ -371,13 +371,17 @@ void decompress(Reader* in, Writer* out) {
   for (int i = 0; i < n; ++i) {
     len[i] = (uint32_t)((i + 1 < n ? off[i + 1] : buf.size()) - off[i]);
     // expected size = decimal number opening the segment comment (after the filename)
+    // (untrusted input: every index is checked against the buffer; the size field is capped at what one block holds)
     size_t p = off[i] + 18;
+    if (p + 2 > buf.size()) error("unexpected end of file");
     p += 2 + buf[p] + 256u * buf[p + 1];      // header
     ++p;                                      // segment marker
+    if (p >= buf.size()) error("unexpected end of file");
     while (p < buf.size() && buf[p]) ++p;     // filename
     ++p;
     uint64_t e = 0;
-    while (p < buf.size() && buf[p] >= '0' && buf[p] <= '9') e = e * 10 + (buf[p++] - '0');
+    while (p < buf.size() && buf[p] >= '0' && buf[p] <= '9' && e <= 0xfffffff0ull) e = e * 10 + (buf[p++] - '0');
+    if (e > 0xfffffff0ull) error("archive corrupted");
     cap += e;
   }
   std::vector<uint8_t> outbuf(cap + 16);

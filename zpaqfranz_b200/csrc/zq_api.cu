@@ -12,20 +12,12 @@
 #include <vector>
 
 #include "../../include/zq_b200.h"
-#ifdef ZQ_CM_V1   // first CM engine (one warp per block, interpreter inline), kept for A/B builds
-#include "zq_cm_v1.cuh"
-#else
 #include "zq_cm.cuh"
-#endif
 #include "zq_cm_host.h"
 #include "zq_jit.h"
 #include "zq_common.cuh"
 #include "zq_config.h"
-#ifdef ZQ_CM_V1
-#include "zq_decode_v1.cuh"
-#else
 #include "zq_decode.cuh"
-#endif
 #include "zq_fragment.cuh"
 #include "zq_frame.cuh"
 #include "zq_hashes.cuh"
@@ -82,12 +74,10 @@ struct zq_ctx {
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 0;                         // 1: warp-per-block LZ77 parser for every block (ZQ_LZ_OLD=1); 0: position-parallel scan/walk/emit (zq_lz77_scan.cuh)
   int scan_occ[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of k_lz_scan<u16/u32, pass> (queried once)
-  int cm_occ = 2;                         // first engine only: CTAs (16 warps) per SM of the CM coder
   int cm_jit = 0;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter; 2: generated coder too (ZQ_CM_JIT)
   struct JitProg { cudaLibrary_t lib = nullptr; cudaKernel_t ctx = nullptr, code = nullptr; };
   std::map<std::string, JitProg> jit_cache;   // translated context program (+ generated coder) per model header
   DevBuf d_ctx, d_ctxoff, d_ctxargs;
-  int cm_vm = 0;                          // ZPAQL interpreter: 0 switch, 1 arithmetic selects, 2 selects + predicated loads (ZQ_CM_VM)
   int cm_fast = 1;                        // encoder fast path for chain models (ZQ_CM_FAST=0: generic lanes)
   int cm_prefetch = 1;                    // context warp prefetches the coder's table lines (ZQ_CM_PREFETCH=0 to turn off)
 };
@@ -517,18 +507,6 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       k_cm_init<<<nt * maxjobs, 256, 0, c->stream>>>(du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_fills.as<ZqCmFill>(), c->d_todo3.as<int>(), nt,
                                                      maxjobs, c->d_tables.as<CmTablesDev>(), c->d_model.as<u8>());
       ++c->launches;
-#ifdef ZQ_CM_V1
-      if (!c->attr_cm_enc) {   // per context (= per device): function attributes are per device
-        cudaFuncSetAttribute(k_cm_encode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem));
-        cudaFuncSetAttribute(k_cm_encode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CmSmem));
-        c->attr_cm_enc = true;
-      }
-      const int cgrid = std::min((nt + 15) / 16, c->num_sms * (c->cm_occ >= 2 ? 2 : 1));
-      auto cmk = c->cm_occ >= 2 ? k_cm_encode<2> : k_cm_encode<1>;
-      cmk<<<cgrid, 512, sizeof(CmSmem), c->stream>>>(d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt,
-                                                             c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(), c->d_lz.as<u8>(), c->d_lzlen.as<u32>(),
-                                                             c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr);
-#else
       // ---- optional: translated context program (ZQ_CM_JIT=1) and generated straight-line coder (ZQ_CM_JIT=2), one
       // NVRTC-compiled module per model, cached.  Blocks whose program the translator does not cover stay with
       // k_cm_encode's interpreter; with JIT=2 the others do not go through k_cm_encode at all.
@@ -537,7 +515,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       if (c->cm_jit) {
         std::vector<uint64_t> ctxoff(units.size(), ~(uint64_t)0);     // by unit id, in u32 elements; ~0: interpret
         std::map<u32, std::vector<int>> groups;                       // cm plan -> units of this wave
-        for (int ui : todo_cm) groups[dplans[units[ui].plan].cm_plan].push_back(ui);
+        for (int ui : todo_cm) groups[dplans[units[w0 + ui].plan].cm_plan].push_back(ui);   // ui: index inside this wave
         struct Launch { zq_ctx::JitProg prog; std::vector<int> ids; u32 plan; };
         std::vector<Launch> launches;
         uint64_t ctx_elems = 0;
@@ -563,7 +541,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
           if (!it->second.ctx) continue;
           Launch L; L.prog = it->second; L.plan = g.first;
           for (int ui : g.second) {
-            const ZqUnit& zu = units[ui];
+            const ZqUnit& zu = units[w0 + ui];
             const ZqPlan& p = dplans[zu.plan];
             ctxoff[ui] = ctx_elems;
             ctx_elems += ((uint64_t)p.payload_len + (p.lz_level ? zu.lz_cap : zu.n)) * (uint64_t)cp.n;
@@ -591,7 +569,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
             k_ctx_args<<<(gn + 127) / 128, 128, 0, c->stream>>>(du, dp, d_ids, gn, c->d_lzlen.as<u32>(), c->d_ctxoff.as<u64>(), d_soff, d_slen, d_moff, d_coff,
                                                                 d_cdoff, d_cdcap);
             const ZqCmPlan& cp = cmplans[L.plan];
-            const ZqPlan& p0 = dplans[units[L.ids[0]].plan];
+            const ZqPlan& p0 = dplans[units[w0 + L.ids[0]].plan];
             const u8* head = c->d_blob.as<u8>() + p0.payload_off; unsigned hlen = p0.payload_len;
             const u8* sbase = p0.lz_level ? c->d_lz.as<u8>() : d_in;
             u8* mbase = c->d_model.as<u8>(); unsigned long long mo = cp.m_off, ho = cp.h_off, ro = cp.r_off;
@@ -625,18 +603,15 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       if (!c->attr_cm_enc) {   // per context (= per device): function attributes are per device
         const int cm_smem_max = (int)(sizeof(CmSmem) + ZQ_CM_MAX_PAIRS * sizeof(CmUnitSmem));
         cudaFuncSetAttribute(k_cm_encode<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cm_smem_max);
-        cudaFuncSetAttribute(k_cm_encode<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cm_smem_max);
-        cudaFuncSetAttribute(k_cm_encode<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cm_smem_max);
         cudaFuncSetAttribute(k_cm_encode<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cm_smem_max);
         c->attr_cm_enc = true;
       }
-      auto cmk = d_ctx ? k_cm_encode<0, true> : c->cm_vm == 2 ? k_cm_encode<2, false> : c->cm_vm == 1 ? k_cm_encode<1, false> : k_cm_encode<0, false>;
+      auto cmk = d_ctx ? k_cm_encode<0, true> : k_cm_encode<0, false>;
       if (nt_enc > 0)
       cmk<<<std::min((nt_enc + pairs - 1) / pairs, c->num_sms), pairs * 64, cm_smem, c->stream>>>(
           d_in, du, dp, c->d_cmplans.as<ZqCmPlan>(), c->d_todo3.as<int>(), nt_enc, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
           c->d_lz.as<u8>(), c->d_lzlen.as<u32>(), c->d_model.as<u8>(), c->d_coded.as<u8>(), c->d_codedlen.as<u32>(), c->d_err.as<u32>(), ctr,
           c->cm_prefetch, c->cm_fast, d_ctx, d_ctxoff);
-#endif
       ++c->launches;
       tstop(c, 5);
       ZQ_CUDA(c, cudaMemcpyAsync(coded_len_h.data() + w0, c->d_codedlen.p, (size_t)wn * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -748,10 +723,8 @@ zq_ctx* zq_create(int device) {
   for (int k = 0; k < 4; ++k) cudaEventCreate(&c->ev[k]);
   if (const char* s = getenv("ZQ_MODEL_BUDGET")) { size_t v = strtoull(s, nullptr, 10); if (v >= 1024) c->model_budget = v; }
   if (const char* s = getenv("ZQ_FRAG_SEG")) { uint64_t v = strtoull(s, nullptr, 10); if (v >= 64) c->frag_seg = v; }
-  if (const char* s = getenv("ZQ_CM_OCC")) c->cm_occ = atoi(s);
   if (const char* s = getenv("ZQ_CM_PREFETCH")) c->cm_prefetch = atoi(s);
   if (const char* s = getenv("ZQ_CM_FAST")) c->cm_fast = atoi(s);
-  if (const char* s = getenv("ZQ_CM_VM")) c->cm_vm = atoi(s);
   if (const char* s = getenv("ZQ_CM_JIT")) c->cm_jit = atoi(s);
   if (const char* s = getenv("ZQ_LZ_OLD")) c->lz_old = atoi(s) ? 1 : 0;
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
@@ -1025,22 +998,12 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
   size_t budget = c->model_budget;
   { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); fr += c->d_model.cap; budget = std::min<size_t>(budget, fr > ((size_t)6 << 30) ? fr - ((size_t)6 << 30) : fr / 2); }
   std::vector<ZqDecResult> res(n);
-#ifdef ZQ_CM_V1
-  const size_t dec_smem = sizeof(CmSmem);
-#else
   const size_t dec_smem = sizeof(CmSmem) + 16 * sizeof(CmUnitSmem);
-#endif
-#ifdef ZQ_CM_V1
-  if (!c->attr_cm_dec) { cudaFuncSetAttribute(k_cm_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem); c->attr_cm_dec = true; }
-#else
   if (!c->attr_cm_dec) {
     cudaFuncSetAttribute(k_cm_decode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
-    cudaFuncSetAttribute(k_cm_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
-    cudaFuncSetAttribute(k_cm_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
     c->attr_cm_dec = true;
   }
-  auto cmd = c->cm_vm == 2 ? k_cm_decode<2> : c->cm_vm == 1 ? k_cm_decode<1> : k_cm_decode<0>;
-#endif
+  auto cmd = k_cm_decode<0>;
   int w0 = 0;
   while (w0 < n) {
     size_t model = 0; int w1 = w0, maxjobs = 1;
@@ -1066,15 +1029,9 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
     k_cm_init_pairs<<<wn * maxjobs, 256, 0, c->stream>>>(d_moff, d_pof, c->d_cmplans.as<ZqCmPlan>(), c->d_fills.as<ZqCmFill>(), wn, maxjobs,
                                                         c->d_tables.as<CmTablesDev>(), c->d_model.as<u8>());
     ++c->launches;
-#ifdef ZQ_CM_V1
-    k_cm_decode<<<std::min((wn + 15) / 16, c->num_sms), 512, dec_smem, c->stream>>>(
-        c->d_in.as<u8>(), c->d_units.as<ZqDecUnit>(), c->d_cmplans.as<ZqCmPlan>(), wn, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
-        c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr);
-#else
     cmd<<<std::min((wn + 15) / 16, c->num_sms), 512, dec_smem, c->stream>>>(
         c->d_in.as<u8>(), c->d_units.as<ZqDecUnit>(), c->d_cmplans.as<ZqCmPlan>(), wn, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
         c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr, c->cm_fast);
-#endif
     ++c->launches;
     ZQ_CUDA(c, cudaMemcpyAsync(res.data() + w0, d_res, (size_t)wn * sizeof(ZqDecResult), cudaMemcpyDeviceToHost, c->stream));
     ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1200,9 +1157,9 @@ int zq_blake3(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const 
 
 // CRC-32 slice tables and the "advance through 4 KiB of zeros" operator (see zq_hashes2.cuh)
 static const zqdev::CrcTables& crc_tables() {
-  static zqdev::CrcTables t;
-  static bool done = false;
-  if (!done) {
+  // built once, by whichever thread comes first (C++11 magic static: contexts on several host threads may race here)
+  static const zqdev::CrcTables t = [] {
+    zqdev::CrcTables t;
     for (uint32_t v = 0; v < 256; ++v) {
       uint32_t c = v;
       for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
@@ -1216,8 +1173,8 @@ static const zqdev::CrcTables& crc_tables() {
         for (uint32_t z = 0; z < zqdev::CRC_CHUNK; ++z) s = t.T[0][s & 255] ^ (s >> 8);
         t.Z[k][v] = s;
       }
-    done = true;
-  }
+    return t;
+  }();
   return t;
 }
 

@@ -1,6 +1,7 @@
 // zq_cm.cuh -- the ZPAQ context-mixing compressor (methods -m3/-m4/-m5 and any explicit model of
 // <= 32 components): HCOMP virtual machine, component chain, logistic mixing and the binary
-// arithmetic coder.  Second engine (the first one is kept as zq_cm_v1.cuh, build flag -DZQ_CM_V1).
+// arithmetic coder.  (A first engine -- one warp per block with the interpreter inline -- was 2-3x slower and is gone;
+// its numbers are in profiles/README.md, r01_configs vs r01i.)
 //
 // Replaces (bit-exactly): ZPAQL::run0/execute Z:14232-14467, Predictor::predict0 Z:15041,
 // update0 Z:15139, find Z:15254, train Z:13161, Encoder::encode/compress Z:15557-15589.
@@ -181,9 +182,10 @@ __device__ void cm_vm_run_switch(CmVm& v, u32 input, VmOut* o) {
   const u32 mm = v.mmask, hm = v.hmask;
   const int len = v.len;
   int pc = 0, stop = 0;
+  int budget = 1 << 24;   // instructions per run: a program that loops forever (the reference would hang) ends as a ZPAQL error
   u32 a = input, b = v.b, c = v.c, d = v.d; int f = v.f;
   while (!stop) {
-    if ((u32)pc >= (u32)len) { stop = 2; break; }
+    if ((u32)pc >= (u32)len || --budget < 0) { stop = 2; break; }
     const u32 op = P[pc++];
     switch (op) {
       case 1: ++a; break; case 2: --a; break; case 3: a = ~a; break; case 4: a = 0; break;
@@ -232,136 +234,10 @@ __device__ void cm_vm_run_switch(CmVm& v, u32 input, VmOut* o) {
 }
 #undef ZQ_VM_X8
 
-
-#ifdef ZQ_EMU
-__device__ __forceinline__ u32 zq_sel(bool p, u32 x, u32 y) { return p ? x : y; }
-__device__ __forceinline__ void zq_st8_if(bool p, u8* a, u32 v) { if (p) *a = (u8)v; }
-__device__ __forceinline__ void zq_st32_if(bool p, u32* a, u32 v) { if (p) *a = v; }
-__device__ __forceinline__ u32 zq_ld8_if(bool p, const u8* a, u32 other) { return p ? (u32)*a : other; }
-__device__ __forceinline__ u32 zq_ld32_if(bool p, const u32* a, u32 other) { return p ? *a : other; }
-#else
-__device__ __forceinline__ u32 zq_sel(bool p, u32 x, u32 y) {
-  u32 r;
-  asm("{ .reg .pred q; setp.ne.u32 q, %1, 0; selp.u32 %0, %2, %3, q; }" : "=r"(r) : "r"((u32)p), "r"(x), "r"(y));
-  return r;
-}
-__device__ __forceinline__ void zq_st8_if(bool p, u8* a, u32 v) {
-  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.u8 [%1], %2; }" ::"r"((u32)p), "l"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ void zq_st32_if(bool p, u32* a, u32 v) {
-  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.u32 [%1], %2; }" ::"r"((u32)p), "l"(a), "r"(v) : "memory");
-}
-// predicated loads: only the operand the instruction names is fetched (a load that is not wanted would still wait
-// for a line the machine has just written through to L2)
-__device__ __forceinline__ u32 zq_ld8_if(bool p, const u8* a, u32 other) {
-  u32 r = other;
-  asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q ld.u8 %0, [%2]; }" : "+r"(r) : "r"((u32)p), "l"(a) : "memory");
-  return r;
-}
-__device__ __forceinline__ u32 zq_ld32_if(bool p, const u32* a, u32 other) {
-  u32 r = other;
-  asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q ld.u32 %0, [%2]; }" : "+r"(r) : "r"((u32)p), "l"(a) : "memory");
-  return r;
-}
-#endif
-template <bool WITH_OUT, bool PRED_LD>
-__device__ void cm_vm_run_sel(CmVm& v, u32 input, VmOut* o) {
-  const u8* P = v.code;
-  u8* M = v.m; u32* H = v.h; u32* R = v.r;
-  const u32 mm = v.mmask, hm = v.hmask;
-  const int len = v.len;
-  int pc = 0, stop = 0;
-  u32 a = input, b = v.b, c = v.c, d = v.d; u32 f = (u32)v.f;
-  while (!stop) {
-    if ((u32)pc >= (u32)len) { stop = 2; break; }
-    const u32 op = P[pc], arg = P[pc + 1];
-    const u32 lo = op & 7u, hi = op >> 3;
-    if (op >= 64u) {
-      // ---- two operands.  b&mm, c&mm, d&hm always index inside M / H, so all three are fetched and one is picked
-      const u32 xb = PRED_LD ? zq_ld8_if(lo == 4u, M + (b & mm), 0u) : (u32)M[b & mm];
-      const u32 xc = PRED_LD ? zq_ld8_if(lo == 5u, M + (c & mm), 0u) : (u32)M[c & mm];
-      const u32 xd = PRED_LD ? zq_ld32_if(lo == 6u, H + (d & hm), 0u) : H[d & hm];
-      u32 x = zq_sel(lo & 4u, zq_sel(lo & 2u, zq_sel(lo & 1u, arg, xd), zq_sel(lo & 1u, xc, xb)),
-                     zq_sel(lo & 2u, zq_sel(lo & 1u, d, c), zq_sel(lo & 1u, b, a)));
-      pc += 1 + (int)(lo == 7u);
-      const u32 sh = x & 31u;
-      // a op= x, operation hi-16 in 0..10 (3: div, 4: mod handled below)
-      const u32 k = hi - 16u;
-      const u32 r0 = zq_sel(k & 1u, a - x, a + x);            // 0 add, 1 sub
-      const u32 r2 = zq_sel(k & 1u, a, a * x);                // 2 mul, (3 div)
-      const u32 r4 = zq_sel(k & 1u, a & x, a);                // (4 mod), 5 and
-      const u32 r6 = zq_sel(k & 1u, a | x, a & ~x);           // 6 andn, 7 or
-      const u32 r8 = zq_sel(k & 1u, a << sh, a ^ x);          // 8 xor, 9 shl
-      const u32 ra = a >> sh;                                  // 10 shr
-      const u32 lo8 = zq_sel(k & 4u, zq_sel(k & 2u, r6, r4), zq_sel(k & 2u, r2, r0));
-      const u32 alu = zq_sel(k & 8u, zq_sel(k & 2u, ra, r8), lo8);
-      const bool is_alu = k <= 10u;
-      const u32 cmp = zq_sel(hi == 27u, a == x, zq_sel(hi == 28u, a < x, a > x));
-      f = zq_sel(hi - 27u <= 2u, cmp, f);
-      const u32 na = zq_sel(is_alu, alu, zq_sel(hi == 8u, x, a));
-      const u32 a_old = a;
-      // stores use the registers as they were before this instruction
-      zq_st8_if(hi == 12u, M + (b & mm), x);
-      zq_st8_if(hi == 13u, M + (c & mm), x);
-      zq_st32_if(hi == 14u, H + (d & hm), x);
-      a = na;
-      b = zq_sel(hi == 9u, x, b); c = zq_sel(hi == 10u, x, c); d = zq_sel(hi == 11u, x, d);
-      if (k == 3u || k == 4u || hi == 15u || hi >= 30u) {   // rare: division, long jump, invalid
-        if (k == 3u) a = x ? a_old / x : 0u;
-        else if (k == 4u) a = x ? a_old % x : 0u;
-        else if (op == 255u) pc = (int)arg + 256 * (int)P[pc];
-        else stop = 2;
-      }
-    } else if (op < 32u) {
-      // ---- register target a/b/c/d = hi: <>a, ++, --, !, =0, =r N
-      const u32 val = zq_sel(hi & 2u, zq_sel(hi & 1u, d, c), zq_sel(hi & 1u, b, a));
-      const u32 rn = PRED_LD ? zq_ld32_if(lo == 7u, R + arg, 0u) : R[arg];   // always a valid slot (256 words)
-      const u32 nv = zq_sel(lo & 4u, zq_sel(lo & 2u, rn, 0u), zq_sel(lo & 2u, zq_sel(lo & 1u, ~val, val - 1u), zq_sel(lo & 1u, val + 1u, a)));
-      pc += 1 + (int)(lo == 7u);
-      if (lo == 5u || lo == 6u || op == 0u) { stop = 2; break; }
-      a = zq_sel(lo == 0u, val, a);
-      a = zq_sel(hi == 0u, nv, a); b = zq_sel(hi == 1u, nv, b); c = zq_sel(hi == 2u, nv, c); d = zq_sel(hi == 3u, nv, d);
-    } else if (op < 56u && lo <= 4u) {
-      // ---- memory target *b/*c/*d: <>a, ++, --, !, =0
-      if (op >= 48u) {
-        const u32 old = H[d & hm];
-        H[d & hm] = zq_sel(lo & 4u, 0u, zq_sel(lo & 2u, zq_sel(lo & 1u, ~old, old - 1u), zq_sel(lo & 1u, old + 1u, a)));
-        a = zq_sel(lo == 0u, old, a);
-      } else {
-        const u32 idx = zq_sel(op >= 40u, c, b) & mm;
-        const u32 old = M[idx];
-        M[idx] = (u8)zq_sel(lo & 4u, 0u, zq_sel(lo & 2u, zq_sel(lo & 1u, ~old, old - 1u), zq_sel(lo & 1u, old + 1u, a)));
-        a = zq_sel(lo == 0u, (a & ~255u) | old, a);
-      }
-      pc += 1;
-    } else {
-      const int rel = (int)((arg + 128u) & 255u) - 127;   // jump distance counted from the operand byte
-      switch (op) {
-        case 39: pc = f ? pc + 1 + rel : pc + 2; break;
-        case 47: pc = !f ? pc + 1 + rel : pc + 2; break;
-        case 63: pc = pc + 1 + rel; break;
-        case 55: R[arg] = a; pc += 2; break;
-        case 56: stop = 1; break;
-        case 57:
-          if (WITH_OUT) { if (o->len < o->cap) o->out[o->len] = (u8)a; else o->error = 3; ++o->len; }
-          pc += 1;
-          break;
-        case 59: a = (a + M[b & mm] + 512u) * 773u; pc += 1; break;
-        case 60: H[d & hm] = (H[d & hm] + a + 512u) * 773u; pc += 1; break;
-        default: stop = 2;
-      }
-    }
-  }
-  if (stop == 2) v.error = 1;
-  v.a = a; v.b = b; v.c = c; v.d = d; v.f = (int)f;
-}
-
+// (two branch-free forms of this interpreter -- arithmetic selects, with and without predicated loads -- were measured
+//  slower on B200: 355 / 262 ms vs 236 ms per 100 MB of BWT blocks, profiles/README.md r01l, r01m -- and removed)
 template <int VM, bool WITH_OUT>
-__device__ __forceinline__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) {
-  if (VM == 2) cm_vm_run_sel<WITH_OUT, true>(v, input, o);
-  else if (VM == 1) cm_vm_run_sel<WITH_OUT, false>(v, input, o);
-  else cm_vm_run_switch<WITH_OUT>(v, input, o);
-}
+__device__ __forceinline__ void cm_vm_run(CmVm& v, u32 input, VmOut* o) { cm_vm_run_switch<WITH_OUT>(v, input, o); }
 
 __device__ __forceinline__ int cm_clamp2k(int x) { return min(max(x, -2048), 2047); }
 __device__ __forceinline__ int cm_clamp512k(int x) { return min(max(x, -(1 << 19)), (1 << 19) - 1); }

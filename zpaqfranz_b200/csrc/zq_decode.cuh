@@ -229,7 +229,12 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
         u32 cl = 0;
         for (int k = 0; k < 4; ++k) cl = cl << 8 | (u32)in.get();
         if (cl == 0 || in.error) break;
-        for (u32 k = 0; k < cl; ++k) dec_post_write<VM, false>(pp, in.get());
+        // the length comes from the archive: never loop past the bytes that are there, stop at the first error
+        if ((u64)cl > (u64)in.len - in.pos) { in.error = 1; break; }
+        for (u32 k = 0; k < cl; ++k) {
+          dec_post_write<VM, false>(pp, in.get());
+          if (in.error || pp.error || pp.vm.error) break;
+        }
         if (in.error || pp.error || pp.vm.error) break;
       }
     }

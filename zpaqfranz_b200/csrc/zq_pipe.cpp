@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <deque>
 #include <map>
+#include <set>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -35,6 +36,7 @@ struct zq_pipe {
   std::condition_variable cv_job, cv_done;
   std::deque<Job> queue;
   std::map<int, Done> done;
+  std::set<int> collected;   // tickets already waited for
   int next_ticket = 0;
   bool stop = false;
   std::string last_error;
@@ -105,10 +107,11 @@ int zq_pipe_submit(zq_pipe* p, int n, const uint8_t* in_base, const uint64_t* in
 int zq_pipe_wait(zq_pipe* p, int ticket) {
   if (!p) return ZQ_E_NODEVICE;
   std::unique_lock<std::mutex> lk(p->mu);
-  if (ticket < 0 || ticket >= p->next_ticket) return ZQ_E_ARG;
+  if (ticket < 0 || ticket >= p->next_ticket || p->collected.count(ticket)) return ZQ_E_ARG;   // unknown, or waited for already
   p->cv_done.wait(lk, [&] { return p->done.count(ticket) != 0; });
   Done d = p->done[ticket];
   p->done.erase(ticket);
+  p->collected.insert(ticket);
   if (d.rc) p->last_error = d.err;
   return d.rc;
 }
