@@ -329,6 +329,15 @@ def main():
     stream = torch.cuda.current_stream()
     ctx = zq.Context(local)
     ctx.set_stream(stream.cuda_stream)
+    # the library's own communicator (zq_dist_*, NCCL): rank 0's unique id travels through the launcher's process group
+    uid = None
+    if world > 1:
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(zq.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().numpy().tobytes())
+    zd = zq.Dist(local, rank, world, unique_id=uid)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -360,7 +369,7 @@ def main():
     line = None
 
     if cfg == "c4":
-        line = run_c4(args, zq, corpus, ctx, ref, rank, world, local, dist, torch, bracket, sync_all, peak, peak_src)
+        line = run_c4(args, zq, corpus, ctx, zd, ref, rank, world, local, dist, torch, bracket, sync_all, peak, peak_src)
     else:
         arena_np, offs, lens = make_units(corpus, cfg, rank, args)
         U = len(offs)
@@ -378,8 +387,14 @@ def main():
         def step_device(k=0):
             state["dev"] = ctx.compress_blocks_device(d_in.data_ptr(), offs, lens, d_outs[0].data_ptr(), cap, method=method, filename="", comment="")
 
+        def exchange(olen):
+            # archive offsets of every block of every rank: all-gather of the 4-byte sizes (zq_dist_exchange_sizes, NCCL)
+            state["sizes"], state["goff"] = zd.exchange_sizes(olen, U * world)
+
         def step_host(k=0):
             state["host"] = ctx.compress_blocks(h_in.numpy(), offs, lens, method=method, filename="", comment="", out=h_outs[0].numpy())
+            if world > 1:
+                exchange(state["host"][2])
 
         def piped(steps, device):
             sync_all()
@@ -389,13 +404,17 @@ def main():
             tickets = []
             for k in range(steps):
                 if k >= depth:
-                    pipe.wait(tickets[k - depth])
+                    r_ = pipe.wait(tickets[k - depth])
+                    if world > 1 and not device:
+                        exchange(r_[1])
                 if device:
                     tickets.append(pipe.submit(d_in.data_ptr(), offs, lens, d_outs[k % depth].data_ptr(), cap, method=method, filename="", comment="", device=True))
                 else:
                     tickets.append(pipe.submit(h_in.data_ptr(), offs, lens, h_outs[k % depth].data_ptr(), cap, method=method, filename="", comment="", device=False))
             for t in tickets[-depth:]:
-                pipe.wait(t)
+                r_ = pipe.wait(t)
+                if world > 1 and not device:
+                    exchange(r_[1])
             torch.cuda.synchronize()
             e1.record(stream)
             sync_all()
@@ -501,7 +520,10 @@ def main():
             "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOADS[cfg] % U, "method": method, "units_per_gpu": U, "unit_bytes": UNIT,
-                       "parallelism": "units sharded over the ranks, no data-path collective",
+                       "parallelism": "units sharded over the ranks, no data-path collective; per step one all-gather of the 4-byte block sizes "
+                                      "(zq_dist_exchange_sizes over NCCL, inside the e2e region) -> global archive offsets" if world > 1 else
+                                      "one rank: units on one GPU, no collective",
+                       "exchanged_bytes_per_rank": zd.bytes_exchanged(),
                        "l2": "inputs %.0f MB per step > 126 MB L2 (no flush needed)" % (nbytes / MB), "parity": parity,
                        "inflight": depth, "serial_ms_per_step": round(float(st["total"]), 3),
                        "compressed_ratio": round(out_bytes / nbytes, 4)},
@@ -527,13 +549,14 @@ def main():
             pipe.close()
     if rank == 0:
         print(json.dumps(line))
+    zd.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def run_c4(args, zq, corpus, ctx, ref, rank, world, local, dist, torch, bracket, sync_all, peak, peak_src):
+def run_c4(args, zq, corpus, ctx, zd, ref, rank, world, local, dist, torch, bracket, sync_all, peak, peak_src):
     """Fragmenter + fragment SHA-1 + per-file BLAKE3 over this rank's share of the image; digests all-gathered."""
     sizes, kinds, srcs = make_image(corpus, int(args.c4_gb * 1e9))
     # files dealt to the ranks longest first (LPT): every rank computes the same assignment
@@ -567,30 +590,15 @@ def run_c4(args, zq, corpus, ctx, ref, rank, world, local, dist, torch, bracket,
     fl, fh, fs, first = res["frag"]
     # dedup key exchange: 20-byte digests of every rank's fragments -> global unique count (the index the archiver keeps)
     nfrag = len(fl)
-    t_x = 0.0
-    uniq = len({bytes(r) for r in fs})
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    is_first, uniq = zd.dedup(fs)            # zq_dist_dedup: all-gather of the 20-byte digests over NCCL, first occurrence wins
+    t_x = time.perf_counter() - t0
+    cnt = torch.tensor([nfrag, int(is_first.sum())], device="cuda", dtype=torch.int64)
     if world > 1:
-        cnt = torch.tensor([nfrag], device="cuda", dtype=torch.int64)
-        cnts = [torch.zeros(1, device="cuda", dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        mx = int(max(int(c.item()) for c in cnts))
-        buf = torch.zeros((mx, 20), dtype=torch.uint8, device="cuda")
-        buf[:nfrag] = torch.from_numpy(np.ascontiguousarray(fs)).cuda()
-        allb = [torch.zeros_like(buf) for _ in range(world)]
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        dist.all_gather(allb, buf)
-        torch.cuda.synchronize()
-        t_x = time.perf_counter() - t0
-        if rank == 0:
-            seen = set()
-            for r in range(world):
-                arr = allb[r][: int(cnts[r].item())].cpu().numpy()
-                seen.update(bytes(x) for x in arr)
-            uniq = len(seen)
-        tot_frag = int(sum(int(c.item()) for c in cnts))
-    else:
-        tot_frag = nfrag
+        dist.all_reduce(cnt)
+    tot_frag = int(cnt[0].item())
+    assert int(cnt[1].item()) == uniq, "dedup bookkeeping differs between the ranks"
     # parity: every fragment table and digest of a bounded prefix of this rank's files against the reference
     parity, cpu = "unchecked", None
     if rank == 0 and ref is not None and not args.no_parity:
@@ -631,7 +639,7 @@ def run_c4(args, zq, corpus, ctx, ref, rank, world, local, dist, torch, bracket,
                                "filesystem image of %d files (log-normal sizes <= 64 MiB; text / random / copies / zero pages), files dealt to "
                                "the ranks longest first" % (total / 1e9, len(sizes)),
                    "files": int(len(sizes)), "image_bytes": int(total), "fragments": tot_frag, "unique_fragments": int(uniq),
-                   "parallelism": "files sharded over the ranks; one all-gather of 20-byte fragment digests (%.1f ms, outside the step)" % (t_x * 1e3),
+                   "parallelism": "files sharded over the ranks; one all-gather of the 20-byte fragment digests (zq_dist_dedup over NCCL: %.1f ms, %d bytes received per rank, outside the step)" % (t_x * 1e3, zd.bytes_exchanged()),
                    "l2": "inputs %.0f MB per rank per step > 126 MB L2" % (nbytes / MB), "parity": parity,
                    "note": "host buffers in, tables out: value == e2e (this path has no device-pointer entry point); a file is never split across GPUs"},
         "e2e": {"value": round(value, 3), "unit": "GB/s", "h2d_bytes_per_step": int(2 * nbytes), "d2h_bytes_per_step": int(out_b // world),

@@ -199,6 +199,35 @@ int zq_add_files(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* o
                  uint32_t* nblocks);
 uint64_t zq_file_sort_key(const char* path, int64_t size);
 
+
+/* ---- several GPUs (one process per GPU) -------------------------------------------------------------------------
+ * Units shard over the ranks with no data-path collective: every rank runs the single-device
+ * entry points above on its own units.  What is exchanged, through NCCL over NVLink, is small:
+ *   zq_dist_exchange_sizes  the compressed size of every block (4 B each) -> global archive offsets on every rank;
+ *                           replaces the running offset of the reference's single writer thread (Z:71445-71518)
+ *   zq_dist_dedup           the 20-byte SHA-1 of every fragment -> which local fragments are new to the archive;
+ *                           replaces the HTIndex lookup of Jidac::add (Z:122569-122573, Z:71567-71604)
+ * Rank 0 calls zq_dist_unique_id and hands the 128 bytes to the other ranks (launcher's job: environment, file, MPI,
+ * torch.distributed ...); every rank then calls zq_dist_create.  world == 1 needs neither NCCL nor an id.
+ * zq_dist_create_cb runs the same logic over a caller-supplied all-gather (tests: gloo on CPUs). */
+typedef struct zq_dist zq_dist;
+/* every rank contributes `bytes` bytes at `in`; `out` receives world * bytes in rank order; returns 0 on success */
+typedef int (*zq_allgather_fn)(void* user, const void* in, void* out, size_t bytes);
+int zq_dist_unique_id(uint8_t out[128]);
+zq_dist* zq_dist_create(int device, int rank, int world, const uint8_t id[128]);
+zq_dist* zq_dist_create_cb(int rank, int world, zq_allgather_fn fn, void* user);
+void zq_dist_destroy(zq_dist* d);
+const char* zq_dist_last_error(zq_dist* d);     /* d may be NULL: error of the last failed create / unique_id */
+uint64_t zq_dist_bytes_exchanged(zq_dist* d);   /* payload bytes received by this rank so far */
+/* contiguous balanced shard [lo, hi) of `total` units; longest-first assignment for units of unequal cost */
+int zq_dist_shard_range(uint64_t total, int rank, int world, uint64_t* lo, uint64_t* hi);
+int zq_dist_shard_lpt(const uint64_t* cost, uint64_t n, int world, int32_t* owner);
+/* local_sizes: compressed sizes of this rank's shard (zq_dist_shard_range order) -> all_sizes[total], offsets[total] */
+int zq_dist_exchange_sizes(zq_dist* d, const uint32_t* local_sizes, uint64_t total, uint32_t* all_sizes, uint64_t* offsets);
+/* local_digests: n_local x 20 bytes in archive order -> is_first[n_local] (1: store it, 0: reference an earlier one),
+ * unique_total: fragments stored by all ranks together */
+int zq_dist_dedup(zq_dist* d, const uint8_t* local_digests, uint64_t n_local, uint8_t* is_first, uint64_t* unique_total);
+
 /* ---- introspection for tests / bench ---------------------------------------------------------- */
 /* number of kernel launches issued by this context since creation */
 uint64_t zq_launch_count(zq_ctx* ctx);

@@ -83,6 +83,20 @@ def _load():
     lib.zq_launch_count.restype = C.c_uint64
     lib.zq_launch_count.argtypes = [C.c_void_p]
     lib.zq_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.zq_dist_create.restype = C.c_void_p
+    lib.zq_dist_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.zq_dist_create_cb.restype = C.c_void_p
+    lib.zq_dist_create_cb.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.zq_dist_destroy.argtypes = [C.c_void_p]
+    lib.zq_dist_last_error.restype = C.c_char_p
+    lib.zq_dist_last_error.argtypes = [C.c_void_p]
+    lib.zq_dist_bytes_exchanged.restype = C.c_uint64
+    lib.zq_dist_bytes_exchanged.argtypes = [C.c_void_p]
+    lib.zq_dist_unique_id.argtypes = [C.c_void_p]
+    lib.zq_dist_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.zq_dist_shard_lpt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    lib.zq_dist_exchange_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zq_dist_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zq_last_timings_ex.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
     lib.zq_suffix_array.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     return lib
@@ -143,6 +157,86 @@ def _cstr_array(v, n, uniform):
         v = [v]
     arr = (C.c_char_p * len(v))(*[(s.encode() if isinstance(s, str) else s) for s in v])
     return arr
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+def shard_range(total, rank, world):
+    lo, hi = C.c_uint64(0), C.c_uint64(0)
+    lib.zq_dist_shard_range(int(total), int(rank), int(world), C.byref(lo), C.byref(hi))
+    return int(lo.value), int(hi.value)
+
+
+def shard_lpt(costs, world):
+    """owner[i] of every unit, longest first onto the least loaded rank (zq_dist_shard_lpt)."""
+    c = np.ascontiguousarray(costs, dtype=np.uint64)
+    owner = np.zeros(len(c), dtype=np.int32)
+    if len(c):
+        lib.zq_dist_shard_lpt(c.ctypes.data, len(c), int(world), owner.ctypes.data)
+    return owner
+
+
+def dist_unique_id():
+    """Rank 0: the 128 bytes every rank passes to Dist(...) (ncclGetUniqueId)."""
+    buf = (C.c_uint8 * 128)()
+    rc = lib.zq_dist_unique_id(buf)
+    if rc:
+        raise ZqError(rc, lib.zq_dist_last_error(None).decode(errors="replace"))
+    return bytes(buf)
+
+
+class Dist:
+    """The exchanges of a multi-GPU run (zq_dist_*): NCCL when unique_id is given, a Python all-gather callable
+    `allgather(in_bytes) -> list of world bytes objects` otherwise (CPU tests over gloo), nothing for world == 1."""
+
+    def __init__(self, device, rank, world, unique_id=None, allgather=None):
+        self.rank, self.world = int(rank), int(world)
+        self._cb = None
+        if allgather is not None and world > 1:
+            def cb(user, pin, pout, nbytes):
+                try:
+                    parts = allgather(C.string_at(pin, nbytes))
+                    C.memmove(pout, b"".join(parts), nbytes * self.world)
+                    return 0
+                except Exception:
+                    return 1
+            self._cb = ALLGATHER_FN(cb)
+            self._h = lib.zq_dist_create_cb(self.rank, self.world, C.cast(self._cb, C.c_void_p), None)
+        else:
+            idb = (C.c_uint8 * 128)(*unique_id) if (unique_id is not None and world > 1) else None
+            self._h = lib.zq_dist_create(int(device), self.rank, self.world, idb)
+        if not self._h:
+            raise ZqError(ZQ_E_NODEVICE, lib.zq_dist_last_error(None).decode(errors="replace"))
+
+    def close(self):
+        if self._h:
+            lib.zq_dist_destroy(self._h)
+            self._h = None
+
+    def _check(self, rc):
+        if rc:
+            raise ZqError(rc, lib.zq_dist_last_error(self._h).decode(errors="replace"))
+
+    def exchange_sizes(self, local_sizes, total):
+        """(all_sizes u32[total], offsets u64[total]) from every rank's contiguous shard of compressed sizes."""
+        loc = np.ascontiguousarray(local_sizes, dtype=np.uint32)
+        sizes = np.zeros(int(total), dtype=np.uint32)
+        offs = np.zeros(int(total), dtype=np.uint64)
+        self._check(lib.zq_dist_exchange_sizes(self._h, loc.ctypes.data if len(loc) else None, int(total),
+                                               sizes.ctypes.data if total else None, offs.ctypes.data if total else None))
+        return sizes, offs
+
+    def dedup(self, digests):
+        """digests u8[n,20] of this rank's fragments in archive order -> (is_first bool[n], unique fragments of all ranks)."""
+        dg = np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1, 20)
+        first = np.zeros(len(dg), dtype=np.uint8)
+        uniq = C.c_uint64(0)
+        self._check(lib.zq_dist_dedup(self._h, dg.ctypes.data if len(dg) else None, len(dg), first.ctypes.data if len(dg) else None, C.byref(uniq)))
+        return first.astype(bool), int(uniq.value)
+
+    def bytes_exchanged(self):
+        return int(lib.zq_dist_bytes_exchanged(self._h))
 
 
 class Pipe:

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("ZQ_LIB", os.path.join(HERE, "libzqb200.so"))   # ZQ_LIB: a tuning build beside the shipped one
-SOURCES = ["zq_api.cu", "zq_config.cpp", "zq_cm_host.cpp", "libzpaq_b200.cpp", "zq_archive.cpp", "zq_pipe.cpp", "zq_jit.cpp"]
+SOURCES = ["zq_api.cu", "zq_config.cpp", "zq_cm_host.cpp", "libzpaq_b200.cpp", "zq_archive.cpp", "zq_pipe.cpp", "zq_jit.cpp", "zq_dist.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared", "-cudart", "static",
