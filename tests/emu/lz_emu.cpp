@@ -5,6 +5,7 @@
 
 #include "zq_lz77.cuh"
 #include "zq_lz77_scan.cuh"
+#include "zq_sufsort16.cuh"
 
 using namespace zqdev;
 
@@ -77,6 +78,28 @@ extern "C" long emu_lz_scan(const uint8_t* data, uint32_t n, const int* args, ui
     k_suffix_sort<256, 4>(in.data(), &u, &todo, 1, work.data(), kbuf.data(), vbuf.data(), scr);
   });
   return idx16 ? run_scan_pipeline<u16>(in, u, pl, work, out, ntok_out) : run_scan_pipeline<u32>(in, u, pl, work, out, ntok_out);
+}
+
+// Shared-memory suffix sort of a block of up to 64 KiB (zq_sufsort16.cuh), followed by k_suffix_sort for what it hands
+// back.  Outputs the four arrays + packed rows the parse kernels read; returns 1 if the general sorter was needed.
+extern "C" int emu_sort16(const uint8_t* data, uint32_t n, uint16_t* sa, uint16_t* isa, uint16_t* lcp, uint8_t* bwt, uint32_t* pk) {
+  std::vector<u8> in(data, data + n); in.resize(n + 64);
+  std::vector<u8> work(zq_work_bytes_scan(n, 2) + 256);
+  ZqUnit u; memset(&u, 0, sizeof u);
+  u.n = n; u.idx16 = 1; u.want_pk = 1;
+  int todo = 0;
+  u32 flag = 7, next = 0;
+  emu::launch(1, S16_NT, sizeof(Sort16Smem), [&] { k_suffix_sort16(in.data(), &u, &todo, 1, work.data(), &flag, &next); });
+  if (flag) {
+    const size_t scr = (((size_t)n + 1) + 63) & ~(size_t)63;
+    std::vector<u64> kbuf(2 * scr); std::vector<u32> vbuf(6 * scr);
+    emu::launch(1, 256, sizeof(SortSmem<256>), [&] { k_suffix_sort<256, 4>(in.data(), &u, &todo, 1, work.data(), kbuf.data(), vbuf.data(), scr, &flag); });
+  }
+  const u64 stride = zq_work_stride(n, 2);
+  memcpy(sa, work.data(), 2 * (size_t)n); memcpy(isa, work.data() + stride, 2 * (size_t)n);
+  memcpy(lcp, work.data() + 2 * stride, 2 * (size_t)n); memcpy(bwt, work.data() + 2 * stride + zq_work_stride(n, 2), n);
+  memcpy(pk, work.data() + zq_work_bytes(n, 2), 4 * (size_t)n);
+  return (int)flag;
 }
 
 #include "zq_frame.cuh"

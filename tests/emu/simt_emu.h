@@ -30,6 +30,8 @@ struct alignas(16) uint4 { unsigned x, y, z, w; };
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 struct uint2 { unsigned x, y; };
 inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
+inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { ulonglong2 r; r.x = x; r.y = y; return r; }
 struct int2 { int x, y; };
 inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 
@@ -167,6 +169,7 @@ inline int __ffs(unsigned x) { return x ? __builtin_ctz(x) + 1 : 0; }
 inline int __ffs(int x) { return __ffs((unsigned)x); }
 inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 inline int __clz(int x) { return __clz((unsigned)x); }
+inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i); return r; }
 inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {

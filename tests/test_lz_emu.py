@@ -21,7 +21,7 @@ def emu():
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "liblzemu.so")
     deps = [os.path.join(EMU, "lz_emu.cpp"), os.path.join(EMU, "simt_emu.h")] + [os.path.join(CSRC, f) for f in
-                                                                                   ("zq_lz77.cuh", "zq_lz77_scan.cuh", "zq_sufsort.cuh", "zq_common.cuh", "zq_frame.cuh")]
+                                                                                   ("zq_lz77.cuh", "zq_lz77_scan.cuh", "zq_sufsort.cuh", "zq_sufsort16.cuh", "zq_common.cuh", "zq_frame.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC,
                         "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-o", lib, deps[0]], check=True)
@@ -87,6 +87,39 @@ def test_scan_pipeline_full_block(emu, oracle, n):
     ntok = C.c_uint32(0)
     r = emu.emu_lz_scan(data, n, (C.c_int * 9)(*a), out, cap, C.byref(ntok))
     assert r >= 0 and bytes(out[:r]) == oracle.lz_stream(data, a)
+
+
+SORT16_CASES = [corpus.text_unit(3, 3000), corpus.random_unit(6, 5000), b"abracadabra" * 100, bytes(2000), b"a", b"ab", corpus.text_unit(8, 20000),
+                corpus.mixed_unit(6, 9000), bytes(range(256)) * 40, corpus.text_unit(5, 30000)[:-3] + b"\0\0\0", corpus.repeats_unit(2, 12000),
+                corpus.text_unit(21, 65536)]
+
+
+@pytest.mark.parametrize("k", range(len(SORT16_CASES)))
+def test_shared_memory_sort_matches_oracle(emu, oracle, k):
+    # k_suffix_sort16 (zq_sufsort16.cuh): bins -> bitonic sort on 6-byte prefixes -> direct comparison of ties, with the hand-over
+    # to k_suffix_sort for blocks with long repeats; suffix array, inverse, capped LCP, BWT bytes and packed rows
+    import numpy as np
+    data = bytes(SORT16_CASES[k])
+    n = len(data)
+    sa, isa, lcp = (np.zeros(max(n, 1), np.uint16) for _ in range(3))
+    bwt, pk = np.zeros(max(n, 1), np.uint8), np.zeros(max(n, 1), np.uint32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    emu.emu_sort16(data, n, vp(sa), vp(isa), vp(lcp), vp(bwt), vp(pk))
+    want = oracle.suffix_array(data)
+    assert (sa[:n] == want).all()
+    inv = np.zeros(n, np.int64)
+    inv[want] = np.arange(n)
+    assert (isa[:n] == inv).all()
+    wl = np.zeros(n, np.int64)
+    for j in range(1, n):
+        a, b, l = int(want[j - 1]), int(want[j]), 0
+        while a + l < n and b + l < n and l < 256 and data[a + l] == data[b + l]:
+            l += 1
+        wl[j] = l
+    assert (lcp[:n] == wl).all()
+    wb = np.array([data[int(x) - 1] if x > 0 else 0 for x in want], dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    assert (bwt[:n] == wb).all()
+    assert (pk[:n] == (want.astype(np.uint32) | (np.minimum(wl, 255).astype(np.uint32) << 16) | (wb.astype(np.uint32) << 24))).all()
 
 
 HASH_CASES = [("1", corpus.text_unit(3, 3000)), ("1", b"abracadabra" * 100), ("1", bytes(2000)), ("1", corpus.mixed_unit(4, 4000)),

@@ -26,6 +26,7 @@
 #include "zq_lz77_scan.cuh"
 #include "zq_sha1.cuh"
 #include "zq_sufsort.cuh"
+#include "zq_sufsort16.cuh"
 
 namespace {
 
@@ -63,10 +64,11 @@ struct zq_ctx {
   std::string err;
   uint64_t launches = 0;
   DevBuf d_in, d_out, d_units, d_plans, d_blob, d_todo, d_outoff, d_work, d_ht, d_todo2, d_todo3, d_todo4, d_todo5, d_dec, d_tok, d_bitpos, d_lz, d_lzlen, d_sha, d_tables, d_cmplans, d_fills, d_model, d_coded, d_codedlen,
-      d_kbuf, d_vbuf, d_err, d_misc, d_lzs;
+      d_kbuf, d_vbuf, d_err, d_misc, d_lzs, d_sortflag;
   Timer tm[16];
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // h2d / d2h timing of the host-pointer entry point
-  bool attr_cm_enc = false, attr_cm_dec = false;
+  bool attr_cm_enc = false, attr_cm_dec = false, attr_sort16 = false;
+  int sort16 = 1;                         // blocks <= 64 KiB: shared-memory sort (zq_sufsort16.cuh); ZQ_SORT16=0 sends everything to k_suffix_sort
   float last_ms[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   size_t wave_bytes = (size_t)24 << 30;  // sa|isa|lcp|bwt|scan-table bytes per wave
   size_t model_budget = (size_t)120 << 30; // component-table bytes per wave (capped by free memory)
@@ -348,11 +350,24 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
       ZQ_CUDA(c, c->d_vbuf.ensure((size_t)sort_grid * 6 * scr * 4));
       ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo.p, todo_sa.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
       tstart(c, 2);
+      // blocks of up to 64 KiB: sorted in shared memory (zq_sufsort16.cuh); what that kernel hands back (larger blocks,
+      // blocks with long repeats) goes to the general prefix-doubling sort
+      const u32* d_only = nullptr;
+      if (c->sort16) {
+        ZQ_CUDA(c, c->d_sortflag.ensure((size_t)nt * 4 + 16));
+        u32* ctr16 = c->d_err.as<u32>() + 3;
+        ZQ_CUDA(c, cudaMemsetAsync(ctr16, 0, 4, c->stream));
+        if (!c->attr_sort16) { cudaFuncSetAttribute(k_suffix_sort16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sort16Smem)); c->attr_sort16 = true; }
+        k_suffix_sort16<<<std::min(nt, c->num_sms), S16_NT, sizeof(Sort16Smem), c->stream>>>(d_in, du, c->d_todo.as<int>(), nt, c->d_work.as<u8>(),
+                                                                                         c->d_sortflag.as<u32>(), ctr16);
+        ++c->launches;
+        d_only = c->d_sortflag.as<u32>();
+      }
 #define ZQ_SORT_LAUNCH(NT, MB)                                                                                            \
   do {                                                                                                                   \
     cudaFuncSetAttribute(k_suffix_sort<NT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem<NT>)); \
     k_suffix_sort<NT, MB><<<sort_grid, NT, sizeof(SortSmem<NT>), c->stream>>>(                                           \
-        d_in, du, c->d_todo.as<int>(), nt, c->d_work.as<u8>(), c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr);          \
+        d_in, du, c->d_todo.as<int>(), nt, c->d_work.as<u8>(), c->d_kbuf.as<u64>(), c->d_vbuf.as<u32>(), scr, d_only);  \
   } while (0)
       if (sort_nt == 1024) ZQ_SORT_LAUNCH(1024, 1);
       else if (sort_nt == 512 && sort_minb == 2) ZQ_SORT_LAUNCH(512, 2);
@@ -727,6 +742,7 @@ zq_ctx* zq_create(int device) {
   if (const char* s = getenv("ZQ_CM_FAST")) c->cm_fast = atoi(s);
   if (const char* s = getenv("ZQ_CM_JIT")) c->cm_jit = atoi(s);
   if (const char* s = getenv("ZQ_LZ_OLD")) c->lz_old = atoi(s) ? 1 : 0;
+  if (const char* s = getenv("ZQ_SORT16")) c->sort16 = atoi(s);
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
   if (const char* s = getenv("ZQ_SORT_MINB")) c->sort_minb = atoi(s);
   if (c->sort_nt != 1024 && c->sort_nt != 512 && c->sort_nt != 256 && c->sort_nt != 128) c->sort_nt = 256;

@@ -577,7 +577,7 @@ __device__ void suffix_sort_block(const u8* __restrict__ T, u32 n, u8* __restric
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_suffix_sort(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const int* __restrict__ todo, int ntodo,
-              u8* __restrict__ work_base, u64* kbuf, u32* vbuf, u64 scratch_elems) {
+              u8* __restrict__ work_base, u64* kbuf, u32* vbuf, u64 scratch_elems, const u32* __restrict__ only = nullptr) {
   ZQ_DYN_SMEM(smem_raw);
   SortSmem<NT>& sm = *reinterpret_cast<SortSmem<NT>*>(smem_raw);
   SortScratch sc;
@@ -586,6 +586,7 @@ k_suffix_sort(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, 
   sc.vA = vb; sc.vB = vb + scratch_elems; sc.pA = vb + 2 * scratch_elems; sc.pB = vb + 3 * scratch_elems;
   sc.sa = vb + 4 * scratch_elems; sc.rank = vb + 5 * scratch_elems;
   for (int t = blockIdx.x; t < ntodo; t += gridDim.x) {
+    if (only && !only[t]) continue;     // already sorted by k_suffix_sort16 (zq_sufsort16.cuh)
     const ZqUnit u = units[todo[t]];
     suffix_sort_block<NT>(in_base + u.in_off, u.n, work_base + u.work_off, u.idx16 != 0, sc, sm, u.want_pk != 0);
     __syncthreads();

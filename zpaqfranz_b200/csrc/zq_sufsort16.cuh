@@ -1,0 +1,318 @@
+// zq_sufsort16.cuh -- suffix array + inverse + capped LCP + BWT + packed rows of a block of up to 64 KiB, built
+// ENTIRELY in shared memory by one CTA (the 64 KiB unit of the headline benchmark).  Same result as divsufsort
+// (Z:19121): the suffix array of a string is unique.
+//
+// Why a second sorter: k_suffix_sort (zq_sufsort.cuh) is a general prefix-doubling sort whose 40 bytes of scratch per
+// input byte live in global memory -- 22 MB of DRAM traffic per 64 KiB block.  Text-like and random blocks do not need
+// doubling at all: their suffixes differ within a few bytes.  This kernel therefore sorts by the first 6 bytes with a
+// bitonic network over 64-bit words (48-bit prefix | 16-bit suffix index) held in shared memory, then orders the few
+// suffixes that still tie (groups of 2..32) by comparing the text directly.  A block where that stops paying -- a
+// group of more than 32 suffixes sharing 6 bytes, or two suffixes sharing more than 512 -- is handed to k_suffix_sort
+// through a flag; nothing is approximated.
+//
+//   shared memory (196 KB, one CTA per SM):  text 64 KiB | 8192 bin starts | 8192 bin cursors | 8192 x u64 sort buffer
+//   1. text -> shared memory (bulk async copy when the block is 16-byte aligned)
+//   2. histogram of the 13-bit key (byte 0, top 5 bits of byte 1) with shared-memory atomics, exclusive scan: the
+//      start row of every bin.  Bins are only a way to cut the suffix array into batches that fit the sort buffer:
+//      a batch takes as many whole bins as fit 8192 rows.
+//      Every position is dealt to its bin's rows of the (global, L2-resident) sa array -- a counting sort on 13 bits.
+//   3. per batch: its rows are read back (coalesced), keyed by the first 6 bytes of their suffix, sorted; ties
+//      resolved; then the rows are final and sa / lcp / bwt / pk are written in row order and isa is scattered.
+#pragma once
+#include "zq_sufsort.cuh"
+
+namespace zqdev {
+
+constexpr int S16_NT = 1024;
+constexpr u32 S16_BINS = 8192;
+constexpr u32 S16_BUF = 8192;        // sort buffer capacity (elements) = rows per batch at most
+constexpr u32 S16_MAXGROUP = 32;     // largest tie group ordered by direct comparison
+constexpr u32 S16_MAXDEPTH = 512;    // longest common prefix followed by direct comparison
+
+struct Sort16Smem {
+  u32 bins[S16_BINS + 8];
+  u32 cursor[S16_BINS];                  // next free row of every bin while the positions are dealt to their bins
+  u32 cnt, prev_idx, fallback, pad0;     // pad0: end row of the current batch
+  u32 wsum[32];
+  ZqMbar bar;
+  u64 pad1;
+  alignas(16) u8 text[65536 + 64];
+  alignas(16) u64 buf[S16_BUF];
+};
+
+// 4 text bytes at any offset as a big-endian number (reads up to 7 bytes past p: the text is zero padded)
+__device__ __forceinline__ u32 s16_be32(const u8* p) { return __byte_perm(ld32_unaligned(p), 0, 0x0123); }
+
+// suffix a < suffix b, both known to share their first `from` bytes; *deep is set when the comparison gives up
+__device__ __forceinline__ bool s16_less(const u8* __restrict__ T, u32 n, u32 a, u32 b, u32 from, u32* deep) {
+  u32 k = from;
+  for (;;) {
+    const u32 pa = a + k, pb = b + k;
+    if (pa >= n || pb >= n) return pa >= n;          // the suffix that ends first is the smaller one (Z:17721: implicit terminator)
+    if (pa + 4 <= n && pb + 4 <= n) {
+      const u32 wa = s16_be32(T + pa), wb = s16_be32(T + pb);
+      if (wa != wb) return wa < wb;
+      k += 4;
+    } else {
+      if (T[pa] != T[pb]) return T[pa] < T[pb];
+      ++k;
+    }
+    if (k > S16_MAXDEPTH) { *deep = 1; return a < b; }
+  }
+}
+
+// common prefix length of suffixes a and b, starting the comparison at `from`, capped
+__device__ __forceinline__ u32 s16_lcp(const u8* __restrict__ T, u32 n, u32 a, u32 b, u32 from, u32 cap) {
+  const u32 lim = min(cap, n - max(a, b));
+  u32 l = min(from, lim);
+  while (l + 4 <= lim) {
+    const u32 d = ld32_unaligned(T + a + l) ^ ld32_unaligned(T + b + l);
+    if (d) return l + ((u32)(__ffs(d) - 1) >> 3);
+    l += 4;
+  }
+  while (l < lim && T[a + l] == T[b + l]) ++l;
+  return l;
+}
+
+__device__ __forceinline__ void s16_cx(u64& a, u64& b, bool up) {
+  const bool sw = (a > b) == up;
+  const u64 lo = sw ? b : a, hi = sw ? a : b;
+  a = lo; b = hi;
+}
+
+// the comparator stages of strides 4, 2, 1 (and, when `head`, the whole phases k = 2, 4, 8) on 8 consecutive
+// elements held in registers
+__device__ __forceinline__ void s16_reg8(u64* __restrict__ S, u32 base, u32 k, bool head) {
+  u64 v[8];
+  const ulonglong2* src = reinterpret_cast<const ulonglong2*>(S + base);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const ulonglong2 t = src[q]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+  if (head) {
+#pragma unroll
+    for (int kk = 2; kk <= 8; kk <<= 1) {
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = 2 * c - (c & (j - 1));
+          s16_cx(v[i], v[i + j], ((base + i) & kk) == 0);
+        }
+      }
+    }
+  } else {
+    const bool up = (base & k) == 0;
+#pragma unroll
+    for (int j = 4; j > 0; j >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = 2 * c - (c & (j - 1));
+        s16_cx(v[i], v[i + j], up);
+      }
+    }
+  }
+  ulonglong2* dst = reinterpret_cast<ulonglong2*>(S + base);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dst[q] = make_ulonglong2(v[2 * q], v[2 * q + 1]);
+}
+
+// bitonic sort of S[0..P), P a power of two >= 16.  Strides below 8 run in registers (8 consecutive elements per
+// thread); strides >= 8 in shared memory, two strides (j, j/2) per pass when both are >= 8: a thread then owns the
+// four elements i, i+j/2, i+j, i+3j/2.
+__device__ void s16_bitonic(u64* __restrict__ S, u32 P) {
+  const u32 tid = threadIdx.x;
+  for (u32 t = tid; t < P / 8; t += S16_NT) s16_reg8(S, 8 * t, 0, true);
+  __syncthreads();
+  for (u32 k = 16; k <= P; k <<= 1) {
+    u32 j = k >> 1;
+    while (j >= 8) {
+      if (j >= 16) {
+        const u32 h = j >> 1;
+        for (u32 t = tid; t < P / 4; t += S16_NT) {
+          const u32 i = 4 * t - 3 * (t & (h - 1));        // t = q*h + r  ->  i = q*2j + r
+          const bool up = (i & k) == 0;
+          u64 a = S[i], b = S[i + h], c = S[i + j], d = S[i + j + h];
+          s16_cx(a, c, up); s16_cx(b, d, up);
+          s16_cx(a, b, up); s16_cx(c, d, up);
+          S[i] = a; S[i + h] = b; S[i + j] = c; S[i + j + h] = d;
+        }
+        j >>= 2;
+      } else {
+        for (u32 t = tid; t < P / 2; t += S16_NT) {
+          const u32 i = 2 * t - (t & (j - 1));
+          const bool up = (i & k) == 0;
+          u64 a = S[i], b = S[i + j];
+          s16_cx(a, b, up);
+          S[i] = a; S[i + j] = b;
+        }
+        j >>= 1;
+      }
+      __syncthreads();
+    }
+    for (u32 t = tid; t < P / 8; t += S16_NT) s16_reg8(S, 8 * t, k, false);
+    __syncthreads();
+  }
+}
+
+// One block.  Returns false (and writes nothing) when the block has to go to the general sorter.
+__device__ bool suffix_sort16_block(const u8* __restrict__ gT, u32 n, u8* __restrict__ w, bool want_pk, Sort16Smem& sm) {
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u8* __restrict__ T = sm.text;
+  // 1. text
+  const bool aligned = ((uintptr_t)gT & 15) == 0;
+  const u32 nb = n & ~15u;
+  if (aligned && nb) {
+    if (tid == 0) { zq_mbar_expect_tx(&sm.bar, nb); zq_bulk_g2s(T, gT, nb, &sm.bar); }
+  }
+  for (u32 i = (aligned ? nb : 0) + tid; i < n + 64; i += S16_NT) T[i] = i < n ? gT[i] : (u8)0;
+  for (u32 b = tid; b < S16_BINS + 8; b += S16_NT) sm.bins[b] = 0;
+  if (tid == 0) { sm.fallback = 0; sm.prev_idx = 0; }
+  __syncthreads();
+  return true;   // (continued in suffix_sort16_rest: the bulk copy's barrier phase is tracked by the caller)
+}
+
+template <bool DUMMY>
+__device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort16Smem& sm) {
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u8* __restrict__ T = sm.text;
+  u64* __restrict__ S = sm.buf;
+  // 2. bins
+  for (u32 i = tid; i < n; i += S16_NT) atomicAdd(&sm.bins[((u32)T[i] << 5) | (T[i + 1] >> 3)], 1u);
+  __syncthreads();
+  {
+    // exclusive scan of 8192 counters, 8 per thread; the largest bin decides whether the batches fit
+    u32 loc[8], s = 0, mx = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { loc[q] = sm.bins[tid * 8 + q]; s += loc[q]; mx = max(mx, loc[q]); }
+    u32 inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(ZQ_FULL, inc, o); if (lane >= (u32)o) inc += t; }
+    mx = __reduce_max_sync(ZQ_FULL, mx);
+    if (lane == 31) sm.wsum[warp] = inc;
+    if (lane == 0 && mx > S16_BUF) sm.fallback = 1;
+    __syncthreads();
+    u32 pre = 0;
+    for (u32 q = 0; q < warp; ++q) pre += sm.wsum[q];
+    u32 run = pre + inc - s;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { sm.bins[tid * 8 + q] = run; run += loc[q]; }
+    if (tid == S16_NT - 1) sm.bins[S16_BINS] = run;     // = n
+    __syncthreads();
+  }
+  if (sm.fallback) return false;
+  const u64 stride = zq_work_stride(n, 2);
+  u16* __restrict__ o_sa = (u16*)w; u16* __restrict__ o_isa = (u16*)(w + stride);
+  // deal the positions to the rows of their bins (order inside a bin does not matter: it is sorted next)
+  for (u32 b = tid; b < S16_BINS; b += S16_NT) sm.cursor[b] = sm.bins[b];
+  __syncthreads();
+  for (u32 i = tid; i < n; i += S16_NT) o_sa[atomicAdd(&sm.cursor[((u32)T[i] << 5) | (T[i + 1] >> 3)], 1u)] = (u16)i;
+  __syncthreads();
+  u16* __restrict__ o_lcp = (u16*)(w + 2 * stride);
+  u8* __restrict__ o_bwt = w + 2 * stride + zq_work_stride(n, 2);
+  u32* __restrict__ o_pk = (u32*)(w + zq_work_bytes(n, 2));
+  u32 rowbase = 0;
+  while (rowbase < n) {
+    // the batch: whole bins from row `rowbase` on, as many as fit the buffer.  rowend = the largest bin end <= limit
+    // (every thread looks at its 8 bins; at least the first bin fits: no bin is larger than the buffer)
+    const u32 limit = rowbase + S16_BUF;
+    {
+      u32 best = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const u32 e = sm.bins[tid * 8 + q + 1]; if (e <= limit) best = max(best, e); }
+      best = __reduce_max_sync(ZQ_FULL, best);
+      if (lane == 0) sm.wsum[warp] = best;
+      if (tid == 0) sm.cnt = 0;
+      __syncthreads();
+      best = 0;
+      for (u32 q = 0; q < S16_NT / 32; ++q) best = max(best, sm.wsum[q]);
+      __syncthreads();
+      sm.pad0 = best;     // (every thread writes the same value)
+    }
+    const u32 rowend = sm.pad0;
+    // 3a. this batch's rows, keyed by the first 6 bytes of their suffix
+    for (u32 j = tid; j < rowend - rowbase; j += S16_NT) {
+      const u32 i = o_sa[rowbase + j];
+      S[j] = ((u64)s16_be32(T + i) << 32) | ((u64)(s16_be32(T + i + 4) >> 16) << 16) | i;
+    }
+    const u32 m = rowend - rowbase;
+    u32 P = 16;
+    while (P < m) P <<= 1;
+    for (u32 t = m + tid; t < P; t += S16_NT) S[t] = ~0ull;
+    __syncthreads();
+    // 3b. sort by (first 6 bytes, index)
+    s16_bitonic(S, P);
+    // 3c. suffixes that share their first 6 bytes: the first of each run orders the run by direct comparison
+    for (u32 j = tid; j < m; j += S16_NT) {
+      const u64 kj = S[j] >> 16;
+      const bool head = (j == 0 || (S[j - 1] >> 16) != kj) && (j + 1 < m && (S[j + 1] >> 16) == kj);
+      if (!head) continue;
+      u32 e = j + 1;
+      while (e < m && e - j <= S16_MAXGROUP && (S[e] >> 16) == kj) ++e;
+      if (e - j > S16_MAXGROUP) { sm.fallback = 1; continue; }
+      u32 deep = 0;
+      for (u32 x = j + 1; x < e; ++x) {         // insertion sort on the index part
+        const u32 v = (u32)S[x] & 0xffffu;
+        u32 y = x;
+        while (y > j && s16_less(T, n, v, (u32)S[y - 1] & 0xffffu, 6, &deep)) { S[y] = S[y - 1]; --y; }
+        S[y] = (kj << 16) | v;
+      }
+      if (deep) sm.fallback = 1;
+    }
+    __syncthreads();
+    if (sm.fallback) return false;
+    // 3d. rows rowbase .. rowbase+m are final
+    const u32 prev_last = sm.prev_idx;
+    for (u32 j = tid; j < m; j += S16_NT) {
+      const u64 cur = S[j];
+      const u32 b = (u32)cur & 0xffffu, row = rowbase + j;
+      u32 l = 0;
+      if (row > 0) {
+        const u64 prv = j ? S[j - 1] : 0;
+        const u32 a = j ? ((u32)prv & 0xffffu) : prev_last;
+        const u64 x = j ? ((cur ^ prv) >> 16) : 1;   // 48-bit prefixes; across batches the bins differ: compare from 0
+        if (j && x != 0) l = min((u32)(__clzll((long long)(x << 16)) >> 3), n - max(a, b));
+        else l = s16_lcp(T, n, a, b, j ? 6u : 0u, ZQ_LCP_CAP);
+      }
+      const u32 bw = b > 0 ? (u32)T[b - 1] : 0u;
+      o_sa[row] = (u16)b; o_lcp[row] = (u16)l; o_bwt[row] = (u8)bw; o_isa[b] = (u16)row;
+      if (want_pk) o_pk[row] = LzsPack<u16>::make(b, l, bw);
+    }
+    __syncthreads();
+    if (tid == 0) sm.prev_idx = (u32)S[m - 1] & 0xffffu;
+    rowbase = rowend;
+    __syncthreads();
+  }
+  return true;
+}
+
+// Persistent CTAs pull blocks from a counter.  need_old[t] = 1 for the blocks left to k_suffix_sort (too large for
+// 16-bit indices, or not text-like enough for this method).
+__global__ void __launch_bounds__(S16_NT, 1)
+k_suffix_sort16(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const int* __restrict__ todo, int ntodo,
+                u8* __restrict__ work_base, u32* __restrict__ need_old, u32* next_unit) {
+  ZQ_DYN_SMEM(smem_raw);
+  Sort16Smem& sm = *reinterpret_cast<Sort16Smem*>(smem_raw);
+  __shared__ int s_t;
+  if (threadIdx.x == 0) zq_mbar_init(&sm.bar, 1);
+  __syncthreads();
+  u32 uses = 0;
+  for (;;) {
+    if (threadIdx.x == 0) s_t = (int)atomicAdd(next_unit, 1u);
+    __syncthreads();
+    const int t = s_t;
+    __syncthreads();
+    if (t >= ntodo) break;
+    const ZqUnit u = units[todo[t]];
+    bool ok = u.idx16 != 0 && u.n > 0;
+    if (ok) {
+      const u8* gT = in_base + u.in_off;
+      suffix_sort16_block(gT, u.n, work_base + u.work_off, u.want_pk != 0, sm);
+      if ((((uintptr_t)gT & 15) == 0) && (u.n & ~15u)) { zq_mbar_wait(&sm.bar, uses & 1u); ++uses; }
+      __syncthreads();
+      ok = suffix_sort16_rest<true>(u.n, work_base + u.work_off, u.want_pk != 0, sm);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) need_old[t] = ok || u.n == 0 ? 0u : 1u;
+  }
+}
+
+}  // namespace zqdev
