@@ -147,6 +147,10 @@ int zq_decompress_blocks_ex(zq_ctx* ctx, int n,
                             const uint32_t* expect_len /* may be NULL */,
                             uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
                             uint32_t* in_used, uint8_t* sha1_out);
+/* The first max_out[i] bytes of each block's first segment (== Decompresser::decompress(n), Z:15480: a caller that only
+ * wants the head of a segment); stops there, looks at no trailer, verifies no checksum.  out_len[i] <= max_out[i]. */
+int zq_decompress_prefix(zq_ctx* ctx, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                         const uint32_t* max_out, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len);
 
 /* Upper bound of one block's compressed size for an n-byte input (any method, names <= 255 bytes). */
 uint64_t zq_compress_bound(uint32_t n);

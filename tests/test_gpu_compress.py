@@ -108,6 +108,22 @@ def test_modeled_blocks_bit_exact(ctx, zq, oracle, ref, method):
     assert ref.decompress(out[:total].tobytes(), int(lens.sum())) == b"".join(units)
 
 
+@pytest.mark.parametrize("jit", ["0", "1", "2"])
+def test_context_program_forms_over_several_waves(zq, ref, monkeypatch, jit):
+    # the three forms of the context machine / coder -- ZPAQL interpreter on its own warp (ZQ_CM_JIT=0), HCOMP translated
+    # to CUDA C and compiled with NVRTC (=1, the default), generated straight-line coder as well (=2) -- with the work
+    # arena cut so small that the batch runs in several waves (the per-wave bookkeeping of the translated path)
+    monkeypatch.setenv("ZQ_CM_JIT", jit)
+    monkeypatch.setenv("ZQ_MODEL_BUDGET", str(3 << 20))     # ~2 blocks of -m3 per wave
+    units = [corpus.text_unit(40 + k, 9000 + 700 * k) for k in range(7)] + [corpus.mixed_unit(9, 8000), b"abc" * 900]
+    arena, offs, lens = _arena(units)
+    with zq.Context(0) as c2:
+        for method in ("3", "36,200,1", "4"):
+            out, ooff, olen = c2.compress_blocks(arena, offs, lens, method=method, filename="", comment="")
+            for i, u in enumerate(units):
+                assert out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes() == ref.compress_block(u, method, "", ""), (jit, method, i)
+
+
 def test_modeled_matches_c_oracle(ctx, zq, oracle):
     u = corpus.text_unit(11, 12000)
     arena, offs, lens = _arena([u])

@@ -60,8 +60,6 @@ def test_fragmenter_matches_oracle_and_reference(ctx, oracle, ref):
                 pos += int(fl[k])
 
 
-@pytest.mark.skipif(not os.environ.get("ZQ_TEST_UNVERIFIED"), reason="CRC-32 / XXH64 kernels are emulator-verified only so far; set "
-                    "ZQ_TEST_UNVERIFIED=1 to run them on hardware (round 2)")
 def test_crc32_xxh64_match_reference(ctx, ref):
     import zlib
     bufs = [b"", b"ABCDE", bytes(5000), corpus.random_unit(3, 4096).tobytes() if hasattr(corpus.random_unit(3, 4096), "tobytes") else bytes(corpus.random_unit(3, 4096)),

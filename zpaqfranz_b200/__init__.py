@@ -408,6 +408,20 @@ class Context:
                                              ooff.ctypes.data, olen.ctypes.data))
         return out, ooff, olen
 
+    def decompress_prefix(self, arena, offsets, lengths, max_out):
+        """The first max_out[i] bytes of every block (zq_decompress_prefix).  Returns (out, out_off, out_len)."""
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+        mx = np.ascontiguousarray(max_out, dtype=np.uint32)
+        n = len(off)
+        out = np.empty(max(int(mx.sum()), 1), dtype=np.uint8)
+        ooff = np.zeros(n, dtype=np.uint64)
+        olen = np.zeros(n, dtype=np.uint32)
+        self._check(lib.zq_decompress_prefix(self._h, n, arena.ctypes.data, off.ctypes.data, ln.ctypes.data, mx.ctypes.data,
+                                             out.ctypes.data, out.size, ooff.ctypes.data, olen.ctypes.data))
+        return out, ooff, olen
+
     # -- hashes -------------------------------------------------------------------------------------
     def _hash(self, fn, dlen, arena, offsets, lengths):
         arena = np.ascontiguousarray(arena, dtype=np.uint8)

@@ -76,7 +76,7 @@ struct zq_ctx {
   uint64_t frag_seg = 128 << 10;          // fragmenter segment size
   int lz_old = 0;                         // 1: warp-per-block LZ77 parser for every block (ZQ_LZ_OLD=1); 0: position-parallel scan/walk/emit (zq_lz77_scan.cuh)
   int scan_occ[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of k_lz_scan<u16/u32, pass> (queried once)
-  int cm_jit = 0;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter; 2: generated coder too (ZQ_CM_JIT)
+  int cm_jit = 1;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter; 2: generated coder too (ZQ_CM_JIT)
   struct JitProg { cudaLibrary_t lib = nullptr; cudaKernel_t ctx = nullptr, code = nullptr; };
   std::map<std::string, JitProg> jit_cache;   // translated context program (+ generated coder) per model header
   DevBuf d_ctx, d_ctxoff, d_ctxargs;
@@ -928,9 +928,9 @@ int zq_decompress_blocks(zq_ctx* c, int n, const uint8_t* in_base, const uint64_
   return zq_decompress_blocks_ex(c, n, in_base, in_off, in_len, expect_len, out_base, out_cap, out_off, out_len, nullptr, nullptr);
 }
 
-int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
-                            const uint32_t* expect_len, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
-                            uint32_t* in_used, uint8_t* sha1_out) {
+static int decompress_impl(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                           const uint32_t* expect_len, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
+                           uint32_t* in_used, uint8_t* sha1_out, bool prefix) {
   using namespace zqdev;
   if (!c) return ZQ_E_NODEVICE;
   if (n < 0 || (n > 0 && (!in_base || !in_off || !in_len || !out_base || !out_off || !out_len))) return fail(c, ZQ_E_ARG, "bad argument");
@@ -1059,6 +1059,12 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
   for (int u = 0; u < n; ++u) {
     const ZqDecResult& r = res[u];
     static const char* msg[] = {"", "archive corrupted", "unexpected end of file", "decoded size exceeds the expected size", "ZPAQL execution error", "unknown post processing type"};
+    if (prefix && (r.error == 3 || r.error == 0)) {   // Decompresser::decompress(n): stop after n bytes, no trailer is looked at
+      out_len[u] = r.out_len;
+      if (in_used) in_used[u] = 0;
+      if (sha1_out) sha1_out[(size_t)u * 21] = 0;
+      continue;
+    }
     if (r.error) return fail(c, r.error == 3 ? ZQ_E_OUTPUT : ZQ_E_METHOD, msg[r.error < 6 ? r.error : 1]);
     out_len[u] = r.out_len;
     const uint8_t* b = in_base + in_off[u];
@@ -1094,6 +1100,18 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
   }
   if (out_pos) ZQ_CUDA(c, cudaMemcpy(out_base, c->d_out.p, out_pos, cudaMemcpyDeviceToHost));
   return ZQ_OK;
+}
+
+int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                            const uint32_t* expect_len, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
+                            uint32_t* in_used, uint8_t* sha1_out) {
+  return decompress_impl(c, n, in_base, in_off, in_len, expect_len, out_base, out_cap, out_off, out_len, in_used, sha1_out, false);
+}
+
+int zq_decompress_prefix(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                         const uint32_t* max_out, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len) {
+  if (c && n > 0 && !max_out) return fail(c, ZQ_E_ARG, "bad argument");
+  return decompress_impl(c, n, in_base, in_off, in_len, max_out, out_base, out_cap, out_off, out_len, nullptr, nullptr, true);
 }
 
 // ---- hashes --------------------------------------------------------------------------------------

@@ -6,8 +6,8 @@
 // input byte live in global memory -- 22 MB of DRAM traffic per 64 KiB block.  Text-like and random blocks do not need
 // doubling at all: their suffixes differ within a few bytes.  This kernel therefore sorts by the first 6 bytes with a
 // bitonic network over 64-bit words (48-bit prefix | 16-bit suffix index) held in shared memory, then orders the few
-// suffixes that still tie (groups of 2..32) by comparing the text directly.  A block where that stops paying -- a
-// group of more than 32 suffixes sharing 6 bytes, or two suffixes sharing more than 512 -- is handed to k_suffix_sort
+// suffixes that still tie (groups of 2..128) by comparing the text directly.  A block where that stops paying -- a
+// group of more than 128 suffixes sharing 6 bytes, or two suffixes sharing more than 512 -- is handed to k_suffix_sort
 // through a flag; nothing is approximated.
 //
 //   shared memory (196 KB, one CTA per SM):  text 64 KiB | 8192 bin starts | 8192 bin cursors | 8192 x u64 sort buffer
@@ -26,7 +26,7 @@ namespace zqdev {
 constexpr int S16_NT = 1024;
 constexpr u32 S16_BINS = 8192;
 constexpr u32 S16_BUF = 8192;        // sort buffer capacity (elements) = rows per batch at most
-constexpr u32 S16_MAXGROUP = 32;     // largest tie group ordered by direct comparison
+constexpr u32 S16_MAXGROUP = 128;    // largest tie group ordered by direct comparison
 constexpr u32 S16_MAXDEPTH = 512;    // longest common prefix followed by direct comparison
 
 struct Sort16Smem {
