@@ -29,6 +29,36 @@ namespace libzpaq_b200 {
 // exactly like zpaqfranz's own handler (Z:27148-27154).
 [[noreturn]] void error(const char* msg);
 
+// == libzpaq::Array<T> (Z:12585): zero-initialised array whose element [0] sits on a 64-byte boundary; resize()
+// erases the content; no copy, no assignment.  The front end uses it for its own tables; nothing on the device path
+// does, it is here so that code written against the reference's header compiles against this one.
+template <typename T>
+class Array {
+  std::vector<unsigned char> raw_;
+  T* data_ = nullptr;
+  size_t n_ = 0;
+  Array(const Array&) = delete;
+  void operator=(const Array&) = delete;
+
+ public:
+  explicit Array(size_t sz = 0, int ex = 0) { resize(sz, ex); }
+  void resize(size_t sz, int ex = 0) {      // sz << ex elements, all zero
+    for (; ex > 0; --ex) { if (sz > sz * 2) error("Array too big"); sz *= 2; }
+    raw_.clear(); raw_.shrink_to_fit(); data_ = nullptr; n_ = 0;
+    if (sz == 0) return;
+    const size_t nb = 128 + sz * sizeof(T);
+    if (nb <= 128 || (nb - 128) / sizeof(T) != sz) error("Array too big");
+    try { raw_.assign(nb, 0); } catch (...) { error("Out of memory"); }
+    const size_t mis = reinterpret_cast<uintptr_t>(raw_.data()) & 63;
+    data_ = reinterpret_cast<T*>(raw_.data() + (64 - mis));
+    n_ = sz;
+  }
+  size_t size() const { return n_; }
+  int isize() const { return int(n_); }
+  T& operator[](size_t i) { if (!(n_ > 0 && i < n_)) error("09386: operator[] kaputt"); return data_[i]; }
+  T& operator()(size_t i) { return data_[i & (n_ - 1)]; }     // n a power of two
+};
+
 class Reader {
  public:
   virtual int get() = 0;                   // next byte or -1 at EOF
@@ -167,3 +197,9 @@ void compressBlocks(int n, StringBuffer* const* ins, Writer* const* outs, const 
 void decompress(Reader* in, Writer* out);
 
 }  // namespace libzpaq_b200
+
+// The archiver's sources say `libzpaq::`: with this alias they compile against the mirror unchanged.  Define
+// ZQ_NO_LIBZPAQ_ALIAS when the reference's own namespace is in the same translation unit (the parity tests).
+#ifndef ZQ_NO_LIBZPAQ_ALIAS
+namespace libzpaq = libzpaq_b200;
+#endif

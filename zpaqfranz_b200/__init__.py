@@ -49,6 +49,7 @@ def _load():
     lib.zq_decompress_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zq_decompress_blocks_ex.argtypes = lib.zq_decompress_blocks.argtypes + [C.c_void_p, C.c_void_p]
+    lib.zq_decompress_prefix.argtypes = lib.zq_decompress_blocks.argtypes
     lib.zq_compress_segments.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32,
                                          C.c_char_p, C.c_uint32, cpp, cpp, C.c_int, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]

@@ -1060,7 +1060,7 @@ static int decompress_impl(zq_ctx* c, int n, const uint8_t* in_base, const uint6
     const ZqDecResult& r = res[u];
     static const char* msg[] = {"", "archive corrupted", "unexpected end of file", "decoded size exceeds the expected size", "ZPAQL execution error", "unknown post processing type"};
     if (prefix && (r.error == 3 || r.error == 0)) {   // Decompresser::decompress(n): stop after n bytes, no trailer is looked at
-      out_len[u] = r.out_len;
+      out_len[u] = std::min<uint32_t>(r.out_len, units[u].out_cap);   // (the writer counts the byte that did not fit)
       if (in_used) in_used[u] = 0;
       if (sha1_out) sha1_out[(size_t)u * 21] = 0;
       continue;
