@@ -203,23 +203,37 @@ k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
   u32 wseq = 0, qhead = 0, qlen = 0, pend = 0, swept = 0, held = 0, dead = 0;
   bool wwait = true, wdone = false;
   // per lane
-  bool have = false, defer = false, stop0 = false, stop1 = false;
+  // PASS 1 runs ONE state machine per row: first for "literals pending" (no penalty).  The "no literal pending" state
+  // scores a candidate that needs a leading literal 4 lower (Z:19421); it can only end differently if the first run
+  // ACCEPTED such a candidate (a rejected one is rejected with the penalty too, and nothing else differs) -- true for
+  // one row in ten, which then runs a second time with the penalty on (`pen`).
+  bool have = false, defer = false, stop0 = false, pen = false, div = false;
   u32 qq = 0, s = 0, x = 0, carry = 0, runmin = 0, aux = 0, lb = 0;   // aux: PASS 0 consumer row, PASS 1 own BWT byte
-  u32 blen0 = 0, bp0 = 0, blit0 = 0, blen1 = 0, bp1 = 0, blit1 = 0;
-  int left = 0, fwd_left = 0, dstep = 1, bs0 = 0, bs1 = 0, mm = 0;
+  u32 blen0 = 0, bp0 = 0, blit0 = 0;
+  R0T keep = 0;                                                       // PASS 1: the row's r0 word, for the second run
+  int left = 0, fwd_left = 0, bwd_left = 0, dstep = 1, bs0 = 0, mm = 0;
   for (;;) {
     // ---- event round ----
-    const bool fin = have && left == 0;
+    bool fin = have && left == 0;
     if (fin) {
       const LzsDesc& d = sm.d[lb];
       if (PASS == 0) ((R0T*)d.r0)[aux] = defer ? F::R0_DEFER : (bs0 > 0 ? F::r0_pack(blen0, bp0) : (R0T)0);
       else {
         const u32 i = s - 1;
         FT* fo = (FT*)d.f + 2 * (u64)i;
-        fo[0] = defer ? F::F_DEFER : lzs_decide<IdxT>(d.minMatch, d.level, i - bp0, blen0, blit0, bs0);
-        fo[1] = defer ? F::F_DEFER : lzs_decide<IdxT>(d.minMatch, d.level, i - bp1, blen1, blit1, bs1);
+        const FT dd = defer ? F::F_DEFER : lzs_decide<IdxT>(d.minMatch, d.level, i - bp0, blen0, blit0, bs0);
+        if (pen) fo[0] = dd;                       // second run: the "no literal pending" decision
+        else if (div && !defer) {                  // first run accepted a candidate with a leading literal: run again
+          fo[1] = dd;
+          pen = true; div = false; fin = false;
+          const u32 bl = F::r0_blen(keep), bpp = F::r0_bp(keep);
+          blen0 = bl; bp0 = bpp; blit0 = 0; bs0 = (int)(bl * 8u) - zq_bitlen(i - bpp) - 11; stop0 = false;
+          x = qq - 1; dstep = -1; runmin = 0xffffffffu; carry = K::lcp(s_pk[qq]);
+          left = bwd_left;
+          if (left == 0) { x = qq + 1; dstep = 1; left = fwd_left; }
+        } else { fo[0] = dd; fo[1] = dd; }
       }
-      have = false;
+      if (fin) have = false;
     }
     pend -= __reduce_add_sync(ZQ_FULL, fin ? 1u << (8 * lb) : 0u);
     // leave the tiles this warp is through with
@@ -305,12 +319,12 @@ k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
           const u32 i = ss - 1;
           const u32 bl = F::r0_blen(a), bpp = F::r0_bp(a);
           const int bsc = (int)(bl * 8u) - zq_bitlen(i - bpp) - 11;
-          aux = K::bwt(w);
-          blen0 = blen1 = bl; bp0 = bp1 = bpp; blit0 = blit1 = 0; bs0 = bs1 = bsc; stop0 = stop1 = false;
+          aux = K::bwt(w); keep = a;
+          blen0 = bl; bp0 = bpp; blit0 = 0; bs0 = bsc; stop0 = false; pen = false; div = false;
         }
         qq = q0; s = ss; carry = K::lcp(w);
         have = true; x = qq - 1; dstep = -1; runmin = 0xffffffffu; defer = false;
-        left = (int)min(d.bucket, r);
+        left = bwd_left = (int)min(d.bucket, r);
         fwd_left = (int)min(d.bucket, n - 1 - r);
         mm = (int)d.minMatch;
         if (left == 0) { x = qq + 1; dstep = 1; left = fwd_left; }   // first row of the block: forward only
@@ -350,22 +364,19 @@ k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
         const u32 bw = K::bwt(w);
         const int ub = lzs_scale58((int)(rm * 8u) - 4);      // ((1+rm)*8 - 12) * 5/8
         stop0 = stop0 || ub <= bs0;
-        stop1 = stop1 || ub <= bs1;
-        const bool live = inr && !(stop0 && stop1);
+        const bool live = inr && !stop0;
         const bool valid = live && p != 0 && p < s;          // candidate p-1 < i
         const u32 l = 1u + rm;
         const u32 l1 = bw == aux ? 0u : 1u;
         const int base = (int)((l - l1) * 8u) - (32 - __clz(s - p)) - 11;
-        const int sc0 = lzs_scale58(base - (l1 ? 4 : 0)), sc1 = lzs_scale58(base);
+        const int sc = lzs_scale58(base - ((pen && l1) ? 4 : 0));
         const bool ok = valid && !capped;
-        const bool t0 = ok && !stop0 && sc0 > bs0, t1b = ok && !stop1 && sc1 > bs1;
-        blen0 = t0 ? l : blen0; bp0 = t0 ? p - 1 : bp0; blit0 = t0 ? l1 : blit0; bs0 = t0 ? sc0 : bs0;
-        blen1 = t1b ? l : blen1; bp1 = t1b ? p - 1 : bp1; blit1 = t1b ? l1 : blit1; bs1 = t1b ? sc1 : bs1;
-        const bool brk = (int)l < mm;                        // (l > 255 cannot happen below the cap)
-        stop0 = stop0 || (ok && (l < blen0 || brk));
-        stop1 = stop1 || (ok && (l < blen1 || brk));
+        const bool t0 = ok && sc > bs0;
+        blen0 = t0 ? l : blen0; bp0 = t0 ? p - 1 : bp0; blit0 = t0 ? l1 : blit0; bs0 = t0 ? sc : bs0;
+        div = div || (t0 && l1 != 0);
+        stop0 = stop0 || (ok && ((int)l < max((int)blen0, mm)));   // (l > 255 cannot happen below the cap)
         dnow = valid && capped;
-        go = live && !dnow && !(stop0 && stop1);
+        go = live && !dnow && !stop0;
       }
       defer = defer || dnow;
       // next step: same direction, or the first forward neighbour once the backward direction has ended
@@ -374,7 +385,7 @@ k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
       runmin = sw ? 0xffffffffu : rm;
       left = sw ? fwd_left : (go ? left - 1 : 0);
       dstep = sw ? 1 : dstep;
-      if (PASS == 1) { stop0 = stop0 && !sw; stop1 = stop1 && !sw; }
+      if (PASS == 1) stop0 = stop0 && !sw;
     }
   }
 }
