@@ -33,7 +33,8 @@ struct Sort16Smem {
   u32 bins[S16_BINS + 8];
   u32 cursor[S16_BINS];                  // next free row of every bin while the positions are dealt to their bins
   u32 cnt, prev_idx, fallback, pad0;     // pad0: end row of the current batch
-  u32 wsum[32];
+  u32 wsum[32], wlo[32], whi[32];
+  u32 blo, bhi, pad2[2];                 // first / last non-empty bin of the current batch
   ZqMbar bar;
   u64 pad1;
   alignas(16) u8 text[65536 + 64];
@@ -215,32 +216,41 @@ __device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort
     // (every thread looks at its 8 bins; at least the first bin fits: no bin is larger than the buffer)
     const u32 limit = rowbase + S16_BUF;
     {
-      u32 best = 0;
+      u32 best = 0, blo = S16_BINS, bhi = 0;     // end row of the batch; first / last non-empty bin in it
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { const u32 e = sm.bins[tid * 8 + q + 1]; if (e <= limit) best = max(best, e); }
-      best = __reduce_max_sync(ZQ_FULL, best);
-      if (lane == 0) sm.wsum[warp] = best;
-      if (tid == 0) sm.cnt = 0;
+      for (int q = 0; q < 8; ++q) {
+        const u32 b = tid * 8 + q, st = sm.bins[b], e = sm.bins[b + 1];
+        if (e <= limit) best = max(best, e);
+        if (e > st && st >= rowbase && e <= limit) { blo = min(blo, b); bhi = max(bhi, b); }
+      }
+      best = __reduce_max_sync(ZQ_FULL, best); blo = __reduce_min_sync(ZQ_FULL, blo); bhi = __reduce_max_sync(ZQ_FULL, bhi);
+      if (lane == 0) { sm.wsum[warp] = best; sm.wlo[warp] = blo; sm.whi[warp] = bhi; }
       __syncthreads();
-      best = 0;
-      for (u32 q = 0; q < S16_NT / 32; ++q) best = max(best, sm.wsum[q]);
+      best = 0; blo = S16_BINS; bhi = 0;
+      for (u32 q = 0; q < S16_NT / 32; ++q) { best = max(best, sm.wsum[q]); blo = min(blo, sm.wlo[q]); bhi = max(bhi, sm.whi[q]); }
       __syncthreads();
-      sm.pad0 = best;     // (every thread writes the same value)
+      sm.pad0 = best; sm.blo = blo; sm.bhi = bhi;     // (every thread writes the same values)
     }
     const u32 rowend = sm.pad0;
-    // 3a. this batch's rows, keyed by the first 6 bytes of their suffix
+    // 3a. this batch's rows, keyed by the leading bits of their suffix.  The 13 bin bits are replaced by the bin's number
+    // inside the batch (nb bits, usually 4-6), which leaves room for 48 - nb more bits of the suffix: two keys are equal
+    // iff the suffixes share their first 61 - nb bits, i.e. at least `from` whole bytes (7 for the text corpus).
+    const u32 blo = sm.blo, nb = (u32)zq_bitlen(sm.bhi - sm.blo), from = (61u - nb) >> 3;
     for (u32 j = tid; j < rowend - rowbase; j += S16_NT) {
       const u32 i = o_sa[rowbase + j];
-      S[j] = ((u64)s16_be32(T + i) << 32) | ((u64)(s16_be32(T + i + 4) >> 16) << 16) | i;
+      const u32 hi = s16_be32(T + i), lo = s16_be32(T + i + 4);
+      const u64 p64 = ((u64)hi << 32) | lo;
+      const u64 rel = (u64)((hi >> 19) - blo);
+      S[j] = (((rel << (48 - nb)) | ((p64 << 13) >> (16 + nb))) << 16) | i;
     }
     const u32 m = rowend - rowbase;
     u32 P = 16;
     while (P < m) P <<= 1;
     for (u32 t = m + tid; t < P; t += S16_NT) S[t] = ~0ull;
     __syncthreads();
-    // 3b. sort by (first 6 bytes, index)
+    // 3b. sort by (key, index)
     s16_bitonic(S, P);
-    // 3c. suffixes that share their first 6 bytes: the first of each run orders the run by direct comparison
+    // 3c. suffixes with equal keys: the first of each run orders the run by direct comparison
     for (u32 j = tid; j < m; j += S16_NT) {
       const u64 kj = S[j] >> 16;
       const bool head = (j == 0 || (S[j - 1] >> 16) != kj) && (j + 1 < m && (S[j + 1] >> 16) == kj);
@@ -252,7 +262,7 @@ __device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort
       for (u32 x = j + 1; x < e; ++x) {         // insertion sort on the index part
         const u32 v = (u32)S[x] & 0xffffu;
         u32 y = x;
-        while (y > j && s16_less(T, n, v, (u32)S[y - 1] & 0xffffu, 6, &deep)) { S[y] = S[y - 1]; --y; }
+        while (y > j && s16_less(T, n, v, (u32)S[y - 1] & 0xffffu, from, &deep)) { S[y] = S[y - 1]; --y; }
         S[y] = (kj << 16) | v;
       }
       if (deep) sm.fallback = 1;
@@ -266,11 +276,8 @@ __device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort
       const u32 b = (u32)cur & 0xffffu, row = rowbase + j;
       u32 l = 0;
       if (row > 0) {
-        const u64 prv = j ? S[j - 1] : 0;
-        const u32 a = j ? ((u32)prv & 0xffffu) : prev_last;
-        const u64 x = j ? ((cur ^ prv) >> 16) : 1;   // 48-bit prefixes; across batches the bins differ: compare from 0
-        if (j && x != 0) l = min((u32)(__clzll((long long)(x << 16)) >> 3), n - max(a, b));
-        else l = s16_lcp(T, n, a, b, j ? 6u : 0u, ZQ_LCP_CAP);
+        const u32 a = j ? ((u32)S[j - 1] & 0xffffu) : prev_last;
+        l = s16_lcp(T, n, a, b, 0u, ZQ_LCP_CAP);
       }
       const u32 bw = b > 0 ? (u32)T[b - 1] : 0u;
       o_sa[row] = (u16)b; o_lcp[row] = (u16)l; o_bwt[row] = (u8)bw; o_isa[b] = (u16)row;
