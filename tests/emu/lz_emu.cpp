@@ -52,7 +52,9 @@ static long run_scan_pipeline(std::vector<u8>& in, ZqUnit& u, ZqPlan& pl, std::v
   std::vector<LzToken> tok(tokcap);
   std::vector<u64> bitpos(tokcap);
   u64 tok_off = 0; u32 ntok = 0, next = 0, lzlen = 0, err = 0;
-  emu::launch(1, 128, 0, [&] { k_lz_walk<IdxT>(in.data(), &u, &pl, &todo, 1, work.data(), &tok_off, tok.data(), &ntok, &next); });
+  emu::launch(1, 128, 0, [&] { k_lz_walk<IdxT, false>(in.data(), &u, &pl, &todo, 1, work.data(), &tok_off, tok.data(), &ntok, &next); });
+  next = 0;
+  emu::launch(1, 128, 0, [&] { k_lz_walk<IdxT, true>(in.data(), &u, &pl, &todo, 1, work.data(), &tok_off, tok.data(), &ntok, &next); });
   if (ntok_out) *ntok_out = ntok;
   std::vector<u8> lz(((size_t)u.lz_cap + 15) / 16 * 16 + 16, 0);   // malloc'ed: 16-byte aligned like the device arena
   emu::launch(1, LZE_NT, sizeof(LzeSmem), [&] { k_lz_emit(in.data(), &u, &pl, &todo, 1, &tok_off, tok.data(), &ntok, bitpos.data(), lz.data(), &lzlen, &err); });

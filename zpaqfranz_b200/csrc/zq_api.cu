@@ -399,6 +399,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
         ZQ_CUDA(c, c->d_todo2.ensure(flat.size() * 4 + 4));
         ZQ_CUDA(c, cudaMemcpyAsync(c->d_todo2.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, c->stream));
         ZQ_CUDA(c, cudaMemsetAsync(c->d_err.as<u32>() + 4, 0, 48, c->stream));   // the work-queue counters of this wave
+        ZQ_CUDA(c, cudaMemsetAsync(c->d_err.as<u32>() + 1, 0, 8, c->stream));    // (slots 1, 2: the exact walk's)
         if (nscan) {
           const size_t LZS_SMEM16 = sizeof(LzsSmem<u16>) + (LZS_NT / 32) * sizeof(LzsQueue<u16>);
           const size_t LZS_SMEM32 = sizeof(LzsSmem<u32>) + (LZS_NT / 32) * sizeof(LzsQueue<u32>);
@@ -463,8 +464,16 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
             else k_lz_scan<u32, 1><<<sgrid1, LZS_NT, LZS_SMEM32, c->stream>>>(du, dp, tl, tf, cnt, tpu, c->d_work.as<u8>(), ctr + 3 * v + 1);
             tstop(c, 8 + 1);
             tstart(c, 8 + 2);
-            if (v == 0) k_lz_walk<u16><<<wgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), d_tokoff + first, c->d_tok.as<LzToken>(), d_ntok + first, ctr + 3 * v + 2);
-            else k_lz_walk<u32><<<wgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), d_tokoff + first, c->d_tok.as<LzToken>(), d_ntok + first, ctr + 3 * v + 2);
+            // lean walk first, then the form with the exact evaluator for the blocks that met a deferred position
+            ZQ_CUDA(c, cudaMemsetAsync(d_ntok + first, 0, (size_t)cnt * 4, c->stream));
+            if (v == 0) {
+              k_lz_walk<u16, false><<<wgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), d_tokoff + first, c->d_tok.as<LzToken>(), d_ntok + first, ctr + 3 * v + 2);
+              k_lz_walk<u16, true><<<wgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), d_tokoff + first, c->d_tok.as<LzToken>(), d_ntok + first, c->d_err.as<u32>() + 2);
+            } else {
+              k_lz_walk<u32, false><<<wgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), d_tokoff + first, c->d_tok.as<LzToken>(), d_ntok + first, ctr + 3 * v + 2);
+              k_lz_walk<u32, true><<<wgrid, 128, 0, c->stream>>>(d_in, du, dp, tl, cnt, c->d_work.as<u8>(), d_tokoff + first, c->d_tok.as<LzToken>(), d_ntok + first, c->d_err.as<u32>() + 1);
+            }
+            ++c->launches;
             tstop(c, 8 + 2);
             c->launches += 3;
             first += cnt;

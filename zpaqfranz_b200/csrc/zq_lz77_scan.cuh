@@ -418,8 +418,12 @@ __device__ LzsDecision lzs_decide_exact(const u8* __restrict__ in, u32 n, const 
 }
 
 // One warp per block.  tok_off[t] = first token slot of todo entry t; ntok[t] = tokens written.
-template <typename IdxT>
-__global__ void __launch_bounds__(128, 6)
+// EXACT = false: the lean form (no exact evaluator in the kernel: half the registers, twice the warps per SM); a block
+// in which the walk meets a deferred position is abandoned with ntok[t] = LZW_REDO and walked again by the EXACT = true
+// form, which is launched right after and looks at those blocks only.
+constexpr u32 LZW_REDO = 0xffffffffu;
+template <typename IdxT, bool EXACT>
+__global__ void __launch_bounds__(128, EXACT ? 6 : 12)
 k_lz_walk(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans,
           const int* __restrict__ todo, int ntodo, u8* __restrict__ work_base, const u64* __restrict__ tok_off,
           LzToken* __restrict__ tok_base, u32* __restrict__ ntok, u32* next_unit) {
@@ -431,10 +435,12 @@ k_lz_walk(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, cons
     if (lane == 0) t = (int)atomicAdd(next_unit, 1u);
     t = __shfl_sync(ZQ_FULL, t, 0);
     if (t >= ntodo) break;
+    if (EXACT && ntok[t] != LZW_REDO) continue;
     const ZqUnit u = units[todo[t]];
     const LzsParams P = lzs_params(plans[u.plan]);
     const u32 n = u.n;
     const u8* in = in_base + u.in_off;
+    bool redo = false;
     const LzsView<IdxT> v = lzs_view<IdxT>(work_base, u.work_off, n);
     LzToken* tok = tok_base + tok_off[t];
     const u32 maxLiteral = 1u << 12;
@@ -451,7 +457,7 @@ k_lz_walk(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, cons
     FT c0 = 0, c1 = 0, n0 = 0, n1 = 0;   // decisions of the current / next window for lit == 0 / lit > 0
     if (lane < n) { c0 = v.f[2 * (u64)lane]; c1 = v.f[2 * (u64)lane + 1]; }
     if (32 + lane < n) { n0 = v.f[2 * (u64)(32 + lane)]; n1 = v.f[2 * (u64)(32 + lane) + 1]; }
-    while (i < n) {
+    while (i < n && !redo) {
       if (i >= w0 + 32) {
         if (i < w0 + 64) { w0 += 32; c0 = n0; c1 = n1; }
         else { w0 = i & ~31u; c0 = c1 = 0; if (w0 + lane < n) { c0 = v.f[2 * (u64)(w0 + lane)]; c1 = v.f[2 * (u64)(w0 + lane) + 1]; } }
@@ -461,7 +467,7 @@ k_lz_walk(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, cons
       // positions of this window that do not end as a plain literal, per state
       const u32 m0 = __ballot_sync(ZQ_FULL, c0 != 0), m1 = __ballot_sync(ZQ_FULL, c1 != 0);
       const u32 wend = min(32u, n - w0);
-      while (i < w0 + wend) {
+      while (i < w0 + wend && !redo) {
         const u32 j = i - w0;
         if (lit > 0) {   // hop over the literals up to the next candidate position of the lit > 0 state
           const u32 ahead = m1 >> j;
@@ -476,8 +482,10 @@ k_lz_walk(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, cons
         }
         const FT dd = __shfl_sync(ZQ_FULL, lit ? c1 : c0, j);
         LzsDecision dc;
-        if (dd & F::F_DEFER) dc = lzs_decide_exact<IdxT>(in, n, v, P, i, lit);
-        else { dc.match = (dd & F::F_MATCH) != 0; dc.blit = F::f_blit(dd); dc.blen = F::f_blen(dd); dc.off = F::f_off(dd); }
+        if (dd & F::F_DEFER) {
+          if (EXACT) dc = lzs_decide_exact<IdxT>(in, n, v, P, i, lit);
+          else { redo = true; dc.match = false; dc.blit = dc.blen = dc.off = 0; }
+        } else { dc.match = (dd & F::F_MATCH) != 0; dc.blit = F::f_blit(dd); dc.blen = F::f_blen(dd); dc.off = F::f_off(dd); }
         if (dc.match) {
           const u32 blit = dc.blit, blen = dc.blen, off = dc.off;
           lit += blit;
@@ -490,6 +498,7 @@ k_lz_walk(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, cons
         }
       }
     }
+    if (redo) { if (lane == 0) ntok[t] = LZW_REDO; continue; }
     if (lit) LZS_PUSH(n - lit, lit, 0u, 0u);
     if ((nt & 31u) && lane < (nt & 31u)) *(uint4*)&tok[(nt & ~31u) + lane] = make_uint4(mine.pos, mine.lit, mine.mlen, mine.off);
 #undef LZS_PUSH

@@ -10,11 +10,11 @@
 // group of more than 128 suffixes sharing 6 bytes, or two suffixes sharing more than 512 -- is handed to k_suffix_sort
 // through a flag; nothing is approximated.
 //
-//   shared memory (196 KB, one CTA per SM):  text 64 KiB | 8192 bin starts | 8192 bin cursors | 8192 x u64 sort buffer
+//   shared memory (225 KB, one CTA per SM):  text 64 KiB | 8192 bin starts | 16384 x u64 sort buffer (bin cursors first)
 //   1. text -> shared memory (bulk async copy when the block is 16-byte aligned)
 //   2. histogram of the 13-bit key (byte 0, top 5 bits of byte 1) with shared-memory atomics, exclusive scan: the
 //      start row of every bin.  Bins are only a way to cut the suffix array into batches that fit the sort buffer:
-//      a batch takes as many whole bins as fit 8192 rows.
+//      a batch takes as many whole bins as fit the buffer.
 //      Every position is dealt to its bin's rows of the (global, L2-resident) sa array -- a counting sort on 13 bits.
 //   3. per batch: its rows are read back (coalesced), keyed by the first 6 bytes of their suffix, sorted; ties
 //      resolved; then the rows are final and sa / lcp / bwt / pk are written in row order and isa is scattered.
@@ -25,13 +25,15 @@ namespace zqdev {
 
 constexpr int S16_NT = 1024;
 constexpr u32 S16_BINS = 8192;
-constexpr u32 S16_BUF = 8192;        // sort buffer capacity (elements) = rows per batch at most
+#ifndef S16_BUF_ELEMS
+#define S16_BUF_ELEMS 16384
+#endif
+constexpr u32 S16_BUF = S16_BUF_ELEMS;   // sort buffer capacity (elements) = rows per batch at most
 constexpr u32 S16_MAXGROUP = 128;    // largest tie group ordered by direct comparison
 constexpr u32 S16_MAXDEPTH = 512;    // longest common prefix followed by direct comparison
 
 struct Sort16Smem {
   u32 bins[S16_BINS + 8];
-  u32 cursor[S16_BINS];                  // next free row of every bin while the positions are dealt to their bins
   u32 cnt, prev_idx, fallback, pad0;     // pad0: end row of the current batch
   u32 wsum[32], wlo[32], whi[32];
   u32 blo, bhi, pad2[2];                 // first / last non-empty bin of the current batch
@@ -203,9 +205,10 @@ __device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort
   const u64 stride = zq_work_stride(n, 2);
   u16* __restrict__ o_sa = (u16*)w; u16* __restrict__ o_isa = (u16*)(w + stride);
   // deal the positions to the rows of their bins (order inside a bin does not matter: it is sorted next)
-  for (u32 b = tid; b < S16_BINS; b += S16_NT) sm.cursor[b] = sm.bins[b];
+  u32* cursor = reinterpret_cast<u32*>(sm.buf);     // next free row of every bin (the sort buffer is not in use yet)
+  for (u32 b = tid; b < S16_BINS; b += S16_NT) cursor[b] = sm.bins[b];
   __syncthreads();
-  for (u32 i = tid; i < n; i += S16_NT) o_sa[atomicAdd(&sm.cursor[((u32)T[i] << 5) | (T[i + 1] >> 3)], 1u)] = (u16)i;
+  for (u32 i = tid; i < n; i += S16_NT) o_sa[atomicAdd(&cursor[((u32)T[i] << 5) | (T[i + 1] >> 3)], 1u)] = (u16)i;
   __syncthreads();
   u16* __restrict__ o_lcp = (u16*)(w + 2 * stride);
   u8* __restrict__ o_bwt = w + 2 * stride + zq_work_stride(n, 2);
