@@ -250,6 +250,10 @@ int zq_suffix_array(zq_ctx* ctx, const uint8_t* data, uint32_t n, uint32_t* sa_o
  * zlib and the reference's XXH64; not yet run on hardware. */
 int zq_crc32(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests);
 int zq_xxh64(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests);
+/* MD5 (16 bytes) and SHA3-256 (32 bytes) of n buffers: the -md5 / -sha3 file hashes of updatehash (MD5::add Z:21616,
+ * SHA3::add Z:21337). */
+int zq_md5(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests16);
+int zq_sha3_256(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests32);
 
 /* ---- ZPAQL -> CUDA C translation (host only, no GPU needed) -------------------------------------
  * libzpaq compiles a block's HCOMP/PCOMP to x86 when the block starts (ZPAQL::assemble, Z:16358, called from ZPAQL::run Z:17677).

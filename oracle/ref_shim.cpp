@@ -120,6 +120,14 @@ void zref_xxh3_128(const unsigned char* in, unsigned long long n, unsigned char*
   for (int i = 0; i < 8; ++i) out16[i] = (unsigned char)(h.high64 >> (56 - 8 * i));
   for (int i = 0; i < 8; ++i) out16[8 + i] = (unsigned char)(h.low64 >> (56 - 8 * i));
 }
+// MD5 / SHA3-256 as Jidac::updatehash feeds them (MD5::add Z:21616, SHA3::add Z:21337); digests as raw bytes
+void zref_md5(const unsigned char* in, unsigned long long n, unsigned char* out16) {
+  MD5 h; h.add(in, n); h.getHash(out16);
+}
+void zref_sha3_256(const unsigned char* in, unsigned long long n, unsigned char* out32) {
+  SHA3 h; h.add(in, n); const std::string x = h.getHash();
+  for (int k = 0; k < 32; ++k) out32[k] = (unsigned char)strtoul(x.substr(2 * k, 2).c_str(), 0, 16);
+}
 void zref_blake3(const unsigned char* in, unsigned long long n, unsigned char* out32) {
   blake3_hasher h; blake3_hasher_init(&h); blake3_hasher_update(&h, in, n);
   blake3_hasher_finalize(&h, out32, 32);

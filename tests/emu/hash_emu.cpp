@@ -7,10 +7,13 @@
 #include "zq_sha1.cuh"
 #include "zq_hashes.cuh"
 #include "zq_hashes2.cuh"
+#include "zq_hashes3.cuh"
+#include <cmath>
 
 using namespace zqdev;
 
-// kind: 0 SHA-1 (20 B), 1 SHA-256 (32 B), 2 XXH3-128 (16 B), 3 BLAKE3 (32 B), 4 CRC-32 (4 B), 5 XXH64 (8 B)
+// kind: 0 SHA-1 (20 B), 1 SHA-256 (32 B), 2 XXH3-128 (16 B), 3 BLAKE3 (32 B), 4 CRC-32 (4 B), 5 XXH64 (8 B), 6 MD5 (16 B),
+// 7 SHA3-256 (32 B)
 extern "C" int emu_hash(int kind, const uint8_t* base, const uint64_t* off, const uint64_t* len, int n, uint8_t* digests) {
   if (n <= 0) return 0;
   if (kind == 0) {
@@ -34,6 +37,12 @@ extern "C" int emu_hash(int kind, const uint8_t* base, const uint64_t* off, cons
     emu::launch((n + 127) / 128, 128, 0, [&] { k_crc32_fold(len, first.data(), n, &t, part.data(), (u32*)digests); });
   } else if (kind == 5) {
     emu::launch((n + 127) / 128, 128, 0, [&] { k_xxh64_many(base, off, len, n, (u64*)digests); });
+  } else if (kind == 6) {
+    static Md5Consts K;     // as zq_md5 in zq_api.cu builds it
+    for (int i = 0; i < 64; ++i) K.K[i] = (uint32_t)(long long)floor(fabs(sin((double)(i + 1))) * 4294967296.0);
+    emu::launch((n + 127) / 128, 128, 0, [&] { k_md5_many(base, off, len, n, &K, digests); });
+  } else if (kind == 7) {
+    emu::launch((n + 127) / 128, 128, 0, [&] { k_sha3_256_many(base, off, len, n, digests); });
   } else {
     std::vector<u64> first(n + 1);
     std::vector<int> multi;

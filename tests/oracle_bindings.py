@@ -143,6 +143,12 @@ class Ref:
     def blake3(self, d):
         return self._digest(self.lib.zref_blake3, 32, d)
 
+    def md5(self, d):
+        return self._digest(self.lib.zref_md5, 16, d)
+
+    def sha3_256(self, d):
+        return self._digest(self.lib.zref_sha3_256, 32, d)
+
     def xxh64(self, d):
         return self._digest(self.lib.zref_xxh64, 8, d)
 

@@ -73,3 +73,18 @@ def test_crc32_xxh64_match_reference(ctx, ref):
         assert crc[i].tobytes() == zlib.crc32(b).to_bytes(4, "little")
         if ref is not None:
             assert xx[i].tobytes() == ref.xxh64(b)
+
+
+def test_md5_sha3_match_reference(ctx, ref):
+    import hashlib
+    bufs = [b"", b"ABCDE", bytes(5000), bytes(corpus.text_unit(4, 70001)), bytes(corpus.random_unit(5, 1 << 20))] + \
+           [bytes(corpus.random_unit(80, k)) for k in (55, 56, 64, 119, 135, 136, 137)]
+    lens = np.array([len(b) for b in bufs], dtype=np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    arena = np.frombuffer(b"".join(bufs) + b"\0", dtype=np.uint8)
+    m, s3 = ctx.md5(arena, offs, lens), ctx.sha3_256(arena, offs, lens)
+    for i, b in enumerate(bufs):
+        assert m[i].tobytes() == hashlib.md5(b).digest()
+        assert s3[i].tobytes() == hashlib.sha3_256(b).digest()
+        if ref is not None:
+            assert m[i].tobytes() == ref.md5(b) and s3[i].tobytes() == ref.sha3_256(b)

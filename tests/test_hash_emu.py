@@ -23,7 +23,8 @@ def emu():
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "libhashemu.so")
     deps = [os.path.join(EMU, "hash_emu.cpp"), os.path.join(EMU, "simt_emu.h"), os.path.join(CSRC, "zq_sha1.cuh"),
-            os.path.join(CSRC, "zq_hashes.cuh"), os.path.join(CSRC, "zq_hashes2.cuh"), os.path.join(CSRC, "zq_common.cuh")]
+            os.path.join(CSRC, "zq_hashes.cuh"), os.path.join(CSRC, "zq_hashes2.cuh"), os.path.join(CSRC, "zq_hashes3.cuh"),
+            os.path.join(CSRC, "zq_common.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I" + os.path.join(EMU, "shim"), "-I" + CSRC,
                         "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-o", lib, deps[0]], check=True)
@@ -71,3 +72,13 @@ def test_crc32_xxh64(emu, ref, shift):
     if ref is not None:
         assert _run(emu, 4, 4, bufs, shift) == [ref.crc32(b) for b in bufs]
         assert _run(emu, 5, 8, bufs, shift) == [ref.xxh64(b) for b in bufs]
+
+
+@pytest.mark.parametrize("shift", [0, 1, 5])
+def test_md5_sha3(emu, ref, shift):
+    bufs = BUFS + [bytes(corpus.random_unit(80, k)) for k in (55, 56, 63, 64, 65, 119, 120, 135, 136, 137, 272, 4097)]
+    assert _run(emu, 6, 16, bufs, shift) == [hashlib.md5(b).digest() for b in bufs]
+    assert _run(emu, 7, 32, bufs, shift) == [hashlib.sha3_256(b).digest() for b in bufs]
+    if ref is not None:       # the reference's own classes (MD5 Z:21432, SHA3 Z:21189) agree
+        assert [ref.md5(b) for b in bufs[:12]] == [hashlib.md5(b).digest() for b in bufs[:12]]
+        assert [ref.sha3_256(b) for b in bufs[:12]] == [hashlib.sha3_256(b).digest() for b in bufs[:12]]

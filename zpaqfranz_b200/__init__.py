@@ -77,7 +77,7 @@ def _load():
     lib.zq_model_config.argtypes = [C.c_int]
     lib.zq_assemble_config.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_void_p, u32p, C.c_void_p, u32p, C.c_char_p, C.c_size_t,
                                        C.c_char_p, C.c_size_t]
-    for name in ("zq_sha1", "zq_sha256", "zq_xxh3_128", "zq_blake3", "zq_sha1_device", "zq_crc32", "zq_xxh64"):
+    for name in ("zq_sha1", "zq_sha256", "zq_xxh3_128", "zq_blake3", "zq_sha1_device", "zq_crc32", "zq_xxh64", "zq_md5", "zq_sha3_256"):
         getattr(lib, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.zq_fragment.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -443,6 +443,12 @@ class Context:
 
     def blake3(self, arena, offsets, lengths):
         return self._hash(lib.zq_blake3, 32, arena, offsets, lengths)
+
+    def md5(self, arena, offsets, lengths):
+        return self._hash(lib.zq_md5, 16, arena, offsets, lengths)
+
+    def sha3_256(self, arena, offsets, lengths):
+        return self._hash(lib.zq_sha3_256, 32, arena, offsets, lengths)
 
     def crc32(self, arena, offsets, lengths):
         """CRC-32 per buffer as little-endian bytes (4 per row)."""

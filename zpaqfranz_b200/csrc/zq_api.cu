@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +23,7 @@
 #include "zq_frame.cuh"
 #include "zq_hashes.cuh"
 #include "zq_hashes2.cuh"
+#include "zq_hashes3.cuh"
 #include "zq_lz77.cuh"
 #include "zq_lz77_scan.cuh"
 #include "zq_sha1.cuh"
@@ -1248,6 +1250,30 @@ int zq_crc32(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const u
 int zq_xxh64(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
   return hash_many(c, n, base, off, len, digests, 8, [&](u64* d_off, u64* d_len, std::vector<uint64_t>&) {
     zqdev::k_xxh64_many<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_in.as<u8>(), d_off, d_len, n, c->d_sha.as<u64>());
+    ++c->launches;
+    return ZQ_OK;
+  });
+}
+
+// MD5 / SHA3-256 of n buffers (Jidac::updatehash with -md5 / -sha3: MD5::add Z:21616, SHA3::add Z:21337)
+int zq_md5(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
+  return hash_many(c, n, base, off, len, digests, 16, [&](u64* d_off, u64* d_len, std::vector<uint64_t>&) -> int {
+    static const zqdev::Md5Consts K = [] {      // floor(2^32 |sin(i+1)|), RFC 1321 section 3.4
+      zqdev::Md5Consts k;
+      for (int i = 0; i < 64; ++i) k.K[i] = (uint32_t)(long long)floor(fabs(sin((double)(i + 1))) * 4294967296.0);
+      return k;
+    }();
+    ZQ_CUDA(c, c->d_tok.ensure(sizeof K));
+    ZQ_CUDA(c, cudaMemcpyAsync(c->d_tok.p, &K, sizeof K, cudaMemcpyHostToDevice, c->stream));
+    zqdev::k_md5_many<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_in.as<u8>(), d_off, d_len, n, c->d_tok.as<zqdev::Md5Consts>(), c->d_sha.as<u8>());
+    ++c->launches;
+    return ZQ_OK;
+  });
+}
+
+int zq_sha3_256(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests) {
+  return hash_many(c, n, base, off, len, digests, 32, [&](u64* d_off, u64* d_len, std::vector<uint64_t>&) {
+    zqdev::k_sha3_256_many<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_in.as<u8>(), d_off, d_len, n, c->d_sha.as<u8>());
     ++c->launches;
     return ZQ_OK;
   });
