@@ -79,6 +79,7 @@ struct zq_ctx {
   int lz_old = 0;                         // 1: warp-per-block LZ77 parser for every block (ZQ_LZ_OLD=1); 0: position-parallel scan/walk/emit (zq_lz77_scan.cuh)
   int scan_occ[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of k_lz_scan<u16/u32, pass> (queried once)
   int cm_jit = 1;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter; 2: generated coder too (ZQ_CM_JIT)
+  bool cm_jit_auto = true;                // no ZQ_CM_JIT in the environment: translate only the models whose context warp is the bottleneck (<= 8 components)
   struct JitProg { cudaLibrary_t lib = nullptr; cudaKernel_t ctx = nullptr, code = nullptr; };
   std::map<std::string, JitProg> jit_cache;   // translated context program (+ generated coder) per model header
   DevBuf d_ctx, d_ctxoff, d_ctxargs;
@@ -547,6 +548,9 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
         uint64_t ctx_elems = 0;
         for (auto& g : groups) {
           const ZqCmPlan& cp = cmplans[g.first];
+          // measured on B200: -m3 (2 components) 442 -> 294 ms per 100 MB with the translated program, -m5 (22) 10 % slower
+          // (its coder is the critical path and the context table of every byte costs traffic)
+          if (c->cm_jit_auto && cp.n > 8) continue;
           const u8* hc = blob.data() + cp.hcomp_off;
           ZqCmPlan kp = cp; kp.hcomp_off = 0; kp.fill_first = 0;       // per-call positions are not part of the model
           std::string key((const char*)&kp, sizeof(ZqCmPlan));          // components, sizes and table offsets
@@ -751,7 +755,7 @@ zq_ctx* zq_create(int device) {
   if (const char* s = getenv("ZQ_FRAG_SEG")) { uint64_t v = strtoull(s, nullptr, 10); if (v >= 64) c->frag_seg = v; }
   if (const char* s = getenv("ZQ_CM_PREFETCH")) c->cm_prefetch = atoi(s);
   if (const char* s = getenv("ZQ_CM_FAST")) c->cm_fast = atoi(s);
-  if (const char* s = getenv("ZQ_CM_JIT")) c->cm_jit = atoi(s);
+  if (const char* s = getenv("ZQ_CM_JIT")) { c->cm_jit = atoi(s); c->cm_jit_auto = false; }
   if (const char* s = getenv("ZQ_LZ_OLD")) c->lz_old = atoi(s) ? 1 : 0;
   if (const char* s = getenv("ZQ_SORT16")) c->sort16 = atoi(s);
   if (const char* s = getenv("ZQ_SORT_NT")) c->sort_nt = atoi(s);
