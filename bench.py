@@ -304,7 +304,7 @@ def main():
     ap.add_argument("--ref-sample-mb", type=float, default=400.0, help="reference arm / cpu_baseline: input MB per step (c2 scale)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2,
+    ap.add_argument("--inflight", type=int, default=4,
                     help="c2: batches in flight (zq_pipe lanes): the next step's copies/kernels fill the tail of the current one")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -303,22 +303,154 @@ const char* kPcompE8Only =
     "c++ a=c a> 4 if a=*b out a&= 254 a== 232 if a=b a>>= 24 a++ a&= 254 a== 0 if a=b a>>= 24 "
     "a<<= 24 d=a a=b a-=c a+= 5 a<<= 8 a>>= 8 a|=d b=a endif endif endif endif halt end\n";
 
-// One parsed model command: letter + numeric arguments.
-struct Cmd { char letter; std::vector<int> v; };  // v[0] unused (keeps the reference's 1-based N indices)
+// One parsed model command: letter + numeric arguments (v[0] = the letter, v[1..] = its numbers: the format's own
+// 1-based $N numbering).
+typedef std::vector<int> Cmd;
 
-}  // namespace
-
-// -------------------------------------------------------------------------------------------------
-std::string make_config(const std::string& method_s, int args[9]) {
-  const char* m = method_s.c_str();
-  const char type = m[0];
-  if (!(type == 'x' || type == 's' || type == '0' || type == 'i')) throw Error("Unsupported method");
+// "x4,1,4,0,7,21,1c0,0,511i2..." -> args[0..8] and the list of model commands behind them
+std::vector<Cmd> split_method(const std::string& method_s, int args[9]) {
+  const char* m = method_s.c_str() + 1;
   for (int i = 0; i < 9; ++i) args[i] = 0;
-  ++m;
   for (int i = 0; i < 9 && (isdigit((unsigned char)*m) || *m == ',' || *m == '.'); ++m) {
     if (isdigit((unsigned char)*m)) args[i] = args[i] * 10 + (*m - '0');
     else if (++i < 9) args[i] = 0;
   }
+  std::vector<Cmd> cmds;
+  while (*m) {
+    Cmd v(1, (unsigned char)*m++);
+    if (isdigit((unsigned char)*m)) {
+      v.push_back(*m++ - '0');
+      while (isdigit((unsigned char)*m) || *m == ',' || *m == '.') {
+        if (isdigit((unsigned char)*m)) v.back() = v.back() * 10 + (*m++ - '0');
+        else { v.push_back(0); ++m; }
+      }
+    }
+    cmds.push_back(v);
+  }
+  return cmds;
+}
+
+// Grows the COMP list and the HCOMP program of a model, one method command at a time.  Conventions of every generated
+// HCOMP (they are part of the stored header, hence of the format): M = backwards-filling history of the last 64 KiB,
+// C -> newest byte, H[0..254] = component contexts, H[255+b] = position of byte b's last occurrence; for byte-LZ77 R1/R2
+// track the parse state of the code stream.
+struct ModelBuilder {
+  int membits, ncomp = 0, sb = 5;
+  std::string comp, hc;
+
+  void context(Cmd v) {   // 'c': ICM or CM over a hashed (periodic | distance | masked-byte) context
+    while (v.size() < 3) v.push_back(0);
+    sb = 11 + (v[2] < 256 ? bitlen((unsigned)v[2]) : 6);
+    for (size_t i = 3; i < v.size(); ++i) if (v[i] < 512) sb += popcount_u((unsigned)v[i]) * 3 / 4;
+    if (sb > membits) sb = membits;
+    comp += num(ncomp) + " ";
+    if (v[1] % 1000 == 0) comp += "icm " + num(sb - 6 - v[1] / 1000) + "\n";
+    else comp += "cm " + num(sb - 2 - v[1] / 1000) + " " + num(v[1] % 1000 - 1) + "\n";
+    hc += "d= " + num(ncomp) + " *d=0\n";
+    if (v[2] > 1 && v[2] <= 255) {
+      const bool pow2 = bitlen((unsigned)v[2]) != bitlen((unsigned)v[2] - 1);
+      hc += pow2 ? "a=c a&= " + num(v[2] - 1) + " hashd\n" : "a=c a%= " + num(v[2]) + " hashd\n";
+    } else if (v[2] >= 1000 && v[2] <= 1255) {
+      hc += "a= 255 a+= " + num(v[2] - 1000) + " d=a a=*d a-=c a> 255 if a= 255 endif d= " + num(ncomp) + " hashd\n";
+    }
+    for (size_t i = 3; i < v.size(); ++i) {
+      const int x = v[i];
+      if (i == 3) hc += "b=c ";
+      if (x == 255) hc += "a=*b hashd\n";
+      else if (x > 0 && x < 255) hc += "a=*b a&= " + num(x) + " hashd\n";
+      else if (x >= 256 && x < 512) {
+        hc += "a=r 1 a> 1 if a=r 2 a< 64 if a=*b ";
+        if (x < 511) hc += "a&= " + num(x - 256);
+        hc += " hashd else a>>= 6 hashd a=r 1 hashd endif else a= 255 hashd a=r 2 hashd endif\n";
+      }
+      else if (x >= 1256) hc += "a= " + num(((x - 1000) >> 8) & 255) + " a<<= 8 a+= " + num((x - 1000) & 255) + " a+=b b=a\n";
+      else if (x > 1000) hc += "a= " + num(x - 1000) + " a+=b b=a\n";
+      if (i + 1 < v.size() && x < 512) hc += "b++ ";
+    }
+    ++ncomp;
+  }
+
+  void combiner(Cmd v) {   // 'm' MIX, 't' MIX2, 's' SSE over the components so far
+    const int L = v[0];
+    if (ncomp <= (L == 't' ? 1 : 0)) return;
+    if (v.size() <= 1) v.push_back(8);
+    if (v.size() <= 2) v.push_back(24 + 8 * (L == 's'));
+    if (L == 's' && v.size() <= 3) v.push_back(255);
+    comp += num(ncomp);
+    sb = 5 + v[1] * 3 / 4;
+    if (L == 'm') comp += " mix " + num(v[1]) + " 0 " + num(ncomp) + " " + num(v[2]) + " 255\n";
+    else if (L == 't') comp += " mix2 " + num(v[1]) + " " + num(ncomp - 1) + " " + num(ncomp - 2) + " " + num(v[2]) + " 255\n";
+    else comp += " sse " + num(v[1]) + " " + num(ncomp - 1) + " " + num(v[2]) + " " + num(v[3]) + "\n";
+    if (v[1] > 8) {  // order-1/2 byte context shifted past the 8 partial-byte bits
+      hc += "d= " + num(ncomp) + " *d=0 b=c a=0\n";
+      int bits = v[1];
+      for (; bits >= 16; bits -= 8) { hc += "a<<= 8 a+=*b"; if (bits > 16) hc += " b++"; hc += "\n"; }
+      if (bits > 8) hc += "a<<= 8 a+=*b a>>= " + num(16 - bits) + "\n";
+      hc += "a<<= 8 *d=a\n";
+    }
+    ++ncomp;
+  }
+
+  void isse_chain(Cmd v) {   // 'i': each link extends the previous hash by N bytes
+    if (ncomp <= 0) return;
+    hc += "d= " + num(ncomp - 1) + " b=c a=*d d++\n";
+    for (size_t i = 1; i < v.size() && ncomp < 254; ++i) {
+      for (int j = 0; j < v[i] % 10; ++j) {
+        hc += "hash ";
+        if (i + 1 < v.size() || j < v[i] % 10 - 1) hc += "b++ ";
+        sb += 6;
+      }
+      hc += "*d=a";
+      if (i + 1 < v.size()) hc += " d++";
+      hc += "\n";
+      if (sb > membits) sb = membits;
+      comp += num(ncomp) + " isse " + num(sb - 6 - v[i] / 10) + " " + num(ncomp - 1) + "\n";
+      ++ncomp;
+    }
+  }
+
+  void match(Cmd v) {   // 'a'
+    if (v.size() <= 1) v.push_back(24);
+    while (v.size() < 4) v.push_back(0);
+    comp += num(ncomp) + " match " + num(membits - v[3] - 2) + " " + num(membits - v[2]) + "\n";
+    hc += "d= " + num(ncomp) + " a=*d a*= " + num(v[1]) + " a+=*c a++ *d=a\n";
+    sb = 5 + (membits - v[2]) * 3 / 4;
+    ++ncomp;
+  }
+
+  void words(Cmd v) {   // 'w': word-oriented ICM-ISSE chain
+    static const int dflt[7] = {0, 1, 65, 26, 223, 20, 0};
+    for (size_t k = v.size(); k <= 6; ++k) v.push_back(dflt[k]);
+    comp += num(ncomp) + " icm " + num(membits - 6 - v[6]) + "\n";
+    for (int i = 1; i < v[1]; ++i)
+      comp += num(ncomp + i) + " isse " + num(membits - 6 - v[6]) + " " + num(ncomp + i - 1) + "\n";
+    hc += "a=*c a&= " + num(v[4]) + " a-= " + num(v[2]) + " a&= 255 a< " + num(v[3]) + " if\n";
+    for (int i = 0; i < v[1]; ++i)
+      hc += (i == 0 ? "  d= " + num(ncomp) : std::string("  d++")) + " a=*d a*= " + num(v[5]) + " a+=*c a++ *d=a\n";
+    hc += "else\n";
+    for (int i = v[1] - 1; i > 0; --i) hc += "  d= " + num(ncomp + i - 1) + " a=*d d++ *d=a\n";
+    hc += "  d= " + num(ncomp) + " *d=0\nendif\n";
+    ncomp += v[1] - 1;
+    sb = membits - v[6];
+    ++ncomp;
+  }
+};
+
+// method letter -> what it adds to the model
+const struct { char letter; void (ModelBuilder::*add)(Cmd); } kModelCommands[] = {
+    {'c', &ModelBuilder::context}, {'m', &ModelBuilder::combiner}, {'t', &ModelBuilder::combiner}, {'s', &ModelBuilder::combiner},
+    {'i', &ModelBuilder::isse_chain}, {'a', &ModelBuilder::match}, {'w', &ModelBuilder::words},
+};
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// Method string -> ZPAQL source of the block's model and post-processor (the job of makeConfig, Z:19615): a pre-pass
+// header chosen by args[1], then one table-driven step per model command.
+std::string make_config(const std::string& method_s, int args[9]) {
+  const char type = method_s.c_str()[0];
+  if (!(type == 'x' || type == 's' || type == '0' || type == 'i')) throw Error("Unsupported method");
+  const std::vector<Cmd> cmds = split_method(method_s, args);
   if (type == '0') return "comp 0 0 0 0 0 hcomp end\n";
 
   const int lz = args[1] & 3;
@@ -329,118 +461,18 @@ std::string make_config(const std::string& method_s, int args[9]) {
   else if (lz == 3) { hdr = "comp 9 16 $1+20 $1+20 "; post = pcomp_ibwt(e8, args[0]); }
   else { hdr = "comp 9 16 0 0 "; post = e8 ? kPcompE8Only : "end\n"; }
 
-  // Context model. Conventions of every generated HCOMP: M = backwards-filling history of the last
-  // 64 KiB, C -> newest byte, H[0..254] = component contexts, H[255+b] = position of byte b's last
-  // occurrence; for byte-LZ77 R1/R2 track the parse state of the code stream.
-  const int membits = args[0] + 20;
-  int ncomp = 0, sb = 5;
-  std::string comp, hc = "hcomp\nc-- *c=a a+= 255 d=a *d=c\n";
+  ModelBuilder mb;
+  mb.membits = args[0] + 20;
+  mb.hc = "hcomp\nc-- *c=a a+= 255 d=a *d=c\n";
   if (lz == 2)
-    hc += "a=r 1 a== 0 if a= " + num(111 + 57 * (e8 ? 1 : 0)) +
-          " else a== 1 if a=*c r=a 2 a> 63 if a>>= 6 a++ a++ else a++ a++ endif else a-- endif endif r=a 1\n";
-
-  while (*m && ncomp < 254) {
-    std::vector<int> v;
-    v.push_back((unsigned char)*m++);
-    if (isdigit((unsigned char)*m)) {
-      v.push_back(*m++ - '0');
-      while (isdigit((unsigned char)*m) || *m == ',' || *m == '.') {
-        if (isdigit((unsigned char)*m)) v.back() = v.back() * 10 + (*m++ - '0');
-        else { v.push_back(0); ++m; }
-      }
-    }
-    const int L = v[0];
-    if (L == 'c') {  // context model: ICM or CM over a hashed (periodic|distance|masked-byte) context
-      while (v.size() < 3) v.push_back(0);
-      sb = 11 + (v[2] < 256 ? bitlen((unsigned)v[2]) : 6);
-      for (size_t i = 3; i < v.size(); ++i) if (v[i] < 512) sb += popcount_u((unsigned)v[i]) * 3 / 4;
-      if (sb > membits) sb = membits;
-      comp += num(ncomp) + " ";
-      if (v[1] % 1000 == 0) comp += "icm " + num(sb - 6 - v[1] / 1000) + "\n";
-      else comp += "cm " + num(sb - 2 - v[1] / 1000) + " " + num(v[1] % 1000 - 1) + "\n";
-      hc += "d= " + num(ncomp) + " *d=0\n";
-      if (v[2] > 1 && v[2] <= 255) {
-        const bool pow2 = bitlen((unsigned)v[2]) != bitlen((unsigned)v[2] - 1);
-        hc += pow2 ? "a=c a&= " + num(v[2] - 1) + " hashd\n" : "a=c a%= " + num(v[2]) + " hashd\n";
-      } else if (v[2] >= 1000 && v[2] <= 1255) {
-        hc += "a= 255 a+= " + num(v[2] - 1000) + " d=a a=*d a-=c a> 255 if a= 255 endif d= " + num(ncomp) + " hashd\n";
-      }
-      for (size_t i = 3; i < v.size(); ++i) {
-        const int x = v[i];
-        if (i == 3) hc += "b=c ";
-        if (x == 255) hc += "a=*b hashd\n";
-        else if (x > 0 && x < 255) hc += "a=*b a&= " + num(x) + " hashd\n";
-        else if (x >= 256 && x < 512) {
-          hc += "a=r 1 a> 1 if a=r 2 a< 64 if a=*b ";
-          if (x < 511) hc += "a&= " + num(x - 256);
-          hc += " hashd else a>>= 6 hashd a=r 1 hashd endif else a= 255 hashd a=r 2 hashd endif\n";
-        }
-        else if (x >= 1256) hc += "a= " + num(((x - 1000) >> 8) & 255) + " a<<= 8 a+= " + num((x - 1000) & 255) + " a+=b b=a\n";
-        else if (x > 1000) hc += "a= " + num(x - 1000) + " a+=b b=a\n";
-        if (i + 1 < v.size() && x < 512) hc += "b++ ";
-      }
-      ++ncomp;
-    }
-    if ((L == 'm' || L == 't' || L == 's') && ncomp > (L == 't' ? 1 : 0)) {  // mixers / SSE
-      if (v.size() <= 1) v.push_back(8);
-      if (v.size() <= 2) v.push_back(24 + 8 * (L == 's'));
-      if (L == 's' && v.size() <= 3) v.push_back(255);
-      comp += num(ncomp);
-      sb = 5 + v[1] * 3 / 4;
-      if (L == 'm') comp += " mix " + num(v[1]) + " 0 " + num(ncomp) + " " + num(v[2]) + " 255\n";
-      else if (L == 't') comp += " mix2 " + num(v[1]) + " " + num(ncomp - 1) + " " + num(ncomp - 2) + " " + num(v[2]) + " 255\n";
-      else comp += " sse " + num(v[1]) + " " + num(ncomp - 1) + " " + num(v[2]) + " " + num(v[3]) + "\n";
-      if (v[1] > 8) {  // order-1/2 byte context shifted past the 8 partial-byte bits
-        hc += "d= " + num(ncomp) + " *d=0 b=c a=0\n";
-        int bits = v[1];
-        for (; bits >= 16; bits -= 8) { hc += "a<<= 8 a+=*b"; if (bits > 16) hc += " b++"; hc += "\n"; }
-        if (bits > 8) hc += "a<<= 8 a+=*b a>>= " + num(16 - bits) + "\n";
-        hc += "a<<= 8 *d=a\n";
-      }
-      ++ncomp;
-    }
-    if (L == 'i' && ncomp > 0) {  // ISSE chain, each link extends the previous hash by N bytes
-      hc += "d= " + num(ncomp - 1) + " b=c a=*d d++\n";
-      for (size_t i = 1; i < v.size() && ncomp < 254; ++i) {
-        for (int j = 0; j < v[i] % 10; ++j) {
-          hc += "hash ";
-          if (i + 1 < v.size() || j < v[i] % 10 - 1) hc += "b++ ";
-          sb += 6;
-        }
-        hc += "*d=a";
-        if (i + 1 < v.size()) hc += " d++";
-        hc += "\n";
-        if (sb > membits) sb = membits;
-        comp += num(ncomp) + " isse " + num(sb - 6 - v[i] / 10) + " " + num(ncomp - 1) + "\n";
-        ++ncomp;
-      }
-    }
-    if (L == 'a') {  // MATCH
-      if (v.size() <= 1) v.push_back(24);
-      while (v.size() < 4) v.push_back(0);
-      comp += num(ncomp) + " match " + num(membits - v[3] - 2) + " " + num(membits - v[2]) + "\n";
-      hc += "d= " + num(ncomp) + " a=*d a*= " + num(v[1]) + " a+=*c a++ *d=a\n";
-      sb = 5 + (membits - v[2]) * 3 / 4;
-      ++ncomp;
-    }
-    if (L == 'w') {  // word-oriented ICM-ISSE chain
-      static const int dflt[7] = {0, 1, 65, 26, 223, 20, 0};
-      for (size_t k = v.size(); k <= 6; ++k) v.push_back(dflt[k]);
-      comp += num(ncomp) + " icm " + num(membits - 6 - v[6]) + "\n";
-      for (int i = 1; i < v[1]; ++i)
-        comp += num(ncomp + i) + " isse " + num(membits - 6 - v[6]) + " " + num(ncomp + i - 1) + "\n";
-      hc += "a=*c a&= " + num(v[4]) + " a-= " + num(v[2]) + " a&= 255 a< " + num(v[3]) + " if\n";
-      for (int i = 0; i < v[1]; ++i)
-        hc += (i == 0 ? "  d= " + num(ncomp) : std::string("  d++")) + " a=*d a*= " + num(v[5]) + " a+=*c a++ *d=a\n";
-      hc += "else\n";
-      for (int i = v[1] - 1; i > 0; --i) hc += "  d= " + num(ncomp + i - 1) + " a=*d d++ *d=a\n";
-      hc += "  d= " + num(ncomp) + " *d=0\nendif\n";
-      ncomp += v[1] - 1;
-      sb = membits - v[6];
-      ++ncomp;
-    }
+    mb.hc += "a=r 1 a== 0 if a= " + num(111 + 57 * (e8 ? 1 : 0)) +
+             " else a== 1 if a=*c r=a 2 a> 63 if a>>= 6 a++ a++ else a++ a++ endif else a-- endif endif r=a 1\n";
+  for (const Cmd& c : cmds) {
+    if (mb.ncomp >= 254) break;
+    for (const auto& k : kModelCommands)
+      if (k.letter == (char)c[0]) { (mb.*k.add)(c); break; }
   }
-  return hdr + num(ncomp) + "\n" + comp + hc + "halt\n" + post;
+  return hdr + num(mb.ncomp) + "\n" + mb.comp + mb.hc + "halt\n" + post;
 }
 
 // -------------------------------------------------------------------------------------------------
