@@ -194,7 +194,7 @@ int zq_fragment_ex(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t*
  *   d_out:    the "d" blocks back to back, as they follow the version's header block in the archive
  *   h_out:    the "h" blocks (compressed size + SHA-1/size per fragment of each data block), in order
  *   file_frags[file_first[f] .. file_first[f+1]): fragment ids of file f (what its index entry lists).
- * Not written here: the "c" header and "i" index blocks (file names, dates, attributes: the front end's). */
+ * The "c" header and "i" index blocks of the transaction are written by zq_journal_header / zq_journal_index. */
 int zq_add_files(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* off, const uint64_t* len,
                  const char* method, int fragment, const char* date14, uint32_t first_id,
                  uint8_t* d_out, uint64_t d_cap, uint64_t* d_len,
@@ -202,6 +202,24 @@ int zq_add_files(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* o
                  uint32_t* file_frags, uint64_t file_frags_cap, uint64_t* file_first /* nfiles+1 */,
                  uint32_t* nblocks);
 uint64_t zq_file_sort_key(const char* path, int64_t size);
+
+/* The fragment index (replaces HTIndex::find, zpaqfranz.cpp:71567-71604): first[i] = the smallest j <= i whose 20-byte
+ * digest equals fragment i's, for n digests laid out back to back.  first[i] == i marks a fragment new to the set. */
+int zq_dedup_first(zq_ctx* ctx, uint64_t n, const uint8_t* sha1, uint32_t* first);
+
+/* The other two journaling blocks of a transaction (device compression, method "0" / "1", comment "jDC\x01").
+ * zq_journal_header: the "c" block -- 8 bytes, cdata = size of the data blocks that follow, or -1 while the update is
+ *   open; htsize = id of the first new fragment.  Replaces writeJidacHeader (zpaqfranz.cpp:71521-71540).
+ * zq_journal_index: the "i" blocks -- per record date (0 = deletion), name, and for live files the attribute bytes
+ *   (attr_base + attr_off[r], attr_len[r] bytes, as the front end's writefranzattr lays them out; opaque here) and the
+ *   fragment ids frags[frag_first[r] .. frag_first[r+1]); a block closes once it passes 16 000 bytes.  Replaces the
+ *   index loop of Jidac::add (zpaqfranz.cpp:122915-123100).  out: the blocks back to back. */
+int zq_journal_header(zq_ctx* ctx, const char* date14, int64_t cdata, uint32_t htsize,
+                      uint8_t* out, uint64_t cap, uint64_t* len);
+int zq_journal_index(zq_ctx* ctx, const char* date14, int nrec, const int64_t* date, const char* const* name,
+                     const uint8_t* attr_base, const uint64_t* attr_off, const uint32_t* attr_len,
+                     const uint64_t* frag_first /* nrec+1 */, const uint32_t* frags,
+                     uint8_t* out, uint64_t cap, uint64_t* len, uint32_t* nblocks);
 
 
 /* ---- several GPUs (one process per GPU) -------------------------------------------------------------------------

@@ -62,3 +62,14 @@ extern "C" int emu_hash(int kind, const uint8_t* base, const uint64_t* off, cons
   }
   return 0;
 }
+
+// the fragment index kernels (k_dedup_insert / k_dedup_lookup) as zq_dedup_first launches them
+extern "C" int emu_dedup_first(const uint8_t* sha1, uint32_t n, uint32_t* first) {
+  u32 slots = 1024;
+  while (slots < 2 * (u64)n) slots <<= 1;
+  std::vector<u32> tab(slots, 0xffffffffu);
+  const u32* dg = (const u32*)sha1;
+  emu::launch((n + 255) / 256, 256, 0, [&] { k_dedup_insert(dg, n, tab.data(), slots - 1); });
+  emu::launch((n + 255) / 256, 256, 0, [&] { k_dedup_lookup(dg, n, tab.data(), slots - 1, first); });
+  return 0;
+}

@@ -161,6 +161,7 @@ template <class T, class V> inline T atomicOr(T* p, V v) { const T o = *p; *p = 
 template <class T, class V> inline T atomicAnd(T* p, V v) { const T o = *p; *p = (T)(o & (T)v); return o; }
 template <class T, class V> inline T atomicMax(T* p, V v) { const T o = *p; if ((T)v > o) *p = (T)v; return o; }
 template <class T, class V> inline T atomicMin(T* p, V v) { const T o = *p; if ((T)v < o) *p = (T)v; return o; }
+template <class T, class A, class V> inline T atomicCAS(T* p, A cmp, V v) { const T o = *p; if (o == (T)cmp) *p = (T)v; return o; }
 template <class T, class V> inline T atomicExch(T* p, V v) { const T o = *p; *p = (T)v; return o; }
 inline void __threadfence_block() {}
 inline void __threadfence() {}

@@ -64,3 +64,50 @@ def test_autotest_archive_decodes_on_device(ctx):
     for (name, _), c, g in zip(whole, content, dg):
         assert len(c) == 37000
         assert g.tobytes().hex().upper() == name == hashlib.sha256(c).hexdigest().upper()
+
+
+def test_journal_blocks_of_the_fixture_are_rewritten_byte_for_byte(ctx):
+    """The "c" and "i" blocks of AUTOTEST/sha256.zpaq, parsed back into (date, name, attribute bytes, fragment ids)
+    records and written again by zq_journal_header / zq_journal_index, are the archive's own bytes (the writer of
+    Jidac::add, zpaqfranz.cpp:71521-71540 and 122915-123100; 16 000-byte block rule included: three index blocks)."""
+    gold = json.load(open(os.path.join(HERE, "golden", "sha256_zpaq.json")))
+    a = np.fromfile(os.path.join(HERE, "golden", "sha256.zpaq"), dtype=np.uint8)
+    blocks = gold["blocks"]
+    raw = a.tobytes()
+    names = []
+    for b in blocks:
+        blk = raw[b["offset"]: b["offset"] + b["length"]]
+        i = blk.find(b"jDC")
+        names.append(blk[i: i + 28])
+    kinds = [n[17:18] for n in names]
+    assert kinds == [b"c", b"d", b"h", b"i", b"i", b"i"]
+    date14 = names[0][3:17].decode()
+    small = [k for k in range(len(blocks)) if kinds[k] != b"d"]
+    offs = np.array([blocks[k]["offset"] for k in small], dtype=np.uint64)
+    lens = np.array([blocks[k]["length"] for k in small], dtype=np.uint32)
+    out, ooff, olen = ctx.decompress_blocks(a, offs, lens)
+    dec = {k: out[int(ooff[j]): int(ooff[j]) + int(olen[j])].tobytes() for j, k in enumerate(small)}
+    cdata = struct.unpack("<q", dec[0])[0]
+    first = int(names[0][18:28])
+    assert ctx.journal_header(date14, cdata, first) == raw[: blocks[0]["length"]]
+    records = []
+    for k in (3, 4, 5):
+        idx, p = dec[k], 0
+        while p < len(idx):
+            date = struct.unpack("<q", idx[p:p + 8])[0]
+            p += 8
+            q = idx.index(0, p)
+            name, p = idx[p:q], q + 1
+            attr, fr = b"", ()
+            if date:
+                na = struct.unpack("<I", idx[p:p + 4])[0]
+                attr = idx[p + 4: p + 4 + na]
+                p += 4 + na
+                ni = struct.unpack("<I", idx[p:p + 4])[0]
+                fr = struct.unpack("<%dI" % ni, idx[p + 4: p + 4 + 4 * ni])
+                p += 4 + 4 * ni
+            records.append((date, name, attr, fr))
+    assert len(records) >= 256
+    got, nb = ctx.journal_index(date14, records)
+    assert nb == 3
+    assert got == raw[blocks[3]["offset"]:]

@@ -88,3 +88,19 @@ def test_md5_sha3_match_reference(ctx, ref):
         assert s3[i].tobytes() == hashlib.sha3_256(b).digest()
         if ref is not None:
             assert m[i].tobytes() == ref.md5(b) and s3[i].tobytes() == ref.sha3_256(b)
+
+
+def test_fragment_index_first_occurrence(ctx):
+    """zq_dedup_first over 1 000 000 digests drawn from 200 000 (plus a run sharing one home slot): the earliest equal
+    fragment, whatever order the threads insert in -- the HTIndex answer of Jidac::add (zpaqfranz.cpp:71567-71604)."""
+    rng = np.random.default_rng(11)
+    pool = rng.integers(0, 256, size=(200000, 20), dtype=np.uint8)
+    pool[1000:1400, :8] = pool[0, :8]
+    pick = rng.integers(0, len(pool), size=1000000)
+    dg = np.ascontiguousarray(pool[pick])
+    first = ctx.dedup_first(dg)
+    _, idx = np.unique(pick, return_index=True)          # first position of every pool entry that was drawn
+    want = np.zeros(len(pool), dtype=np.int64)
+    want[np.unique(pick)] = idx
+    assert np.array_equal(first.astype(np.int64), want[pick])
+    assert ctx.dedup_first(np.zeros((0, 20), dtype=np.uint8)).size == 0

@@ -82,3 +82,19 @@ def test_md5_sha3(emu, ref, shift):
     if ref is not None:       # the reference's own classes (MD5 Z:21432, SHA3 Z:21189) agree
         assert [ref.md5(b) for b in bufs[:12]] == [hashlib.md5(b).digest() for b in bufs[:12]]
         assert [ref.sha3_256(b) for b in bufs[:12]] == [hashlib.sha3_256(b).digest() for b in bufs[:12]]
+
+
+def test_fragment_index(emu):
+    """k_dedup_insert / k_dedup_lookup: first[i] = the earliest fragment with fragment i's digest (HTIndex, Z:71567-71604);
+    colliding table slots (digests sharing their first 8 bytes) included."""
+    rng = np.random.default_rng(5)
+    pool = rng.integers(0, 256, size=(300, 20), dtype=np.uint8)
+    pool[100:200, :8] = pool[0, :8]                          # same home slot, different digests
+    pick = rng.integers(0, 300, size=5000)
+    dg = np.ascontiguousarray(pool[pick])
+    first = np.zeros(5000, dtype=np.uint32)
+    emu.emu_dedup_first(dg.ctypes.data_as(C.c_void_p), 5000, first.ctypes.data_as(C.c_void_p))
+    seen, want = {}, []
+    for i, k in enumerate(pick):
+        want.append(seen.setdefault(dg[i].tobytes(), i))
+    assert first.tolist() == want

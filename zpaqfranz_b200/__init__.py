@@ -63,6 +63,10 @@ def _load():
     lib.zq_jit_compile.argtypes = [C.c_char_p, u32p, C.c_char_p, C.c_size_t]
     lib.zq_file_sort_key.restype = C.c_uint64
     lib.zq_file_sort_key.argtypes = [C.c_char_p, C.c_int64]
+    lib.zq_dedup_first.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zq_journal_header.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.zq_journal_index.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zq_pipe_create.restype = C.c_void_p
     lib.zq_pipe_create.argtypes = [C.c_int, C.c_int]
     lib.zq_pipe_destroy.argtypes = [C.c_void_p]
@@ -481,6 +485,39 @@ class Context:
                                      C.byref(hl), ids.ctypes.data, ids.size, first.ctypes.data, C.byref(nb)))
         return dict(d=d[: dl.value].tobytes(), h=h[: hl.value].tobytes(), nblocks=nb.value,
                     file_frags=[ids[int(first[i]): int(first[i + 1])].tolist() for i in range(n)])
+
+    def dedup_first(self, sha1):
+        """first[i] = earliest fragment with the digest of fragment i (the device fragment index); sha1: (n, 20) uint8."""
+        dg = np.ascontiguousarray(sha1, dtype=np.uint8).reshape(-1, 20)
+        first = np.zeros(len(dg), dtype=np.uint32)
+        self._check(lib.zq_dedup_first(self._h, len(dg), dg.ctypes.data, first.ctypes.data))
+        return first
+
+    def journal_header(self, date14, cdata, htsize):
+        """The transaction's "c" block (writeJidacHeader): bytes."""
+        out = np.empty(4096, dtype=np.uint8)
+        n = C.c_uint64(0)
+        self._check(lib.zq_journal_header(self._h, date14.encode(), int(cdata), int(htsize), out.ctypes.data, out.size, C.byref(n)))
+        return out[: n.value].tobytes()
+
+    def journal_index(self, date14, records):
+        """The transaction's "i" blocks from records (date, name: bytes, attr: bytes, fragment ids): (bytes, nblocks)."""
+        nrec = len(records)
+        dates = np.array([r[0] for r in records], dtype=np.int64)
+        names = (C.c_char_p * max(nrec, 1))(*[bytes(r[1]) for r in records])
+        attrs = [bytes(r[2]) if r[0] else b"" for r in records]
+        ab = np.frombuffer(b"".join(attrs) + b"\0", dtype=np.uint8)
+        al = np.array([len(a) for a in attrs], dtype=np.uint32)
+        ao = (np.cumsum(al, dtype=np.uint64) - al).astype(np.uint64)
+        fr = [list(r[3]) if r[0] else [] for r in records]
+        ff = np.concatenate([[0], np.cumsum([len(f) for f in fr])]).astype(np.uint64)
+        fa = np.array([x for f in fr for x in f] + [0], dtype=np.uint32)
+        total = sum(len(r[1]) + 17 for r in records) + int(al.sum()) + 4 * fa.size
+        out = np.empty(total * 2 + 4096 * (total // 16000 + 2), dtype=np.uint8)
+        n, nb = C.c_uint64(0), C.c_uint32(0)
+        self._check(lib.zq_journal_index(self._h, date14.encode(), nrec, dates.ctypes.data, names, ab.ctypes.data, ao.ctypes.data,
+                                         al.ctypes.data, ff.ctypes.data, fa.ctypes.data, out.ctypes.data, out.size, C.byref(n), C.byref(nb)))
+        return out[: n.value].tobytes(), nb.value
 
     # -- fragmenter ---------------------------------------------------------------------------------
     def fragment(self, arena, offsets, lengths, fragment=6, blocksize=(1 << 26) - 4096, want_sha1=True):

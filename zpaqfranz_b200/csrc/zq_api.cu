@@ -1283,6 +1283,28 @@ int zq_sha3_256(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, cons
   });
 }
 
+int zq_dedup_first(zq_ctx* c, uint64_t n, const uint8_t* sha1, uint32_t* first) {
+  using namespace zqdev;
+  if (!c) return ZQ_E_NODEVICE;
+  if (n > 0x7fffffffu || (n > 0 && (!sha1 || !first))) return fail(c, ZQ_E_ARG, "bad argument");
+  if (n == 0) return ZQ_OK;
+  cudaSetDevice(c->device);
+  u32 slots = 1024;
+  while (slots < 2 * n) slots <<= 1;
+  ZQ_CUDA(c, c->d_sha.ensure(n * 20));
+  ZQ_CUDA(c, c->d_ht.ensure((size_t)slots * 4));
+  ZQ_CUDA(c, c->d_tok.ensure(n * 4));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_sha.p, sha1, n * 20, cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, cudaMemsetAsync(c->d_ht.p, 0xff, (size_t)slots * 4, c->stream));
+  const u32 grid = (u32)((n + 255) / 256);
+  k_dedup_insert<<<grid, 256, 0, c->stream>>>(c->d_sha.as<u32>(), (u32)n, c->d_ht.as<u32>(), slots - 1);
+  k_dedup_lookup<<<grid, 256, 0, c->stream>>>(c->d_sha.as<u32>(), (u32)n, c->d_ht.as<u32>(), slots - 1, c->d_tok.as<u32>());
+  c->launches += 2;
+  ZQ_CUDA(c, cudaMemcpyAsync(first, c->d_tok.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  return ZQ_OK;
+}
+
 int zq_fragment(zq_ctx* c, int nfiles, const uint8_t* base, const uint64_t* off, const uint64_t* len, int fragment,
                 uint32_t blocksize, uint32_t* frag_len, uint32_t* frag_hits, uint8_t* frag_sha1, uint64_t frag_cap,
                 uint64_t* frag_first) {

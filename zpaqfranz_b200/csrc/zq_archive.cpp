@@ -14,7 +14,6 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
-#include <unordered_map>
 #include <vector>
 
 #include "../../include/zq_b200.h"
@@ -34,7 +33,6 @@ struct Sha1Key {
   uint8_t b[20];
   bool operator==(const Sha1Key& o) const { return memcmp(b, o.b, 20) == 0; }
 };
-struct Sha1KeyHash { size_t operator()(const Sha1Key& k) const { size_t h; memcpy(&h, k.b, sizeof h); return h; } };
 
 // What one fragment tells about its data (Z:122592-122638): updates `hits` in place.
 void analyse_fragment(const uint8_t* o1, int64_t sz, const uint8_t* o1prev, unsigned& hits, int& text1, int& exe1) {
@@ -114,8 +112,14 @@ int zq_add_files(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* o
   uint8_t sha_empty[20];
   { const uint64_t z = 0; static const uint8_t none = 0; rc = zq_sha1(ctx, 1, &none, &z, &z, sha_empty); if (rc != ZQ_OK) return rc; }
 
-  // ---- host: dedup + block assembly ------------------------------------------------------------------
-  std::unordered_map<Sha1Key, uint32_t, Sha1KeyHash> index;
+  // ---- device: the fragment index (first fragment with the same digest) ------------------------------
+  const uint64_t nfrag = ffirst[nfiles];
+  std::vector<uint32_t> first_same(nfrag + 1), frag_id(nfrag + 1, 0);
+  rc = zq_dedup_first(ctx, nfrag, fsha.data(), first_same.data());
+  if (rc != ZQ_OK) return rc;
+  uint32_t empty_id = 0;                // the one fragment of size 0 (only empty files have it)
+
+  // ---- host: block assembly ---------------------------------------------------------------------------
   struct Frag { Sha1Key sha; uint32_t usize; };
   std::vector<Frag> ht;                 // new fragments; id = first_id + position
   std::vector<uint8_t> arena;           // block payloads back to back
@@ -146,8 +150,8 @@ int zq_add_files(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* o
           pos += flen[g];
         } else if (fj > 0) break;                      // end of file
         else memcpy(key.b, sha_empty, 20);             // an empty file is one empty fragment (Z:122562)
-        auto it = index.find(key);
-        if (it != index.end()) id = it->second;
+        if (fj < nf) { const uint64_t g = ffirst[fi] + fj; if (first_same[g] != g) id = frag_id[first_same[g]]; }
+        else id = empty_id;
       }
       if (id == 0) {
         int text1 = 0, exe1 = 0;
@@ -200,8 +204,9 @@ int zq_add_files(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* o
           id = first_id + (uint32_t)ht.size();
           Frag fr; fr.sha = key; fr.usize = (uint32_t)sz;
           ht.push_back(fr);
-          index.emplace(key, id);
+          if (fj >= nf) empty_id = id;
         }
+        if (fj < nf) frag_id[ffirst[fi] + fj] = id;
         if (file_frags) { if (nptr >= file_frags_cap) return ZQ_E_OUTPUT; file_frags[nptr] = id; }
         ++nptr;
       }
@@ -240,6 +245,73 @@ int zq_add_files(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* o
   rc = zq_compress_blocks(ctx, nb, tarena.data(), toff.data(), tlen.data(), mp.data(), np.data(), cp.data(), 0, 1, h_out, h_cap, ooff.data(), olen.data());
   if (rc != ZQ_OK) return rc;
   *h_len = ooff[nb - 1] + olen[nb - 1];
+  return ZQ_OK;
+}
+
+int zq_journal_header(zq_ctx* ctx, const char* date14, int64_t cdata, uint32_t htsize, uint8_t* out, uint64_t cap, uint64_t* len) {
+  // the transaction header: 8 bytes (size of the data blocks that follow, or -1 while the update is open), stored,
+  // named jDC<date>c<first fragment id> (writeJidacHeader, Z:71521-71540)
+  if (!ctx) return ZQ_E_NODEVICE;
+  if (!date14 || strlen(date14) != 14 || !out || !len) return ZQ_E_ARG;
+  uint8_t payload[32] = {0};
+  for (int i = 0; i < 8; ++i) payload[i] = (uint8_t)((uint64_t)cdata >> (8 * i));
+  const uint64_t off = 0; const uint32_t n = 8; uint64_t ooff = 0; uint32_t olen = 0;
+  const std::string name = "jDC" + std::string(date14) + "c" + digits(htsize, 10);
+  const char* m = "0"; const char* nm = name.c_str(); const char* cm = "jDC\x01";
+  const int rc = zq_compress_blocks(ctx, 1, payload, &off, &n, &m, &nm, &cm, 0, 1, out, cap, &ooff, &olen);
+  if (rc != ZQ_OK) return rc;
+  *len = ooff + olen;
+  return ZQ_OK;
+}
+
+int zq_journal_index(zq_ctx* ctx, const char* date14, int nrec, const int64_t* date, const char* const* name,
+                     const uint8_t* attr_base, const uint64_t* attr_off, const uint32_t* attr_len,
+                     const uint64_t* frag_first, const uint32_t* frags,
+                     uint8_t* out, uint64_t cap, uint64_t* len, uint32_t* nblocks) {
+  // the index of one transaction: per record the date, the name, and for a live file its attribute bytes and fragment
+  // ids (deletions carry date 0 and nothing else); a block is closed once it passes 16 000 bytes and all of them are
+  // compressed in one batch with method "1" as jDC<date>i<count> (Z:122915-123100)
+  if (!ctx) return ZQ_E_NODEVICE;
+  if (!date14 || strlen(date14) != 14 || nrec < 0 || !len || (nrec > 0 && (!date || !name || !out))) return ZQ_E_ARG;
+  std::vector<uint8_t> arena; std::vector<uint64_t> boff; std::vector<uint32_t> blen;
+  std::vector<uint8_t> is;
+  auto close_block = [&]() {
+    boff.push_back(arena.size()); blen.push_back((uint32_t)is.size());
+    arena.insert(arena.end(), is.begin(), is.end());
+    arena.resize((arena.size() + 15) & ~(size_t)15);
+    is.clear();
+  };
+  for (int r = 0; r < nrec; ++r) {
+    if (!name[r]) return ZQ_E_ARG;
+    const size_t nl = strlen(name[r]);
+    if (nl > 65535) return ZQ_E_ARG;
+    for (int i = 0; i < 8; ++i) is.push_back((uint8_t)((uint64_t)date[r] >> (8 * i)));
+    is.insert(is.end(), name[r], name[r] + nl + 1);
+    if (date[r]) {
+      const uint32_t na = attr_len ? attr_len[r] : 0;
+      if (na > 65535 || (na && (!attr_base || !attr_off))) return ZQ_E_ARG;
+      put_le32(is, na);
+      if (na) is.insert(is.end(), attr_base + attr_off[r], attr_base + attr_off[r] + na);
+      const uint64_t a = frag_first ? frag_first[r] : 0, b = frag_first ? frag_first[r + 1] : 0;
+      if (b < a || (b > a && !frags)) return ZQ_E_ARG;
+      put_le32(is, b - a);
+      for (uint64_t j = a; j < b; ++j) put_le32(is, frags[j]);
+    }
+    if (is.size() > 16000) close_block();
+  }
+  if (!is.empty()) close_block();
+  const int nb = (int)boff.size();
+  if (nblocks) *nblocks = (uint32_t)nb;
+  *len = 0;
+  if (nb == 0) return ZQ_OK;
+  std::vector<std::string> names(nb);
+  std::vector<const char*> mp(nb, "1"), np(nb), cp(nb, "jDC\x01");
+  for (int i = 0; i < nb; ++i) { names[i] = "jDC" + std::string(date14) + "i" + digits((uint64_t)i + 1, 10); np[i] = names[i].c_str(); }
+  std::vector<uint64_t> ooff(nb); std::vector<uint32_t> olen(nb);
+  arena.resize(arena.size() + 16);
+  const int rc = zq_compress_blocks(ctx, nb, arena.data(), boff.data(), blen.data(), mp.data(), np.data(), cp.data(), 0, 1, out, cap, ooff.data(), olen.data());
+  if (rc != ZQ_OK) return rc;
+  *len = ooff[nb - 1] + olen[nb - 1];
   return ZQ_OK;
 }
 

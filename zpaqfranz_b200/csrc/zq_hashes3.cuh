@@ -163,4 +163,43 @@ k_sha3_256_many(const u8* __restrict__ base, const u64* __restrict__ off, const 
     for (int b = 0; b < 8; ++b) out[(size_t)i * 32 + 8 * k + b] = (u8)(s[k] >> (8 * b));
 }
 
+// ---- the fragment index: which earlier fragment has the same SHA-1 (HTIndex::find, Z:71567-71604) --------------------
+// Open addressing over a table of fragment numbers; a slot belongs to one digest for good and holds the SMALLEST
+// fragment number seen with it (atomicMin), so the answer does not depend on the order the threads arrive in.
+static const u32 DEDUP_EMPTY = 0xffffffffu;
+
+__device__ __forceinline__ bool dedup_same(const u32* __restrict__ dg, u32 a, const u32 (&w)[5]) {
+  const u32* q = dg + 5 * (size_t)a;
+  return q[0] == w[0] && q[1] == w[1] && q[2] == w[2] && q[3] == w[3] && q[4] == w[4];
+}
+
+__device__ __forceinline__ u32 dedup_slot(const u32 (&w)[5], u32 mask) { return (w[0] ^ (w[1] * 0x9E3779B1u)) & mask; }
+
+__global__ void __launch_bounds__(256) k_dedup_insert(const u32* __restrict__ dg, u32 n, u32* tab, u32 mask) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 w[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) w[k] = dg[5 * (size_t)i + k];
+  for (u32 slot = dedup_slot(w, mask);; slot = (slot + 1) & mask) {
+    const u32 cur = atomicCAS(&tab[slot], DEDUP_EMPTY, i);
+    if (cur == DEDUP_EMPTY) return;
+    if (dedup_same(dg, cur, w)) { atomicMin(&tab[slot], i); return; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dedup_lookup(const u32* __restrict__ dg, u32 n, const u32* __restrict__ tab, u32 mask,
+                                                      u32* __restrict__ first) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 w[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) w[k] = dg[5 * (size_t)i + k];
+  for (u32 slot = dedup_slot(w, mask);; slot = (slot + 1) & mask) {
+    const u32 cur = tab[slot];
+    if (cur == DEDUP_EMPTY) { first[i] = i; return; }      // cannot happen after k_dedup_insert; keeps the loop finite
+    if (dedup_same(dg, cur, w)) { first[i] = cur; return; }
+  }
+}
+
 }  // namespace zqdev
