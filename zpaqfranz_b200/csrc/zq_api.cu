@@ -79,6 +79,8 @@ struct zq_ctx {
   int lz_old = 0;                         // 1: warp-per-block LZ77 parser for every block (ZQ_LZ_OLD=1); 0: position-parallel scan/walk/emit (zq_lz77_scan.cuh)
   int scan_occ[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of k_lz_scan<u16/u32, pass> (queried once)
   int cm_jit = 1;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter; 2: generated coder too (ZQ_CM_JIT)
+  void (*gate_fn)(void*, int) = nullptr;  // zq_set_compute_gate: called with 1 before the first kernel of a batch, 0 after its last
+  void* gate_arg = nullptr;
   bool cm_jit_auto = true;                // no ZQ_CM_JIT in the environment: translate only the models whose context warp is the bottleneck (<= 8 components)
   struct JitProg { cudaLibrary_t lib = nullptr; cudaKernel_t ctx = nullptr, code = nullptr; };
   std::map<std::string, JitProg> jit_cache;   // translated context program (+ generated coder) per model header
@@ -123,6 +125,13 @@ static const unsigned char kTag[13] = {0x37, 0x6b, 0x53, 0x74, 0xa0, 0x31, 0x83,
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // The core: inputs and outputs already on the device.
+struct GateHold {   // the batch's kernels run between acquire() and the end of the scope
+  zq_ctx* c; bool held = false;
+  explicit GateHold(zq_ctx* c_) : c(c_) {}
+  void acquire() { if (c->gate_fn && !held) { c->gate_fn(c->gate_arg, 1); held = true; } }
+  ~GateHold() { if (held) c->gate_fn(c->gate_arg, 0); }
+};
+
 int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off, const uint32_t* in_len,
                   const char* const* method, const char* const* filename, const char* const* comment,
                   int uniform, int dosha1, uint8_t* d_out, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
@@ -284,6 +293,8 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
     model_budget = std::min<size_t>(model_budget, fr > ((size_t)6 << 30) ? fr - ((size_t)6 << 30) : fr / 2);
   }
   // waves: contiguous unit ranges whose suffix-array and model footprints fit the budgets
+  GateHold gate(c);
+  gate.acquire();
   std::vector<uint32_t> lz_len_h(n, 0), coded_len_h(n, 0);
   uint64_t out_pos = 0;
   int w0 = 0;
@@ -781,6 +792,12 @@ void zq_destroy(zq_ctx* c) {
   for (int k = 0; k < 4; ++k) cudaEventDestroy(c->ev[k]);
   cudaStreamDestroy(c->own_stream);
   delete c;
+}
+
+int zq_set_compute_gate(zq_ctx* c, void (*fn)(void*, int), void* arg) {
+  if (!c) return ZQ_E_NODEVICE;
+  c->gate_fn = fn; c->gate_arg = arg;
+  return ZQ_OK;
 }
 
 int zq_set_stream(zq_ctx* c, void* s) {

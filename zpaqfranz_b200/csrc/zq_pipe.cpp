@@ -8,6 +8,7 @@
 // the gaps of batch k.  Results are identical to the synchronous calls (same code underneath).
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <deque>
 #include <map>
 #include <set>
@@ -33,6 +34,8 @@ struct zq_pipe {
   std::vector<zq_ctx*> ctx;
   std::vector<std::thread> workers;
   std::mutex mu;
+  std::mutex compute;        // host-pointer batches: one batch's kernels at a time, the others copy meanwhile
+  bool gated = true;
   std::condition_variable cv_job, cv_done;
   std::deque<Job> queue;
   std::map<int, Done> done;
@@ -40,6 +43,11 @@ struct zq_pipe {
   int next_ticket = 0;
   bool stop = false;
   std::string last_error;
+
+  static void gate(void* self, int acquire) {
+    zq_pipe* p = static_cast<zq_pipe*>(self);
+    if (acquire) p->compute.lock(); else p->compute.unlock();
+  }
 
   void run(int lane) {
     for (;;) {
@@ -51,6 +59,7 @@ struct zq_pipe {
         j = queue.front(); queue.pop_front();
       }
       zq_ctx* c = ctx[lane];
+      zq_set_compute_gate(c, (gated && !j.device_pointers) ? &zq_pipe::gate : nullptr, this);
       const int rc = j.device_pointers
           ? zq_compress_blocks_device(c, j.n, j.in, j.in_off, j.in_len, j.method, j.filename, j.comment, j.uniform, j.dosha1, j.out, j.out_cap, j.out_off, j.out_len)
           : zq_compress_blocks(c, j.n, j.in, j.in_off, j.in_len, j.method, j.filename, j.comment, j.uniform, j.dosha1, j.out, j.out_cap, j.out_off, j.out_len);
@@ -69,6 +78,7 @@ zq_pipe* zq_pipe_create(int device, int depth) {
   if (depth < 1) depth = 1;
   if (depth > 8) depth = 8;
   zq_pipe* p = new zq_pipe();
+  if (const char* s = getenv("ZQ_PIPE_GATE")) p->gated = atoi(s) != 0;
   for (int i = 0; i < depth; ++i) {
     zq_ctx* c = zq_create(device);
     if (!c) { for (zq_ctx* x : p->ctx) zq_destroy(x); delete p; return nullptr; }
