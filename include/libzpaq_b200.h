@@ -172,7 +172,10 @@ class Decompresser {
   Reader* in_ = 0;
   Writer* out_ = 0;
   SHA1* sha1_ = 0;
-  std::vector<unsigned char> buf_, obuf_;
+  std::vector<unsigned char> buf_, obuf_, block_out_;   // block_out_: every segment of the current block, restored at once
+  struct Seg { uint32_t out_begin, out_end, trailer; };
+  std::vector<Seg> segs_;
+  size_t seg_idx_ = 0;
   size_t pos_ = 0, blk_ = 0, hdr_ = 0, hdr_len_ = 0, opos_ = 0, seg_end_ = 0;
   bool eof_ = false, decoded_ = false, first_seg_ = true;
   unsigned char trailer_[21];

@@ -131,13 +131,14 @@ int zq_assemble_config(const char* config, const int args9[9],
 const char* zq_model_config(int level);
 
 /* ---- block decompression -------------------------------------------------------------------------
- * Element-wise == Decompresser::findBlock/findFilename/readComment/decompress/readSegmentEnd for one
- * block holding one segment (what compressBlock writes; Z:15418-15534) and libzpaq::decompress (Z:15536):
- * unit u is a complete block at in_base[in_off[u] .. +in_len[u]) (the 13-byte locator tag is optional);
- * the restored bytes go to out_base[out_off[u] .. +out_len[u]), laid out back to back.  The expected size
- * of each block is taken from expect_len[u] or, when expect_len is NULL, from the decimal number that
- * starts the segment comment (the archiver writes "<n> jDC\x01", Z:20404).  A stored SHA-1 is verified
- * on the device.  Host pointers. */
+ * Element-wise == Decompresser::findBlock/findFilename/readComment/decompress/readSegmentEnd over every segment of
+ * one block (Z:15418-15534) and libzpaq::decompress (Z:15536): unit u is a complete block at
+ * in_base[in_off[u] .. +in_len[u]) (the 13-byte locator tag is optional); the restored bytes of all its segments,
+ * concatenated, go to out_base[out_off[u] .. +out_len[u]), laid out back to back.  The expected size of each block is
+ * taken from expect_len[u] or, when expect_len is NULL, from the decimal number that starts the FIRST segment's comment
+ * (the archiver writes "<n> jDC\x01", Z:20404; a block of several segments needs expect_len, else ZQ_E_OUTPUT).  Every
+ * stored SHA-1 is verified on the device.  Where the segments of the last call lie: zq_decompress_last_segments.
+ * Host pointers. */
 int zq_decompress_blocks(zq_ctx* ctx, int n,
                          const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
                          const uint32_t* expect_len /* may be NULL */,
@@ -152,6 +153,13 @@ int zq_decompress_blocks_ex(zq_ctx* ctx, int n,
                             const uint32_t* expect_len /* may be NULL */,
                             uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
                             uint32_t* in_used, uint8_t* sha1_out);
+/* The segments of the blocks of the last zq_decompress_* call on this context, ordered by block, then position:
+ * restored bytes [out_begin, out_end) of the block's output, and the offset within the block of the segment's trailer
+ * byte (253 + SHA-1, or 254); the next segment's header (1, filename, 0, comment, 0, 0) follows the trailer.  The table
+ * belongs to the context and is valid until its next decompress call. */
+typedef struct zq_segment { uint32_t block, out_begin, out_end, trailer; } zq_segment;
+int zq_decompress_last_segments(zq_ctx* ctx, const zq_segment** segs, uint64_t* nsegs);
+
 /* The first max_out[i] bytes of each block's first segment (== Decompresser::decompress(n), Z:15480: a caller that only
  * wants the head of a segment); stops there, looks at no trailer, verifies no checksum.  out_len[i] <= max_out[i]. */
 int zq_decompress_prefix(zq_ctx* ctx, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,

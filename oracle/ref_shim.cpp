@@ -77,6 +77,36 @@ long long zref_compress_segment(int level, const unsigned char* header, const un
   } catch (std::exception& e) { g_lasterr = e.what(); return -1; }
 }
 
+// One block holding nseg segments (what the streaming archiver writes; Compressor Z:15970-16187): segment k is
+// in[off[k] .. off[k]+len[k]), named "<filename><k>", with the SHA-1 of its data stored when sha != 0.
+long long zref_compress_multi(int level, const unsigned char* header, const unsigned char* pcomp, int plen, int nseg,
+                              const unsigned char* in, const unsigned long long* off, const unsigned* len,
+                              const char* filename, const char* comment, int sha, unsigned char* out, unsigned long long cap) {
+  try {
+    VecWriter w;
+    libzpaq::Compressor co;
+    co.setOutput(&w);
+    co.writeTag();
+    if (level > 0) co.startBlock(level); else co.startBlock((const char*)header);
+    for (int k = 0; k < nseg; ++k) {
+      MemReader r(in + off[k], len[k]);
+      co.setInput(&r);
+      const std::string name = std::string(filename ? filename : "") + std::to_string(k);
+      co.startSegment(name.c_str(), comment);
+      if (k == 0) { if (plen > 0) co.postProcess((const char*)pcomp, plen); else co.postProcess(); }
+      co.compress();
+      if (sha) {
+        libzpaq::SHA1 s1; s1.write((const char*)in + off[k], (int64_t)len[k]);
+        co.endSegment(s1.result());
+      } else co.endSegment(0);
+    }
+    co.endBlock();
+    if (w.v.size() > cap) return -2;
+    memcpy(out, w.v.data(), w.v.size());
+    return (long long)w.v.size();
+  } catch (std::exception& e) { g_lasterr = e.what(); return -1; }
+}
+
 // The reference's own command line (its main(), Z:78458), for archive-level comparisons: run it in a child
 // process -- it calls exit().
 int zref_main(int argc, const char** argv) { return zpaqfranz_reference_main(argc, argv); }

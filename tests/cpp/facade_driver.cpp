@@ -68,6 +68,35 @@ int main(int argc, char** argv) {
     dump(dir + "/out.bin", out.c_str(), out.size());
     printf("blocks %d\n", nblock);
 
+    // (e) optional: an archive given by the caller (blocks of several segments), walked segment by segment and through
+    //     the free function decompress()
+    if (argc > 3) {
+      const std::vector<char> ar = slurp(argv[3]);
+      StringBuffer src2; src2.write(ar.data(), (int)ar.size());
+      Decompresser d2; d2.setInput(&src2);
+      StringBuffer out2;
+      int nb = 0;
+      while (d2.findBlock()) {
+        for (int k = 0;; ++k) {
+          StringBuffer fn, cm;
+          if (!d2.findFilename(&fn)) break;
+          d2.readComment(&cm);
+          SHA1 check; d2.setOutput(&out2); d2.setSHA1(&check);
+          if (k & 1) d2.decompress(); else { while (d2.decompress(777)) {} }
+          char tr[21]; d2.readSegmentEnd(tr);
+          const uint64_t sz = check.usize();
+          const bool ok = tr[0] == 1 && memcmp(tr + 1, check.result(), 20) == 0;
+          printf("seg %d.%d name %s size %llu stored_sha1 %d match %d\n", nb, k, std::string(fn.c_str(), fn.size()).c_str(), (unsigned long long)sz, tr[0], ok ? 1 : 0);
+        }
+        ++nb;
+      }
+      dump(dir + "/out2.bin", out2.c_str(), out2.size());
+      StringBuffer src3; src3.write(ar.data(), (int)ar.size());
+      StringBuffer out3;
+      decompress(&src3, &out3);
+      dump(dir + "/out3.bin", out3.c_str(), out3.size());
+    }
+
     // (d) errors surface as exceptions carrying the library's message
     try { Compressor bad; StringBuffer o; bad.setOutput(&o); int args[9] = {0}; bad.startBlock("comp 0 0 0 0 1 0 nosuch 1 hcomp halt end", args); printf("error none\n"); }
     catch (std::exception& e) { printf("error %s\n", e.what()); }

@@ -91,6 +91,13 @@ extern "C" long emu_cm_encode(const uint8_t* header, uint32_t hlen, const uint8_
 }
 // Decodes the coded data of one block (everything after the segment header) with the device decoder.
 // Returns the number of restored bytes or -(1000 + device error code).
+static std::vector<ZqDecSeg> g_segs;     // segment table and input position of the last emu_cm_decode
+static u32 g_consumed = 0;
+extern "C" unsigned emu_cm_decode_segments(uint32_t* out3, unsigned cap, uint32_t* consumed) {
+  for (size_t k = 0; k < g_segs.size() && k < cap; ++k) { out3[3 * k] = g_segs[k].unit; out3[3 * k + 1] = g_segs[k].out_end; out3[3 * k + 2] = g_segs[k].trailer; }
+  if (consumed) *consumed = g_consumed;
+  return (unsigned)g_segs.size();
+}
 extern "C" long emu_cm_decode(const uint8_t* header, uint32_t hlen, const uint8_t* coded, uint32_t clen, uint8_t* out, uint32_t cap, int fast) {
   (void)fast;
   try {
@@ -110,15 +117,18 @@ extern "C" long emu_cm_decode(const uint8_t* header, uint32_t hlen, const uint8_
     ZqDecUnit u; memset(&u, 0, sizeof u);
     u.data_off = 0; u.data_len = clen; u.out_off = 0; u.model_off = 0; u.out_cap = cap; u.plan = 0;
     ZqDecResult res; memset(&res, 0, sizeof res);
-    u32 next = 0;
+    u32 next = 0, nseg = 0;
+    std::vector<ZqDecSeg> segs(64);
     const CmTablesDev* dtab = (const CmTablesDev*)&tab;
     const size_t smem = sizeof(CmSmem) + sizeof(CmUnitSmem);
     emu::launch(1, 32, smem, [&] {
-      if (fast & 8) k_cm_decode<2>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
-      else if (fast & 4) k_cm_decode<1>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
-      else k_cm_decode<0>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1);
+      if (fast & 8) k_cm_decode<2>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1, segs.data(), &nseg, 64u, 0u);
+      else if (fast & 4) k_cm_decode<1>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1, segs.data(), &nseg, 64u, 0u);
+      else k_cm_decode<0>(coded, &u, &cp, 1, dtab, blob.data(), model, out, &res, &next, fast & 1, segs.data(), &nseg, 64u, 0u);
     });
     free(model);
+    segs.resize(nseg < 64 ? nseg : 64);
+    g_segs = segs; g_consumed = res.consumed;
     if (res.error) return -(1000 + (long)res.error);
     return (long)res.out_len;
   } catch (const zq::Error& e) {

@@ -119,6 +119,23 @@ class Ref:
             raise RuntimeError("reference Compressor failed: %s" % self.lib.zref_last_error().decode(errors="replace"))
         return out.raw[:r]
 
+    def compress_multi(self, segments, header=None, level=0, pcomp=b"", filename="seg", comment="", sha=True):
+        """One block with several segments through the reference's Compressor class."""
+        import numpy as _np
+        data = b"".join(bytes(x) for x in segments)
+        lens = _np.array([len(x) for x in segments], dtype=_np.uint32)
+        offs = (_np.cumsum(lens, dtype=_np.uint64) - lens).astype(_np.uint64)
+        cap = len(data) + len(data) // 8 + 200000 + 400 * len(segments)
+        out = C.create_string_buffer(cap)
+        self.lib.zref_compress_multi.restype = C.c_longlong
+        r = self.lib.zref_compress_multi(C.c_int(level), bytes(header) if header else None, bytes(pcomp) if pcomp else None,
+                                         C.c_int(len(pcomp)), C.c_int(len(segments)), data + b"\0", offs.ctypes.data_as(C.c_void_p),
+                                         lens.ctypes.data_as(C.c_void_p), filename.encode(), comment.encode(), C.c_int(1 if sha else 0),
+                                         out, C.c_ulonglong(cap))
+        if r < 0:
+            raise RuntimeError("reference Compressor failed: %s" % self.lib.zref_last_error().decode(errors="replace"))
+        return out.raw[:r]
+
     def decompress(self, blob, cap):
         out = C.create_string_buffer(cap + 16)
         r = self.lib.zref_decompress(bytes(blob), C.c_ulonglong(len(blob)), out, C.c_ulonglong(cap + 16))

@@ -118,3 +118,36 @@ def test_pairs_share_a_cta_and_prefetch_is_transparent(emu, oracle):
     s3 = oracle.lz_stream(data, plan3["args"])
     h3, p3 = bytes(plan3["header"]), bytes(plan3["pcomp"])
     assert _emu_encode(emu, h3, p3, s3, ctx=1) == _coded_by_oracle(oracle, h3, p3, s3)
+
+
+@pytest.mark.parametrize("kind", ["level1", "level2", "icm_chain", "stored"])
+def test_blocks_of_several_segments_decode(emu, oracle, ref, kind):
+    """A block of four segments written by the reference's Compressor class: the device decoder carries the model, the
+    coder's range and the post-processor from one segment into the next (Decompresser::decompress, Z:15481-15508),
+    reads the trailers and segment headers in between itself and reports where every segment ends."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    segs = [bytes(corpus.text_unit(1, 3000)), b"", bytes(corpus.mixed_unit(2, 2500)), bytes(corpus.text_unit(1, 1200))]
+    if kind.startswith("level"):
+        header = zq.assemble_config(zq.model_config(int(kind[-1])))["header"]
+    elif kind == "icm_chain":
+        header = zq.assemble_config("comp 1 1 0 0 2 0 icm 12 1 isse 14 0 hcomp *d=a d++ hash *d=a halt end")["header"]    # the one-lane fast path
+    else:
+        header = zq.assemble_config("comp 0 0 0 0 0 hcomp end")["header"]
+    for sha in (True, False):
+        blk = ref.compress_multi(segs, header=header, comment="c", sha=sha)
+        assert ref.decompress(blk, 1 << 20) == b"".join(segs)
+        pre = 13 + 5 + len(header) + len(b"\x01seg0\0c\0\0")
+        coded = blk[pre:]
+        for fast in (1, 0):
+            got = _emu_decode(emu, header, coded, 20000, fast=fast)
+            assert got == b"".join(segs), (kind, sha, fast)
+            buf = (C.c_uint32 * (3 * 16))()
+            used = C.c_uint32(0)
+            k = emu.emu_cm_decode_segments(buf, 16, C.byref(used))
+            assert k == 3
+            ends = [buf[3 * i + 1] for i in range(3)]
+            assert ends == [len(segs[0]), len(segs[0]), len(segs[0]) + len(segs[2])]
+            for i in range(3):
+                assert coded[buf[3 * i + 2]] == (253 if sha else 254)
+            assert coded[used.value] == (253 if sha else 254) and coded[-1] == 255

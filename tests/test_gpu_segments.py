@@ -81,9 +81,22 @@ def test_cpp_facade_driver(ref, tmp_path):
                     "-Wl,-rpath," + os.path.join(ROOT, "zpaqfranz_b200")], check=True)
     data = corpus.text_unit(11, 50000) + corpus.random_unit(12, 700) + corpus.repeats_unit(13, 9000)
     (tmp_path / "in.bin").write_bytes(data)
-    r = subprocess.run([str(exe), str(tmp_path / "in.bin"), str(tmp_path)], capture_output=True, text=True, timeout=600)
+    # a stream the reference's Compressor wrote: a block of five segments (-m2 model), a one-segment block, a block of three
+    multi = [[corpus.text_unit(21, 9000), b"", corpus.random_unit(22, 3000), corpus.text_unit(21, 4000), corpus.repeats_unit(23, 5000)],
+             [corpus.text_unit(24, 20000)], [b"x" * 100, corpus.mixed_unit(25, 7000), b"tail"]]
+    stream = (ref.compress_multi(multi[0], level=2, filename="m", comment="c") + ref.compress_multi(multi[1], level=1, filename="s", comment="20000")
+              + b"junk" + ref.compress_multi(multi[2], level=1, filename="t", comment="", sha=False))
+    (tmp_path / "multi.zpaq").write_bytes(stream)
+    r = subprocess.run([str(exe), str(tmp_path / "in.bin"), str(tmp_path), str(tmp_path / "multi.zpaq")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    lines = dict(l.split(" ", 1) for l in r.stdout.strip().splitlines())
+    want = b"".join(bytes(x) for blk in multi for x in blk)
+    assert (tmp_path / "out2.bin").read_bytes() == want and (tmp_path / "out3.bin").read_bytes() == want
+    segrows = [l.split() for l in r.stdout.splitlines() if l.startswith("seg ")]
+    assert [row[1] for row in segrows] == ["0.0", "0.1", "0.2", "0.3", "0.4", "1.0", "2.0", "2.1", "2.2"]
+    assert [row[3] for row in segrows] == ["m0", "m1", "m2", "m3", "m4", "s0", "t0", "t1", "t2"]
+    assert [int(row[5]) for row in segrows] == [len(x) for blk in multi for x in blk]
+    assert all(row[7] == "1" and row[9] == "1" for row in segrows[:6]) and all(row[7] == "0" for row in segrows[6:])
+    lines = dict(l.split(" ", 1) for l in r.stdout.strip().splitlines() if not l.startswith("seg "))
     assert lines["sha1"] == hashlib.sha1(data).hexdigest()
     assert lines["sha256"] == hashlib.sha256(data).hexdigest()
     assert (tmp_path / "a.zpaq").read_bytes() == ref.compress_block(data, "2", "file_a", "jDC\x01")
@@ -95,3 +108,30 @@ def test_cpp_facade_driver(ref, tmp_path):
     assert "name file_a" in rows[0] and "stored_sha1 1 match 1" in rows[0] and "size %d" % len(data) in rows[0]
     assert "name file_b" in rows[1] and "stored_sha1 1 match 1" in rows[1] and "size %d" % len(data) in rows[1]
     assert lines["error"] != "none"
+
+
+def test_blocks_of_several_segments_through_the_c_abi(ctx, ref):
+    """zq_decompress_blocks on blocks of several segments (reference-written): output = the segments concatenated, every
+    stored SHA-1 verified on the device, zq_decompress_last_segments lists the pieces; a corrupted inner segment is caught."""
+    segs = [[corpus.text_unit(31, 12000), corpus.mixed_unit(32, 5000), b"", corpus.text_unit(31, 800)],
+            [corpus.repeats_unit(33, 30000)],
+            [corpus.random_unit(34, 2000), corpus.text_unit(35, 2000)]]
+    hdr3 = zqmod.assemble_config("comp 1 1 0 0 2 0 icm 12 1 isse 14 0 hcomp *d=a d++ hash *d=a halt end")["header"]
+    blocks = [ref.compress_multi(segs[0], level=2, comment="c"), ref.compress_multi(segs[1], level=1, comment="c"),
+              ref.compress_multi(segs[2], header=hdr3, comment="c")]
+    arena, offs, lens = _pack(blocks)
+    expect = np.array([sum(len(x) for x in b) for b in segs], dtype=np.uint32)
+    dec, doff, dlen, used, tr = ctx.decompress_blocks(arena, offs, lens, expect_len=expect, details=True)
+    for i, b in enumerate(segs):
+        assert dec[int(doff[i]): int(doff[i]) + int(dlen[i])].tobytes() == b"".join(bytes(x) for x in b)
+        assert blocks[i][int(used[i])] == 255
+    table = ctx.last_segments()
+    assert [(s[0], s[2] - s[1]) for s in table] == [(i, len(x)) for i, b in enumerate(segs) for x in b]
+    for s in table:
+        assert blocks[s[0]][s[3]] == 253
+    bad = bytearray(blocks[0])
+    t1 = [s for s in table if s[0] == 0][1][3]          # SHA-1 stored after the second segment
+    bad[t1 + 5] ^= 1
+    arena2, offs2, lens2 = _pack([bytes(bad)])
+    with pytest.raises(Exception, match="SHA-1"):
+        ctx.decompress_blocks(arena2, offs2, lens2, expect_len=expect[:1])

@@ -50,6 +50,7 @@ def _load():
                                          C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zq_decompress_blocks_ex.argtypes = lib.zq_decompress_blocks.argtypes + [C.c_void_p, C.c_void_p]
     lib.zq_decompress_prefix.argtypes = lib.zq_decompress_blocks.argtypes
+    lib.zq_decompress_last_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.zq_compress_segments.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32,
                                          C.c_char_p, C.c_uint32, cpp, cpp, C.c_int, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -485,6 +486,15 @@ class Context:
                                      C.byref(hl), ids.ctypes.data, ids.size, first.ctypes.data, C.byref(nb)))
         return dict(d=d[: dl.value].tobytes(), h=h[: hl.value].tobytes(), nblocks=nb.value,
                     file_frags=[ids[int(first[i]): int(first[i + 1])].tolist() for i in range(n)])
+
+    def last_segments(self):
+        """(block, out_begin, out_end, trailer offset) of every segment of the last decompress call."""
+        p, n = C.c_void_p(0), C.c_uint64(0)
+        self._check(lib.zq_decompress_last_segments(self._h, C.byref(p), C.byref(n)))
+        if not n.value:
+            return []
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n.value, 4))
+        return [tuple(int(x) for x in row) for row in a]
 
     def dedup_first(self, sha1):
         """first[i] = earliest fragment with the digest of fragment i (the device fragment index); sha1: (n, 20) uint8."""

@@ -3,6 +3,7 @@
 // arena, calls zq_compress_blocks and hands the blocks to the Writers.
 #include "../../include/libzpaq_b200.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -254,7 +255,6 @@ bool Decompresser::findFilename(Writer* filename) {
   if (state_ != FILENAME) error("findFilename: not at a segment boundary");
   int c = byte();
   if (c == 1) {
-    if (!first_seg_) error("blocks with more than one segment have no device path yet");
     while (true) {
       c = byte();
       if (c == -1) error("unexpected EOF");
@@ -280,30 +280,49 @@ void Decompresser::readComment(Writer* comment) {
 }
 
 void Decompresser::decode_segment() {
-  // the block runs to the next locator or to EOF; decoding stops at the segment's end by itself
-  size_t from = pos_, nxt;
-  while ((nxt = find_locator(buf_, from)) == (size_t)-1) {
-    from = buf_.size() > 15 ? buf_.size() - 15 : 0;
-    if (from < pos_) from = pos_;
-    if (!fill(buf_.size() + 1)) break;
+  // The device restores a block whole -- the model, the coder's range and the post-processor carry on from one
+  // segment into the next -- so the block's first segment decodes all of them and the later ones are served from
+  // that result (zq_decompress_last_segments says where each one ends).
+  if (first_seg_) {
+    // the block runs to the next locator or to EOF; decoding stops at the last segment's end by itself
+    size_t from = pos_, nxt;
+    while ((nxt = find_locator(buf_, from)) == (size_t)-1) {
+      from = buf_.size() > 15 ? buf_.size() - 15 : 0;
+      if (from < pos_) from = pos_;
+      if (!fill(buf_.size() + 1)) break;
+    }
+    const size_t end = nxt == (size_t)-1 ? buf_.size() : nxt;
+    zq_ctx* c = t_ctx.get();
+    const uint64_t off = blk_;
+    const uint32_t len = (uint32_t)(end - blk_);
+    uint64_t ooff = 0; uint32_t olen = 0, used = 0;
+    unsigned char last_trailer[21];
+    // expected size: the number that opens the comment, else (or with more segments) grow until the decoder stops complaining
+    uint64_t cap = have_expect_ && expect_ <= 0xfffffff0ull ? expect_ : (uint64_t)len * 8 + 65536;
+    for (;;) {
+      const uint32_t e32 = (uint32_t)cap;
+      block_out_.resize(cap + 16);
+      const int rc = zq_decompress_blocks_ex(c, 1, buf_.data(), &off, &len, &e32, block_out_.data(), block_out_.size(), &ooff, &olen, &used, last_trailer);
+      if (rc == ZQ_OK) break;
+      if (rc == ZQ_E_OUTPUT && cap < 0xf0000000ull) { cap = cap * 4 < 0xfffffff0ull ? std::max<uint64_t>(cap * 4, 65536) : 0xfffffff0ull; continue; }
+      error(zq_last_error(c));
+    }
+    block_out_.resize(olen);
+    const zq_segment* zs = nullptr; uint64_t nz = 0;
+    if (zq_decompress_last_segments(c, &zs, &nz) != ZQ_OK || nz == 0) error(zq_last_error(c));
+    segs_.clear();
+    for (uint64_t k = 0; k < nz; ++k) { Seg g; g.out_begin = zs[k].out_begin; g.out_end = zs[k].out_end; g.trailer = zs[k].trailer; segs_.push_back(g); }
+    seg_idx_ = 0;
   }
-  const size_t end = nxt == (size_t)-1 ? buf_.size() : nxt;
-  zq_ctx* c = t_ctx.get();
-  const uint64_t off = blk_;
-  const uint32_t len = (uint32_t)(end - blk_);
-  uint64_t ooff = 0; uint32_t olen = 0, used = 0;
-  // expected size: the number that opens the comment, else grow until the decoder stops complaining
-  uint64_t cap = have_expect_ && expect_ <= 0xfffffff0ull ? expect_ : (uint64_t)len * 8 + 65536;
-  for (;;) {
-    const uint32_t e32 = (uint32_t)cap;
-    obuf_.resize(cap + 16);
-    const int rc = zq_decompress_blocks_ex(c, 1, buf_.data(), &off, &len, &e32, obuf_.data(), obuf_.size(), &ooff, &olen, &used, trailer_);
-    if (rc == ZQ_OK) break;
-    if (rc == ZQ_E_OUTPUT && cap < 0xf0000000ull) { cap = cap * 4 < 0xfffffff0ull ? cap * 4 : 0xfffffff0ull; continue; }
-    error(zq_last_error(c));
-  }
-  obuf_.resize(olen); opos_ = 0;
-  seg_end_ = blk_ + used;
+  if (seg_idx_ >= segs_.size()) error("segment not found in the decoded block");
+  const Seg& g = segs_[seg_idx_];
+  obuf_.assign(block_out_.begin() + g.out_begin, block_out_.begin() + g.out_end);
+  opos_ = 0;
+  const size_t t = blk_ + g.trailer;
+  if (t >= buf_.size()) error("unexpected end of file");
+  memset(trailer_, 0, sizeof trailer_);
+  if (buf_[t] == 253) { if (t + 21 > buf_.size()) error("unexpected end of file"); trailer_[0] = 1; memcpy(trailer_ + 1, &buf_[t + 1], 20); }
+  seg_end_ = t + (buf_[t] == 253 ? 21 : 1);
   decoded_ = true;
 }
 
@@ -328,6 +347,7 @@ void Decompresser::readSegmentEnd(char* sha1string) {
   if (sha1string) memcpy(sha1string, trailer_, trailer_[0] ? 21 : 1);
   pos_ = seg_end_;
   obuf_.clear(); opos_ = 0; decoded_ = false; first_seg_ = false;
+  ++seg_idx_;
   state_ = FILENAME;
 }
 
@@ -365,7 +385,7 @@ void decompress(Reader* in, Writer* out) {
     if (memcmp(&buf[i], tag, 13) == 0 && buf[i + 13] == 'z' && buf[i + 14] == 'P' && buf[i + 15] == 'Q') off.push_back(i);
   if (off.empty()) return;
   const int n = (int)off.size();
-  std::vector<uint32_t> len(n), olen(n);
+  std::vector<uint32_t> len(n), olen(n), expect(n);
   std::vector<uint64_t> ooff(n);
   uint64_t cap = 0;
   for (int i = 0; i < n; ++i) {
@@ -382,11 +402,25 @@ void decompress(Reader* in, Writer* out) {
     uint64_t e = 0;
     while (p < buf.size() && buf[p] >= '0' && buf[p] <= '9' && e <= 0xfffffff0ull) e = e * 10 + (buf[p++] - '0');
     if (e > 0xfffffff0ull) error("archive corrupted");
+    expect[i] = (uint32_t)e;
     cap += e;
   }
   std::vector<uint8_t> outbuf(cap + 16);
   zq_ctx* c = t_ctx.get();
-  int rc = zq_decompress_blocks(c, n, buf.data(), off.data(), len.data(), nullptr, outbuf.data(), outbuf.size(), ooff.data(), olen.data());
+  int rc;
+  for (int attempt = 0;; ++attempt) {
+    // the comment's number is the FIRST segment's size: blocks of several segments (or comments without a number) need
+    // more room -- grow and decode again
+    rc = zq_decompress_blocks(c, n, buf.data(), off.data(), len.data(), expect.data(), outbuf.data(), outbuf.size(), ooff.data(), olen.data());
+    if (rc != ZQ_E_OUTPUT || attempt >= 8) break;
+    cap = 0;
+    for (int i = 0; i < n; ++i) {
+      const uint64_t g = std::max<uint64_t>((uint64_t)expect[i] * 4, (uint64_t)len[i] * 8 + 65536);
+      expect[i] = (uint32_t)std::min<uint64_t>(g, 0xfffffff0ull);
+      cap += expect[i];
+    }
+    outbuf.resize(cap + 16);
+  }
   if (rc != ZQ_OK) error(zq_last_error(c));
   for (int i = 0; i < n; ++i) out->write((const char*)outbuf.data() + ooff[i], (int)olen[i]);
 }

@@ -79,6 +79,7 @@ struct zq_ctx {
   int lz_old = 0;                         // 1: warp-per-block LZ77 parser for every block (ZQ_LZ_OLD=1); 0: position-parallel scan/walk/emit (zq_lz77_scan.cuh)
   int scan_occ[2][2] = {{0, 0}, {0, 0}};  // resident CTAs per SM of k_lz_scan<u16/u32, pass> (queried once)
   int cm_jit = 1;                         // 1: contexts from the translated HCOMP (zq_jit.cpp, NVRTC) instead of the interpreter; 2: generated coder too (ZQ_CM_JIT)
+  std::vector<zq_segment> last_segs;      // every segment of the last zq_decompress_* call, in (block, position) order
   void (*gate_fn)(void*, int) = nullptr;  // zq_set_compute_gate: called with 1 before the first kernel of a batch, 0 after its last
   void* gate_arg = nullptr;
   bool cm_jit_auto = true;                // no ZQ_CM_JIT in the environment: translate only the models whose context warp is the bottleneck (<= 8 components)
@@ -1046,6 +1047,11 @@ static int decompress_impl(zq_ctx* c, int n, const uint8_t* in_base, const uint6
   size_t budget = c->model_budget;
   { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); fr += c->d_model.cap; budget = std::min<size_t>(budget, fr > ((size_t)6 << 30) ? fr - ((size_t)6 << 30) : fr / 2); }
   std::vector<ZqDecResult> res(n);
+  // segments that are followed by another one in their block are reported through a table (most blocks have none)
+  const u32 segcap = (u32)std::min<uint64_t>((uint64_t)n + 65536, 1u << 24);
+  ZQ_CUDA(c, c->d_kbuf.ensure(16 + (size_t)segcap * sizeof(ZqDecSeg)));
+  u32* d_nseg = c->d_kbuf.as<u32>(); ZqDecSeg* d_segs = (ZqDecSeg*)(c->d_kbuf.as<u8>() + 16);
+  ZQ_CUDA(c, cudaMemsetAsync(d_nseg, 0, 16, c->stream));
   const size_t dec_smem = sizeof(CmSmem) + 16 * sizeof(CmUnitSmem);
   if (!c->attr_cm_dec) {
     cudaFuncSetAttribute(k_cm_decode<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
@@ -1079,7 +1085,7 @@ static int decompress_impl(zq_ctx* c, int n, const uint8_t* in_base, const uint6
     ++c->launches;
     cmd<<<std::min((wn + 15) / 16, c->num_sms), 512, dec_smem, c->stream>>>(
         c->d_in.as<u8>(), c->d_units.as<ZqDecUnit>(), c->d_cmplans.as<ZqCmPlan>(), wn, c->d_tables.as<CmTablesDev>(), c->d_blob.as<u8>(),
-        c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr, c->cm_fast);
+        c->d_model.as<u8>(), c->d_out.as<u8>(), d_res, ctr, c->cm_fast, d_segs, d_nseg, segcap, (u32)w0);
     ++c->launches;
     ZQ_CUDA(c, cudaMemcpyAsync(res.data() + w0, d_res, (size_t)wn * sizeof(ZqDecResult), cudaMemcpyDeviceToHost, c->stream));
     ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1087,32 +1093,54 @@ static int decompress_impl(zq_ctx* c, int n, const uint8_t* in_base, const uint6
     w0 = w1;
   }
   // results, trailers, checksums
-  std::vector<uint64_t> soff; std::vector<uint64_t> slen; std::vector<int> sidx;
+  u32 nseg = 0;
+  ZQ_CUDA(c, cudaMemcpyAsync(&nseg, d_nseg, 4, cudaMemcpyDeviceToHost, c->stream));
+  ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<ZqDecSeg> inner(std::min(nseg, segcap));
+  if (!inner.empty()) {
+    ZQ_CUDA(c, cudaMemcpyAsync(inner.data(), d_segs, inner.size() * sizeof(ZqDecSeg), cudaMemcpyDeviceToHost, c->stream));
+    ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::sort(inner.begin(), inner.end(), [](const ZqDecSeg& a, const ZqDecSeg& b) { return a.unit != b.unit ? a.unit < b.unit : a.trailer < b.trailer; });
+  }
+  c->last_segs.clear();
+  std::vector<uint64_t> soff; std::vector<uint64_t> slen; std::vector<const uint8_t*> swant;
+  size_t ip = 0;
   for (int u = 0; u < n; ++u) {
     const ZqDecResult& r = res[u];
-    static const char* msg[] = {"", "archive corrupted", "unexpected end of file", "decoded size exceeds the expected size", "ZPAQL execution error", "unknown post processing type"};
+    static const char* msg[] = {"", "archive corrupted", "unexpected end of file", "decoded size exceeds the expected size", "ZPAQL execution error", "unknown post processing type", "too many segments in one call"};
+    const uint8_t* b = in_base + in_off[u];
+    const size_t data0 = (size_t)(units[u].data_off + lo - in_off[u]);     // offset of the first coded byte in the block
+    uint32_t seg_begin = 0;
+    for (; ip < inner.size() && inner[ip].unit == (u32)u; ++ip) {          // the segments before the last one
+      const ZqDecSeg& sg = inner[ip];
+      const size_t p = data0 + sg.trailer;
+      zq_segment zs; zs.block = (uint32_t)u; zs.out_begin = seg_begin; zs.out_end = sg.out_end; zs.trailer = (uint32_t)p;
+      c->last_segs.push_back(zs);
+      if (b[p] == 253) { soff.push_back(units[u].out_off + seg_begin); slen.push_back(sg.out_end - seg_begin); swant.push_back(b + p + 1); }
+      seg_begin = sg.out_end;
+    }
     if (prefix && (r.error == 3 || r.error == 0)) {   // Decompresser::decompress(n): stop after n bytes, no trailer is looked at
       out_len[u] = std::min<uint32_t>(r.out_len, units[u].out_cap);   // (the writer counts the byte that did not fit)
       if (in_used) in_used[u] = 0;
       if (sha1_out) sha1_out[(size_t)u * 21] = 0;
       continue;
     }
-    if (r.error) return fail(c, r.error == 3 ? ZQ_E_OUTPUT : ZQ_E_METHOD, msg[r.error < 6 ? r.error : 1]);
+    if (r.error) return fail(c, r.error == 3 ? ZQ_E_OUTPUT : r.error == 6 ? ZQ_E_UNSUPPORTED : ZQ_E_METHOD, msg[r.error < 7 ? r.error : 1]);
     out_len[u] = r.out_len;
-    const uint8_t* b = in_base + in_off[u];
-    const size_t p = (size_t)(units[u].data_off + lo - in_off[u]) + r.consumed;
+    const size_t p = data0 + r.consumed;
     if (p >= in_len[u]) return fail(c, ZQ_E_METHOD, "missing end of segment marker");
     if (b[p] == 253) {
       if (p + 21 > in_len[u]) return fail(c, ZQ_E_METHOD, "unexpected EOF");
-      soff.push_back(units[u].out_off); slen.push_back(r.out_len); sidx.push_back(u);
+      soff.push_back(units[u].out_off + seg_begin); slen.push_back(r.out_len - seg_begin); swant.push_back(b + p + 1);
     } else if (b[p] != 254) return fail(c, ZQ_E_METHOD, "missing end of segment marker");
+    { zq_segment zs; zs.block = (uint32_t)u; zs.out_begin = seg_begin; zs.out_end = r.out_len; zs.trailer = (uint32_t)p; c->last_segs.push_back(zs); }
     const size_t e = p + (b[p] == 253 ? 21 : 1);
-    if (e < in_len[u] && b[e] == 1) return fail(c, ZQ_E_UNSUPPORTED, "blocks with more than one segment have no device path yet");
+    if (e < in_len[u] && b[e] == 1) return fail(c, ZQ_E_METHOD, "segment header corrupted");
     if (in_used) in_used[u] = (uint32_t)e;       // offset of the end-of-block byte (255)
     if (sha1_out) { sha1_out[(size_t)u * 21] = b[p] == 253; if (b[p] == 253) memcpy(sha1_out + (size_t)u * 21 + 1, b + p + 1, 20); }
   }
-  if (!sidx.empty()) {
-    const int k = (int)sidx.size();
+  if (!soff.empty()) {
+    const int k = (int)soff.size();
     ZQ_CUDA(c, c->d_misc.ensure((size_t)k * 16));
     ZQ_CUDA(c, c->d_sha.ensure((size_t)k * 20));
     u64* d_off = c->d_misc.as<u64>(); u64* d_len = d_off + k;
@@ -1123,12 +1151,8 @@ static int decompress_impl(zq_ctx* c, int n, const uint8_t* in_base, const uint6
     std::vector<uint8_t> dg((size_t)k * 20);
     ZQ_CUDA(c, cudaMemcpyAsync(dg.data(), c->d_sha.p, dg.size(), cudaMemcpyDeviceToHost, c->stream));
     ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < k; ++i) {
-      const int u = sidx[i];
-      const uint8_t* b = in_base + in_off[u];
-      const size_t p = (size_t)(units[u].data_off + lo - in_off[u]) + res[u].consumed;
-      if (memcmp(b + p + 1, dg.data() + (size_t)i * 20, 20) != 0) return fail(c, ZQ_E_METHOD, "SHA-1 checksum mismatch after decompression");
-    }
+    for (int i = 0; i < k; ++i)
+      if (memcmp(swant[i], dg.data() + (size_t)i * 20, 20) != 0) return fail(c, ZQ_E_METHOD, "SHA-1 checksum mismatch after decompression");
   }
   if (out_pos) ZQ_CUDA(c, cudaMemcpy(out_base, c->d_out.p, out_pos, cudaMemcpyDeviceToHost));
   return ZQ_OK;
@@ -1138,6 +1162,13 @@ int zq_decompress_blocks_ex(zq_ctx* c, int n, const uint8_t* in_base, const uint
                             const uint32_t* expect_len, uint8_t* out_base, uint64_t out_cap, uint64_t* out_off, uint32_t* out_len,
                             uint32_t* in_used, uint8_t* sha1_out) {
   return decompress_impl(c, n, in_base, in_off, in_len, expect_len, out_base, out_cap, out_off, out_len, in_used, sha1_out, false);
+}
+
+int zq_decompress_last_segments(zq_ctx* c, const zq_segment** segs, uint64_t* nsegs) {
+  if (!c) return ZQ_E_NODEVICE;
+  if (!segs || !nsegs) return fail(c, ZQ_E_ARG, "bad argument");
+  *segs = c->last_segs.data(); *nsegs = c->last_segs.size();
+  return ZQ_OK;
 }
 
 int zq_decompress_prefix(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,

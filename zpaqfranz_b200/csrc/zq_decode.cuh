@@ -22,7 +22,14 @@ struct ZqDecUnit {
 struct ZqDecResult {
   u32 out_len;      // restored bytes
   u32 consumed;     // coded bytes read, including the 4 end-of-stream zeros
-  u32 error;        // 0 ok; 1 corrupted; 2 unexpected end; 3 output overflow; 4 ZPAQL error; 5 bad post-processing type
+  u32 error;        // 0 ok; 1 corrupted; 2 unexpected end; 3 output overflow; 4 ZPAQL error; 5 bad post-processing type; 6 segment table full
+  u32 pad;
+};
+
+struct ZqDecSeg {     // one record per segment that is FOLLOWED by another one in its block (the last one is in ZqDecResult)
+  u32 unit;         // index of the block in the launch
+  u32 out_end;      // restored bytes of the block up to the end of this segment
+  u32 trailer;      // offset (from data_off) of this segment's 253 / 254 byte
   u32 pad;
 };
 
@@ -30,6 +37,28 @@ struct DecIn {
   const u8* p; u64 len, pos; u32 error;
   __device__ __forceinline__ int get() { if (pos < len) return p[pos++]; error = 2; return 0; }
 };
+
+// After an end of stream: does another segment follow in this block (Decompresser::readSegmentEnd + findFilename +
+// readComment, Z:15509-15534, Z:15440-15475)?  The trailer is 254, or 253 and a 20-byte SHA-1; a following segment
+// opens with 1, filename, 0, comment, 0, reserved 0.  Leaves `in` at the trailer when the block ends here (the host
+// reads it), else at the next segment's first coded byte and returns the trailer's position.
+__device__ __forceinline__ bool dec_next_segment(DecIn& in, u32& trailer) {
+  if (in.pos >= in.len) return false;
+  const u32 c = in.p[in.pos];
+  const u64 nxt = in.pos + (c == 253 ? 21 : 1);
+  if ((c != 253 && c != 254) || nxt >= in.len || in.p[nxt] != 1) return false;
+  trailer = (u32)in.pos;
+  in.pos = nxt + 1;
+  while (in.get() != 0 && !in.error) {}
+  while (in.get() != 0 && !in.error) {}
+  if (in.get() != 0 && !in.error) in.error = 1;
+  return !in.error;
+}
+__device__ __forceinline__ void dec_record_segment(ZqDecSeg* segs, u32* nseg, u32 segcap, u32 unit, u32 out_end, u32 trailer, u32& err) {
+  const u32 k = atomicAdd(nseg, 1u);
+  if (k < segcap) { ZqDecSeg r; r.unit = unit; r.out_end = out_end; r.trailer = trailer; r.pad = 0; segs[k] = r; }
+  else err = 6;
+}
 
 // The post-processor state machine (PostProcessor::write, Z:15368)
 struct DecPost {
@@ -133,7 +162,8 @@ template <int VM>
 __global__ void __launch_bounds__(512, 1)
 k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units, const ZqCmPlan* __restrict__ cmplans, int nunits,
             const CmTablesDev* __restrict__ tab, const u8* __restrict__ blob, u8* __restrict__ model_base,
-            u8* __restrict__ out_base, ZqDecResult* __restrict__ results, u32* __restrict__ next_unit, int fast) {
+            u8* __restrict__ out_base, ZqDecResult* __restrict__ results, u32* __restrict__ next_unit, int fast,
+            ZqDecSeg* __restrict__ segs, u32* __restrict__ nseg, u32 segcap, u32 unit_base) {
   ZQ_DYN_SMEM(smem_raw);
   CmSmem& T = *reinterpret_cast<CmSmem*>(smem_raw);
   {
@@ -171,20 +201,27 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
         chain_setup(A, cp.comp[0], model);
         chain_setup(B, cp.comp[1], model);
         ChainDec D; D.low = 1; D.high = 0xffffffffu; D.curr = 0; D.err = 0; D.in = in;
-        for (int k = 0; k < 4; ++k) D.curr = D.curr << 8 | (u32)D.in.get();
         u32 ha = 0, hb = 0;
-        for (;;) {
-          if (D.bit(0)) { if (D.curr != 0 && !D.err) D.err = 1; break; }
-          chain_row_switch(A, ha + 16u); chain_row_switch(B, hb + 16u);
-          const u32 hi = chain1_dec_nibble(A, B, D, T);
-          chain_row_switch(A, ha + 16u * (16u + hi)); chain_row_switch(B, hb + 16u * (16u + hi));
-          const u32 c = hi << 4 | chain1_dec_nibble(A, B, D, T);
-          cm_vm_run<VM, false>(vm, c, nullptr);
-          ha = vm.h[0]; hb = vm.h[1 & vm.hmask];
-          dec_post_write<VM, true>(pp, (int)c);
+        for (;;) {   // segments: the model, the coder's range and the post-processor carry on (Z:15481-15508)
+          for (int k = 0; k < 4; ++k) D.curr = D.curr << 8 | (u32)D.in.get();
+          for (;;) {
+            if (D.bit(0)) { if (D.curr != 0 && !D.err) D.err = 1; break; }
+            chain_row_switch(A, ha + 16u); chain_row_switch(B, hb + 16u);
+            const u32 hi = chain1_dec_nibble(A, B, D, T);
+            chain_row_switch(A, ha + 16u * (16u + hi)); chain_row_switch(B, hb + 16u * (16u + hi));
+            const u32 c = hi << 4 | chain1_dec_nibble(A, B, D, T);
+            cm_vm_run<VM, false>(vm, c, nullptr);
+            ha = vm.h[0]; hb = vm.h[1 & vm.hmask];
+            dec_post_write<VM, true>(pp, (int)c);
+            if (D.err || D.in.error || pp.error || vm.error || pp.vm.error) break;
+          }
           if (D.err || D.in.error || pp.error || vm.error || pp.vm.error) break;
+          dec_post_write<VM, true>(pp, -1);
+          u32 trailer = 0;
+          if (pp.error || pp.vm.error || !dec_next_segment(D.in, trailer)) break;
+          dec_record_segment(segs, nseg, segcap, unit_base + (u32)t, pp.o.len, trailer, D.err);
+          if (D.err) break;
         }
-        if (!D.err && !D.in.error && !pp.error && !vm.error && !pp.vm.error) dec_post_write<VM, true>(pp, -1);
         ZqDecResult r;
         r.out_len = pp.o.len; r.consumed = (u32)D.in.pos; r.pad = 0;
         r.error = D.err ? D.err : D.in.error ? D.in.error : pp.error ? pp.error : (vm.error || pp.vm.error) ? 4u : 0u;
@@ -195,7 +232,6 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
     }
     if (cp.n > 0) {
       u32 low = 1, high = 0xffffffffu, curr = 0;
-      for (int k = 0; k < 4; ++k) curr = curr << 8 | (u32)in.get();
       auto decode = [&](u32 p16) -> int {   // Decoder::decode, Z:15282
         if (curr < low || curr > high) { err = 1; return 0; }
         const u32 mid = low + (u32)(((u64)(high - low) * p16) >> 16);
@@ -207,38 +243,56 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
         }
         return y;
       };
-      for (;;) {
-        if (decode(0)) { if (curr != 0 && !err) err = 1; break; }
-        int c = 1;
-        while (c < 256) {
-          const u32 p16 = (u32)cm_predict(L, X, T) * 2 + 1;
-          const int y = decode(p16);
-          c += c + y;
-          if (cm_update(L, X, T, y)) {   // byte complete: contexts of the next one
-            if (lane == 0) cm_vm_run<VM, false>(vm, (u32)(c - 256), nullptr);
-            __syncwarp();
-            if (lane < (u32)X.n) L.h = vm.h[lane & vm.hmask];
-            vmerr = (u32)__shfl_sync(ZQ_FULL, vm.error, 0);
+      for (;;) {   // segments: the model, the coder's range and the post-processor carry on (Z:15481-15508)
+        for (int k = 0; k < 4; ++k) curr = curr << 8 | (u32)in.get();
+        for (;;) {
+          if (decode(0)) { if (curr != 0 && !err) err = 1; break; }
+          int c = 1;
+          while (c < 256) {
+            const u32 p16 = (u32)cm_predict(L, X, T) * 2 + 1;
+            const int y = decode(p16);
+            c += c + y;
+            if (cm_update(L, X, T, y)) {   // byte complete: contexts of the next one
+              if (lane == 0) cm_vm_run<VM, false>(vm, (u32)(c - 256), nullptr);
+              __syncwarp();
+              if (lane < (u32)X.n) L.h = vm.h[lane & vm.hmask];
+              vmerr = (u32)__shfl_sync(ZQ_FULL, vm.error, 0);
+            }
           }
+          dec_post_write<VM, false>(pp, c - 256);
+          if (err || in.error || pp.error || vmerr || pp.vm.error) break;
         }
-        dec_post_write<VM, false>(pp, c - 256);
         if (err || in.error || pp.error || vmerr || pp.vm.error) break;
+        dec_post_write<VM, false>(pp, -1);
+        u32 trailer = 0;
+        if (pp.error || pp.vm.error || !dec_next_segment(in, trailer)) break;
+        if (lane == 0) dec_record_segment(segs, nseg, segcap, unit_base + (u32)t, pp.o.len, trailer, err);
+        err = __shfl_sync(ZQ_FULL, err, 0);
+        if (err) break;
       }
     } else {
-      for (;;) {   // unmodeled: big-endian u32 length, that many bytes, ... , length 0
-        u32 cl = 0;
-        for (int k = 0; k < 4; ++k) cl = cl << 8 | (u32)in.get();
-        if (cl == 0 || in.error) break;
-        // the length comes from the archive: never loop past the bytes that are there, stop at the first error
-        if ((u64)cl > (u64)in.len - in.pos) { in.error = 1; break; }
-        for (u32 k = 0; k < cl; ++k) {
-          dec_post_write<VM, false>(pp, in.get());
+      for (;;) {   // segments
+        for (;;) {   // unmodeled: big-endian u32 length, that many bytes, ... , length 0
+          u32 cl = 0;
+          for (int k = 0; k < 4; ++k) cl = cl << 8 | (u32)in.get();
+          if (cl == 0 || in.error) break;
+          // the length comes from the archive: never loop past the bytes that are there, stop at the first error
+          if ((u64)cl > (u64)in.len - in.pos) { in.error = 1; break; }
+          for (u32 k = 0; k < cl; ++k) {
+            dec_post_write<VM, false>(pp, in.get());
+            if (in.error || pp.error || pp.vm.error) break;
+          }
           if (in.error || pp.error || pp.vm.error) break;
         }
         if (in.error || pp.error || pp.vm.error) break;
+        dec_post_write<VM, false>(pp, -1);
+        u32 trailer = 0;
+        if (pp.error || pp.vm.error || !dec_next_segment(in, trailer)) break;
+        if (lane == 0) dec_record_segment(segs, nseg, segcap, unit_base + (u32)t, pp.o.len, trailer, err);
+        err = __shfl_sync(ZQ_FULL, err, 0);
+        if (err) break;
       }
     }
-    if (!err && !in.error && !pp.error && !vmerr && !pp.vm.error) dec_post_write<VM, false>(pp, -1);
     if (lane == 0) {
       ZqDecResult r;
       r.out_len = pp.o.len; r.consumed = (u32)in.pos; r.pad = 0;
