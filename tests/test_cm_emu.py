@@ -151,3 +151,28 @@ def test_blocks_of_several_segments_decode(emu, oracle, ref, kind):
             for i in range(3):
                 assert coded[buf[3 * i + 2]] == (253 if sha else 254)
             assert coded[used.value] == (253 if sha else 254) and coded[-1] == 255
+
+
+def test_models_wider_than_a_warp(emu, oracle):
+    """33 components: method 5 on text in which two periods are detected (fixed-width records).  One lane evaluates the
+    components in index order (zq_cm_wide.cuh) -- coded bytes equal the oracle's, the decoder restores the input."""
+    data = b"".join(b"%06d,abcde,%08d,xyzxyz\n" % (i, i * 7) for i in range(60))
+    plan = zq.plan_block("56,200,1", data)
+    header, pcomp = bytes(plan["header"]), bytes(plan["pcomp"])
+    assert header[6] == 33
+    stream = oracle.lz_stream(data, plan["args"]) if (plan["args"][1] & 3) else data
+    want = _coded_by_oracle(oracle, header, pcomp, stream)
+    assert _emu_encode(emu, header, pcomp, stream) == want
+    assert _emu_decode(emu, header, want + b"\0\0\0\0", len(data)) == data
+    # a hand-written model of 40 components with every type beyond lane 31
+    comps = " ".join("%d cm 10 16" % i if i % 3 == 0 else "%d icm 8" % i if i % 3 == 1 else "%d isse 8 %d" % (i, i - 1) for i in range(32))
+    cfg = ("comp 3 3 0 0 40 " + comps + " 32 match 10 12 33 avg 0 1 100 34 mix2 6 32 33 20 255 35 mix 8 0 35 20 255 "
+           "36 sse 8 35 8 255 37 const 150 38 mix 0 30 8 24 0 39 mix2 0 36 38 16 0 "
+           "hcomp c++ *c=a b=c a=0 d= 0 hash *d=a d++ b-- hash *d=a d++ a=*c a<<= 9 *d=a d++ hash *d=a d++ "
+           "a=*c *d=a d++ a=c *d=a d++ hash *d=a d++ a+=*c *d=a halt end")
+    h40 = bytes(zq.assemble_config(cfg)["header"])
+    assert h40[6] == 40
+    for d in (b"", b"abracadabra" * 20, corpus.text_unit(4, 500)):
+        want = _coded_by_oracle(oracle, h40, b"", d)
+        assert _emu_encode(emu, h40, b"", d) == want, len(d)
+        assert _emu_decode(emu, h40, want + b"\0\0\0\0", len(d)) == d, len(d)

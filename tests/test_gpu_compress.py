@@ -218,12 +218,25 @@ def test_level5_period_models_on_device(ctx, zq, ref):
     for i, u in enumerate(units):
         assert "c0,0,%d" % (999 + 37) in zq.plan_block("5", units[0])["method"]
         assert out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes() == ref.compress_block(u, "5", "p", ""), i
-    # text + two periodic models = 33 components: no device path, reported loudly (never a CPU fallback)
-    two = (corpus.random_unit(41, 41) * 200)[:8000]
-    if zq.plan_block("56,180,1", two)["header"][6] > 32:
-        a2, o2, l2 = _arena([two])
-        with pytest.raises(zq.ZqError):
-            ctx.compress_blocks(a2, o2, l2, method="56,180,1")
+    # text + two periodic models = 33 components, one more than a warp has lanes: coded by one lane component by
+    # component (zq_cm_wide.cuh), bit-exact, and the device decoder restores it; mixed in a batch with ordinary blocks
+    wide = [(corpus.random_unit(41, 41) * 200)[:8000], b"".join(b"%06d,abcde,%08d,xyzxyz\n" % (i, i * 7) for i in range(400)),
+            corpus.text_unit(5, 6000), b""]
+    assert zq.plan_block("56,180,1", wide[0])["header"][6] == 33 and zq.plan_block("56,180,1", wide[1])["header"][6] == 33
+    a2, o2, l2 = _arena(wide)
+    out, ooff, olen = ctx.compress_blocks(a2, o2, l2, method="56,180,1", filename="w", comment="")
+    for i, u in enumerate(wide):
+        assert out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes() == ref.compress_block(u, "56,180,1", "w", ""), i
+    dec, doff, dlen = ctx.decompress_blocks(out, ooff, olen, expect_len=l2)
+    for i, u in enumerate(wide):
+        assert dec[int(doff[i]): int(doff[i]) + int(dlen[i])].tobytes() == u, i
+    # beyond 64 components there is no device path: reported loudly (never a CPU fallback)
+    comps = " ".join("%d cm 8 16" % i for i in range(65))
+    cfg = "comp 0 0 0 0 66 " + comps + " 65 mix 0 0 65 24 0 hcomp halt end"
+    hdr = zq.assemble_config(cfg)["header"]
+    a3, o3, l3 = _arena([b"abc" * 100])
+    with pytest.raises(zq.ZqError):
+        ctx.compress_segments(a3, o3, l3, hdr)
 
 
 def test_unsupported_is_loud(ctx, zq):

@@ -563,6 +563,7 @@ int compress_core(zq_ctx* c, int n, const uint8_t* d_in, const uint64_t* in_off,
           // measured on B200: -m3 (2 components) 442 -> 294 ms per 100 MB with the translated program, -m5 (22) 10 % slower
           // (its coder is the critical path and the context table of every byte costs traffic)
           if (c->cm_jit_auto && cp.n > 8) continue;
+          if (cp.n > ZQ_CM_LANES) continue;                                // wide models: one lane does everything (zq_cm_wide.cuh)
           const u8* hc = blob.data() + cp.hcomp_off;
           ZqCmPlan kp = cp; kp.hcomp_off = 0; kp.fill_first = 0;       // per-call positions are not part of the model
           std::string key((const char*)&kp, sizeof(ZqCmPlan));          // components, sizes and table offsets

@@ -470,6 +470,10 @@ __device__ bool cm_update(CmLane& L, CmCtx& X, const CmSmem& T, int y) {
   return false;
 }
 
+}  // namespace zqdev
+#include "zq_cm_wide.cuh"
+namespace zqdev {
+
 // Lane state for a block: component `lane` of plan `cp`, tables in `model`, row cache in `S`.
 __device__ __forceinline__ void cm_setup(CmLane& L, CmCtx& X, const ZqCmPlan& cp, u8* model, CmUnitSmem& S) {
   const u32 lane = lane_id();
@@ -728,6 +732,35 @@ k_cm_encode(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units, co
     else { stream = in_base + u.in_off; slen = u.n; }
     const u8* __restrict__ head = blob + pl.payload_off;
     const u32 hlen = pl.payload_len, K = hlen + slen;
+    if (cp.n > ZQ_CM_LANES) {
+      // ---- a model wider than the warp: the coder warp's lane 0 runs the context machine and every component itself
+      if (role == 0) {
+        CmVm vm;
+        cm_vm_setup(vm, cp, model, blob, S);
+        if (lane == 0) {
+          CmCoder E; E.init(coded_base + u.coded_off, u.coded_cap);
+          CmWide W;
+          cmw_setup(W, cp, model);
+          for (u32 k = 0; k < K; ++k) {
+            const u32 c = k < hlen ? head[k] : stream[k - hlen];
+            E.encode(0, 0);
+            for (int i = 7; i >= 0; --i) {
+              const u32 p16 = (u32)cmw_predict(W, vm.h, vm.hmask, T) * 2 + 1;
+              const int y = (c >> i) & 1;
+              E.encode(y, p16);
+              cmw_update(W, vm.h, vm.hmask, T, y);
+            }
+            if (k + 1 < K) cm_vm_run<VM, false>(vm, c, nullptr);
+          }
+          E.encode(1, 0);   // end of segment
+          coded_len[ui] = (u32)(E.out - (coded_base + u.coded_off));
+          if (E.overflow) atomicOr(err_flag, 1u);
+          if (vm.error) atomicOr(err_flag, 2u);
+        }
+        __syncwarp();
+      }
+      continue;
+    }
     if (role == 1) {
       // ---- context warp: HCOMP on byte k -> ring slot k, for every byte but the last.  When the block's contexts
       // were already computed by the translated program (zq_jit.cpp: ctx_off[ui] != ~0), they are only streamed in.

@@ -93,7 +93,7 @@ const CmTables& cm_tables() {
 ZqCmPlan make_cm_plan(const Assembled& code, std::vector<ZqCmFill>& fills) {
   ZqCmPlan p;
   memset(&p, 0, sizeof p);
-  if (code.ncomp > ZQ_CM_MAXCOMP) throw Error("models with more than 32 components have no device path yet");
+  if (code.ncomp > ZQ_CM_MAXCOMP) throw Error("models with more than 64 components have no device path yet");
   p.n = code.ncomp; p.hh = code.hh; p.hm = code.hm;
   if (p.hh > 24 || p.hm > 28) throw Error("HCOMP memory too large for the device path");
   p.fill_first = (uint32_t)fills.size();
@@ -168,7 +168,7 @@ ZqCmPlan make_cm_plan(const Assembled& code, std::vector<ZqCmFill>& fills) {
         c.cm_off = off; c.cm_mask = (uint32_t)(((uint64_t)1 << c.a1) - 1);   // rows-1
         add_fill(off, bytes, ZQ_FILL_U32, (uint32_t)(65536 / c.a3)); off = align256(off + bytes);
         for (int j = 0; j < c.a3; ++j) lv = std::max(lv, 1 + level[c.a2 + j]);
-        p.mix_mask |= 1u << i;
+        if (i < ZQ_CM_LANES) p.mix_mask |= 1u << i;
         break;
       }
       case ZQ_ISSE: {
@@ -199,6 +199,10 @@ ZqCmPlan make_cm_plan(const Assembled& code, std::vector<ZqCmFill>& fills) {
     level[i] = lv; c.level = (uint8_t)lv;
     p.nlevels = std::max(p.nlevels, lv + 1);
     cp += len;
+  }
+  if (p.n > ZQ_CM_LANES) {   // one lane evaluates such a model component by component: its per-component registers
+    p.wide_off = off;
+    add_fill(off, (uint64_t)p.n * 64, ZQ_FILL_ZERO, 0); off = align256(off + (uint64_t)p.n * 64);
   }
   p.model_bytes = align256(off);
   p.fill_count = (uint32_t)fills.size() - p.fill_first;

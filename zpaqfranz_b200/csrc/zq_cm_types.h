@@ -3,7 +3,8 @@
 #include <stdint.h>
 
 enum { ZQ_CONS = 1, ZQ_CM, ZQ_ICM, ZQ_MATCH, ZQ_AVG, ZQ_MIX2, ZQ_MIX, ZQ_ISSE, ZQ_SSE };
-#define ZQ_CM_MAXCOMP 32
+#define ZQ_CM_MAXCOMP 64   // components per model on the device; above ZQ_CM_LANES one lane evaluates them in turn (zq_cm_wide.cuh)
+#define ZQ_CM_LANES 32
 
 // One component as a lane sees it (descriptor bytes = ZPAQ COMP section, Z:13938 compsize).
 struct ZqCmComp {
@@ -27,6 +28,7 @@ struct ZqCmPlan {
   // decoder only: post-processor (PCOMP) machine of the block, Z:15358-15414
   int32_t ph, pm;                    // PCOMP H (2^ph u32) and M (2^pm bytes)
   uint64_t pm_off, ph_off, pr_off, pcode_off;
+  uint64_t wide_off;                 // n > ZQ_CM_LANES: 64 B of per-component state each (zq_cm_wide.cuh)
   ZqCmComp comp[ZQ_CM_MAXCOMP];
 };
 

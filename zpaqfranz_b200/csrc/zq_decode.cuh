@@ -231,6 +231,9 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
       continue;
     }
     if (cp.n > 0) {
+      const bool wide = cp.n > ZQ_CM_LANES;   // lane 0 evaluates every component (zq_cm_wide.cuh); the warp still shares the coder
+      CmWide W;
+      if (wide && lane == 0) cmw_setup(W, cp, model);
       u32 low = 1, high = 0xffffffffu, curr = 0;
       auto decode = [&](u32 p16) -> int {   // Decoder::decode, Z:15282
         if (curr < low || curr > high) { err = 1; return 0; }
@@ -249,10 +252,16 @@ k_cm_decode(const u8* __restrict__ in_base, const ZqDecUnit* __restrict__ units,
           if (decode(0)) { if (curr != 0 && !err) err = 1; break; }
           int c = 1;
           while (c < 256) {
-            const u32 p16 = (u32)cm_predict(L, X, T) * 2 + 1;
+            int pr = 0;
+            if (!wide) pr = cm_predict(L, X, T);
+            else { if (lane == 0) pr = cmw_predict(W, vm.h, vm.hmask, T); pr = __shfl_sync(ZQ_FULL, pr, 0); }
+            const u32 p16 = (u32)pr * 2 + 1;
             const int y = decode(p16);
             c += c + y;
-            if (cm_update(L, X, T, y)) {   // byte complete: contexts of the next one
+            bool done;
+            if (!wide) done = cm_update(L, X, T, y);
+            else { int d = 0; if (lane == 0) d = cmw_update(W, vm.h, vm.hmask, T, y) ? 1 : 0; done = __shfl_sync(ZQ_FULL, d, 0) != 0; }
+            if (done) {   // byte complete: contexts of the next one
               if (lane == 0) cm_vm_run<VM, false>(vm, (u32)(c - 256), nullptr);
               __syncwarp();
               if (lane < (u32)X.n) L.h = vm.h[lane & vm.hmask];
