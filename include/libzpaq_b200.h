@@ -97,12 +97,16 @@ inline int toU16(const char* p) { return (p[0] & 255) + 256 * (p[1] & 255); }   
 // == libzpaq::SHA1 (Z:12637): put/write accumulate, result() returns the 20-byte digest and resets.
 // The bytes are kept until result() and hashed there by the device kernel (zq_sha1).
 class SHA1 {
-  std::vector<unsigned char> buf_;
+  std::vector<unsigned char> buf_;   // bytes not hashed yet; flushed to the device in whole 64-byte blocks at kFlush
   uint64_t len_ = 0;
+  uint32_t st_[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
+  bool streamed_ = false;            // some blocks already went through zq_sha1_continue
   char h_[20];
+  void flush();
  public:
-  void put(int c) { buf_.push_back((unsigned char)c); ++len_; }
-  void write(const char* b, int64_t n) { if (n > 0) { buf_.insert(buf_.end(), (const unsigned char*)b, (const unsigned char*)b + n); len_ += (uint64_t)n; } }
+  static const size_t kFlush = 4u << 20;
+  void put(int c) { buf_.push_back((unsigned char)c); ++len_; if (buf_.size() >= kFlush) flush(); }
+  void write(const char* b, int64_t n);
   double size() const { return (double)len_; }
   uint64_t usize() const { return len_; }
   const char* result();
@@ -112,10 +116,14 @@ class SHA1 {
 class SHA256 {
   std::vector<unsigned char> buf_;
   uint64_t len_ = 0;
+  uint32_t st_[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+  bool streamed_ = false;
   char h_[32];
+  void flush();
  public:
-  void put(int c) { buf_.push_back((unsigned char)c); ++len_; }
-  void write(const char* b, int64_t n) { if (n > 0) { buf_.insert(buf_.end(), (const unsigned char*)b, (const unsigned char*)b + n); len_ += (uint64_t)n; } }
+  static const size_t kFlush = 4u << 20;
+  void put(int c) { buf_.push_back((unsigned char)c); ++len_; if (buf_.size() >= kFlush) flush(); }
+  void write(const char* b, int64_t n);
   double size() const { return (double)len_; }
   uint64_t usize() const { return len_; }
   const char* result();

@@ -216,6 +216,14 @@ int zq_add_files(zq_ctx* ctx, int nfiles, const uint8_t* base, const uint64_t* o
                  uint32_t* nblocks);
 uint64_t zq_file_sort_key(const char* path, int64_t size);
 
+/* One stream hashed in pieces (what the streaming classes libzpaq::SHA1 / SHA256 do, zpaqfranz.cpp:12637 / 12828):
+ * the compression function over nblocks whole 64-byte blocks of data, from and to the chaining value in state
+ * (SHA-1: 5 words from 67452301 ...; SHA-256: 8 words from 6a09e667 ...).  Padding and the length field are the
+ * caller's last block(s) (include/libzpaq_b200.h does it).  One dependency chain = one thread: this bounds the host
+ * memory of a long stream, it is not the fast way to hash many buffers (zq_sha1 / zq_sha256 are). */
+int zq_sha1_continue(zq_ctx* ctx, uint32_t state[5], const uint8_t* data, uint64_t nblocks);
+int zq_sha256_continue(zq_ctx* ctx, uint32_t state[8], const uint8_t* data, uint64_t nblocks);
+
 /* The fragment index (replaces HTIndex::find, zpaqfranz.cpp:71567-71604): first[i] = the smallest j <= i whose 20-byte
  * digest equals fragment i's, for n digests laid out back to back.  first[i] == i marks a fragment new to the set. */
 int zq_dedup_first(zq_ctx* ctx, uint64_t n, const uint8_t* sha1, uint32_t* first);

@@ -35,6 +35,24 @@ int main(int argc, char** argv) {
     SHA256 s2; for (char c : in) s2.put(c & 255);
     printf("sha1 %s\nsha256 %s\n", hex(sha1, 20).c_str(), hex(s2.result(), 32).c_str());
 
+    // a stream longer than the classes keep on the host (kFlush): written in uneven pieces, hashed block by block
+    {
+      SHA1 big1; SHA256 big2;
+      std::vector<char> piece;
+      uint64_t total = 0, x = 12345;
+      while (total < 9500000) {
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        const size_t k = 1 + (size_t)((x >> 33) % 300000);
+        piece.resize(k);
+        for (size_t i = 0; i < k; ++i) piece[i] = (char)((total + i) * 2654435761u >> 13);
+        big1.write(piece.data(), (int64_t)k); big2.write(piece.data(), (int64_t)k);
+        total += k;
+      }
+      big1.put(7); big2.put(7); ++total;
+      char d1[20]; memcpy(d1, big1.result(), 20);
+      printf("bigsize %llu\nbigsha1 %s\nbigsha256 %s\n", (unsigned long long)total, hex(d1, 20).c_str(), hex(big2.result(), 32).c_str());
+    }
+
     // (b) Compressor by hand, built-in model 2, checksum stored
     StringBuffer src; src.write(in.data(), (int)in.size());
     StringBuffer b;

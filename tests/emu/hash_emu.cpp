@@ -73,3 +73,12 @@ extern "C" int emu_dedup_first(const uint8_t* sha1, uint32_t n, uint32_t* first)
   emu::launch((n + 255) / 256, 256, 0, [&] { k_dedup_lookup(dg, n, tab.data(), slots - 1, first); });
   return 0;
 }
+
+// k_sha1_continue / k_sha256_continue: `words` = 5 or 8
+extern "C" int emu_sha_continue(int words, uint32_t* state, const uint8_t* data, uint64_t nblocks) {
+  std::vector<uint4> al(nblocks * 4 + 1);            // the kernels read 16-byte words
+  memcpy(al.data(), data, nblocks * 64);
+  if (words == 5) emu::launch(1, 32, 0, [&] { k_sha1_continue((const u8*)al.data(), nblocks, state); });
+  else emu::launch(1, 32, 0, [&] { k_sha256_continue((const u8*)al.data(), nblocks, state); });
+  return 0;
+}

@@ -97,6 +97,16 @@ def test_cpp_facade_driver(ref, tmp_path):
     assert [int(row[5]) for row in segrows] == [len(x) for blk in multi for x in blk]
     assert all(row[7] == "1" and row[9] == "1" for row in segrows[:6]) and all(row[7] == "0" for row in segrows[6:])
     lines = dict(l.split(" ", 1) for l in r.stdout.strip().splitlines() if not l.startswith("seg "))
+    # the 9.5 MB stream of the driver, regenerated here
+    big, x, total = bytearray(), 12345, 0
+    while total < 9500000:
+        x = (x * 6364136223846793005 + 1442695040888963407) & (2 ** 64 - 1)
+        k = 1 + (x >> 33) % 300000
+        big += ((((np.arange(total, total + k, dtype=np.uint64) * np.uint64(2654435761)) & np.uint64(0xffffffff)) >> np.uint64(13)) & np.uint64(255)).astype(np.uint8).tobytes()
+        total += k
+    big.append(7)
+    assert int(lines["bigsize"]) == len(big)
+    assert lines["bigsha1"] == hashlib.sha1(big).hexdigest() and lines["bigsha256"] == hashlib.sha256(big).hexdigest()
     assert lines["sha1"] == hashlib.sha1(data).hexdigest()
     assert lines["sha256"] == hashlib.sha256(data).hexdigest()
     assert (tmp_path / "a.zpaq").read_bytes() == ref.compress_block(data, "2", "file_a", "jDC\x01")

@@ -98,3 +98,22 @@ def test_fragment_index(emu):
     for i, k in enumerate(pick):
         want.append(seen.setdefault(dg[i].tobytes(), i))
     assert first.tolist() == want
+
+
+@pytest.mark.parametrize("words,name", [(5, "sha1"), (8, "sha256")])
+def test_streamed_sha_continues_from_a_chaining_value(emu, words, name):
+    """k_sha1_continue / k_sha256_continue (the streaming SHA1 / SHA256 classes of the boundary): whole blocks fed in
+    uneven pieces from the initial chaining value, padded by the caller, equal hashlib."""
+    init = {5: [0x67452301, 0xEFCDAB89, 0x98BADCFE, 0x10325476, 0xC3D2E1F0],
+            8: [0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19]}[words]
+    for size in (0, 1, 55, 56, 64, 1000, 4096 + 17):
+        msg = bytes(corpus.random_unit(size + 3, size)) if size else b""
+        padded = msg + b"\x80" + b"\0" * ((55 - len(msg)) % 64) + (8 * len(msg)).to_bytes(8, "big")
+        st = (C.c_uint32 * words)(*init)
+        pos, step = 0, 1
+        while pos < len(padded):                      # 1, 2, 3 ... blocks at a time
+            k = min(step, (len(padded) - pos) // 64)
+            emu.emu_sha_continue(words, st, padded[pos: pos + 64 * k], k)
+            pos += 64 * k
+            step += 1
+        assert b"".join(int(x).to_bytes(4, "big") for x in st) == getattr(hashlib, name)(msg).digest(), size

@@ -54,20 +54,71 @@ thread_local ThreadCtx t_ctx;
 }  // namespace
 
 // ---- digests ---------------------------------------------------------------------------------------
-const char* SHA1::result() {
-  const uint64_t off = 0, len = buf_.size();
-  static const unsigned char none = 0;
+// The classes stream: at most kFlush bytes wait on the host.  A stream that never reaches kFlush (every segment the
+// archiver hashes here is a block, <= 64 MiB, and most are far smaller) is hashed in one go by the batch kernel at
+// result(); a longer one is fed to the device in whole 64-byte blocks (zq_sha*_continue) and padded at the end.
+template <int WORDS, class Cont>
+static void hash_flush(std::vector<unsigned char>& buf, uint32_t* st, bool& streamed, Cont cont) {
+  const size_t whole = buf.size() & ~(size_t)63;
+  if (!whole) return;
   zq_ctx* c = t_ctx.get();
-  if (zq_sha1(c, 1, buf_.empty() ? &none : buf_.data(), &off, &len, (uint8_t*)h_) != ZQ_OK) error(zq_last_error(c));
-  buf_.clear(); len_ = 0;
+  if (cont(c, st, buf.data(), whole / 64) != ZQ_OK) error(zq_last_error(c));
+  buf.erase(buf.begin(), buf.begin() + whole);
+  streamed = true;
+}
+template <int WORDS, class Cont>
+static void hash_finish(std::vector<unsigned char>& buf, uint64_t total, uint32_t* st, Cont cont, char* out) {
+  // FIPS 180-4 padding: 0x80, zeros, the bit length as a big-endian 64-bit number
+  buf.push_back(0x80);
+  while (buf.size() % 64 != 56) buf.push_back(0);
+  for (int i = 7; i >= 0; --i) buf.push_back((unsigned char)((total * 8) >> (8 * i)));
+  zq_ctx* c = t_ctx.get();
+  if (cont(c, st, buf.data(), buf.size() / 64) != ZQ_OK) error(zq_last_error(c));
+  for (int k = 0; k < WORDS; ++k) for (int b = 0; b < 4; ++b) out[4 * k + b] = (char)(st[k] >> (24 - 8 * b));
+}
+
+void SHA1::flush() { hash_flush<5>(buf_, st_, streamed_, zq_sha1_continue); }
+void SHA256::flush() { hash_flush<8>(buf_, st_, streamed_, zq_sha256_continue); }
+void SHA1::write(const char* b, int64_t n) {
+  while (n > 0) {
+    const size_t k = (size_t)std::min<int64_t>(n, (int64_t)(kFlush - buf_.size()));
+    buf_.insert(buf_.end(), (const unsigned char*)b, (const unsigned char*)b + k);
+    b += k; n -= (int64_t)k; len_ += k;
+    if (buf_.size() >= kFlush) flush();
+  }
+}
+void SHA256::write(const char* b, int64_t n) {
+  while (n > 0) {
+    const size_t k = (size_t)std::min<int64_t>(n, (int64_t)(kFlush - buf_.size()));
+    buf_.insert(buf_.end(), (const unsigned char*)b, (const unsigned char*)b + k);
+    b += k; n -= (int64_t)k; len_ += k;
+    if (buf_.size() >= kFlush) flush();
+  }
+}
+const char* SHA1::result() {
+  zq_ctx* c = t_ctx.get();
+  if (streamed_) hash_finish<5>(buf_, len_, st_, zq_sha1_continue, h_);
+  else {
+    const uint64_t off = 0, len = buf_.size();
+    static const unsigned char none = 0;
+    if (zq_sha1(c, 1, buf_.empty() ? &none : buf_.data(), &off, &len, (uint8_t*)h_) != ZQ_OK) error(zq_last_error(c));
+  }
+  static const uint32_t init[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
+  memcpy(st_, init, sizeof init);
+  buf_.clear(); len_ = 0; streamed_ = false;
   return h_;
 }
 const char* SHA256::result() {
-  const uint64_t off = 0, len = buf_.size();
-  static const unsigned char none = 0;
   zq_ctx* c = t_ctx.get();
-  if (zq_sha256(c, 1, buf_.empty() ? &none : buf_.data(), &off, &len, (uint8_t*)h_) != ZQ_OK) error(zq_last_error(c));
-  buf_.clear(); len_ = 0;
+  if (streamed_) hash_finish<8>(buf_, len_, st_, zq_sha256_continue, h_);
+  else {
+    const uint64_t off = 0, len = buf_.size();
+    static const unsigned char none = 0;
+    if (zq_sha256(c, 1, buf_.empty() ? &none : buf_.data(), &off, &len, (uint8_t*)h_) != ZQ_OK) error(zq_last_error(c));
+  }
+  static const uint32_t init[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+  memcpy(st_, init, sizeof init);
+  buf_.clear(); len_ = 0; streamed_ = false;
   return h_;
 }
 

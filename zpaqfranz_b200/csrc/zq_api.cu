@@ -1332,6 +1332,27 @@ int zq_sha3_256(zq_ctx* c, int n, const uint8_t* base, const uint64_t* off, cons
   });
 }
 
+// state: 5 (SHA-1) or 8 (SHA-256) chaining words, host; data: nblocks * 64 bytes, host
+static int hash_continue(zq_ctx* c, int words, uint32_t* state, const uint8_t* data, uint64_t nblocks) {
+  using namespace zqdev;
+  if (!c) return ZQ_E_NODEVICE;
+  if (!state || (nblocks && !data)) return fail(c, ZQ_E_ARG, "bad argument");
+  if (nblocks == 0) return ZQ_OK;
+  cudaSetDevice(c->device);
+  ZQ_CUDA(c, c->d_in.ensure(nblocks * 64 + 64));
+  ZQ_CUDA(c, c->d_sha.ensure(64));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, data, nblocks * 64, cudaMemcpyHostToDevice, c->stream));
+  ZQ_CUDA(c, cudaMemcpyAsync(c->d_sha.p, state, (size_t)words * 4, cudaMemcpyHostToDevice, c->stream));
+  if (words == 5) k_sha1_continue<<<1, 1, 0, c->stream>>>(c->d_in.as<u8>(), nblocks, c->d_sha.as<u32>());
+  else k_sha256_continue<<<1, 1, 0, c->stream>>>(c->d_in.as<u8>(), nblocks, c->d_sha.as<u32>());
+  ++c->launches;
+  ZQ_CUDA(c, cudaMemcpyAsync(state, c->d_sha.p, (size_t)words * 4, cudaMemcpyDeviceToHost, c->stream));
+  ZQ_CUDA(c, cudaStreamSynchronize(c->stream));
+  return ZQ_OK;
+}
+int zq_sha1_continue(zq_ctx* c, uint32_t state[5], const uint8_t* data, uint64_t nblocks) { return hash_continue(c, 5, state, data, nblocks); }
+int zq_sha256_continue(zq_ctx* c, uint32_t state[8], const uint8_t* data, uint64_t nblocks) { return hash_continue(c, 8, state, data, nblocks); }
+
 int zq_dedup_first(zq_ctx* c, uint64_t n, const uint8_t* sha1, uint32_t* first) {
   using namespace zqdev;
   if (!c) return ZQ_E_NODEVICE;

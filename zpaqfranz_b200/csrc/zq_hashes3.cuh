@@ -4,6 +4,8 @@
 // (RFC 1321; FIPS 202 with the 0x06 domain byte): the sine table and the round constants are computed, not copied.
 #pragma once
 #include "zq_common.cuh"
+#include "zq_sha1.cuh"
+#include "zq_hashes.cuh"
 
 namespace zqdev {
 
@@ -200,6 +202,43 @@ __global__ void __launch_bounds__(256) k_dedup_lookup(const u32* __restrict__ dg
     if (cur == DEDUP_EMPTY) { first[i] = i; return; }      // cannot happen after k_dedup_insert; keeps the loop finite
     if (dedup_same(dg, cur, w)) { first[i] = cur; return; }
   }
+}
+
+// ---- one stream, continued: the compression function over whole 64-byte blocks from a given chaining value ---------
+// (libzpaq::SHA1 / SHA256 as STREAMING classes, Z:12637 / Z:12828: write() in pieces, result() at the end.)  A single
+// stream is a dependency chain -- one thread; the point is bounded memory on the host, not speed: batches of buffers go
+// through k_sha1_many / k_sha256_many.
+__global__ void k_sha1_continue(const u8* __restrict__ p, u64 nblocks, u32* __restrict__ state) {
+  if (blockIdx.x | threadIdx.x) return;
+  Sha1State st; st.h0 = state[0]; st.h1 = state[1]; st.h2 = state[2]; st.h3 = state[3]; st.h4 = state[4];
+  u32 w[16];
+  const uint4* __restrict__ p4 = (const uint4*)p;    // device staging buffer: 16-byte aligned
+  for (u64 b = 0; b < nblocks; ++b) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = p4[b * 4 + q];
+      w[4 * q] = bswap32(v.x); w[4 * q + 1] = bswap32(v.y); w[4 * q + 2] = bswap32(v.z); w[4 * q + 3] = bswap32(v.w);
+    }
+    sha1_rounds(st, w);
+  }
+  state[0] = st.h0; state[1] = st.h1; state[2] = st.h2; state[3] = st.h3; state[4] = st.h4;
+}
+__global__ void k_sha256_continue(const u8* __restrict__ p, u64 nblocks, u32* __restrict__ state) {
+  if (blockIdx.x | threadIdx.x) return;
+  u32 st[8], w[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) st[k] = state[k];
+  const uint4* __restrict__ p4 = (const uint4*)p;
+  for (u64 b = 0; b < nblocks; ++b) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = p4[b * 4 + q];
+      w[4 * q] = bswap32(v.x); w[4 * q + 1] = bswap32(v.y); w[4 * q + 2] = bswap32(v.z); w[4 * q + 3] = bswap32(v.w);
+    }
+    sha256_rounds(st, w);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) state[k] = st[k];
 }
 
 }  // namespace zqdev
