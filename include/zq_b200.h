@@ -38,10 +38,11 @@ const char* zq_version(void);
 /* Run all of this context's work on the caller's CUDA stream (a cudaStream_t, e.g. torch's current
  * stream) instead of the context's own; pass NULL to go back. The stream is not owned. */
 int zq_set_stream(zq_ctx* ctx, void* cuda_stream);
-/* Several contexts on one device (zq_pipe does this): fn(arg, 1) is called after a batch's input copy and planning
- * are queued and before its first kernel, fn(arg, 0) after its last kernel has finished and before the output copy.
- * A mutex behind fn makes the batches' kernels take turns, so that one batch's copies always run under another's
- * kernels instead of both copying and both computing at the same time.  fn = NULL removes the gate. */
+/* Several contexts on one device (zq_pipe does this): fn(arg, 2) is called before a batch's input copy is queued and
+ * fn(arg, 3) once it has landed; fn(arg, 1) after the batch's planning and before its first kernel, fn(arg, 0) after its
+ * last kernel has finished and before the output copy.  Mutexes behind fn make the batches copy in and compute in
+ * turns, so that one batch's copies always run under another's kernels instead of all copying and then all computing
+ * at the same time.  fn = NULL removes the gate. */
 int zq_set_compute_gate(zq_ctx* ctx, void (*fn)(void* arg, int acquire), void* arg);
 
 /* ---- host-side planning (no GPU needed) ------------------------------------------------------ */

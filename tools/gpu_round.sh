@@ -26,7 +26,7 @@ for s in $STEPS; do
       timeout 300 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/${TAG}_launches_bench_m2.csv \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-parity > $O/${TAG}_launches_bench.log 2>&1 ;;
     ncu_m2)
-      timeout 400 $NCU --set full --import-source on -k regex:'k_lz_scan|k_lz_walk|k_lz_emit|k_suffix_sort' -c 5 -f -o $O/${TAG}_m2 \
+      timeout 400 $NCU --set full --import-source on -k regex:'k_lz_scan|k_lz_walk|k_lz_emit|k_suffix_sort' -c 7 -f -o $O/${TAG}_m2 \
         python tools/prof_step.py --units 10000 --steps 1 > $O/${TAG}_ncu_m2.log 2>&1 ;;
     ncu_cm)
       timeout 300 $NCU --set full --import-source on -k regex:k_cm_encode -c 1 -f -o $O/${TAG}_cm_m3 \

@@ -82,6 +82,7 @@ struct zq_ctx {
   std::vector<zq_segment> last_segs;      // every segment of the last zq_decompress_* call, in (block, position) order
   void (*gate_fn)(void*, int) = nullptr;  // zq_set_compute_gate: called with 1 before the first kernel of a batch, 0 after its last
   void* gate_arg = nullptr;
+  bool copy_held = false;                 // between fn(arg, 2) and fn(arg, 3): this batch's input copy owns the H2D turn
   bool cm_jit_auto = true;                // no ZQ_CM_JIT in the environment: translate only the models whose context warp is the bottleneck (<= 8 components)
   struct JitProg { cudaLibrary_t lib = nullptr; cudaKernel_t ctx = nullptr, code = nullptr; };
   std::map<std::string, JitProg> jit_cache;   // translated context program (+ generated coder) per model header
@@ -129,7 +130,13 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct GateHold {   // the batch's kernels run between acquire() and the end of the scope
   zq_ctx* c; bool held = false;
   explicit GateHold(zq_ctx* c_) : c(c_) {}
-  void acquire() { if (c->gate_fn && !held) { c->gate_fn(c->gate_arg, 1); held = true; } }
+  void acquire() {
+    if (c->gate_fn && c->copy_held) {   // the input copy (queued before the planning above) must have landed: next batch's turn to copy
+      cudaEventSynchronize(c->ev[1]);
+      c->gate_fn(c->gate_arg, 3); c->copy_held = false;
+    }
+    if (c->gate_fn && !held) { c->gate_fn(c->gate_arg, 1); held = true; }
+  }
   ~GateHold() { if (held) c->gate_fn(c->gate_arg, 0); }
 };
 
@@ -870,6 +877,11 @@ int compress_host(zq_ctx* c, int n, const uint8_t* in_base, const uint64_t* in_o
   ZQ_CUDA(c, c->d_in.ensure(span + 64));
   ZQ_CUDA(c, c->d_out.ensure(std::min<uint64_t>(bound, std::max<uint64_t>(out_cap, 1)) + 64));
   cudaEvent_t e0 = c->ev[0], e1 = c->ev[1], e2 = c->ev[2], e3 = c->ev[3];
+  struct CopyTurn {   // several batches in flight copy their inputs one after the other, not all at once at a third of the rate
+    zq_ctx* c;
+    explicit CopyTurn(zq_ctx* c_) : c(c_) { if (c->gate_fn) { c->gate_fn(c->gate_arg, 2); c->copy_held = true; } }
+    ~CopyTurn() { if (c->copy_held) { c->gate_fn(c->gate_arg, 3); c->copy_held = false; } }
+  } turn(c);
   cudaEventRecord(e0, c->stream);
   if (span) ZQ_CUDA(c, cudaMemcpyAsync(c->d_in.p, in_base + lo, span, cudaMemcpyHostToDevice, c->stream));
   cudaEventRecord(e1, c->stream);

@@ -35,6 +35,7 @@ struct zq_pipe {
   std::vector<std::thread> workers;
   std::mutex mu;
   std::mutex compute;        // host-pointer batches: one batch's kernels at a time, the others copy meanwhile
+  std::mutex copy_in;        // and one input copy at a time
   bool gated = true;
   std::condition_variable cv_job, cv_done;
   std::deque<Job> queue;
@@ -46,7 +47,12 @@ struct zq_pipe {
 
   static void gate(void* self, int acquire) {
     zq_pipe* p = static_cast<zq_pipe*>(self);
-    if (acquire) p->compute.lock(); else p->compute.unlock();
+    switch (acquire) {
+      case 1: p->compute.lock(); break;
+      case 0: p->compute.unlock(); break;
+      case 2: p->copy_in.lock(); break;
+      default: p->copy_in.unlock(); break;
+    }
   }
 
   void run(int lane) {
