@@ -403,14 +403,13 @@ def main():
             e0.record(stream)
             tickets = []
             for k in range(steps):
-                if k >= depth:
-                    r_ = pipe.wait(tickets[k - depth])
-                    if world > 1 and not device:
-                        exchange(r_[1])
+                done = pipe.wait(tickets[k - depth]) if k >= depth else None
                 if device:
                     tickets.append(pipe.submit(d_in.data_ptr(), offs, lens, d_outs[k % depth].data_ptr(), cap, method=method, filename="", comment="", device=True))
                 else:
                     tickets.append(pipe.submit(h_in.data_ptr(), offs, lens, h_outs[k % depth].data_ptr(), cap, method=method, filename="", comment="", device=False))
+                if done is not None and world > 1 and not device:
+                    exchange(done[1])      # (the freed lane is already copying the next batch in)
             for t in tickets[-depth:]:
                 r_ = pipe.wait(t)
                 if world > 1 and not device:
