@@ -286,8 +286,8 @@ int zq_last_timings_ex(zq_ctx* ctx, float* ms, int n);
 int zq_suffix_array(zq_ctx* ctx, const uint8_t* data, uint32_t n, uint32_t* sa_out);
 
 /* CRC-32 (crc32_16bytes, Z:30299: always on in Jidac::updatehash, Z:85948) and XXH64 seed 0 (the archiver's default
- * file hash, XXH64 Z:24688) of n buffers: digests = 4 / 8 bytes per buffer, little-endian.  Emulator-verified against
- * zlib and the reference's XXH64; not yet run on hardware. */
+ * file hash, XXH64 Z:24688) of n buffers: digests = 4 / 8 bytes per buffer, little-endian.  Bit-exact against zlib and
+ * the reference's XXH64 under the emulator and on the B200. */
 int zq_crc32(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests);
 int zq_xxh64(zq_ctx* ctx, int n, const uint8_t* base, const uint64_t* off, const uint64_t* len, uint8_t* digests);
 /* MD5 (16 bytes) and SHA3-256 (32 bytes) of n buffers: the -md5 / -sha3 file hashes of updatehash (MD5::add Z:21616,

@@ -152,20 +152,11 @@ struct CmVm {   // registers live on the lane that owns the machine (lane 0)
 };
 struct VmOut { u8* out; u32 len, cap, error; };   // PCOMP's OUT sink (decoder)
 
-// One run of the program (ZPAQL::run0, Z:14232) by ONE lane.  Two interpreters, chosen per launch (template
-// parameter VM of the kernels, ZQ_CM_VM):
-//  0  a single switch over the opcode byte, the two-operand group (opcode >= 64: operation = op>>3, source =
-//     op&7) expanded case by case.  nvcc lowers it to a nine-level compare/branch tree over 25 KB of code: ncu
-//     (profiles/r01j) puts ~290 of the ~380 cycles per ZPAQL instruction there, and with the chain fast path
-//     the context warp is the critical path.
-//  1  the opcode byte is decoded arithmetically (ZPAQL's encoding is regular) and each group runs as
-//     straight-line select code: all three possible memory operands are fetched (b&mm, c&mm, d&hm always index
-//     inside M / H) and one is picked, every ALU result is formed and one is picked, stores are predicated; only
-//     the group choice and the rare opcodes (division, long jump, jumps, hash) branch.  Selects are inline PTX
-//     selp: written as C conditionals nvcc turns them back into branch trees (measured slower, r01k).
-//     Measured (r01l): decode a little faster, encode slower than 0 (BWT model 355 vs 236 ms) -- the two unwanted
-//     operand loads wait on lines the machine has just stored to (write-through, L1 line dropped).
-//  2  as 1, operand loads predicated (inline PTX @p ld): not measured yet, next round.
+// One run of the program (ZPAQL::run0, Z:14232) by ONE lane: a single switch over the opcode byte, the two-operand group
+// (opcode >= 64: operation = op>>3, source = op&7) expanded case by case.  nvcc lowers it to a nine-level compare/branch
+// tree over 25 KB of code: ncu (profiles/r01j) puts ~290 of the ~380 cycles per ZPAQL instruction there -- which is why
+// the small models get their program translated and compiled instead (zq_jit.cpp).  (The template parameter VM of the
+// kernels is kept for the emulator tests' signatures; every value runs this interpreter.)
 #define ZQ_VM_X8(B, STMT)                                                  \
   case (B) + 0: { const u32 x = a; STMT; } break;                          \
   case (B) + 1: { const u32 x = b; STMT; } break;                          \

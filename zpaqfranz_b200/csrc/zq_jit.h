@@ -6,9 +6,10 @@
 // constants, then NVRTC -> cubin for sm_100a.  ncu (profiles/r01j) has the interpreted context machine as the critical
 // path of the chain models (~380 cycles per ZPAQL instruction against a handful of SASS instructions translated).
 //
-// Status: translator + NVRTC compilation are exercised by the CPU tests (generated code is compiled for the host and
-// stepped against the interpreter; NVRTC compiles it for sm_100a without a GPU).  Loading the module and feeding the
-// coder from its output is the next round's work; nothing on the compress path calls this yet.
+// Status: on the compress path (zq_api.cu loads the module per model, cached; default for models of <= 8 components,
+// ZQ_CM_JIT forces a form).  The CPU tests compile the generated code for the host and step it against the
+// interpreter, NVRTC compiles it for sm_100a without a GPU, the GPU tests run all three forms bit for bit
+// (tests/test_gpu_compress.py::test_context_program_forms_over_several_waves).
 #pragma once
 #include <cstdint>
 #include <string>
