@@ -4,19 +4,19 @@
 //
 // Why a second sorter: k_suffix_sort (zq_sufsort.cuh) is a general prefix-doubling sort whose 40 bytes of scratch per
 // input byte live in global memory -- 22 MB of DRAM traffic per 64 KiB block.  Text-like and random blocks do not need
-// doubling at all: their suffixes differ within a few bytes.  This kernel therefore sorts by the first 6 bytes with a
-// bitonic network over 64-bit words (48-bit prefix | 16-bit suffix index) held in shared memory, then orders the few
-// suffixes that still tie (groups of 2..128) by comparing the text directly.  A block where that stops paying -- a
-// group of more than 128 suffixes sharing 6 bytes, or two suffixes sharing more than 512 -- is handed to k_suffix_sort
-// through a flag; nothing is approximated.
+// doubling at all: their suffixes differ within a few bytes.  This kernel therefore sorts by the first 6-7 bytes with a
+// bitonic network over 64-bit words (bin number inside the batch | following text bits | 16-bit suffix index) held in
+// shared memory, then orders the few suffixes that still tie (groups of 2..128) by comparing the text directly.  A block
+// where that stops paying -- a group of more than 128 suffixes sharing the key, or two suffixes sharing more than 512
+// bytes -- is handed to k_suffix_sort through a flag; nothing is approximated.
 //
-//   shared memory (225 KB, one CTA per SM):  text 64 KiB | 8192 bin starts | 16384 x u64 sort buffer (bin cursors first)
+//   shared memory (~225 KB, one CTA per SM):  text 64 KiB | 8192 bin starts | 16384 x u64 sort buffer (bin cursors first)
 //   1. text -> shared memory (bulk async copy when the block is 16-byte aligned)
 //   2. histogram of the 13-bit key (byte 0, top 5 bits of byte 1) with shared-memory atomics, exclusive scan: the
 //      start row of every bin.  Bins are only a way to cut the suffix array into batches that fit the sort buffer:
 //      a batch takes as many whole bins as fit the buffer.
 //      Every position is dealt to its bin's rows of the (global, L2-resident) sa array -- a counting sort on 13 bits.
-//   3. per batch: its rows are read back (coalesced), keyed by the first 6 bytes of their suffix, sorted; ties
+//   3. per batch: its rows are read back (coalesced), keyed by the leading bits of their suffix, sorted; ties
 //      resolved; then the rows are final and sa / lcp / bwt / pk are written in row order and isa is scattered.
 #pragma once
 #include "zq_sufsort.cuh"
