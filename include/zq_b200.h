@@ -272,6 +272,31 @@ int zq_dist_exchange_sizes(zq_dist* d, const uint32_t* local_sizes, uint64_t tot
  * unique_total: fragments stored by all ranks together */
 int zq_dist_dedup(zq_dist* d, const uint8_t* local_digests, uint64_t n_local, uint8_t* is_first, uint64_t* unique_total);
 
+/* One stream (a file larger than one GPU's share, e.g. a disk image) cut across the ranks -- replaces, for that file,
+ * the single sequential chunker loop of Jidac::add (zpaqfranz.cpp:122457-122561): rank r owns the bytes [lo, hi) of the
+ * stream (hi of rank r == lo of rank r+1) and also holds the `overlap` bytes after hi, up to avail_end.  It runs
+ * zq_fragment over [from, avail_end) with from = lo: a speculative chain.  zq_dist_stitch_fragments (collective: one
+ * all-gather of the fragment end offsets, 8 B each) then finds where the real chain, coming from the left, lands on a
+ * boundary this rank's chain shares; the chunker's state is reset at every boundary, so the chains are identical from
+ * there on.  Result, the same fragments the reference cuts from the whole stream:
+ *   again == 0: this rank's fragments first_keep .. first_keep + n_keep are the stream's fragments number
+ *               global_first .. (of global_total), covering the bytes [begin, end); the fragment that straddles hi
+ *               belongs to the left owner.  Their SHA-1s from zq_fragment are valid as they are.
+ *   again == 1: some chain did not meet its neighbour's inside the overlap (constant runs -- zero pages -- never
+ *               re-synchronise).  The rank with restart == 1 fragments [restart_at, avail_end) afresh (restart_at is
+ *               the real boundary it has to start from); then EVERY rank calls again, the others with the arguments
+ *               they used before.  At most world - 1 repetitions.
+ * ZQ_E_UNSUPPORTED: the overlap is shorter than one fragment (choose overlap >= 8128 << fragment). */
+typedef struct zq_stitch {
+  uint64_t first_keep, n_keep;      /* this rank's fragments that are fragments of the stream */
+  uint64_t global_first, global_total;
+  uint64_t begin, end;              /* bytes of the stream they cover */
+  uint64_t restart_at;
+  int32_t again, restart;
+} zq_stitch;
+int zq_dist_stitch_fragments(zq_dist* d, uint64_t stream_total, uint64_t lo, uint64_t hi, uint64_t from, uint64_t avail_end,
+                             const uint32_t* frag_len, uint64_t nfrag, zq_stitch* out);
+
 /* ---- introspection for tests / bench ---------------------------------------------------------- */
 /* number of kernel launches issued by this context since creation */
 uint64_t zq_launch_count(zq_ctx* ctx);

@@ -83,6 +83,55 @@ def test_two_rank_exchanges():
     assert res[0][7] > 0
 
 
+def _stitch_worker(rank, world, port, q):
+    import oracle_bindings
+    from zpaqfranz_b200 import corpus
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = oracle_bindings.load_oracle()
+    data = corpus.text_bytes(17, 300_000).tobytes() + bytes(250_000) + corpus.text_bytes(18, 250_000).tobytes()
+    fragment, total = 1, 800_000
+    d = zq.Dist(-1, rank, world, allgather=_gloo_allgather(world))
+    lo, hi = zq.shard_range(total, rank, world)
+    avail = min(total, hi + 4 * (8128 << fragment)) if rank < world - 1 else total
+    start, rounds = lo, 0
+    while True:
+        lens, _ = orc.fragment(data[start:avail], fragment)
+        while True:
+            st = d.stitch_fragments(total, lo, hi, start, avail, lens)
+            rounds += 1
+            if not st["again"] or st["restart"]:
+                break
+        if not st["again"]:
+            break
+        start = st["restart_at"]
+    kept = lens[st["first_keep"]:st["first_keep"] + st["n_keep"]].tolist()
+    q.put((rank, kept, st, rounds, orc.fragment(data, fragment)[0].tolist() if rank == 0 else None))
+    d.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_stream_split():
+    """One stream cut across two gloo processes (zq_dist_stitch_fragments): the cut lies inside a run of zeros, so the
+    right rank is told where to start again; the kept fragments together are the whole stream's."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_stitch_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+    want = res[0][4]
+    assert res[0][1] + res[1][1] == want
+    assert res[1][2]["global_first"] == len(res[0][1]) and res[1][2]["global_total"] == len(want)
+    assert res[0][2]["end"] == res[1][2]["begin"] == sum(res[0][1])
+    assert res[1][3] == 2 and res[0][3] == 2           # one repetition: the restart of rank 1
+
+
 def test_shard_helpers_and_single_rank():
     for total in (0, 1, 7, 64, 10000):
         for world in (1, 2, 3, 8):

@@ -103,6 +103,7 @@ def _load():
     lib.zq_dist_shard_lpt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     lib.zq_dist_exchange_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zq_dist_dedup.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zq_dist_stitch_fragments.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.zq_last_timings_ex.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
     lib.zq_suffix_array.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     return lib
@@ -192,6 +193,11 @@ def dist_unique_id():
     return bytes(buf)
 
 
+class ZqStitch(C.Structure):
+    _fields_ = [("first_keep", C.c_uint64), ("n_keep", C.c_uint64), ("global_first", C.c_uint64), ("global_total", C.c_uint64),
+                ("begin", C.c_uint64), ("end", C.c_uint64), ("restart_at", C.c_uint64), ("again", C.c_int32), ("restart", C.c_int32)]
+
+
 class Dist:
     """The exchanges of a multi-GPU run (zq_dist_*): NCCL when unique_id is given, a Python all-gather callable
     `allgather(in_bytes) -> list of world bytes objects` otherwise (CPU tests over gloo), nothing for world == 1."""
@@ -240,6 +246,15 @@ class Dist:
         uniq = C.c_uint64(0)
         self._check(lib.zq_dist_dedup(self._h, dg.ctypes.data if len(dg) else None, len(dg), first.ctypes.data if len(dg) else None, C.byref(uniq)))
         return first.astype(bool), int(uniq.value)
+
+    def stitch_fragments(self, stream_total, lo, hi, start, avail_end, frag_len):
+        """One stream cut across the ranks (zq_dist_stitch_fragments): this rank fragmented [start, avail_end) into
+        frag_len.  Returns the zq_stitch record as a dict."""
+        fl = np.ascontiguousarray(frag_len, dtype=np.uint32)
+        st = ZqStitch()
+        self._check(lib.zq_dist_stitch_fragments(self._h, int(stream_total), int(lo), int(hi), int(start), int(avail_end),
+                                                 fl.ctypes.data if len(fl) else None, len(fl), C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in ZqStitch._fields_}
 
     def bytes_exchanged(self):
         return int(lib.zq_dist_bytes_exchanged(self._h))

@@ -213,5 +213,92 @@ int zq_dist_dedup(zq_dist* d, const uint8_t* local_digests, uint64_t n_local, ui
   if (unique_total) *unique_total = seen.size();
   return ZQ_OK;
 }
+// One stream cut across the ranks (a file larger than one GPU's share).  Rank r owns bytes
+// [lo, hi) and also holds the bytes up to avail_end (its right neighbour's first ones).  It has fragmented
+// [from, avail_end) with a fresh chunker started at `from` (zq_fragment on that piece): a SPECULATIVE chain unless
+// `from` is a boundary of the stream's real chain.  The chunker forgets everything at a fragment boundary
+// (Z:122457-122470), so where the real chain, arriving from the left neighbour, ends a fragment at an offset at which
+// this rank's chain also ends one (or starts), the two are identical from there on.  Every rank computes the same
+// decisions from the gathered boundary lists, left to right:
+//   s_0 = 0;  s_r = the first real boundary >= lo_r of rank r-1's chain that rank r's chain shares.
+// Rank r keeps its fragments starting in [s_r, s_{r+1}): the fragment straddling hi_r belongs to the left owner.
+// If the chains do not meet inside the overlap (a constant run -- zero pages -- never re-synchronises), the rank is
+// told the first real boundary >= lo_r (restart_at): it fragments again from there and every rank calls once more.
+int zq_dist_stitch_fragments(zq_dist* d, uint64_t stream_total, uint64_t lo, uint64_t hi, uint64_t from, uint64_t avail_end,
+                             const uint32_t* frag_len, uint64_t nfrag, zq_stitch* out) {
+  if (!d) return ZQ_E_NODEVICE;
+  if (!out || (nfrag && !frag_len) || lo > hi || hi > avail_end || avail_end > stream_total || from < lo || from > avail_end)
+    return d->fail(ZQ_E_ARG, "bad argument");
+  memset(out, 0, sizeof(*out));
+  const int W = d->world;
+  // header: lo, hi, from, avail_end, nfrag; then the end offset of every fragment
+  std::vector<uint64_t> mine(5 + nfrag);
+  mine[0] = lo; mine[1] = hi; mine[2] = from; mine[3] = avail_end; mine[4] = nfrag;
+  uint64_t at = from;
+  for (uint64_t k = 0; k < nfrag; ++k) { at += frag_len[k]; mine[5 + k] = at; }
+  if (at != avail_end) return d->fail(ZQ_E_ARG, "fragment lengths do not add up to the piece");
+  std::vector<uint8_t> all; std::vector<uint64_t> sizes;
+  const int rc = d->allgatherv(mine.data(), mine.size() * 8, all, sizes);
+  if (rc) return rc;
+  struct Piece { uint64_t lo, hi, from, avail, n; const uint64_t* end; uint64_t nreal; };
+  std::vector<Piece> pc(W);
+  size_t off = 0;
+  for (int r = 0; r < W; ++r) {
+    if (sizes[r] < 40 || off + sizes[r] > all.size()) return d->fail(ZQ_E_ARG, "malformed piece description");
+    const uint64_t* p = (const uint64_t*)(all.data() + off);   // (offsets are multiples of 8: every rank sends whole words)
+    pc[r] = Piece{p[0], p[1], p[2], p[3], p[4], p + 5, p[4]};
+    if (sizes[r] != (5 + p[4]) * 8) return d->fail(ZQ_E_ARG, "malformed piece description");
+    // a last fragment cut short by the end of the piece is not a boundary of the stream
+    if (pc[r].n && pc[r].avail < stream_total) pc[r].nreal = pc[r].n - 1;
+    off += (size_t)sizes[r];
+  }
+  if (pc[0].lo != 0 || pc[0].from != 0 || pc[W - 1].hi != stream_total || pc[W - 1].avail != stream_total)
+    return d->fail(ZQ_E_ARG, "the pieces do not cover the stream");
+  for (int r = 1; r < W; ++r) if (pc[r].lo != pc[r - 1].hi) return d->fail(ZQ_E_ARG, "the pieces do not cover the stream");
+  // s[r]: where rank r's chain becomes the real one
+  std::vector<uint64_t> s(W + 1, 0);
+  s[W] = stream_total;
+  int unresolved = -1;
+  uint64_t restart = 0;
+  for (int r = 1; r < W && unresolved < 0; ++r) {
+    const Piece& L = pc[r - 1]; const Piece& R = pc[r];
+    // real boundaries of the left chain at or past lo_r: its ends >= max(s[r-1], lo_r) (a chain that starts at a real
+    // boundary exactly at lo_r counts too)
+    const uint64_t* lb = std::lower_bound(L.end, L.end + L.nreal, std::max(s[r - 1], R.lo));
+    const uint64_t* le = L.end + L.nreal;
+    bool found = false, have_first = false;
+    uint64_t first_real = 0;
+    if (s[r - 1] >= R.lo) { have_first = true; first_real = s[r - 1]; if (s[r - 1] == R.from || std::binary_search(R.end, R.end + R.nreal, s[r - 1])) { s[r] = s[r - 1]; found = true; } }
+    for (const uint64_t* e = lb; e < le && !found; ++e) {
+      if (!have_first) { have_first = true; first_real = *e; }
+      if (*e == R.from || std::binary_search(R.end, R.end + R.nreal, *e)) { s[r] = *e; found = true; }
+    }
+    if (!found) {
+      if (!have_first) return d->fail(ZQ_E_UNSUPPORTED, "overlap shorter than one fragment: the left piece holds no boundary past its end");
+      unresolved = r; restart = first_real;
+    }
+  }
+  if (unresolved >= 0) {
+    out->again = 1;
+    if (d->rank == unresolved) { out->restart = 1; out->restart_at = restart; }
+    return ZQ_OK;
+  }
+  // kept fragments of every rank: those starting in [s[r], s[r+1]); fragment k starts at (k ? end[k-1] : from)
+  uint64_t gtotal = 0;
+  for (int r = 0; r < W; ++r) {
+    const Piece& P = pc[r];
+    if (s[r] < P.from) return d->fail(ZQ_E_ARG, "a piece starts past the boundary it was to join");
+    auto first_from = [&](uint64_t x) -> uint64_t {      // first fragment starting at or after x (x: its `from` or one of its ends)
+      if (x <= P.from) return 0;
+      return std::min<uint64_t>(P.n, (uint64_t)(std::lower_bound(P.end, P.end + P.n, x) - P.end) + 1);
+    };
+    const uint64_t k0 = first_from(s[r]);
+    const uint64_t k1 = std::max(k0, r == W - 1 ? P.n : first_from(s[r + 1]));
+    if (r == d->rank) { out->first_keep = k0; out->n_keep = k1 - k0; out->global_first = gtotal; out->begin = s[r]; out->end = s[r + 1]; }
+    gtotal += k1 - k0;
+  }
+  out->global_total = gtotal;
+  return ZQ_OK;
+}
 
 }  // extern "C"

@@ -31,6 +31,10 @@ constexpr u32 S16_BINS = 8192;
 constexpr u32 S16_BUF = S16_BUF_ELEMS;   // sort buffer capacity (elements) = rows per batch at most
 constexpr u32 S16_MAXGROUP = 128;    // largest tie group ordered by direct comparison
 constexpr u32 S16_MAXDEPTH = 512;    // longest common prefix followed by direct comparison
+#ifndef S16_TIE_ROWS
+#define S16_TIE_ROWS 256
+#endif
+constexpr u32 S16_TIE_CHUNK = S16_TIE_ROWS;   // rows a warp searches for tie-run heads at a time (8 per lane)
 
 struct Sort16Smem {
   u32 bins[S16_BINS + 8];
@@ -253,8 +257,53 @@ __device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort
     __syncthreads();
     // 3b. sort by (key, index)
     s16_bitonic(S, P);
-    // 3c. suffixes with equal keys: the first of each run orders the run by direct comparison
-    for (u32 j = tid; j < m; j += S16_NT) {
+    // 3c. suffixes with equal keys: one thread per run orders it by direct comparison.  Runs are sparse (one row in
+    // twelve starts one in the text corpus), so a warp first finds the run heads among 256 rows (8 per lane) and
+    // deals them out, the h-th head to lane h: every lane of the warp then orders a run at the same time, instead of
+    // the two or three lanes whose own row happened to be a head.  (Neighbouring runs may be permuted by another
+    // lane meanwhile: only the index bits of a word change, the key bits read here never do.)
+#ifndef S16_TIES_PER_ROW
+    for (u32 c0 = warp * S16_TIE_CHUNK; c0 < m; c0 += (S16_NT / 32) * S16_TIE_CHUNK) {
+      u32 hm[S16_TIE_CHUNK / 32], total = 0;
+#pragma unroll
+      for (u32 r = 0; r < S16_TIE_CHUNK / 32; ++r) {
+        const u32 j = c0 + r * 32 + lane;
+        bool head = false;
+        if (j + 1 < m) {
+          const u64 kj = S[j] >> 16;
+          head = (j == 0 || (S[j - 1] >> 16) != kj) && (S[j + 1] >> 16) == kj;
+        }
+        hm[r] = __ballot_sync(ZQ_FULL, head);
+        total += (u32)__popc(hm[r]);
+      }
+      for (u32 h = lane; h < total; h += 32) {
+        u32 j = 0, hh = h;     // row of head number h of the chunk
+#pragma unroll
+        for (u32 r = 0; r < S16_TIE_CHUNK / 32; ++r) {
+          const u32 pc = (u32)__popc(hm[r]);
+          if (hh < pc) {
+            u32 mk = hm[r];
+            for (u32 q = 0; q < hh; ++q) mk &= mk - 1;
+            j = c0 + r * 32 + (u32)(__ffs(mk) - 1);
+            hh = 0xffffffffu;
+          } else if (hh != 0xffffffffu) hh -= pc;
+        }
+        const u64 kj = S[j] >> 16;
+        u32 e = j + 1;
+        while (e < m && e - j <= S16_MAXGROUP && (S[e] >> 16) == kj) ++e;
+        if (e - j > S16_MAXGROUP) { sm.fallback = 1; continue; }
+        u32 deep = 0;
+        for (u32 x = j + 1; x < e; ++x) {         // insertion sort on the index part
+          const u32 v = (u32)S[x] & 0xffffu;
+          u32 y = x;
+          while (y > j && s16_less(T, n, v, (u32)S[y - 1] & 0xffffu, from, &deep)) { S[y] = S[y - 1]; --y; }
+          S[y] = (kj << 16) | v;
+        }
+        if (deep) sm.fallback = 1;
+      }
+    }
+#else
+    for (u32 j = tid; j < m; j += S16_NT) {      // (tuning build: every thread looks at its own row only)
       const u64 kj = S[j] >> 16;
       const bool head = (j == 0 || (S[j - 1] >> 16) != kj) && (j + 1 < m && (S[j + 1] >> 16) == kj);
       if (!head) continue;
@@ -262,7 +311,7 @@ __device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort
       while (e < m && e - j <= S16_MAXGROUP && (S[e] >> 16) == kj) ++e;
       if (e - j > S16_MAXGROUP) { sm.fallback = 1; continue; }
       u32 deep = 0;
-      for (u32 x = j + 1; x < e; ++x) {         // insertion sort on the index part
+      for (u32 x = j + 1; x < e; ++x) {
         const u32 v = (u32)S[x] & 0xffffu;
         u32 y = x;
         while (y > j && s16_less(T, n, v, (u32)S[y - 1] & 0xffffu, from, &deep)) { S[y] = S[y - 1]; --y; }
@@ -270,6 +319,7 @@ __device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort
       }
       if (deep) sm.fallback = 1;
     }
+#endif
     __syncthreads();
     if (sm.fallback) return false;
     // 3d. rows rowbase .. rowbase+m are final
