@@ -94,6 +94,20 @@ SORT16_CASES = [corpus.text_unit(3, 3000), corpus.random_unit(6, 5000), b"abraca
                 corpus.text_unit(21, 65536)]
 
 
+def _skewed(seed, k, n):
+    """n bytes over k byte values, Zipf-like: the dense form of the sort packs them into 1..8 bits per character"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    vals = rng.choice(256, size=k, replace=False)
+    p = 1.0 / np.arange(1, k + 1) ** 1.2
+    return vals[rng.choice(k, size=n, p=p / p.sum())].astype(np.uint8).tobytes()
+
+
+SORT16_CASES += [_skewed(1, 2, 2180), _skewed(2, 3, 9000), _skewed(3, 5, 8471), _skewed(4, 9, 13591), _skewed(5, 17, 20000), _skewed(6, 33, 10392),
+                 _skewed(7, 65, 7468), _skewed(8, 129, 14255), _skewed(9, 256, 11135), corpus.text_unit(77, 12000) + corpus.random_unit(3, 6000),
+                 _skewed(10, 17, 65536)]
+
+
 @pytest.mark.parametrize("k", range(len(SORT16_CASES)))
 def test_shared_memory_sort_matches_oracle(emu, oracle, k):
     # k_suffix_sort16 (zq_sufsort16.cuh): bins -> bitonic sort on 6-byte prefixes -> direct comparison of ties, with the hand-over
