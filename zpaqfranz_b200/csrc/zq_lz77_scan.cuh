@@ -35,7 +35,7 @@ constexpr u32 LZS_ROWS = LZS_TILE + 2 * LZS_HALO;
 constexpr int LZS_NB = 4;        // tiles resident per CTA (ring of bulk-copy buffers)
 constexpr int LZS_NT = 512;      // threads per CTA of the scan kernels
 #ifndef LZS_ROUND_STEPS
-#define LZS_ROUND_STEPS 4
+#define LZS_ROUND_STEPS 6
 #endif
 constexpr int LZS_ROUND = LZS_ROUND_STEPS;   // scan steps between two event rounds
 #ifndef LZS_OCC1
@@ -56,6 +56,12 @@ template <> struct LzsFmt<u16> {
   static __device__ __forceinline__ u32 f_off(u32 d) { return d & 0xffffu; }
   static __device__ __forceinline__ u32 f_blen(u32 d) { return (d >> 16) & 0x1ffu; }
   static __device__ __forceinline__ u32 f_blit(u32 d) { return (d >> 25) & 1u; }
+  // both decisions of a position with one store
+#ifdef LZS_STORE_SPLIT
+  static __device__ __forceinline__ void f_store2(u32* fo, u32 a, u32 b) { fo[0] = a; fo[1] = b; }
+#else
+  static __device__ __forceinline__ void f_store2(u32* fo, u32 a, u32 b) { *reinterpret_cast<uint2*>(fo) = make_uint2(a, b); }
+#endif
 };
 template <> struct LzsFmt<u32> {
   typedef u64 R0T; typedef u64 FT;
@@ -68,6 +74,11 @@ template <> struct LzsFmt<u32> {
   static __device__ __forceinline__ u32 f_off(u64 d) { return (u32)d; }
   static __device__ __forceinline__ u32 f_blen(u64 d) { return (u32)(d >> 32) & 0xffffu; }
   static __device__ __forceinline__ u32 f_blit(u64 d) { return (u32)(d >> 48) & 1u; }
+#ifdef LZS_STORE_SPLIT
+  static __device__ __forceinline__ void f_store2(u64* fo, u64 a, u64 b) { fo[0] = a; fo[1] = b; }
+#else
+  static __device__ __forceinline__ void f_store2(u64* fo, u64 a, u64 b) { *reinterpret_cast<ulonglong2*>(fo) = make_ulonglong2(a, b); }
+#endif
 };
 
 __host__ __device__ inline u32 lzs_tiles(u32 n) { return (n + LZS_TILE - 1) / LZS_TILE; }
@@ -161,6 +172,17 @@ __device__ __forceinline__ typename LzsFmt<IdxT>::FT lzs_decide(u32 minMatch, u3
   return match ? F::f_pack(off, blen, blit) : (typename F::FT)0;
 }
 __device__ __forceinline__ int lzs_scale58(int sc) { return sc * 5 / 8; }   // C division: truncates toward zero like the reference
+// The look-ahead pass only ever compares scaled scores with a best score that is positive (a position without a match
+// has no look-ahead, Z:19412), which makes the truncation irrelevant below zero:
+//   lzs_ub58(rm)  = scale58(8*(1+rm) - 12) = trunc(5*rm - 2.5) = 5*rm - 3 for rm >= 1; for rm == 0 both are negative
+//   lzs_pos58(x)  = floor(5*x/8): equal to scale58(x) for x >= 0, and like it not above zero for x < 0
+#ifdef LZS_SCALE_EXACT
+__device__ __forceinline__ int lzs_ub58(u32 rm) { return lzs_scale58((int)(rm * 8u) - 4); }
+__device__ __forceinline__ int lzs_pos58(int x) { return lzs_scale58(x); }
+#else
+__device__ __forceinline__ int lzs_ub58(u32 rm) { return (int)(rm * 5u) - 3; }
+__device__ __forceinline__ int lzs_pos58(int x) { return (x * 5) >> 3; }
+#endif
 
 // Both passes.  Per-lane state machine, the scan step written without branches so the warp stays converged: `left`
 // counts the steps the lane may still take in its current direction (0 = row done / no row), x is the shared-memory
@@ -231,7 +253,7 @@ k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
           x = qq - 1; dstep = -1; runmin = 0xffffffffu; carry = K::lcp(s_pk[qq]);
           left = bwd_left;
           if (left == 0) { x = qq + 1; dstep = 1; left = fwd_left; }
-        } else { fo[0] = dd; fo[1] = dd; }
+        } else F::f_store2(fo, dd, dd);
       }
       if (fin) have = false;
     }
@@ -282,7 +304,7 @@ k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
           const u32 i = ss > 0 ? ss - 1 : n - 1;
           a = ((const R0T*)d.r0)[ss > 0 ? r : n];
           FT* fo = (FT*)d.f + 2 * (u64)i;
-          if (a == F::R0_DEFER) { fo[0] = F::F_DEFER; fo[1] = F::F_DEFER; push = false; }
+          if (a == F::R0_DEFER) { F::f_store2(fo, F::F_DEFER, F::F_DEFER); push = false; }
           else {
             const u32 bl = a ? F::r0_blen(a) : d.minMatch - 1, bpp = a ? F::r0_bp(a) : 0u;
             const int bsc = a ? (int)(bl * 8u) - zq_bitlen(i - bpp) - 11 : 0;
@@ -290,8 +312,8 @@ k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
             // nothing to gain from the look-ahead either when the rows next to q share too little with it: the
             // first step of each direction would already be pruned (ub <= best score)
             const u32 lcf = r + 1 < n ? K::lcp(s_pk[q0 + 1]) : 0u;
-            const bool nogain = lzs_scale58((int)(max(K::lcp(w), lcf) * 8u) - 4) <= bsc;
-            if (!cont || nogain) { const FT dd = lzs_decide<IdxT>(d.minMatch, d.level, i - bpp, bl, 0, bsc); fo[0] = dd; fo[1] = dd; push = false; }
+            const bool nogain = lzs_ub58(max(K::lcp(w), lcf)) <= bsc;      // (only looked at when cont, i.e. bsc > 0)
+            if (!cont || nogain) { const FT dd = lzs_decide<IdxT>(d.minMatch, d.level, i - bpp, bl, 0, bsc); F::f_store2(fo, dd, dd); push = false; }
           }
         }
         const u32 pm = __ballot_sync(ZQ_FULL, push);
@@ -362,14 +384,14 @@ k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
         go = live && !dnow && !(valid && (int)rm < max((int)blen0, mm));
       } else {
         const u32 bw = K::bwt(w);
-        const int ub = lzs_scale58((int)(rm * 8u) - 4);      // ((1+rm)*8 - 12) * 5/8
+        const int ub = lzs_ub58(rm);                         // ((1+rm)*8 - 12) * 5/8
         stop0 = stop0 || ub <= bs0;
         const bool live = inr && !stop0;
         const bool valid = live && p != 0 && p < s;          // candidate p-1 < i
         const u32 l = 1u + rm;
         const u32 l1 = bw == aux ? 0u : 1u;
         const int base = (int)((l - l1) * 8u) - (32 - __clz(s - p)) - 11;
-        const int sc = lzs_scale58(base - ((pen && l1) ? 4 : 0));
+        const int sc = lzs_pos58(base - ((pen && l1) ? 4 : 0));
         const bool ok = valid && !capped;
         const bool t0 = ok && sc > bs0;
         blen0 = t0 ? l : blen0; bp0 = t0 ? p - 1 : bp0; blit0 = t0 ? l1 : blit0; bs0 = t0 ? sc : bs0;

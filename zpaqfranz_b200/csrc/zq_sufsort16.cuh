@@ -4,20 +4,24 @@
 //
 // Why a second sorter: k_suffix_sort (zq_sufsort.cuh) is a general prefix-doubling sort whose 40 bytes of scratch per
 // input byte live in global memory -- 22 MB of DRAM traffic per 64 KiB block.  Text-like and random blocks do not need
-// doubling at all: their suffixes differ within a few bytes.  This kernel therefore sorts by the first 6-7 bytes with a
-// bitonic network over 64-bit words (bin number inside the batch | following text bits | 16-bit suffix index) held in
-// shared memory, then orders the few suffixes that still tie (groups of 2..128) by comparing the text directly.  A block
-// where that stops paying -- a group of more than 128 suffixes sharing the key, or two suffixes sharing more than 512
-// bytes -- is handed to k_suffix_sort through a flag; nothing is approximated.
+// doubling at all: their suffixes differ within a few characters.  This kernel sorts by the first 10-12 characters
+// with a network over 64-bit words (bin number inside the batch | following stream bits | 16-bit suffix index) held in
+// shared memory, then orders the few suffixes that still tie (groups of 2..128) by comparing the block directly.  A
+// block where that stops paying -- a group of more than 128 suffixes sharing the key, or two suffixes sharing more than
+// 512 characters -- is handed to k_suffix_sort through a flag; nothing is approximated.
 //
-//   shared memory (~225 KB, one CTA per SM):  text 64 KiB | 8192 bin starts | 16384 x u64 sort buffer (bin cursors first)
-//   1. text -> shared memory (bulk async copy when the block is 16-byte aligned)
-//   2. histogram of the 13-bit key (byte 0, top 5 bits of byte 1) with shared-memory atomics, exclusive scan: the
-//      start row of every bin.  Bins are only a way to cut the suffix array into batches that fit the sort buffer:
-//      a batch takes as many whole bins as fit the buffer.
-//      Every position is dealt to its bin's rows of the (global, L2-resident) sa array -- a counting sort on 13 bits.
-//   3. per batch: its rows are read back (coalesced), keyed by the leading bits of their suffix, sorted; ties
-//      resolved; then the rows are final and sa / lcp / bwt / pk are written in row order and isa is scattered.
+//   shared memory (~225 KB, one CTA per SM):  block 64 KiB | 8192 bin starts | 16384 x u64 sort buffer
+//   1. the bytes arrive in the (still unused) sort buffer by bulk async copy; every byte is replaced by its rank among
+//      the byte values that occur (b = 1..8 bits, order preserving) and the block is kept as that packed big-endian bit
+//      stream only (the "dense form", S16Dense below): 64 bits at bit offset b*i = the first 64/b characters of suffix i
+//   2. histogram of the first 13 stream bits of every suffix (shared-memory atomics), exclusive scan: the start row of
+//      every bin (2.6 characters of the word corpus: ~3 500 bins of 19 rows on average).  Every position is dealt to
+//      its bin's rows of the (global, L2-resident) sa array -- a counting sort on 13 bits.
+//   3. per batch (whole bins, as many as fit the buffer): rows read back (coalesced), keyed, sorted by the all-ascending
+//      network cut short at the size of the largest bin (s16_bitonic_bins); tie runs dealt to the lanes of a warp and
+//      ordered by window compares; then the rows are final: sa / lcp / bwt / pk written in row order, isa scattered.
+// Tuning builds keep the round-2 forms selectable (all bit-exact): -DS16_RAW (raw bytes, 7 per sort word, 165 bins for
+// text), -DS16_FULLSORT (the complete network), -DS16_TIES_PER_ROW (tie runs ordered by the thread whose row starts one).
 #pragma once
 #include "zq_sufsort.cuh"
 
@@ -32,9 +36,9 @@ constexpr u32 S16_BUF = S16_BUF_ELEMS;   // sort buffer capacity (elements) = ro
 constexpr u32 S16_MAXGROUP = 128;    // largest tie group ordered by direct comparison
 constexpr u32 S16_MAXDEPTH = 512;    // longest common prefix followed by direct comparison
 #ifndef S16_TIE_ROWS
-#define S16_TIE_ROWS 256
+#define S16_TIE_ROWS 512
 #endif
-constexpr u32 S16_TIE_CHUNK = S16_TIE_ROWS;   // rows a warp searches for tie-run heads at a time (8 per lane)
+constexpr u32 S16_TIE_CHUNK = S16_TIE_ROWS;   // rows a warp searches for tie-run heads at a time (16 per lane)
 
 struct Sort16Smem {
   u32 bins[S16_BINS + 8];
@@ -171,23 +175,32 @@ __device__ void s16_bitonic(u64* __restrict__ S, u32 P) {
 // (2,3) ..., the same phase shifted by K the pairs (1,2), (3,4) ..., and the batch is sorted: log^2(K)/2 + 2 log(2K)
 // comparator stages instead of log^2(P)/2 (65 instead of 105 for K = 512 in a batch of 16 384).
 __device__ __forceinline__ void s16f_reg8(u64* __restrict__ S, u32 base, bool head) {
+  // 8 consecutive words per thread = 64 bytes: with every lane reading its 16-byte pieces in the same order, lanes
+  // L and L+2 hit the same banks (4-way conflict).  Every other lane pair therefore starts with its upper half: slot e
+  // then holds word e ^ 4, which only turns around the pairs that are 4 apart (direction flag `lo4`).
+#ifdef S16_REG8_PLAIN
+  const u32 rot = 0;
+#else
+  const u32 rot = (threadIdx.x >> 1) & 1u;
+#endif
+  const bool lo4 = rot == 0;
   u64 v[8];
   const ulonglong2* src = reinterpret_cast<const ulonglong2*>(S + base);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { const ulonglong2 t = src[q]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+  for (int q = 0; q < 4; ++q) { const ulonglong2 t = src[q ^ (2 * rot)]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
   if (head) {
     s16_cx(v[0], v[1], true); s16_cx(v[2], v[3], true); s16_cx(v[4], v[5], true); s16_cx(v[6], v[7], true);
     s16_cx(v[0], v[3], true); s16_cx(v[1], v[2], true); s16_cx(v[4], v[7], true); s16_cx(v[5], v[6], true);
     s16_cx(v[0], v[1], true); s16_cx(v[2], v[3], true); s16_cx(v[4], v[5], true); s16_cx(v[6], v[7], true);
-    s16_cx(v[0], v[7], true); s16_cx(v[1], v[6], true); s16_cx(v[2], v[5], true); s16_cx(v[3], v[4], true);
+    s16_cx(v[0], v[7], lo4); s16_cx(v[1], v[6], lo4); s16_cx(v[2], v[5], lo4); s16_cx(v[3], v[4], lo4);
   } else {
-    s16_cx(v[0], v[4], true); s16_cx(v[1], v[5], true); s16_cx(v[2], v[6], true); s16_cx(v[3], v[7], true);
+    s16_cx(v[0], v[4], lo4); s16_cx(v[1], v[5], lo4); s16_cx(v[2], v[6], lo4); s16_cx(v[3], v[7], lo4);
   }
   s16_cx(v[0], v[2], true); s16_cx(v[1], v[3], true); s16_cx(v[4], v[6], true); s16_cx(v[5], v[7], true);
   s16_cx(v[0], v[1], true); s16_cx(v[2], v[3], true); s16_cx(v[4], v[5], true); s16_cx(v[6], v[7], true);
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(S + base);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) dst[q] = make_ulonglong2(v[2 * q], v[2 * q + 1]);
+  for (int q = 0; q < 4; ++q) dst[q ^ (2 * rot)] = make_ulonglong2(v[2 * q], v[2 * q + 1]);
 }
 
 // one merge phase of size k >= 16 over S[0..len), len a multiple of k (every thread of the CTA calls it)
@@ -583,7 +596,15 @@ __device__ bool suffix_sort16d_rest(u32 n, u8* __restrict__ w, bool want_pk, Sor
   u32* cursor = reinterpret_cast<u32*>(sm.buf);
   for (u32 b = tid; b < S16_BINS; b += S16_NT) cursor[b] = sm.bins[b];
   __syncthreads();
-  for (u32 i = tid; i < n; i += S16_NT) o_sa[atomicAdd(&cursor[d.hi32(i) >> 19], 1u)] = (u16)i;
+  {
+    u32 i = tid;
+    for (; i + 3 * S16_NT < n; i += 4 * S16_NT) {         // four positions in flight: the atomics' latency overlaps
+      const u32 b0 = d.hi32(i) >> 19, b1 = d.hi32(i + S16_NT) >> 19, b2 = d.hi32(i + 2 * S16_NT) >> 19, b3 = d.hi32(i + 3 * S16_NT) >> 19;
+      const u32 r0 = atomicAdd(&cursor[b0], 1u), r1 = atomicAdd(&cursor[b1], 1u), r2 = atomicAdd(&cursor[b2], 1u), r3 = atomicAdd(&cursor[b3], 1u);
+      o_sa[r0] = (u16)i; o_sa[r1] = (u16)(i + S16_NT); o_sa[r2] = (u16)(i + 2 * S16_NT); o_sa[r3] = (u16)(i + 3 * S16_NT);
+    }
+    for (; i < n; i += S16_NT) o_sa[atomicAdd(&cursor[d.hi32(i) >> 19], 1u)] = (u16)i;
+  }
   __syncthreads();
   u16* __restrict__ o_lcp = (u16*)(w + 2 * stride);
   u8* __restrict__ o_bwt = w + 2 * stride + zq_work_stride(n, 2);
@@ -612,6 +633,7 @@ __device__ bool suffix_sort16d_rest(u32 n, u8* __restrict__ w, bool want_pk, Sor
     // sort words: bin number inside the batch (nb bits) | the 48 - nb stream bits after the bin bits | index.  Equal
     // keys share 61 - nb bits = at least `from` whole characters.
     const u32 blo = sm.blo, nb = (u32)zq_bitlen(sm.bhi - sm.blo), from = ((61u - nb) * d.rcp) >> 16;
+#pragma unroll 4
     for (u32 j = tid; j < rowend - rowbase; j += S16_NT) {
       const u32 i = o_sa[rowbase + j];
       const u64 p64 = d.win(i);
