@@ -20,7 +20,7 @@
 //               codes; level 2: byte codes) into a stream assembled in shared memory, stored with one bulk copy.
 //
 // Lanes finish their rows at very different times (scan lengths 1..254), so each lane pulls the next row of the
-// tile when it is done, at round boundaries every LZS_ROUND steps: ~65-70 % of the lanes do useful steps instead
+// tile when it is done, at round boundaries every LZS_ROUND_STEPS steps: ~65-70 % of the lanes do useful steps instead
 // of 13 % with one row per lane per loop.
 // Bit-exact by construction: the per-row state machine is the reference's loop with one exact pruning rule (no
 // remaining neighbour can beat the best score once 8*(h+runmin)-12, scaled, is not above it).
@@ -35,9 +35,11 @@ constexpr u32 LZS_ROWS = LZS_TILE + 2 * LZS_HALO;
 constexpr int LZS_NB = 4;        // tiles resident per CTA (ring of bulk-copy buffers)
 constexpr int LZS_NT = 512;      // threads per CTA of the scan kernels
 #ifndef LZS_ROUND_STEPS
-#define LZS_ROUND_STEPS 6
+#define LZS_ROUND_STEPS 6      // scan steps between two event rounds, look-ahead-0 pass
 #endif
-constexpr int LZS_ROUND = LZS_ROUND_STEPS;   // scan steps between two event rounds
+#ifndef LZS_ROUND_STEPS1
+#define LZS_ROUND_STEPS1 10    // ... look-ahead-1 pass (its rows are fewer and longer)
+#endif
 #ifndef LZS_OCC1
 #define LZS_OCC1 2      // CTAs per SM the look-ahead-1 pass is compiled for
 #endif
@@ -187,7 +189,7 @@ __device__ __forceinline__ int lzs_pos58(int x) { return (x * 5) >> 3; }
 // Both passes.  Per-lane state machine, the scan step written without branches so the warp stays converged: `left`
 // counts the steps the lane may still take in its current direction (0 = row done / no row), x is the shared-memory
 // index of the next neighbour; the switch from the backward to the forward direction is part of the step.
-// Every LZS_ROUND steps an event round runs, warp-converged except for the result stores:
+// Every LZS_ROUND_STEPS (look-ahead 1: LZS_ROUND_STEPS1) steps an event round runs, warp-converged except for the result stores:
 //   * lanes whose row is done store its result;
 //   * free lanes take rows from the warp's queue; when the queue is empty the warp SWEEPS: it claims 32 rows of its
 //     current tile with one atomic, evaluates all of them at once (PASS 1: coalesced load of r0, rows the look-ahead
@@ -361,9 +363,9 @@ k_lz_scan(const ZqUnit* __restrict__ units, const ZqPlan* __restrict__ plans, co
       if (freemask == ZQ_FULL) __nanosleep(100);
       continue;
     }
-    // ---- LZS_ROUND scan steps ----
+    // ---- scan steps ----
 #pragma unroll
-    for (int r = 0; r < LZS_ROUND; ++r) {
+    for (int r = 0; r < (PASS == 0 ? LZS_ROUND_STEPS : LZS_ROUND_STEPS1); ++r) {
       const bool inr = left > 0;
       const PT w = s_pk[inr ? x : qq];
       const u32 p = K::sa(w), lc = K::lcp(w);

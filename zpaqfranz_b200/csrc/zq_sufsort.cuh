@@ -49,7 +49,11 @@ template <> struct LzsPack<u16> {
   typedef u32 T;
   static __device__ __forceinline__ u32 make(u32 sa, u32 lcp, u32 bw) { return sa | (min(lcp, 255u) << 16) | (bw << 24); }
   static __device__ __forceinline__ u32 sa(u32 w) { return w & 0xffffu; }
+#ifdef LZS_SHIFT_FIELDS
   static __device__ __forceinline__ u32 lcp(u32 w) { return (w >> 16) & 255u; }
+#else   // one byte-permute instead of shift + mask: the scan kernels are bound by the integer pipe
+  static __device__ __forceinline__ u32 lcp(u32 w) { return __byte_perm(w, 0u, 0x4442); }
+#endif
   static __device__ __forceinline__ u32 bwt(u32 w) { return w >> 24; }
 };
 template <> struct LzsPack<u32> {

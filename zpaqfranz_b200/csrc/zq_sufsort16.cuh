@@ -204,30 +204,53 @@ __device__ __forceinline__ void s16f_reg8(u64* __restrict__ S, u32 base, bool he
 }
 
 // one merge phase of size k >= 16 over S[0..len), len a multiple of k (every thread of the CTA calls it)
+// Passes whose smallest stride is 8 words make the two halves of a half-warp read the same banks (lanes 0-7 words
+// 0..7 of one 32-word block, lanes 8-15 words 0..7 of the next): every second group of 8 lanes therefore takes its
+// words in the opposite order (`sw`), which turns around the comparators inside a pair of slots (direction `!sw`).
+#ifdef S16_NO_STAGGER
+#define S16_SW(t) false
+#else
+#define S16_SW(t) ((((t) >> 3) & 1u) != 0)
+#endif
 __device__ void s16f_phase(u64* __restrict__ S, u32 len, u32 k) {
   const u32 tid = threadIdx.x;
   if (k == 16) {
     for (u32 t = tid; t < len / 2; t += S16_NT) {
       const u32 r = t & 7u, blk = (t - r) * 2;
-      u64 a = S[blk + r], d = S[blk + 15 - r];
-      s16_cx(a, d, true);
-      S[blk + r] = a; S[blk + 15 - r] = d;
+      const bool sw = S16_SW(t);
+      const u32 i0 = sw ? blk + 15 - r : blk + r, i1 = sw ? blk + r : blk + 15 - r;
+      u64 x = S[i0], y = S[i1];
+      s16_cx(x, y, !sw);
+      S[i0] = x; S[i1] = y;
     }
     __syncthreads();
   } else {
     const u32 h = k >> 2;                                 // mirror stage and stride k/4 in one pass
-    for (u32 t = tid; t < len / 4; t += S16_NT) {
-      const u32 r = t & (h - 1), blk = (t - r) * 4;
-      const u32 ia = blk + r, ib = ia + h, id = blk + k - 1 - r, ic = id - h;
-      u64 a = S[ia], b = S[ib], c = S[ic], d = S[id];
-      s16_cx(a, d, true); s16_cx(b, c, true);
-      s16_cx(a, b, true); s16_cx(c, d, true);
-      S[ia] = a; S[ib] = b; S[ic] = c; S[id] = d;
+    if (h == 8) {
+      for (u32 t = tid; t < len / 4; t += S16_NT) {
+        const u32 r = t & 7u, blk = (t - r) * 4;
+        const bool sw = S16_SW(t);
+        const u32 ia = blk + r, ib = ia + 8, id = blk + 31 - r, ic = id - 8;
+        const u32 i0 = sw ? ib : ia, i1 = sw ? ia : ib, i2 = sw ? id : ic, i3 = sw ? ic : id;
+        u64 v0 = S[i0], v1 = S[i1], v2 = S[i2], v3 = S[i3];
+        s16_cx(v0, v3, true); s16_cx(v1, v2, true);       // (a,d),(b,c) -- or (b,c),(a,d)
+        s16_cx(v0, v1, !sw); s16_cx(v2, v3, !sw);         // (a,b),(c,d) -- or (b,a),(d,c)
+        S[i0] = v0; S[i1] = v1; S[i2] = v2; S[i3] = v3;
+      }
+    } else {
+      for (u32 t = tid; t < len / 4; t += S16_NT) {
+        const u32 r = t & (h - 1), blk = (t - r) * 4;
+        const u32 ia = blk + r, ib = ia + h, id = blk + k - 1 - r, ic = id - h;
+        u64 a = S[ia], b = S[ib], c = S[ic], d = S[id];
+        s16_cx(a, d, true); s16_cx(b, c, true);
+        s16_cx(a, b, true); s16_cx(c, d, true);
+        S[ia] = a; S[ib] = b; S[ic] = c; S[id] = d;
+      }
     }
     __syncthreads();
     u32 j = h >> 1;
     while (j >= 8) {
-      if (j >= 16) {
+      if (j >= 32) {
         const u32 g = j >> 1;
         for (u32 t = tid; t < len / 4; t += S16_NT) {
           const u32 i = 4 * t - 3 * (t & (g - 1));
@@ -237,12 +260,25 @@ __device__ void s16f_phase(u64* __restrict__ S, u32 len, u32 k) {
           S[i] = a; S[i + g] = b; S[i + j] = c; S[i + j + g] = d;
         }
         j >>= 2;
-      } else {
+      } else if (j == 16) {                               // strides 16 and 8
+        for (u32 t = tid; t < len / 4; t += S16_NT) {
+          const u32 i = 4 * t - 3 * (t & 7u);
+          const bool sw = S16_SW(t);
+          const u32 i0 = sw ? i + 8 : i, i1 = sw ? i : i + 8;
+          u64 v0 = S[i0], v1 = S[i1], v2 = S[i0 + 16], v3 = S[i1 + 16];
+          s16_cx(v0, v2, true); s16_cx(v1, v3, true);     // (a,c),(b,d) either way
+          s16_cx(v0, v1, !sw); s16_cx(v2, v3, !sw);       // (a,b),(c,d) -- or (b,a),(d,c)
+          S[i0] = v0; S[i1] = v1; S[i0 + 16] = v2; S[i1 + 16] = v3;
+        }
+        j >>= 2;
+      } else {                                            // stride 8 alone
         for (u32 t = tid; t < len / 2; t += S16_NT) {
-          const u32 i = 2 * t - (t & (j - 1));
-          u64 a = S[i], b = S[i + j];
-          s16_cx(a, b, true);
-          S[i] = a; S[i + j] = b;
+          const u32 i = 2 * t - (t & 7u);
+          const bool sw = S16_SW(t);
+          const u32 i0 = sw ? i + 8 : i, i1 = sw ? i : i + 8;
+          u64 x = S[i0], y = S[i1];
+          s16_cx(x, y, !sw);
+          S[i0] = x; S[i1] = y;
         }
         j >>= 1;
       }
@@ -459,16 +495,21 @@ __device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort
 // number.  The same 13 bin bits now separate ~3 500 bins (2.6 characters at b = 5), batches fill the sort buffer
 // almost exactly, a sort word holds 10-12 characters (a third of the ties), and comparisons / LCPs run a window of
 // 64/b characters at a time.  Positions past the end read as character 0; every comparison checks the suffix ends.
+// the 32 bits at bit offset sh (0..31) of the 64-bit number hi:lo.  Written out rather than __funnelshift_l: that
+// intrinsic is a volatile asm statement, which pins every shift behind its own loads and keeps the compiler from
+// overlapping the loads of neighbouring positions
+__device__ __forceinline__ u32 s16_bits32(u32 hi, u32 lo, u32 sh) { return (u32)(((((u64)hi << 32) | lo) << sh) >> 32); }
+
 struct S16Dense {
   const u32* D; u32 b, rcp, n;
   __device__ __forceinline__ u32 hi32(u32 i) const {           // first 32 bits of suffix i
     const u32 bit = b * i, j = bit >> 5, sh = bit & 31u;
-    return __funnelshift_l(D[j + 1], D[j], sh);
+    return s16_bits32(D[j], D[j + 1], sh);
   }
   __device__ __forceinline__ u64 win(u32 i) const {            // first 64 bits of suffix i
     const u32 bit = b * i, j = bit >> 5, sh = bit & 31u;
     const u32 w0 = D[j], w1 = D[j + 1], w2 = D[j + 2];
-    return ((u64)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
+    return ((u64)s16_bits32(w0, w1, sh) << 32) | s16_bits32(w1, w2, sh);
   }
   __device__ __forceinline__ u32 code(u32 i) const { return hi32(i) >> (32u - b); }
   __device__ __forceinline__ u32 chars(u64 x) const {          // whole characters two windows share, x = their XOR
