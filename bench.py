@@ -505,7 +505,7 @@ def main():
         algo = a_io + (8 * S_BYTES[method] * coded if method in S_BYTES else 0)
         achieved = algo / 1e9 / (kernels[dom] / 1000) if kernels[dom] > 0 else 0.0
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "traffic_r02.json")
+        tp = os.path.join(ROOT, "profiles", "traffic_r04.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
