@@ -42,6 +42,26 @@ def test_suffix_array_matches_oracle(ctx, oracle):
         assert (sa == oracle.suffix_array(u)).all(), len(u)
 
 
+def _skewed(seed, k, n):
+    """n bytes over k byte values, Zipf-like (the shared-memory suffix sort packs them into 1..8 bits per character)"""
+    rng = np.random.default_rng(seed)
+    vals = rng.choice(256, size=k, replace=False)
+    p = 1.0 / np.arange(1, k + 1) ** 1.2
+    return vals[rng.choice(k, size=n, p=p / p.sum())].astype(np.uint8).tobytes()
+
+
+def test_small_alphabets_bit_exact(ctx, ref):
+    """k_suffix_sort16's dense form at every character width: blocks over 2 .. 256 byte values, -m2 against the reference."""
+    units = [_skewed(10 + k, k, n) for k, n in ((2, 30000), (3, 65536), (5, 50000), (9, 65536), (17, 65536), (33, 40000), (65, 65536),
+                                                (129, 65536), (200, 65535), (256, 65536))]
+    units += [corpus.text_unit(31, 40000) + corpus.random_unit(31, 25536), bytes(range(256)) * 256]
+    arena, offs, lens = _arena(units)
+    out, ooff, olen = ctx.compress_blocks(arena, offs, lens, method="2", filename="", comment="jDC\x01")
+    for i, u in enumerate(units):
+        got = out[int(ooff[i]): int(ooff[i]) + int(olen[i])].tobytes()
+        assert got == ref.compress_block(u, "2", "", "jDC\x01"), (i, len(u))
+
+
 @pytest.mark.parametrize("method", ["2", "0", "26,200,1", "x0,0", "x0,1,4,0,7,21,1", "x0,1,4,0,7,21,0", "x0,1,6,0,5,21,2",
                                      "x0,1,4,0,4,21,1"])
 def test_unmodeled_blocks_bit_exact(ctx, zq, oracle, ref, method):
