@@ -152,6 +152,23 @@ def test_single_rank_keeps_everything(oracle):
     d.close()
 
 
+def test_cpp_caller_of_the_c_abi(zq, oracle, tmp_path):
+    """tests/cpp/stitch_driver.cpp: the same protocol written as the archiver's host code would (C++ threads as ranks,
+    zq_dist_create_cb, zq_dist_stitch_fragments through the C ABI, the checker's chunker linked in)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "stitch_driver"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-I" + os.path.join(root, "include"), os.path.join(root, "tests/cpp/stitch_driver.cpp"),
+                    "-o", str(exe), "-L" + os.path.join(root, "zpaqfranz_b200"), "-lzqb200", "-L" + os.path.join(root, "oracle", "_ref"), "-lzqoracle",
+                    "-Wl,-rpath," + os.path.join(root, "zpaqfranz_b200"), "-Wl,-rpath," + os.path.join(root, "oracle", "_ref")], check=True)
+    for world, kind in ((2, 0), (3, 0), (4, 1)):
+        r = subprocess.run([str(exe), str(world), str(kind)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+        if kind == 1:
+            assert "1 call(s)" not in r.stdout          # the restart path was taken
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,world", [("mixed", 3), ("zeros_at_cut", 2)])
 def test_device_fragmenter_pieces_equal_the_whole_stream(ctx, oracle, kind, world):
