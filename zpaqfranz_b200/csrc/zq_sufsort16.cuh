@@ -20,8 +20,8 @@
 //   3. per batch (whole bins, as many as fit the buffer): rows read back (coalesced), keyed, sorted by the all-ascending
 //      network cut short at the size of the largest bin (s16_bitonic_bins); tie runs dealt to the lanes of a warp and
 //      ordered by window compares; then the rows are final: sa / lcp / bwt / pk written in row order, isa scattered.
-// Tuning builds keep the round-2 forms selectable (all bit-exact): -DS16_RAW (raw bytes, 7 per sort word, 165 bins for
-// text), -DS16_FULLSORT (the complete network), -DS16_TIES_PER_ROW (tie runs ordered by the thread whose row starts one).
+// The forms this one replaced (raw bytes: 7 per sort word, 165 bins for text; the complete network; tie runs ordered by
+// the thread whose row starts one) and their times are in profiles/README.md (r04a); the code is gone.
 #pragma once
 #include "zq_sufsort.cuh"
 
@@ -47,45 +47,11 @@ struct Sort16Smem {
   u32 blo, bhi, pad2[2];                 // first / last non-empty bin of the current batch
   ZqMbar bar;
   u64 pad1;
-  u32 cbits, crcp, kused, bmx;           // dense form: bits per character, 65536 / cbits + 1, characters in use; largest bin of the batch
+  u32 cbits, crcp, kused, bmx;           // bits per character, 65536 / cbits + 1, characters in use; largest bin of the batch
   u8 rank[256], inv[256], present[256];  // byte -> dense code (its rank among the bytes that occur), code -> byte
-  alignas(16) u8 text[65536 + 64];       // the text; in the dense form the packed character stream (see below)
+  alignas(16) u8 text[65536 + 64];       // the block as a packed character stream (S16Dense below)
   alignas(16) u64 buf[S16_BUF];
 };
-
-// 4 text bytes at any offset as a big-endian number (reads up to 7 bytes past p: the text is zero padded)
-__device__ __forceinline__ u32 s16_be32(const u8* p) { return __byte_perm(ld32_unaligned(p), 0, 0x0123); }
-
-// suffix a < suffix b, both known to share their first `from` bytes; *deep is set when the comparison gives up
-__device__ __forceinline__ bool s16_less(const u8* __restrict__ T, u32 n, u32 a, u32 b, u32 from, u32* deep) {
-  u32 k = from;
-  for (;;) {
-    const u32 pa = a + k, pb = b + k;
-    if (pa >= n || pb >= n) return pa >= n;          // the suffix that ends first is the smaller one (Z:17721: implicit terminator)
-    if (pa + 4 <= n && pb + 4 <= n) {
-      const u32 wa = s16_be32(T + pa), wb = s16_be32(T + pb);
-      if (wa != wb) return wa < wb;
-      k += 4;
-    } else {
-      if (T[pa] != T[pb]) return T[pa] < T[pb];
-      ++k;
-    }
-    if (k > S16_MAXDEPTH) { *deep = 1; return a < b; }
-  }
-}
-
-// common prefix length of suffixes a and b, starting the comparison at `from`, capped
-__device__ __forceinline__ u32 s16_lcp(const u8* __restrict__ T, u32 n, u32 a, u32 b, u32 from, u32 cap) {
-  const u32 lim = min(cap, n - max(a, b));
-  u32 l = min(from, lim);
-  while (l + 4 <= lim) {
-    const u32 d = ld32_unaligned(T + a + l) ^ ld32_unaligned(T + b + l);
-    if (d) return l + ((u32)(__ffs(d) - 1) >> 3);
-    l += 4;
-  }
-  while (l < lim && T[a + l] == T[b + l]) ++l;
-  return l;
-}
 
 __device__ __forceinline__ void s16_cx(u64& a, u64& b, bool up) {
   const bool sw = (a > b) == up;
@@ -93,80 +59,7 @@ __device__ __forceinline__ void s16_cx(u64& a, u64& b, bool up) {
   a = lo; b = hi;
 }
 
-// the comparator stages of strides 4, 2, 1 (and, when `head`, the whole phases k = 2, 4, 8) on 8 consecutive
-// elements held in registers
-__device__ __forceinline__ void s16_reg8(u64* __restrict__ S, u32 base, u32 k, bool head) {
-  u64 v[8];
-  const ulonglong2* src = reinterpret_cast<const ulonglong2*>(S + base);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) { const ulonglong2 t = src[q]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
-  if (head) {
-#pragma unroll
-    for (int kk = 2; kk <= 8; kk <<= 1) {
-#pragma unroll
-      for (int j = kk >> 1; j > 0; j >>= 1) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int i = 2 * c - (c & (j - 1));
-          s16_cx(v[i], v[i + j], ((base + i) & kk) == 0);
-        }
-      }
-    }
-  } else {
-    const bool up = (base & k) == 0;
-#pragma unroll
-    for (int j = 4; j > 0; j >>= 1) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int i = 2 * c - (c & (j - 1));
-        s16_cx(v[i], v[i + j], up);
-      }
-    }
-  }
-  ulonglong2* dst = reinterpret_cast<ulonglong2*>(S + base);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) dst[q] = make_ulonglong2(v[2 * q], v[2 * q + 1]);
-}
-
-// bitonic sort of S[0..P), P a power of two >= 16.  Strides below 8 run in registers (8 consecutive elements per
-// thread); strides >= 8 in shared memory, two strides (j, j/2) per pass when both are >= 8: a thread then owns the
-// four elements i, i+j/2, i+j, i+3j/2.
-__device__ void s16_bitonic(u64* __restrict__ S, u32 P) {
-  const u32 tid = threadIdx.x;
-  for (u32 t = tid; t < P / 8; t += S16_NT) s16_reg8(S, 8 * t, 0, true);
-  __syncthreads();
-  for (u32 k = 16; k <= P; k <<= 1) {
-    u32 j = k >> 1;
-    while (j >= 8) {
-      if (j >= 16) {
-        const u32 h = j >> 1;
-        for (u32 t = tid; t < P / 4; t += S16_NT) {
-          const u32 i = 4 * t - 3 * (t & (h - 1));        // t = q*h + r  ->  i = q*2j + r
-          const bool up = (i & k) == 0;
-          u64 a = S[i], b = S[i + h], c = S[i + j], d = S[i + j + h];
-          s16_cx(a, c, up); s16_cx(b, d, up);
-          s16_cx(a, b, up); s16_cx(c, d, up);
-          S[i] = a; S[i + h] = b; S[i + j] = c; S[i + j + h] = d;
-        }
-        j >>= 2;
-      } else {
-        for (u32 t = tid; t < P / 2; t += S16_NT) {
-          const u32 i = 2 * t - (t & (j - 1));
-          const bool up = (i & k) == 0;
-          u64 a = S[i], b = S[i + j];
-          s16_cx(a, b, up);
-          S[i] = a; S[i + j] = b;
-        }
-        j >>= 1;
-      }
-      __syncthreads();
-    }
-    for (u32 t = tid; t < P / 8; t += S16_NT) s16_reg8(S, 8 * t, k, false);
-    __syncthreads();
-  }
-}
-
-// ---- the same network in its all-ascending ("flip") form, cut short -------------------------------------------------
+// ---- the sort network: bitonic merges in their all-ascending ("flip") form, cut short ------------------------------
 // A merge phase of size k first compares every element with its mirror image inside the k-block (i with i ^ (k-1)),
 // then runs the strides k/4 ... 1; every comparator puts the smaller word at the lower index, so padding and whole
 // sorted runs never move against the final order.  That allows stopping early: the batch arrives ordered by bin (the
@@ -303,191 +196,7 @@ __device__ void s16_bitonic_bins(u64* __restrict__ S, u32 P, u32 K) {
   }
 }
 
-// One block.  Returns false (and writes nothing) when the block has to go to the general sorter.
-__device__ bool suffix_sort16_block(const u8* __restrict__ gT, u32 n, u8* __restrict__ w, bool want_pk, Sort16Smem& sm) {
-  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  u8* __restrict__ T = sm.text;
-  // 1. text
-  const bool aligned = ((uintptr_t)gT & 15) == 0;
-  const u32 nb = n & ~15u;
-  if (aligned && nb) {
-    if (tid == 0) { zq_mbar_expect_tx(&sm.bar, nb); zq_bulk_g2s(T, gT, nb, &sm.bar); }
-  }
-  for (u32 i = (aligned ? nb : 0) + tid; i < n + 64; i += S16_NT) T[i] = i < n ? gT[i] : (u8)0;
-  for (u32 b = tid; b < S16_BINS + 8; b += S16_NT) sm.bins[b] = 0;
-  if (tid == 0) { sm.fallback = 0; sm.prev_idx = 0; }
-  __syncthreads();
-  return true;   // (continued in suffix_sort16_rest: the bulk copy's barrier phase is tracked by the caller)
-}
-
-template <bool DUMMY>
-__device__ bool suffix_sort16_rest(u32 n, u8* __restrict__ w, bool want_pk, Sort16Smem& sm) {
-  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const u8* __restrict__ T = sm.text;
-  u64* __restrict__ S = sm.buf;
-  // 2. bins
-  for (u32 i = tid; i < n; i += S16_NT) atomicAdd(&sm.bins[((u32)T[i] << 5) | (T[i + 1] >> 3)], 1u);
-  __syncthreads();
-  {
-    // exclusive scan of 8192 counters, 8 per thread; the largest bin decides whether the batches fit
-    u32 loc[8], s = 0, mx = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { loc[q] = sm.bins[tid * 8 + q]; s += loc[q]; mx = max(mx, loc[q]); }
-    u32 inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(ZQ_FULL, inc, o); if (lane >= (u32)o) inc += t; }
-    mx = __reduce_max_sync(ZQ_FULL, mx);
-    if (lane == 31) sm.wsum[warp] = inc;
-    if (lane == 0 && mx > S16_BUF) sm.fallback = 1;
-    __syncthreads();
-    u32 pre = 0;
-    for (u32 q = 0; q < warp; ++q) pre += sm.wsum[q];
-    u32 run = pre + inc - s;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { sm.bins[tid * 8 + q] = run; run += loc[q]; }
-    if (tid == S16_NT - 1) sm.bins[S16_BINS] = run;     // = n
-    __syncthreads();
-  }
-  if (sm.fallback) return false;
-  const u64 stride = zq_work_stride(n, 2);
-  u16* __restrict__ o_sa = (u16*)w; u16* __restrict__ o_isa = (u16*)(w + stride);
-  // deal the positions to the rows of their bins (order inside a bin does not matter: it is sorted next)
-  u32* cursor = reinterpret_cast<u32*>(sm.buf);     // next free row of every bin (the sort buffer is not in use yet)
-  for (u32 b = tid; b < S16_BINS; b += S16_NT) cursor[b] = sm.bins[b];
-  __syncthreads();
-  for (u32 i = tid; i < n; i += S16_NT) o_sa[atomicAdd(&cursor[((u32)T[i] << 5) | (T[i + 1] >> 3)], 1u)] = (u16)i;
-  __syncthreads();
-  u16* __restrict__ o_lcp = (u16*)(w + 2 * stride);
-  u8* __restrict__ o_bwt = w + 2 * stride + zq_work_stride(n, 2);
-  u32* __restrict__ o_pk = (u32*)(w + zq_work_bytes(n, 2));
-  u32 rowbase = 0;
-  while (rowbase < n) {
-    // the batch: whole bins from row `rowbase` on, as many as fit the buffer.  rowend = the largest bin end <= limit
-    // (every thread looks at its 8 bins; at least the first bin fits: no bin is larger than the buffer)
-    const u32 limit = rowbase + S16_BUF;
-    {
-      u32 best = 0, blo = S16_BINS, bhi = 0;     // end row of the batch; first / last non-empty bin in it
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const u32 b = tid * 8 + q, st = sm.bins[b], e = sm.bins[b + 1];
-        if (e <= limit) best = max(best, e);
-        if (e > st && st >= rowbase && e <= limit) { blo = min(blo, b); bhi = max(bhi, b); }
-      }
-      best = __reduce_max_sync(ZQ_FULL, best); blo = __reduce_min_sync(ZQ_FULL, blo); bhi = __reduce_max_sync(ZQ_FULL, bhi);
-      if (lane == 0) { sm.wsum[warp] = best; sm.wlo[warp] = blo; sm.whi[warp] = bhi; }
-      __syncthreads();
-      best = 0; blo = S16_BINS; bhi = 0;
-      for (u32 q = 0; q < S16_NT / 32; ++q) { best = max(best, sm.wsum[q]); blo = min(blo, sm.wlo[q]); bhi = max(bhi, sm.whi[q]); }
-      __syncthreads();
-      sm.pad0 = best; sm.blo = blo; sm.bhi = bhi;     // (every thread writes the same values)
-    }
-    const u32 rowend = sm.pad0;
-    // 3a. this batch's rows, keyed by the leading bits of their suffix.  The 13 bin bits are replaced by the bin's number
-    // inside the batch (nb bits, usually 4-6), which leaves room for 48 - nb more bits of the suffix: two keys are equal
-    // iff the suffixes share their first 61 - nb bits, i.e. at least `from` whole bytes (7 for the text corpus).
-    const u32 blo = sm.blo, nb = (u32)zq_bitlen(sm.bhi - sm.blo), from = (61u - nb) >> 3;
-    for (u32 j = tid; j < rowend - rowbase; j += S16_NT) {
-      const u32 i = o_sa[rowbase + j];
-      const u32 hi = s16_be32(T + i), lo = s16_be32(T + i + 4);
-      const u64 p64 = ((u64)hi << 32) | lo;
-      const u64 rel = (u64)((hi >> 19) - blo);
-      S[j] = (((rel << (48 - nb)) | ((p64 << 13) >> (16 + nb))) << 16) | i;
-    }
-    const u32 m = rowend - rowbase;
-    u32 P = 16;
-    while (P < m) P <<= 1;
-    for (u32 t = m + tid; t < P; t += S16_NT) S[t] = ~0ull;
-    __syncthreads();
-    // 3b. sort by (key, index)
-    s16_bitonic(S, P);
-    // 3c. suffixes with equal keys: one thread per run orders it by direct comparison.  Runs are sparse (one row in
-    // twelve starts one in the text corpus), so a warp first finds the run heads among 256 rows (8 per lane) and
-    // deals them out, the h-th head to lane h: every lane of the warp then orders a run at the same time, instead of
-    // the two or three lanes whose own row happened to be a head.  (Neighbouring runs may be permuted by another
-    // lane meanwhile: only the index bits of a word change, the key bits read here never do.)
-#ifndef S16_TIES_PER_ROW
-    for (u32 c0 = warp * S16_TIE_CHUNK; c0 < m; c0 += (S16_NT / 32) * S16_TIE_CHUNK) {
-      u32 hm[S16_TIE_CHUNK / 32], total = 0;
-#pragma unroll
-      for (u32 r = 0; r < S16_TIE_CHUNK / 32; ++r) {
-        const u32 j = c0 + r * 32 + lane;
-        bool head = false;
-        if (j + 1 < m) {
-          const u64 kj = S[j] >> 16;
-          head = (j == 0 || (S[j - 1] >> 16) != kj) && (S[j + 1] >> 16) == kj;
-        }
-        hm[r] = __ballot_sync(ZQ_FULL, head);
-        total += (u32)__popc(hm[r]);
-      }
-      for (u32 h = lane; h < total; h += 32) {
-        u32 j = 0, hh = h;     // row of head number h of the chunk
-#pragma unroll
-        for (u32 r = 0; r < S16_TIE_CHUNK / 32; ++r) {
-          const u32 pc = (u32)__popc(hm[r]);
-          if (hh < pc) {
-            u32 mk = hm[r];
-            for (u32 q = 0; q < hh; ++q) mk &= mk - 1;
-            j = c0 + r * 32 + (u32)(__ffs(mk) - 1);
-            hh = 0xffffffffu;
-          } else if (hh != 0xffffffffu) hh -= pc;
-        }
-        const u64 kj = S[j] >> 16;
-        u32 e = j + 1;
-        while (e < m && e - j <= S16_MAXGROUP && (S[e] >> 16) == kj) ++e;
-        if (e - j > S16_MAXGROUP) { sm.fallback = 1; continue; }
-        u32 deep = 0;
-        for (u32 x = j + 1; x < e; ++x) {         // insertion sort on the index part
-          const u32 v = (u32)S[x] & 0xffffu;
-          u32 y = x;
-          while (y > j && s16_less(T, n, v, (u32)S[y - 1] & 0xffffu, from, &deep)) { S[y] = S[y - 1]; --y; }
-          S[y] = (kj << 16) | v;
-        }
-        if (deep) sm.fallback = 1;
-      }
-    }
-#else
-    for (u32 j = tid; j < m; j += S16_NT) {      // (tuning build: every thread looks at its own row only)
-      const u64 kj = S[j] >> 16;
-      const bool head = (j == 0 || (S[j - 1] >> 16) != kj) && (j + 1 < m && (S[j + 1] >> 16) == kj);
-      if (!head) continue;
-      u32 e = j + 1;
-      while (e < m && e - j <= S16_MAXGROUP && (S[e] >> 16) == kj) ++e;
-      if (e - j > S16_MAXGROUP) { sm.fallback = 1; continue; }
-      u32 deep = 0;
-      for (u32 x = j + 1; x < e; ++x) {
-        const u32 v = (u32)S[x] & 0xffffu;
-        u32 y = x;
-        while (y > j && s16_less(T, n, v, (u32)S[y - 1] & 0xffffu, from, &deep)) { S[y] = S[y - 1]; --y; }
-        S[y] = (kj << 16) | v;
-      }
-      if (deep) sm.fallback = 1;
-    }
-#endif
-    __syncthreads();
-    if (sm.fallback) return false;
-    // 3d. rows rowbase .. rowbase+m are final
-    const u32 prev_last = sm.prev_idx;
-    for (u32 j = tid; j < m; j += S16_NT) {
-      const u64 cur = S[j];
-      const u32 b = (u32)cur & 0xffffu, row = rowbase + j;
-      u32 l = 0;
-      if (row > 0) {
-        const u32 a = j ? ((u32)S[j - 1] & 0xffffu) : prev_last;
-        l = s16_lcp(T, n, a, b, 0u, ZQ_LCP_CAP);
-      }
-      const u32 bw = b > 0 ? (u32)T[b - 1] : 0u;
-      o_sa[row] = (u16)b; o_lcp[row] = (u16)l; o_bwt[row] = (u8)bw; o_isa[b] = (u16)row;
-      if (want_pk) o_pk[row] = LzsPack<u16>::make(b, l, bw);
-    }
-    __syncthreads();
-    if (tid == 0) sm.prev_idx = (u32)S[m - 1] & 0xffffu;
-    rowbase = rowend;
-    __syncthreads();
-  }
-  return true;
-}
-
-// ---- dense form ---------------------------------------------------------------------------------------------------
+// ---- the block as a stream of dense characters -------------------------------------------------------------------------
 // Text uses few of the 256 byte values (28 in the word corpus), so 13 bits of raw prefix tell only 165 bins apart and
 // a 64-bit sort word holds 7 characters.  Here every byte is first replaced by its rank among the bytes that occur in
 // the block (order preserving, b = 1..8 bits) and the block is kept in shared memory ONLY as that bit stream, most
@@ -547,7 +256,7 @@ __device__ __forceinline__ u32 s16d_lcp(const S16Dense& d, u32 a, u32 b, u32 cap
   return min(l, lim);
 }
 
-// One block in the dense form.  The raw text is staged in the (still unused) sort buffer.
+// One block.  The raw bytes are staged in the (still unused) sort buffer.
 __device__ void suffix_sort16d_load(const u8* __restrict__ gT, u32 n, Sort16Smem& sm) {
   const u32 tid = threadIdx.x;
   u8* __restrict__ R = reinterpret_cast<u8*>(sm.buf);
@@ -686,16 +395,12 @@ __device__ bool suffix_sort16d_rest(u32 n, u8* __restrict__ w, bool want_pk, Sor
     while (P < m) P <<= 1;
     for (u32 t = m + tid; t < P; t += S16_NT) S[t] = ~0ull;
     __syncthreads();
-#ifdef S16_FULLSORT
-    s16_bitonic(S, P);
-#else
     {
       u32 K = 16;
       while (K < sm.bmx) K <<= 1;
       s16_bitonic_bins(S, P, K);
     }
-#endif
-    for (u32 c0 = warp * S16_TIE_CHUNK; c0 < m; c0 += (S16_NT / 32) * S16_TIE_CHUNK) {   // ties: see the raw form
+    for (u32 c0 = warp * S16_TIE_CHUNK; c0 < m; c0 += (S16_NT / 32) * S16_TIE_CHUNK) {
       u32 hm[S16_TIE_CHUNK / 32], total = 0;
 #pragma unroll
       for (u32 r = 0; r < S16_TIE_CHUNK / 32; ++r) {
@@ -775,18 +480,10 @@ k_suffix_sort16(const u8* __restrict__ in_base, const ZqUnit* __restrict__ units
     bool ok = u.idx16 != 0 && u.n > 0;
     if (ok) {
       const u8* gT = in_base + u.in_off;
-#ifdef S16_RAW
-      suffix_sort16_block(gT, u.n, work_base + u.work_off, u.want_pk != 0, sm);
-#else
       suffix_sort16d_load(gT, u.n, sm);
-#endif
       if ((((uintptr_t)gT & 15) == 0) && (u.n & ~15u)) { zq_mbar_wait(&sm.bar, uses & 1u); ++uses; }
       __syncthreads();
-#ifdef S16_RAW
-      ok = suffix_sort16_rest<true>(u.n, work_base + u.work_off, u.want_pk != 0, sm);
-#else
       ok = suffix_sort16d_rest(u.n, work_base + u.work_off, u.want_pk != 0, sm);
-#endif
     }
     __syncthreads();
     if (threadIdx.x == 0) need_old[t] = ok || u.n == 0 ? 0u : 1u;
