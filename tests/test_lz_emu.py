@@ -106,6 +106,10 @@ def _skewed(seed, k, n):
 SORT16_CASES += [_skewed(1, 2, 2180), _skewed(2, 3, 9000), _skewed(3, 5, 8471), _skewed(4, 9, 13591), _skewed(5, 17, 20000), _skewed(6, 33, 10392),
                  _skewed(7, 65, 7468), _skewed(8, 129, 14255), _skewed(9, 256, 11135), corpus.text_unit(77, 12000) + corpus.random_unit(3, 6000),
                  _skewed(10, 17, 65536)]
+# block ends and the zero padding of the character stream: runs of the smallest byte value at the end, NULs, tiny blocks
+_T9 = corpus.text_unit(5, 9000)
+SORT16_CASES += [_T9 + bytes([min(_T9)]) * 7, _T9 + bytes([min(_T9)]) * 70, b"\0" * 3 + _T9 + b"\0" * 9, _T9[:4000] + b"\0" * 40 + _T9[4000:] + b"\0",
+                 corpus.text_unit(6, 15), corpus.text_unit(6, 17), corpus.text_unit(6, 33), corpus.text_unit(6, 1025), corpus.text_unit(6, 16385)]
 
 
 @pytest.mark.parametrize("k", range(len(SORT16_CASES)))
