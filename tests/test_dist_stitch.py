@@ -117,6 +117,17 @@ def test_stitched_pieces_equal_the_whole_stream(oracle, world, kind):
     assert all(r[4] > 0 for r in res)
 
 
+@pytest.mark.parametrize("total,world", [(0, 2), (1, 3), (5, 4), (300, 4), (5000, 3)])
+def test_streams_shorter_than_the_cut(oracle, total, world):
+    """pieces that are empty or end before their first boundary: the whole stream is the left ranks' fragments"""
+    data = corpus.text_bytes(9, max(total, 1)).tobytes()[:total]
+    want = oracle.fragment(data, 1)[0].tolist() if total else []
+    res = _run_ranks(world, data, 1, overlap=3 * (8128 << 1),
+                     frag_fn=lambda p: (oracle.fragment(p, 1)[0] if len(p) else np.zeros(0, np.uint32), None))
+    assert np.concatenate([r[0] for r in res]).tolist() == want
+    assert all(r[2]["global_total"] == len(want) for r in res)
+
+
 def test_overlap_shorter_than_a_fragment_is_refused(oracle):
     data = corpus.text_bytes(5, 400_000).tobytes()  # no overlap at all: the left piece holds no boundary past its end
     tg = _ThreadGather(2)
